@@ -1,0 +1,219 @@
+/*
+ * lsk.h -- C ABI of the B200-native Krylov inner-loop kernels (liblsk.so).
+ *
+ * This is the drop-in boundary for the reference's GPU leaf tasks.  Each entry point replaces the
+ * cuBLAS / cuSPARSE / hand-kernel call made by one `cuda_task_body` of dzhang314/LegionSolvers
+ * (reference file:line cited per function) and takes exactly what that task body already holds:
+ * raw device pointers borrowed from Legion physical instances (`accessor.ptr(domain.lo())`),
+ * extents, and the task's CUDA stream.  INTEGRATION.md shows the binding for each task.
+ *
+ * Conventions (mirroring SURVEY.md section 8b):
+ *   - plain C types only; every function returns 0 on success, a cudaError_t value (>0) for a CUDA
+ *     failure, or a negative LSK_E_* code for a contract violation.  Nothing is thrown, nothing
+ *     aborts; the reference's CHECK_* macros (src/CUDAUtilities.cpp:13-63) can wrap the result.
+ *   - no entry point synchronises the stream or the device, allocates, or frees.  All scratch
+ *     lives in the per-GPU `lsk_ctx` (the replacement for CUDALibraryContext,
+ *     src/CUDAUtilities.hpp:44-66).  Pointers are borrowed for the duration of the call only.
+ *   - one host thread per context at a time (Realm runs one task at a time per GPU processor).
+ *   - indices are signed 64-bit (`long long` = Legion::coord_t), the only index type the reference
+ *     registers mat-vec tasks for (src/Initialize.cpp:463-482).  Values are fp64 (`_f64`) or fp32
+ *     (`_f32`).  Field data is SoA and stride-1, any 8-byte (4-byte for f32) alignment is accepted;
+ *     16/32-byte alignment (src/LegionSolversMapper.cpp:71-88) enables the 256-bit load paths.
+ *   - scalars are DEVICE-RESIDENT: where a reference task folds `task->futures` into alpha with
+ *     get_alpha (src/LegionUtilities.cpp:72-97), the kernel takes up to four device pointers and
+ *     folds them in its prologue with the same association:
+ *        n=0 -> 1;  n=1 -> f0;  n=2 -> f0/f1;  n=3 -> (f0*f1)/f2;  n=4 -> (f0*f1)/(f2*f3).
+ *     Dot products are written to a device double; the host never waits on them.
+ *   - there is no CPU fallback: without a CUDA device every entry point fails.
+ */
+#ifndef LSK_H
+#define LSK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSK_VERSION 100
+
+/* negative = contract violation detected on the host */
+#define LSK_E_INVALID (-1)   /* null pointer, negative extent, bad enum */
+#define LSK_E_NO_DEVICE (-2) /* no CUDA device / context creation failed */
+#define LSK_E_CAPACITY (-3)  /* per-context scratch exhausted */
+#define LSK_E_NCCL (-4)      /* NCCL failure (lsk_comm_*) */
+
+typedef struct lsk_ctx lsk_ctx;
+/* cudaStream_t, passed as an opaque pointer so the header needs no CUDA include */
+typedef void *lsk_stream;
+
+/* Legion::Rect<1, long long>: INCLUSIVE bounds (rowptr field of CSRMatrix, src/CSRMatrix.hpp:24-26) */
+typedef struct {
+    int64_t lo, hi;
+} lsk_rect;
+
+/* ------------------------------------------------------------------------------------------------
+ * Context -- replaces CUDALibraryContext / LoadCUDALibsTask (src/CUDAUtilities.cpp:66-145,
+ * src/CudaLibs.cu:11-66): one per GPU processor, created once, holds reduction scratch.
+ * ---------------------------------------------------------------------------------------------- */
+int lsk_version(void);
+const char *lsk_error_string(int status);
+int lsk_ctx_create(int device, lsk_ctx **out);
+int lsk_ctx_destroy(lsk_ctx *ctx);
+int lsk_ctx_device(const lsk_ctx *ctx);
+int lsk_ctx_sm_count(const lsk_ctx *ctx);
+/* number of kernels launched through this context since creation (bench.py's gpu_launches claim) */
+uint64_t lsk_ctx_launch_count(const lsk_ctx *ctx);
+/* device pointers to the constants 1.0, -1.0, 0.0 (Scalar(ctx, rt, value), src/Scalar.hpp:30-33) */
+const double *lsk_ctx_const_f64(const lsk_ctx *ctx, int which /*0: 1.0, 1: -1.0, 2: 0.0*/);
+
+/* ------------------------------------------------------------------------------------------------
+ * BLAS-1 leaf tasks (src/LinearAlgebraTasks.cu).  `n` = domain.get_volume() as int64 -- the
+ * reference narrows it to `int` for cuBLAS; these kernels do not.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* ScalTask::cuda_task_body (cublasDscal, src/LinearAlgebraTasks.cu:14-56): x = alpha * x */
+int lsk_scal_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, int n_terms, const double *f0,
+                 const double *f1, const double *f2, const double *f3, double *x);
+/* AxpyTask::cuda_task_body (cublasDaxpy, :59-113): y = fma(alpha, x, y) */
+int lsk_axpy_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, int n_terms, const double *f0,
+                 const double *f1, const double *f2, const double *f3, const double *x, double *y);
+/* XpayTask::cuda_task_body (xpay_kernel, :118-176): y = fma(alpha, y, x) */
+int lsk_xpay_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, int n_terms, const double *f0,
+                 const double *f1, const double *f2, const double *f3, const double *x, double *y);
+/* DotTask::cuda_task_body (cublasDdot + cudaStreamSynchronize, :179-238): *out = sum v[i]*w[i].
+ * `out` is a DEVICE pointer; the reduction is two-stage with a fixed order (deterministic). */
+int lsk_dot_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, const double *v, const double *w, double *out);
+
+int lsk_scal_f32(lsk_ctx *ctx, lsk_stream s, int64_t n, int n_terms, const float *f0,
+                 const float *f1, const float *f2, const float *f3, float *x);
+int lsk_axpy_f32(lsk_ctx *ctx, lsk_stream s, int64_t n, int n_terms, const float *f0,
+                 const float *f1, const float *f2, const float *f3, const float *x, float *y);
+int lsk_xpay_f32(lsk_ctx *ctx, lsk_stream s, int64_t n, int n_terms, const float *f0,
+                 const float *f1, const float *f2, const float *f3, const float *x, float *y);
+int lsk_dot_f32(lsk_ctx *ctx, lsk_stream s, int64_t n, const float *v, const float *w, float *out);
+
+/* IndexFill (PartitionedVector::constant_fill, src/PartitionedVector.cpp:150-173) */
+int lsk_fill_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, double value, double *x);
+int lsk_fill_f32(lsk_ctx *ctx, lsk_stream s, int64_t n, float value, float *x);
+/* fill from a device scalar (constant_fill(const Scalar&)) */
+int lsk_fill_dev_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, const double *value, double *x);
+/* IndexCopy (PartitionedVector::operator=, src/PartitionedVector.cpp:176-192): dst = src */
+int lsk_copy_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, const double *src, double *dst);
+
+/* ------------------------------------------------------------------------------------------------
+ * Scalar futures (src/Scalar.cpp:15-93 -> tasks in src/UtilityTasks.cpp:34-99), device-resident:
+ * one single-thread kernel instead of one CPU task launch.
+ * ---------------------------------------------------------------------------------------------- */
+enum lsk_scalar_op {
+    LSK_OP_NEG = 0,  /* NegateScalarTask    */
+    LSK_OP_ADD = 1,  /* AddScalarTask       */
+    LSK_OP_SUB = 2,  /* SubtractScalarTask  */
+    LSK_OP_MUL = 3,  /* MultiplyScalarTask  */
+    LSK_OP_DIV = 4,  /* DivideScalarTask    */
+    LSK_OP_SQRT = 5, /* SqrtScalarTask      */
+    LSK_OP_RSQRT = 6,/* RSqrtScalarTask: 1 / sqrt(x) */
+    LSK_OP_DUMMY = 7,/* DummyTask: returns 1 */
+    LSK_OP_COPY = 8
+};
+/* *out = op(*a, *b); b is ignored (may be NULL) for the unary ops */
+int lsk_scalar_op_f64(lsk_ctx *ctx, lsk_stream s, int op, const double *a, const double *b, double *out);
+int lsk_scalar_op_f32(lsk_ctx *ctx, lsk_stream s, int op, const float *a, const float *b, float *out);
+
+/* ------------------------------------------------------------------------------------------------
+ * CSR mat-vec -- replaces CSRMatvecTask::cuda_task_body (src/CSRMatrixTasks.cu:14-156) together
+ * with convertGlobalRowptrToLocalIndPtr + makeCuSparseCSR (src/CuSPARSEHelpers.hpp:9-101): reads
+ * the Legion layout directly, no indptr conversion, no descriptor churn, no workspace.
+ *
+ *   y[r] = sum_{k in rowptr[r]} entry[k - k_base] * x_shifted[col[k - k_base]],  r = 0..rows-1
+ *   (beta = 0: y is overwritten, as cusparseSpMV is called with beta = 0, :118-119)
+ *
+ *   rows       output_domain.volume()                       (:73)
+ *   nnz        csr_matrix.get_bounds().volume()             (kernel piece)
+ *   entry,col  entry_reader.ptr(kernel.lo), col_reader.ptr(kernel.lo)
+ *   rowptr     rowptr_reader.ptr(rowptr_domain.lo): `rows` inclusive rects of GLOBAL k
+ *   k_base     kernel_domain.lo[0], the global k of entry[0]
+ *   x_shifted  input_reader.ptr(input.lo) - input.lo[0]: indexable by GLOBAL column id -- the
+ *              same shifted pointer makeShiftedCuSparseDnVec builds (src/CuSPARSEHelpers.hpp:188-201)
+ *   y          output_writer.ptr(output.lo)
+ *   dot_w/dot_out  optional fusion (both NULL to disable): *dot_out = sum_r y[r] * dot_w[r], the
+ *              p.Ap of CGSolver::step (src/CGSolver.hpp:47-48) without a second pass over y.
+ *   dot_yy_out optional (NULL to disable): *dot_yy_out = sum_r y[r] * y[r]  (BiCGStab's u.u,
+ *              src/BiCGStabSolver.hpp:76).
+ *   variant    LSK_SPMV_AUTO picks by mean row length nnz/rows.
+ *
+ * LSK_SPMV_STREAM adds the rounded products of a row in ascending k, exactly the order of the
+ * reference's CPU body (src/CSRMatrixTasks.cpp:73-91): its result is bit-identical to it.
+ * The VECTOR/WARP variants reduce a row across lanes (tree order, fma): <= 1e-12 relative.
+ * ---------------------------------------------------------------------------------------------- */
+enum lsk_spmv_variant {
+    LSK_SPMV_AUTO = 0,
+    LSK_SPMV_STREAM = 1, /* block streams a contiguous run of non-zeros through shared memory */
+    LSK_SPMV_VECTOR = 2, /* 2..16 lanes per row */
+    LSK_SPMV_WARP = 3    /* one warp per row */
+};
+int lsk_csr_spmv_f64(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const double *entry,
+                     const int64_t *col, const lsk_rect *rowptr, int64_t k_base,
+                     const double *x_shifted, double *y, const double *dot_w, double *dot_out,
+                     double *dot_yy_out, int variant);
+int lsk_csr_spmv_f32(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const float *entry,
+                     const int64_t *col, const lsk_rect *rowptr, int64_t k_base,
+                     const float *x_shifted, float *y, const float *dot_w, float *dot_out,
+                     float *dot_yy_out, int variant);
+/* which variant AUTO resolves to for this shape (for reporting) */
+int lsk_csr_spmv_pick(int64_t rows, int64_t nnz);
+
+/* ------------------------------------------------------------------------------------------------
+ * COO mat-vec -- replaces COOMatvecTask::cuda_task_body (src/COOMatrixTasks.cu:12-146):
+ *   y_shifted[row[k]] += entry[k] * x_shifted[col[k]]   for k = 0..nnz-1   (beta = 1, :102-108)
+ * guarded like the CPU body (src/COOMatrixTasks.cpp:70-73) by row in [row_lo,row_hi] and col in
+ * [col_lo,col_hi].  Both vectors are shifted to global index 0 (:78-99).  Segmented warp-shuffle
+ * reduction over runs of equal row; run ends are combined with fp64 atomics.
+ * ---------------------------------------------------------------------------------------------- */
+int lsk_coo_spmv_f64(lsk_ctx *ctx, lsk_stream s, int64_t nnz, const double *entry,
+                     const int64_t *row, const int64_t *col, const double *x_shifted,
+                     double *y_shifted, int64_t row_lo, int64_t row_hi, int64_t col_lo,
+                     int64_t col_hi);
+int lsk_coo_spmv_f32(lsk_ctx *ctx, lsk_stream s, int64_t nnz, const float *entry,
+                     const int64_t *row, const int64_t *col, const float *x_shifted,
+                     float *y_shifted, int64_t row_lo, int64_t row_hi, int64_t col_lo,
+                     int64_t col_hi);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused solver passes.  Each equals a fixed sequence of the leaf tasks above with identical
+ * element-wise arithmetic (same fma / rounding per element), saving HBM passes.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* CGSolver::step lines src/CGSolver.hpp:50-52 in one pass:
+ *   x = fma(rr_old/pq, p, x);  r = fma((-1*rr_old)/pq, q, r);  *rr_new = sum r*r            */
+int lsk_cg_update_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, const double *rr_old, const double *pq,
+                      const double *p, const double *q, double *x, double *r, double *rr_new);
+
+/* y = fma(alpha, x, y) then *out = sum y*w  (axpy followed by dot; w may alias y).
+ * GMRES modified Gram-Schmidt (src/GMRESSolver.hpp:95-101) and BiCGStab use it. */
+int lsk_axpy_dot_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, int n_terms, const double *f0,
+                     const double *f1, const double *f2, const double *f3, const double *x,
+                     double *y, const double *w, double *out);
+
+/* two dots sharing one pass: *out_vw = sum v*w, *out_ww = sum w*w
+ * (BiCGStabSolver::step r.u and u.u, src/BiCGStabSolver.hpp:75-76) */
+int lsk_dot2_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, const double *v, const double *w,
+                 double *out_vw, double *out_ww);
+
+/* BiCGStab direction update (src/BiCGStabSolver.hpp:68-69) in one pass:
+ *   p = fma(-omega, v, p);  p = fma(beta, p, r)   with beta = (rho_new/rho_old)*(alpha/omega)   */
+int lsk_bicg_p_update_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, const double *rho_new,
+                          const double *rho_old, const double *alpha, const double *omega,
+                          const double *v, const double *r, double *p);
+
+/* BiCGStab tail (src/BiCGStabSolver.hpp:78-80) in one pass, omega = ru/uu:
+ *   x = fma(alpha, p, x); x = fma(omega, r, x); r = fma(-omega, u, r); *rho_next = sum r*rt   */
+int lsk_bicg_tail_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, const double *alpha, const double *ru,
+                      const double *uu, const double *p, const double *u, const double *rt,
+                      double *x, double *r, double *rho_next);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSK_H */

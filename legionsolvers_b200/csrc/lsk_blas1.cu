@@ -1,0 +1,492 @@
+// lsk_blas1.cu -- BLAS-1 leaf tasks, device-resident scalar algebra and the fused solver passes.
+//
+// Replaces the cuBLAS calls and xpay_kernel of the reference's src/LinearAlgebraTasks.cu.  All of
+// these kernels are pure HBM streaming: one persistent wave of CTAs (grid from the SM count),
+// 256-bit loads/stores on the 32-byte-aligned body, scalar handling of the ragged head/tail,
+// alpha folded on the device from up to four scalar slots, reductions finished on the device in a
+// fixed order.  Element-wise arithmetic is exactly the reference CPU body's (std::fma where it uses
+// std::fma, a rounded multiply for scal), so vector results are bit-identical to the oracle.
+#include <initializer_list>
+
+#include "lsk_common.cuh"
+
+namespace lsk {
+
+// ---------------------------------------------------------------------------------------------------
+// Generic streaming driver.  F provides:  T, NRED, init(), scalar(i, acc), pack(i, acc), outs(o)
+// ---------------------------------------------------------------------------------------------------
+template <typename F>
+__global__ void __launch_bounds__(kBlock)
+stream_kernel(F f, int64_t n, int64_t head, int64_t npacks, double *partials, unsigned int *ticket) {
+    using T = typename F::T;
+    constexpr int NRED = F::NRED;
+    constexpr int EPP = PackOf<T>::N;
+    f.init();
+    double acc[NRED > 0 ? NRED : 1];
+#pragma unroll
+    for (int j = 0; j < (NRED > 0 ? NRED : 1); ++j) acc[j] = 0.0;
+
+    const int64_t tid = (int64_t) blockIdx.x * kBlock + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * kBlock;
+    for (int64_t p = tid; p < npacks; p += stride) f.pack(head + p * EPP, acc);
+    // ragged edges [0, head) and [head + npacks*EPP, n); everything when the arrays are not
+    // mutually 32-byte congruent (head == n, npacks == 0)
+    const int64_t tail0 = head + npacks * EPP;
+    const int64_t nedge = head + (n - tail0);
+    for (int64_t e = tid; e < nedge; e += stride) f.scalar(e < head ? e : tail0 + (e - head), acc);
+
+    if constexpr (NRED > 0) {
+        T *out[NRED];
+        f.outs(out);
+        grid_reduce_finish<NRED, T>(acc, partials, ticket, out);
+    }
+}
+
+struct Span {
+    int64_t head, npacks;
+};
+
+// Largest 32-byte-aligned body shared by all arrays, or all-scalar when they are not congruent.
+template <typename T>
+static Span plan_span(int64_t n, std::initializer_list<const void *> ptrs) {
+    constexpr int64_t EPP = 32 / sizeof(T);
+    const void *first = *ptrs.begin();
+    bool congruent = true;
+    for (const void *p : ptrs) congruent = congruent && (mod32(p) == mod32(first)) && (mod32(p) % sizeof(T) == 0);
+    Span s;
+    if (!congruent) {
+        s.head = n;
+        s.npacks = 0;
+        return s;
+    }
+    int64_t head = (int64_t) ((32 - mod32(first)) % 32) / (int64_t) sizeof(T);
+    if (head > n) head = n;
+    s.head = head;
+    s.npacks = (n - head) / EPP;
+    return s;
+}
+
+template <typename F>
+static int launch_stream(lsk_ctx *ctx, lsk_stream s, F f, int64_t n, Span sp) {
+    if (n == 0 && F::NRED == 0) return 0;
+    const int64_t items = sp.npacks > 0 ? sp.npacks : n;
+    const int grid = stream_grid(ctx, items > 0 ? items : 1, 8);
+    RedScratch rs = {nullptr, nullptr};
+    if (F::NRED > 0) rs = next_scratch(ctx);
+    stream_kernel<F><<<grid, kBlock, 0, (cudaStream_t) s>>>(f, n, sp.head, sp.npacks, rs.partials, rs.ticket);
+    return after_launch(ctx);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Functors
+// ---------------------------------------------------------------------------------------------------
+template <typename TT>
+struct ScalF {  // ScalTask: x = alpha * x  (src/LinearAlgebraTasks.cpp:41)
+    using T = TT;
+    static constexpr int NRED = 0;
+    Alpha<T> al; T *x; T a;
+    __device__ void init() { a = fold_alpha(al); }
+    __device__ void scalar(int64_t i, double *) { x[i] = mul_rn(a, x[i]); }
+    __device__ void pack(int64_t i, double *) {
+        Pack32 px = ld256(x + i);
+#pragma unroll
+        for (int e = 0; e < PackOf<T>::N; ++e) PackOf<T>::set(px, e, mul_rn(a, PackOf<T>::get(px, e)));
+        st256(x + i, px);
+    }
+};
+
+template <typename TT>
+struct AxpyF {  // AxpyTask: y = fma(alpha, x, y)  (src/LinearAlgebraTasks.cpp:84-85)
+    using T = TT;
+    static constexpr int NRED = 0;
+    Alpha<T> al; const T *x; T *y; T a;
+    __device__ void init() { a = fold_alpha(al); }
+    __device__ void scalar(int64_t i, double *) { y[i] = fma_rn(a, x[i], y[i]); }
+    __device__ void pack(int64_t i, double *) {
+        const Pack32 px = ld256(x + i);
+        Pack32 py = ld256(y + i);
+#pragma unroll
+        for (int e = 0; e < PackOf<T>::N; ++e)
+            PackOf<T>::set(py, e, fma_rn(a, PackOf<T>::get(px, e), PackOf<T>::get(py, e)));
+        st256(y + i, py);
+    }
+};
+
+template <typename TT>
+struct XpayF {  // XpayTask: y = fma(alpha, y, x)  (src/LinearAlgebraTasks.cpp:128-129)
+    using T = TT;
+    static constexpr int NRED = 0;
+    Alpha<T> al; const T *x; T *y; T a;
+    __device__ void init() { a = fold_alpha(al); }
+    __device__ void scalar(int64_t i, double *) { y[i] = fma_rn(a, y[i], x[i]); }
+    __device__ void pack(int64_t i, double *) {
+        const Pack32 px = ld256(x + i);
+        Pack32 py = ld256(y + i);
+#pragma unroll
+        for (int e = 0; e < PackOf<T>::N; ++e)
+            PackOf<T>::set(py, e, fma_rn(a, PackOf<T>::get(py, e), PackOf<T>::get(px, e)));
+        st256(y + i, py);
+    }
+};
+
+template <typename TT>
+struct FillF {  // IndexFill
+    using T = TT;
+    static constexpr int NRED = 0;
+    T *x; T v; const T *vdev;
+    __device__ void init() { if (vdev) v = *vdev; }
+    __device__ void scalar(int64_t i, double *) { x[i] = v; }
+    __device__ void pack(int64_t i, double *) {
+        Pack32 px;
+#pragma unroll
+        for (int e = 0; e < PackOf<T>::N; ++e) PackOf<T>::set(px, e, v);
+        st256(x + i, px);
+    }
+};
+
+template <typename TT>
+struct DotF {  // DotTask: sum v*w
+    using T = TT;
+    static constexpr int NRED = 1;
+    const T *v, *w; T *out;
+    __device__ void init() {}
+    __device__ void outs(T **o) { o[0] = out; }
+    __device__ void scalar(int64_t i, double *acc) { acc[0] = fma((double) v[i], (double) w[i], acc[0]); }
+    __device__ void pack(int64_t i, double *acc) {
+        const Pack32 pv = ld256(v + i);
+        const Pack32 pw = ld256(w + i);
+#pragma unroll
+        for (int e = 0; e < PackOf<T>::N; ++e)
+            acc[0] = fma((double) PackOf<T>::get(pv, e), (double) PackOf<T>::get(pw, e), acc[0]);
+    }
+};
+
+struct Dot2F {  // r.u and u.u in one pass (src/BiCGStabSolver.hpp:75-76)
+    using T = double;
+    static constexpr int NRED = 2;
+    const double *v, *w; double *out_vw, *out_ww;
+    __device__ void init() {}
+    __device__ void outs(double **o) { o[0] = out_vw; o[1] = out_ww; }
+    __device__ void scalar(int64_t i, double *acc) {
+        const double b = w[i];
+        acc[0] = fma(v[i], b, acc[0]);
+        acc[1] = fma(b, b, acc[1]);
+    }
+    __device__ void pack(int64_t i, double *acc) {
+        const Pack32 pv = ld256(v + i);
+        const Pack32 pw = ld256(w + i);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const double b = PackOf<double>::get(pw, e);
+            acc[0] = fma(PackOf<double>::get(pv, e), b, acc[0]);
+            acc[1] = fma(b, b, acc[1]);
+        }
+    }
+};
+
+struct CgUpdateF {  // src/CGSolver.hpp:50-52: two axpys and the r.r dot in one pass
+    using T = double;
+    static constexpr int NRED = 1;
+    const double *rr_old, *pq, *neg_one; const double *p, *q; double *x, *r; double *rr_new;
+    double a1, a2;
+    __device__ void init() {
+        a1 = div_rn(*rr_old, *pq);                      // axpy(SOL, rr_old, p_norm, P): f0/f1
+        a2 = div_rn(mul_rn(*neg_one, *rr_old), *pq);    // axpy(R, -1, rr_old, p_norm, Q): (f0*f1)/f2
+    }
+    __device__ void outs(double **o) { o[0] = rr_new; }
+    __device__ void scalar(int64_t i, double *acc) {
+        x[i] = fma_rn(a1, p[i], x[i]);
+        const double rn = fma_rn(a2, q[i], r[i]);
+        r[i] = rn;
+        acc[0] = fma(rn, rn, acc[0]);
+    }
+    __device__ void pack(int64_t i, double *acc) {
+        const Pack32 pp = ld256(p + i);
+        const Pack32 pqv = ld256(q + i);
+        Pack32 px = ld256(x + i);
+        Pack32 pr = ld256(r + i);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            PackOf<double>::set(px, e, fma_rn(a1, PackOf<double>::get(pp, e), PackOf<double>::get(px, e)));
+            const double rn = fma_rn(a2, PackOf<double>::get(pqv, e), PackOf<double>::get(pr, e));
+            PackOf<double>::set(pr, e, rn);
+            acc[0] = fma(rn, rn, acc[0]);
+        }
+        st256(x + i, px);
+        st256(r + i, pr);
+    }
+};
+
+struct AxpyDotF {  // y = fma(alpha, x, y); out = sum y*w  (w may alias y)
+    using T = double;
+    static constexpr int NRED = 1;
+    Alpha<double> al; const double *x; double *y; const double *w; double *out; double a;
+    __device__ void init() { a = fold_alpha(al); }
+    __device__ void outs(double **o) { o[0] = out; }
+    __device__ void scalar(int64_t i, double *acc) {
+        const double yn = fma_rn(a, x[i], y[i]);
+        const double wv = (w == y) ? yn : w[i];
+        y[i] = yn;
+        acc[0] = fma(yn, wv, acc[0]);
+    }
+    __device__ void pack(int64_t i, double *acc) {
+        const Pack32 px = ld256(x + i);
+        Pack32 py = ld256(y + i);
+        const bool alias = (w == y);
+        Pack32 pw;
+        if (!alias) pw = ld256(w + i);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const double yn = fma_rn(a, PackOf<double>::get(px, e), PackOf<double>::get(py, e));
+            PackOf<double>::set(py, e, yn);
+            acc[0] = fma(yn, alias ? yn : PackOf<double>::get(pw, e), acc[0]);
+        }
+        st256(y + i, py);
+    }
+};
+
+struct BicgPUpdateF {  // src/BiCGStabSolver.hpp:64-69
+    using T = double;
+    static constexpr int NRED = 0;
+    const double *rho_new, *rho_old, *alpha, *omega; const double *v, *r; double *p;
+    double nomega, beta;
+    __device__ void init() {
+        beta = mul_rn(div_rn(*rho_new, *rho_old), div_rn(*alpha, *omega));
+        nomega = -(*omega);
+    }
+    __device__ void scalar(int64_t i, double *) {
+        const double t = fma_rn(nomega, v[i], p[i]);   // axpy(P, -omega, V)
+        p[i] = fma_rn(beta, t, r[i]);                  // xpay(P, beta, R)
+    }
+    __device__ void pack(int64_t i, double *) {
+        const Pack32 pv = ld256(v + i);
+        const Pack32 pr = ld256(r + i);
+        Pack32 pp = ld256(p + i);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const double t = fma_rn(nomega, PackOf<double>::get(pv, e), PackOf<double>::get(pp, e));
+            PackOf<double>::set(pp, e, fma_rn(beta, t, PackOf<double>::get(pr, e)));
+        }
+        st256(p + i, pp);
+    }
+};
+
+struct BicgTailF {  // src/BiCGStabSolver.hpp:77-80 plus the next step's rho = r.rt (:63)
+    using T = double;
+    static constexpr int NRED = 1;
+    const double *alpha, *ru, *uu; const double *p, *u, *rt; double *x, *r; double *rho_next;
+    double al, om, nom;
+    __device__ void init() {
+        al = *alpha;
+        om = div_rn(*ru, *uu);
+        nom = -om;
+    }
+    __device__ void outs(double **o) { o[0] = rho_next; }
+    __device__ void scalar(int64_t i, double *acc) {
+        const double r0 = r[i];
+        double xv = fma_rn(al, p[i], x[i]);   // axpy(SOL, alpha, P)
+        xv = fma_rn(om, r0, xv);              // axpy(SOL, omega, R)
+        x[i] = xv;
+        const double rn = fma_rn(nom, u[i], r0);  // axpy(R, -omega, U)
+        r[i] = rn;
+        acc[0] = fma(rn, rt[i], acc[0]);
+    }
+    __device__ void pack(int64_t i, double *acc) {
+        const Pack32 pp = ld256(p + i);
+        const Pack32 pu = ld256(u + i);
+        const Pack32 prt = ld256(rt + i);
+        Pack32 px = ld256(x + i);
+        Pack32 pr = ld256(r + i);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const double r0 = PackOf<double>::get(pr, e);
+            double xv = fma_rn(al, PackOf<double>::get(pp, e), PackOf<double>::get(px, e));
+            xv = fma_rn(om, r0, xv);
+            PackOf<double>::set(px, e, xv);
+            const double rn = fma_rn(nom, PackOf<double>::get(pu, e), r0);
+            PackOf<double>::set(pr, e, rn);
+            acc[0] = fma(rn, PackOf<double>::get(prt, e), acc[0]);
+        }
+        st256(x + i, px);
+        st256(r + i, pr);
+    }
+};
+
+// ---- scalar futures ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void scalar_op_kernel(int op, const T *a, const T *b, T *out) {
+    const T x = a ? *a : (T) 0;
+    const T y = b ? *b : (T) 0;
+    T r;
+    switch (op) {
+    case LSK_OP_NEG: r = -x; break;
+    case LSK_OP_ADD: r = add_rn(x, y); break;
+    case LSK_OP_SUB: r = add_rn(x, -y); break;
+    case LSK_OP_MUL: r = mul_rn(x, y); break;
+    case LSK_OP_DIV: r = div_rn(x, y); break;
+    case LSK_OP_SQRT: r = sqrt(x); break;                    // IEEE-rounded for fp64 and fp32
+    case LSK_OP_RSQRT: r = div_rn((T) 1, (T) sqrt(x)); break;  // 1 / sqrt(x), as RSqrtScalarTask
+    case LSK_OP_DUMMY: r = (T) 1; break;
+    default: r = x; break;
+    }
+    *out = r;
+}
+
+template <typename T>
+static int scalar_op(lsk_ctx *ctx, lsk_stream s, int op, const T *a, const T *b, T *out) {
+    if (!ctx || !out || op < 0 || op > LSK_OP_COPY) return LSK_E_INVALID;
+    const bool binary = (op >= LSK_OP_ADD && op <= LSK_OP_DIV);
+    if (op != LSK_OP_DUMMY && !a) return LSK_E_INVALID;
+    if (binary && !b) return LSK_E_INVALID;
+    scalar_op_kernel<T><<<1, 1, 0, (cudaStream_t) s>>>(op, a, b, out);
+    return after_launch(ctx);
+}
+
+template <typename T>
+static int do_scal(lsk_ctx *ctx, lsk_stream s, int64_t n, Alpha<T> al, T *x) {
+    if (!ctx || n < 0 || (n > 0 && !x) || !alpha_ok(al)) return LSK_E_INVALID;
+    ScalF<T> f;
+    f.al = al; f.x = x;
+    return launch_stream(ctx, s, f, n, plan_span<T>(n, {x}));
+}
+template <typename T>
+static int do_axpy(lsk_ctx *ctx, lsk_stream s, int64_t n, Alpha<T> al, const T *x, T *y) {
+    if (!ctx || n < 0 || (n > 0 && (!x || !y)) || !alpha_ok(al)) return LSK_E_INVALID;
+    AxpyF<T> f;
+    f.al = al; f.x = x; f.y = y;
+    return launch_stream(ctx, s, f, n, plan_span<T>(n, {x, y}));
+}
+template <typename T>
+static int do_xpay(lsk_ctx *ctx, lsk_stream s, int64_t n, Alpha<T> al, const T *x, T *y) {
+    if (!ctx || n < 0 || (n > 0 && (!x || !y)) || !alpha_ok(al)) return LSK_E_INVALID;
+    XpayF<T> f;
+    f.al = al; f.x = x; f.y = y;
+    return launch_stream(ctx, s, f, n, plan_span<T>(n, {x, y}));
+}
+template <typename T>
+static int do_dot(lsk_ctx *ctx, lsk_stream s, int64_t n, const T *v, const T *w, T *out) {
+    if (!ctx || n < 0 || (n > 0 && (!v || !w)) || !out) return LSK_E_INVALID;
+    DotF<T> f;
+    f.v = v; f.w = w; f.out = out;
+    return launch_stream(ctx, s, f, n, plan_span<T>(n, {v, w}));
+}
+template <typename T>
+static int do_fill(lsk_ctx *ctx, lsk_stream s, int64_t n, T value, const T *vdev, T *x) {
+    if (!ctx || n < 0 || (n > 0 && !x)) return LSK_E_INVALID;
+    FillF<T> f;
+    f.x = x; f.v = value; f.vdev = vdev;
+    return launch_stream(ctx, s, f, n, plan_span<T>(n, {x}));
+}
+
+}  // namespace lsk
+
+using namespace lsk;
+
+extern "C" {
+
+int lsk_scal_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, int nt, const double *f0, const double *f1,
+                 const double *f2, const double *f3, double *x) {
+    return do_scal<double>(ctx, s, n, make_alpha(nt, f0, f1, f2, f3), x);
+}
+int lsk_axpy_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, int nt, const double *f0, const double *f1,
+                 const double *f2, const double *f3, const double *x, double *y) {
+    return do_axpy<double>(ctx, s, n, make_alpha(nt, f0, f1, f2, f3), x, y);
+}
+int lsk_xpay_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, int nt, const double *f0, const double *f1,
+                 const double *f2, const double *f3, const double *x, double *y) {
+    return do_xpay<double>(ctx, s, n, make_alpha(nt, f0, f1, f2, f3), x, y);
+}
+int lsk_dot_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, const double *v, const double *w, double *out) {
+    return do_dot<double>(ctx, s, n, v, w, out);
+}
+int lsk_scal_f32(lsk_ctx *ctx, lsk_stream s, int64_t n, int nt, const float *f0, const float *f1,
+                 const float *f2, const float *f3, float *x) {
+    return do_scal<float>(ctx, s, n, make_alpha(nt, f0, f1, f2, f3), x);
+}
+int lsk_axpy_f32(lsk_ctx *ctx, lsk_stream s, int64_t n, int nt, const float *f0, const float *f1,
+                 const float *f2, const float *f3, const float *x, float *y) {
+    return do_axpy<float>(ctx, s, n, make_alpha(nt, f0, f1, f2, f3), x, y);
+}
+int lsk_xpay_f32(lsk_ctx *ctx, lsk_stream s, int64_t n, int nt, const float *f0, const float *f1,
+                 const float *f2, const float *f3, const float *x, float *y) {
+    return do_xpay<float>(ctx, s, n, make_alpha(nt, f0, f1, f2, f3), x, y);
+}
+int lsk_dot_f32(lsk_ctx *ctx, lsk_stream s, int64_t n, const float *v, const float *w, float *out) {
+    return do_dot<float>(ctx, s, n, v, w, out);
+}
+
+int lsk_fill_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, double value, double *x) {
+    return do_fill<double>(ctx, s, n, value, nullptr, x);
+}
+int lsk_fill_f32(lsk_ctx *ctx, lsk_stream s, int64_t n, float value, float *x) {
+    return do_fill<float>(ctx, s, n, value, nullptr, x);
+}
+int lsk_fill_dev_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, const double *value, double *x) {
+    if (!value) return LSK_E_INVALID;
+    return do_fill<double>(ctx, s, n, 0.0, value, x);
+}
+int lsk_copy_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, const double *src, double *dst) {
+    if (!ctx || n < 0 || (n > 0 && (!src || !dst))) return LSK_E_INVALID;
+    if (n == 0) return 0;
+    LSK_RETURN_IF_CUDA(cudaMemcpyAsync(dst, src, (size_t) n * sizeof(double), cudaMemcpyDeviceToDevice,
+                                       (cudaStream_t) s));
+    return 0;
+}
+
+int lsk_scalar_op_f64(lsk_ctx *ctx, lsk_stream s, int op, const double *a, const double *b, double *out) {
+    return scalar_op<double>(ctx, s, op, a, b, out);
+}
+int lsk_scalar_op_f32(lsk_ctx *ctx, lsk_stream s, int op, const float *a, const float *b, float *out) {
+    return scalar_op<float>(ctx, s, op, a, b, out);
+}
+
+int lsk_cg_update_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, const double *rr_old, const double *pq,
+                      const double *p, const double *q, double *x, double *r, double *rr_new) {
+    if (!ctx || n < 0 || !rr_old || !pq || !rr_new || (n > 0 && (!p || !q || !x || !r))) return LSK_E_INVALID;
+    CgUpdateF f;
+    f.rr_old = rr_old; f.pq = pq; f.neg_one = ctx->consts + 1;
+    f.p = p; f.q = q; f.x = x; f.r = r; f.rr_new = rr_new;
+    return launch_stream(ctx, s, f, n, plan_span<double>(n, {p, q, x, r}));
+}
+
+int lsk_axpy_dot_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, int nt, const double *f0, const double *f1,
+                     const double *f2, const double *f3, const double *x, double *y, const double *w,
+                     double *out) {
+    Alpha<double> al = make_alpha(nt, f0, f1, f2, f3);
+    if (!ctx || n < 0 || !out || !alpha_ok(al) || (n > 0 && (!x || !y || !w))) return LSK_E_INVALID;
+    AxpyDotF f;
+    f.al = al; f.x = x; f.y = y; f.w = w; f.out = out;
+    return launch_stream(ctx, s, f, n, plan_span<double>(n, {x, y, w}));
+}
+
+int lsk_dot2_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, const double *v, const double *w, double *out_vw,
+                 double *out_ww) {
+    if (!ctx || n < 0 || !out_vw || !out_ww || (n > 0 && (!v || !w))) return LSK_E_INVALID;
+    Dot2F f;
+    f.v = v; f.w = w; f.out_vw = out_vw; f.out_ww = out_ww;
+    return launch_stream(ctx, s, f, n, plan_span<double>(n, {v, w}));
+}
+
+int lsk_bicg_p_update_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, const double *rho_new,
+                          const double *rho_old, const double *alpha, const double *omega,
+                          const double *v, const double *r, double *p) {
+    if (!ctx || n < 0 || !rho_new || !rho_old || !alpha || !omega || (n > 0 && (!v || !r || !p)))
+        return LSK_E_INVALID;
+    BicgPUpdateF f;
+    f.rho_new = rho_new; f.rho_old = rho_old; f.alpha = alpha; f.omega = omega;
+    f.v = v; f.r = r; f.p = p;
+    return launch_stream(ctx, s, f, n, plan_span<double>(n, {v, r, p}));
+}
+
+int lsk_bicg_tail_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, const double *alpha, const double *ru,
+                      const double *uu, const double *p, const double *u, const double *rt, double *x,
+                      double *r, double *rho_next) {
+    if (!ctx || n < 0 || !alpha || !ru || !uu || !rho_next || (n > 0 && (!p || !u || !rt || !x || !r)))
+        return LSK_E_INVALID;
+    BicgTailF f;
+    f.alpha = alpha; f.ru = ru; f.uu = uu; f.p = p; f.u = u; f.rt = rt; f.x = x; f.r = r;
+    f.rho_next = rho_next;
+    return launch_stream(ctx, s, f, n, plan_span<double>(n, {p, u, rt, x, r}));
+}
+
+}  // extern "C"

@@ -1,0 +1,249 @@
+// lsk_common.cuh -- shared device/host helpers for the sm_100a Krylov kernels.
+//
+// Everything here is written for Blackwell B200 only (compile with
+// -gencode arch=compute_100a,code=sm_100a): 256-bit global loads/stores (LDG.E.256 / STG.E.256),
+// L2 eviction-priority hints on the streamed matrix arrays, and grids sized from the SM count.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/lsk.h"
+
+namespace lsk {
+
+constexpr int kBlock = 256;          // threads per CTA for every kernel in this library
+constexpr int kWarps = kBlock / 32;
+constexpr int kMaxPartials = 4096;   // >= largest grid of any reducing kernel
+constexpr int kScratchSets = 32;     // rotating reduction scratch (several reductions in flight)
+constexpr int kMaxRed = 2;           // outputs per fused reduction
+
+}  // namespace lsk
+
+// The per-GPU context: replaces the reference's CUDALibraryContext (stream + cuBLAS + cuSPARSE
+// handles, src/CUDAUtilities.hpp:44-66) with the only state these kernels need.
+struct lsk_ctx {
+    int device;
+    int sm_count;
+    double *partials;          // [kScratchSets][kMaxRed][kMaxPartials]
+    unsigned int *tickets;     // [kScratchSets], zero between launches
+    double *consts;            // {1.0, -1.0, 0.0}
+    int cursor;                // next scratch set
+    unsigned long long launches;
+};
+
+namespace lsk {
+
+struct RedScratch {
+    double *partials;      // [kMaxRed][kMaxPartials]
+    unsigned int *ticket;
+};
+
+inline RedScratch next_scratch(lsk_ctx *ctx) {
+    const int set = ctx->cursor;
+    ctx->cursor = (ctx->cursor + 1) % kScratchSets;
+    RedScratch r;
+    r.partials = ctx->partials + (size_t) set * kMaxRed * kMaxPartials;
+    r.ticket = ctx->tickets + set;
+    return r;
+}
+
+// Streaming kernels are persistent: one wave of CTAs sized from the SM count, grid-stride inside.
+inline int stream_grid(const lsk_ctx *ctx, int64_t work_items, int ctas_per_sm) {
+    int64_t want = (work_items + kBlock - 1) / kBlock;
+    int64_t cap = (int64_t) ctx->sm_count * ctas_per_sm;
+    if (cap > kMaxPartials) cap = kMaxPartials;
+    if (want < 1) want = 1;
+    return (int) (want < cap ? want : cap);
+}
+
+template <typename T>
+struct Alpha {  // device-resident get_alpha (src/LegionUtilities.cpp:72-97)
+    const T *f[4];
+    int n;
+};
+
+template <typename T>
+inline Alpha<T> make_alpha(int n, const T *f0, const T *f1, const T *f2, const T *f3) {
+    Alpha<T> a;
+    a.f[0] = f0; a.f[1] = f1; a.f[2] = f2; a.f[3] = f3;
+    a.n = n;
+    return a;
+}
+
+template <typename T>
+inline bool alpha_ok(const Alpha<T> &a) {
+    if (a.n < 0 || a.n > 4) return false;
+    for (int i = 0; i < a.n; ++i)
+        if (a.f[i] == nullptr) return false;
+    return true;
+}
+
+#ifdef __CUDACC__
+
+// ---- exact-rounding arithmetic (never let the compiler contract these) ----------------------------
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double fma_rn(double a, double b, double c) { return __fma_rn(a, b, c); }
+__device__ __forceinline__ float fma_rn(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+
+template <typename T>
+__device__ __forceinline__ T fold_alpha(const Alpha<T> &a) {
+    switch (a.n) {
+    case 0: return (T) 1;
+    case 1: return *a.f[0];
+    case 2: return div_rn(*a.f[0], *a.f[1]);
+    case 3: return div_rn(mul_rn(*a.f[0], *a.f[1]), *a.f[2]);
+    default: return div_rn(mul_rn(*a.f[0], *a.f[1]), mul_rn(*a.f[2], *a.f[3]));
+    }
+}
+
+// ---- 256-bit global memory access (sm_100: LDG.E.256 / STG.E.256) ---------------------------------
+struct alignas(32) Pack32 {
+    unsigned long long q[4];
+};
+
+// default cache policy: vectors, which should stay L2-resident between solver passes
+__device__ __forceinline__ Pack32 ld256(const void *p) {
+    Pack32 r;
+    asm volatile("ld.global.v4.b64 {%0, %1, %2, %3}, [%4];"
+                 : "=l"(r.q[0]), "=l"(r.q[1]), "=l"(r.q[2]), "=l"(r.q[3])
+                 : "l"(p));
+    return r;
+}
+// streamed-once data (matrix values / column indices): bypass L1, mark evict-first in L2 so the
+// 126 MB L2 keeps the solver's vectors instead
+__device__ __forceinline__ Pack32 ld256_stream(const void *p) {
+    Pack32 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0, %1, %2, %3}, [%4];"
+                 : "=l"(r.q[0]), "=l"(r.q[1]), "=l"(r.q[2]), "=l"(r.q[3])
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st256(void *p, const Pack32 &v) {
+    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(v.q[0]), "l"(v.q[1]),
+                 "l"(v.q[2]), "l"(v.q[3])
+                 : "memory");
+}
+// 8-byte streamed loads for the ragged edges of a tile
+__device__ __forceinline__ unsigned long long ld64_stream(const void *p) {
+    unsigned long long r;
+    asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ unsigned int ld32_stream(const void *p) {
+    unsigned int r;
+    asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+
+// element view of a 32-byte pack
+template <typename T>
+struct PackOf;
+template <>
+struct PackOf<double> {
+    static constexpr int N = 4;
+    __device__ static __forceinline__ double get(const Pack32 &p, int i) {
+        return __longlong_as_double((long long) p.q[i]);
+    }
+    __device__ static __forceinline__ void set(Pack32 &p, int i, double v) {
+        p.q[i] = (unsigned long long) __double_as_longlong(v);
+    }
+};
+template <>
+struct PackOf<float> {
+    static constexpr int N = 8;
+    __device__ static __forceinline__ float get(const Pack32 &p, int i) {
+        const unsigned long long w = p.q[i >> 1];
+        return __uint_as_float((unsigned int) ((i & 1) ? (w >> 32) : (w & 0xffffffffull)));
+    }
+    __device__ static __forceinline__ void set(Pack32 &p, int i, float v) {
+        const unsigned long long b = __float_as_uint(v);
+        unsigned long long &w = p.q[i >> 1];
+        w = (i & 1) ? ((w & 0x00000000ffffffffull) | (b << 32)) : ((w & 0xffffffff00000000ull) | b);
+    }
+};
+template <>
+struct PackOf<long long> {
+    static constexpr int N = 4;
+    __device__ static __forceinline__ long long get(const Pack32 &p, int i) { return (long long) p.q[i]; }
+};
+
+// ---- deterministic reductions ----------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// All threads of the CTA call this; the result is valid in thread 0.
+__device__ __forceinline__ double block_sum(double v, double *smem /*[kWarps]*/) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();  // smem may still be in use by a previous call
+    if (lane == 0) smem[warp] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (warp == 0) {
+        r = lane < kWarps ? smem[lane] : 0.0;
+#pragma unroll
+        for (int o = kWarps / 2; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    }
+    return r;
+}
+
+// Two-stage grid reduction with a fixed summation order: every CTA publishes its partial(s); the
+// CTA that draws the last ticket folds them (thread-strided, then block_sum) and writes the result.
+// No second launch, no atomics on the values, bitwise reproducible for a given grid size.
+// Accumulation is fp64 for both entry types; the result is narrowed on the final store.
+template <int NRED, typename T>
+__device__ __forceinline__ void grid_reduce_finish(const double (&acc)[NRED], double *partials,
+                                                   unsigned int *ticket, T *const (&out)[NRED]) {
+    __shared__ double s_red[kWarps];
+    __shared__ bool s_last;
+#pragma unroll
+    for (int j = 0; j < NRED; ++j) {
+        const double b = block_sum(acc[j], s_red);
+        if (threadIdx.x == 0) partials[(size_t) j * kMaxPartials + blockIdx.x] = b;
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int t = atomicAdd(ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+#pragma unroll
+    for (int j = 0; j < NRED; ++j) {
+        double v = 0.0;
+        const volatile double *pj = partials + (size_t) j * kMaxPartials;
+        for (unsigned int i = threadIdx.x; i < gridDim.x; i += kBlock) v += pj[i];
+        v = block_sum(v, s_red);
+        if (threadIdx.x == 0 && out[j] != nullptr) *out[j] = (T) v;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;  // ready for the next launch on this scratch set
+}
+
+#endif  // __CUDACC__
+
+// ---- host-side launch bookkeeping --------------------------------------------------------------------
+#define LSK_RETURN_IF_CUDA(expr)                  \
+    do {                                          \
+        cudaError_t e_ = (expr);                  \
+        if (e_ != cudaSuccess) return (int) e_;   \
+    } while (0)
+
+inline int after_launch(lsk_ctx *ctx) {
+    ctx->launches += 1;
+    const cudaError_t e = cudaPeekAtLastError();
+    return e == cudaSuccess ? 0 : (int) cudaGetLastError();
+}
+
+inline uintptr_t mod32(const void *p) { return (uintptr_t) p & 31u; }
+
+}  // namespace lsk
