@@ -10,6 +10,9 @@
 // in L2, (ii) keeping x on the cached path (L1 + 126 MB L2) so its traffic stays compulsory, and
 // (iii) enough bytes in flight per SM.
 #include <limits.h>
+#include <stdlib.h>
+
+#include <type_traits>
 
 #include "lsk_common.cuh"
 
@@ -186,6 +189,377 @@ csr_stream_kernel(int64_t rows, int rpb, int64_t n_row_blocks, const T *__restri
 }
 
 // ===================================================================================================
+// Software-pipelined form of the stream kernel (the one used whenever entry/col are mutually
+// aligned).  Same arithmetic, same result bits.  The un-pipelined kernel pays three dependent
+// memory latencies per row block (rowptr -> streamed tile -> x gather) with nothing in flight in
+// between; here every thread (i) prefetches its rect of the NEXT row block one block ahead and
+// (ii) issues the 256-bit streamed loads of the next tile BEFORE it adds up the current tile, so
+// HBM requests are outstanding while the CTA is in its shared-memory phase.
+// ===================================================================================================
+template <typename T, int NDOT>
+__global__ void __launch_bounds__(kBlock, 3)
+csr_stream_pipe_kernel(int64_t rows, int rpb, int64_t n_row_blocks, const T *__restrict__ entry,
+                       const long long *__restrict__ col, const lsk_rect *__restrict__ rowptr,
+                       int64_t k_base, const T *__restrict__ x, T *__restrict__ y,
+                       const T *__restrict__ dot_w, double *partials, unsigned int *ticket, T *out_yw,
+                       T *out_yy) {
+    constexpr int U = kTile / (4 * kBlock);
+    __shared__ __align__(16) T s_prod[kTile];
+    __shared__ long long s_lo[kWarps], s_hi[kWarps];
+    const int tid = threadIdx.x;
+    const int64_t G = gridDim.x;
+    double dacc[NDOT > 0 ? NDOT : 1];
+#pragma unroll
+    for (int j = 0; j < (NDOT > 0 ? NDOT : 1); ++j) dacc[j] = 0.0;
+
+    // my row's run [lo, hi1) of row block rb, piece-local element indices (empty: lo > hi1)
+    auto load_rect = [&](int64_t rb, long long &lo, long long &hi1) {
+        lo = LLONG_MAX;
+        hi1 = LLONG_MIN;
+        if (rb < n_row_blocks) {
+            const int64_t r = rb * rpb + tid;
+            if (tid < rpb && r < rows) {
+                const longlong2 rc = __ldg(reinterpret_cast<const longlong2 *>(rowptr + r));
+                if (rc.y >= rc.x) {
+                    lo = rc.x - k_base;
+                    hi1 = rc.y + 1 - k_base;
+                }
+            }
+        }
+    };
+    auto publish_span = [&](long long lo, long long hi1) {
+        const long long wl = warp_min_ll(lo), wh = warp_max_ll(hi1);
+        if ((tid & 31) == 0) {
+            s_lo[tid >> 5] = wl;
+            s_hi[tid >> 5] = wh;
+        }
+    };
+    auto read_span = [&](long long &jb, long long &je) {
+        jb = s_lo[0];
+        je = s_hi[0];
+#pragma unroll
+        for (int w = 1; w < kWarps; ++w) {
+            jb = s_lo[w] < jb ? s_lo[w] : jb;
+            je = s_hi[w] > je ? s_hi[w] : je;
+        }
+        if (je <= jb) jb = je = 0;  // no non-zeros in this row block: one empty tile
+    };
+    long long c[U][4];
+    T v[U][4];
+    bool full[U];
+    auto issue_loads = [&](long long t0, long long jb, long long je) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long j = t0 + (long long) (u * kBlock + tid) * 4;
+            full[u] = (j >= jb) && (j + 4 <= je);
+            if (full[u]) {
+                const Pack32 pc = ld256_stream(col + j);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) c[u][e] = (long long) pc.q[e];
+                load4_stream(entry + j, v[u]);
+            }
+        }
+    };
+    auto tile_start = [&](long long jb) {
+        return jb - (long long) ((reinterpret_cast<uintptr_t>(col + jb) >> 3) & 3);
+    };
+
+    int64_t rb = blockIdx.x;
+    long long lo, hi1, jb, je, nlo, nhi1;
+    load_rect(rb, lo, hi1);
+    publish_span(lo, hi1);
+    __syncthreads();
+    read_span(jb, je);
+    __syncthreads();
+    long long t0 = tile_start(jb);
+    issue_loads(t0, jb, je);
+    load_rect(rb + G, nlo, nhi1);  // in flight until the span exchange below
+    T acc = (T) 0;
+
+    while (rb < n_row_blocks) {
+        // ---- products of the tile held in registers -> shared memory
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int slot = (u * kBlock + tid) * 4;
+            const long long j = t0 + slot;
+            if (full[u]) {
+                T xv[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) xv[e] = __ldg(x + c[u][e]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[u][e] = mul_rn(v[u][e], xv[e]);
+                store4_shared(s_prod + slot, v[u]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const long long jj = j + e;
+                    if (jj >= jb && jj < je)
+                        s_prod[slot + e] = mul_rn(load1_stream(entry + jj), __ldg(x + load1_stream(col + jj)));
+                }
+            }
+        }
+        const bool last_tile = (t0 + kTile >= je);
+        if (last_tile) publish_span(nlo, nhi1);
+        __syncthreads();
+        // ---- put the next tile's HBM loads in flight, then add up this tile
+        const long long cur_t0 = t0;
+        long long njb = 0, nje = 0;
+        if (last_tile) {
+            read_span(njb, nje);
+            if (rb + G < n_row_blocks) issue_loads(tile_start(njb), njb, nje);
+        } else {
+            issue_loads(t0 + kTile, jb, je);
+        }
+        {
+            const long long a = lo > cur_t0 ? lo : cur_t0;
+            const long long b = hi1 < cur_t0 + kTile ? hi1 : cur_t0 + kTile;
+            for (long long j = a; j < b; ++j) acc = add_rn(acc, s_prod[j - cur_t0]);
+        }
+        if (last_tile) {
+            const int64_t r = rb * rpb + tid;
+            if (tid < rpb && r < rows) {
+                y[r] = acc;
+                if constexpr (NDOT >= 1) dacc[0] = fma((double) acc, (double) __ldg(dot_w + r), dacc[0]);
+                if constexpr (NDOT >= 2) dacc[NDOT - 1] = fma((double) acc, (double) acc, dacc[NDOT - 1]);
+            }
+            acc = (T) 0;
+            rb += G;
+            lo = nlo;
+            hi1 = nhi1;
+            jb = njb;
+            je = nje;
+            t0 = tile_start(jb);
+            load_rect(rb + G, nlo, nhi1);
+        } else {
+            t0 += kTile;
+        }
+        __syncthreads();
+    }
+    if constexpr (NDOT > 0) {
+        T *out[NDOT];
+        out[0] = out_yw;
+        if constexpr (NDOT >= 2) out[NDOT - 1] = out_yy;
+        grid_reduce_finish<NDOT, T>(dacc, partials, ticket, out);
+    }
+}
+
+// ===================================================================================================
+// TMA-staged stream kernel (fp64; the default for short and medium rows).
+//
+// ncu on the register-staged kernel above showed DRAM traffic equal to the algorithmic bytes but the
+// L1 data pipe as the busiest unit: with lanes striding the non-zero stream, one 32-lane x-gather
+// touches ~18 rows x 7 stencil legs = ~11 cache lines, and every product crosses shared memory twice.
+// This kernel flips the mapping.  The CTA's run of (col, entry) is copied global->shared by the TMA
+// engine (cp.async.bulk, 16 KB per array per tile, L2 evict-first, completion on an mbarrier, two
+// stages so the next tile is in flight while this one is consumed); threads then own ROWS: lane l
+// of a warp walks row r0+l, so gather e of a warp reads leg e of 32 consecutive rows -- one or two
+// lines for banded matrices -- and shared-memory reads are stride-(row length) 8-byte accesses
+// (conflict-free for odd lengths).  Each thread adds its rounded products in ascending k in a
+// register: bit-identical to the reference CPU body, no product staging, one barrier per tile.
+// ===================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t) __cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar,
+                                             uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
+template <int NDOT>
+__global__ void __launch_bounds__(kBlock, 3)
+csr_tma_kernel(int64_t rows, int64_t nnz, int rpb, int64_t n_row_blocks, const double *__restrict__ entry,
+               const long long *__restrict__ col, const lsk_rect *__restrict__ rowptr, int64_t k_base,
+               const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ dot_w,
+               double *partials, unsigned int *ticket, double *out_yw, double *out_yy) {
+    constexpr int S = 2;  // stages: 2 x (16 KB col + 16 KB entry) = 64 KB dynamic shared memory
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    long long (*s_col)[kTile] = reinterpret_cast<long long (*)[kTile]>(s_dyn);
+    double (*s_ent)[kTile] = reinterpret_cast<double (*)[kTile]>(s_dyn + (size_t) S * kTile * sizeof(long long));
+    __shared__ __align__(8) uint64_t s_full[S];
+    __shared__ long long s_lo[2][kWarps], s_hi[2][kWarps];
+    const int tid = threadIdx.x;
+    const int64_t G = gridDim.x;
+    double dacc[NDOT > 0 ? NDOT : 1];
+#pragma unroll
+    for (int j = 0; j < (NDOT > 0 ? NDOT : 1); ++j) dacc[j] = 0.0;
+
+    uint64_t policy = 0;
+    if (tid == 0) {
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+#pragma unroll
+        for (int s = 0; s < S; ++s) mbar_init(&s_full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+
+    auto load_rect = [&](int64_t rb, long long &lo, long long &hi1) {
+        lo = LLONG_MAX;
+        hi1 = LLONG_MIN;
+        if (rb < n_row_blocks) {
+            const int64_t r = rb * rpb + tid;
+            if (tid < rpb && r < rows) {
+                const longlong2 rc = __ldg(reinterpret_cast<const longlong2 *>(rowptr + r));
+                if (rc.y >= rc.x) {
+                    lo = rc.x - k_base;
+                    hi1 = rc.y + 1 - k_base;
+                }
+            }
+        }
+    };
+    auto publish_span = [&](int pb, long long lo, long long hi1) {
+        const long long wl = warp_min_ll(lo), wh = warp_max_ll(hi1);
+        if ((tid & 31) == 0) {
+            s_lo[pb][tid >> 5] = wl;
+            s_hi[pb][tid >> 5] = wh;
+        }
+    };
+    auto read_span = [&](int pb, long long &jb, long long &je) {
+        jb = s_lo[pb][0];
+        je = s_hi[pb][0];
+#pragma unroll
+        for (int w = 1; w < kWarps; ++w) {
+            jb = s_lo[pb][w] < jb ? s_lo[pb][w] : jb;
+            je = s_hi[pb][w] > je ? s_hi[pb][w] : je;
+        }
+        if (je <= jb) jb = je = 0;
+    };
+    // tiles start where `col` (and the congruent `entry`) are 16-byte aligned
+    auto tile_start = [&](long long jb) { return jb - (long long) ((reinterpret_cast<uintptr_t>(col + jb) >> 3) & 1); };
+    // thread 0: copy elements [t0, t0 + kTile) /\ [jb, je) of both arrays into stage s
+    auto issue_tile = [&](int s, long long t0, long long jb, long long je) {
+        long long a = t0 > jb ? t0 : jb;                       // first needed element
+        long long b = (t0 + kTile) < je ? (t0 + kTile) : je;   // one past the last
+        if (b < a) b = a;
+        // bulk part: 16-byte aligned on both ends, never outside [0, nnz)
+        long long A = a + ((reinterpret_cast<uintptr_t>(col + a) >> 3) & 1);
+        long long B = b - ((reinterpret_cast<uintptr_t>(col + b) >> 3) & 1);
+        if (B < A) B = A;
+        const uint32_t bytes = (uint32_t) (B - A) * 8u;
+        mbar_expect_tx(&s_full[s], 2u * bytes);
+        if (bytes) {
+            tma_bulk_g2s(&s_col[s][A - t0], col + A, bytes, &s_full[s], policy);
+            tma_bulk_g2s(&s_ent[s][A - t0], entry + A, bytes, &s_full[s], policy);
+        }
+        // ragged single elements at either end (generic proxy; visible after the next CTA barrier)
+        if (a < A && a < b) {
+            s_col[s][a - t0] = load1_stream(col + a);
+            s_ent[s][a - t0] = load1_stream(entry + a);
+        }
+        if (B < b && B >= A && !(a < A && B == a)) {
+            s_col[s][B - t0] = load1_stream(col + B);
+            s_ent[s][B - t0] = load1_stream(entry + B);
+        }
+    };
+
+    int64_t rb = blockIdx.x;
+    long long lo, hi1, jb, je, nlo, nhi1;
+    load_rect(rb, lo, hi1);
+    publish_span(0, lo, hi1);
+    __syncthreads();  // also publishes the mbarrier inits
+    read_span(0, jb, je);
+    long long t0 = tile_start(jb);
+    int stage = 0, pb = 1;
+    uint32_t phases = 0;  // bit s = parity to wait for on stage s
+    if (tid == 0) issue_tile(0, t0, jb, je);
+    load_rect(rb + G, nlo, nhi1);
+    double acc = 0.0;
+
+    while (rb < n_row_blocks) {
+        const bool last_tile = (t0 + kTile >= je);
+        if (last_tile) publish_span(pb, nlo, nhi1);
+        // one barrier per tile: (i) stage^1, consumed last iteration, may now be overwritten;
+        // (ii) the next block's span is published; (iii) ragged elements stored by thread 0 are visible
+        __syncthreads();
+        long long njb = 0, nje = 0;
+        if (last_tile) {
+            read_span(pb, njb, nje);
+            pb ^= 1;
+        }
+        if (tid == 0) {
+            if (!last_tile) issue_tile(stage ^ 1, t0 + kTile, jb, je);
+            else if (rb + G < n_row_blocks) issue_tile(stage ^ 1, tile_start(njb), njb, nje);
+        }
+        // ---- consume this tile: thread-per-row, products added in ascending k
+        mbar_wait(&s_full[stage], (phases >> stage) & 1u);
+        phases ^= (1u << stage);
+        {
+            const long long a = lo > t0 ? lo : t0;
+            const long long b = hi1 < t0 + kTile ? hi1 : t0 + kTile;
+            const long long *sc = s_col[stage];
+            const double *se = s_ent[stage];
+            // up to kChunk gathers in flight per thread; the adds stay in ascending k
+            constexpr int kChunk = 8;
+            long long j = a;
+            for (; j + kChunk <= b; j += kChunk) {  // full chunks: no predication
+                const int o = (int) (j - t0);
+                double xv[kChunk];
+#pragma unroll
+                for (int e = 0; e < kChunk; ++e) xv[e] = __ldg(x + sc[o + e]);
+#pragma unroll
+                for (int e = 0; e < kChunk; ++e) acc = add_rn(acc, mul_rn(se[o + e], xv[e]));
+            }
+            if (j < b) {  // 1..kChunk-1 left
+                const int o = (int) (j - t0);
+                const int rem = (int) (b - j);
+                double xv[kChunk - 1];
+#pragma unroll
+                for (int e = 0; e < kChunk - 1; ++e) xv[e] = (e < rem) ? __ldg(x + sc[o + e]) : 0.0;
+#pragma unroll
+                for (int e = 0; e < kChunk - 1; ++e)
+                    if (e < rem) acc = add_rn(acc, mul_rn(se[o + e], xv[e]));
+            }
+        }
+        if (last_tile) {
+            const int64_t r = rb * rpb + tid;
+            if (tid < rpb && r < rows) {
+                y[r] = acc;
+                if constexpr (NDOT >= 1) dacc[0] = fma(acc, __ldg(dot_w + r), dacc[0]);
+                if constexpr (NDOT >= 2) dacc[NDOT - 1] = fma(acc, acc, dacc[NDOT - 1]);
+            }
+            acc = 0.0;
+            rb += G;
+            lo = nlo;
+            hi1 = nhi1;
+            jb = njb;
+            je = nje;
+            t0 = tile_start(jb);
+            load_rect(rb + G, nlo, nhi1);
+        } else {
+            t0 += kTile;
+        }
+        stage ^= 1;
+    }
+    if constexpr (NDOT > 0) {
+        double *out[NDOT];
+        out[0] = out_yw;
+        if constexpr (NDOT >= 2) out[NDOT - 1] = out_yy;
+        grid_reduce_finish<NDOT, double>(dacc, partials, ticket, out);
+    }
+}
+
+// ===================================================================================================
 // CSR "vector" kernel: V lanes per row (V = 32 is warp-per-row).  Lanes stride the row, partial
 // sums are combined with warp shuffles.  For long rows (dense blocks, power-law heads) where a
 // single thread adding the whole row would serialise.  Tree order + fma: <= 1e-12 relative.
@@ -304,6 +678,39 @@ static void launch_stream_kernel(int ndot, int grid, cudaStream_t st, int64_t ro
         csr_stream_kernel<T, VEC, 2><<<grid, kBlock, 0, st>>>(rows, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1);
 }
 
+template <typename T>
+static void launch_pipe_kernel(int ndot, int grid, cudaStream_t st, int64_t rows, int rpb, int64_t nrb,
+                               const T *entry, const long long *col, const lsk_rect *rowptr, int64_t k_base,
+                               const T *x, T *y, const T *dot_w, RedScratch rs, T *o0, T *o1) {
+    if (ndot == 0)
+        csr_stream_pipe_kernel<T, 0><<<grid, kBlock, 0, st>>>(rows, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1);
+    else if (ndot == 1)
+        csr_stream_pipe_kernel<T, 1><<<grid, kBlock, 0, st>>>(rows, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1);
+    else
+        csr_stream_pipe_kernel<T, 2><<<grid, kBlock, 0, st>>>(rows, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1);
+}
+
+constexpr size_t kTmaSmem = (size_t) 2 * kTile * (sizeof(long long) + sizeof(double));
+
+static int launch_tma_kernel(int ndot, int grid, cudaStream_t st, int64_t rows, int64_t nnz, int rpb, int64_t nrb,
+                             const double *entry, const long long *col, const lsk_rect *rowptr, int64_t k_base,
+                             const double *x, double *y, const double *dot_w, RedScratch rs, double *o0, double *o1) {
+    static bool configured = false;
+    if (!configured) {
+        LSK_RETURN_IF_CUDA(cudaFuncSetAttribute(csr_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kTmaSmem));
+        LSK_RETURN_IF_CUDA(cudaFuncSetAttribute(csr_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kTmaSmem));
+        LSK_RETURN_IF_CUDA(cudaFuncSetAttribute(csr_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kTmaSmem));
+        configured = true;
+    }
+    if (ndot == 0)
+        csr_tma_kernel<0><<<grid, kBlock, kTmaSmem, st>>>(rows, nnz, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1);
+    else if (ndot == 1)
+        csr_tma_kernel<1><<<grid, kBlock, kTmaSmem, st>>>(rows, nnz, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1);
+    else
+        csr_tma_kernel<2><<<grid, kBlock, kTmaSmem, st>>>(rows, nnz, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1);
+    return 0;
+}
+
 template <typename T, int V>
 static void launch_vector_kernel(int ndot, int grid, cudaStream_t st, int64_t rows, const T *entry,
                                  const long long *col, const lsk_rect *rowptr, int64_t k_base, const T *x,
@@ -348,7 +755,8 @@ static int csr_spmv(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const
         if (rpb < 32) rpb = 32;
         if (rpb > kBlock) rpb = kBlock;
         const int64_t nrb = rows > 0 ? (rows + rpb - 1) / rpb : 1;
-        int64_t cap = (int64_t) ctx->sm_count * 4;
+        static const char *cta_env = getenv("LSK_SPMV_CTAS");  // developer knob: CTAs per SM
+        int64_t cap = (int64_t) ctx->sm_count * (cta_env ? atoi(cta_env) : 4);
         if (cap > kMaxPartials) cap = kMaxPartials;
         const int grid = (int) (nrb < cap ? nrb : cap);
         // 256-bit path needs entry and col to hit their vector alignment at the same elements
@@ -356,7 +764,21 @@ static int csr_spmv(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const
                           ((reinterpret_cast<uintptr_t>(col) >> 3) & 3)) &&
                          (reinterpret_cast<uintptr_t>(entry) % sizeof(T) == 0) &&
                          (reinterpret_cast<uintptr_t>(col) % 8 == 0);
-        if (vec)
+        static const char *impl_env = getenv("LSK_SPMV_IMPL");  // developer A/B switch: tma | pipe | regs
+        const int impl = !impl_env ? 0 : (impl_env[0] == 'p' ? 1 : impl_env[0] == 'r' ? 2 : 0);
+        // the TMA kernel needs col and entry 16-byte aligned at the same elements
+        const bool par = (((reinterpret_cast<uintptr_t>(entry) >> 3) & 1) == ((reinterpret_cast<uintptr_t>(col) >> 3) & 1));
+        if (std::is_same<T, double>::value && par && impl == 0 && reinterpret_cast<uintptr_t>(entry) % 8 == 0 &&
+            reinterpret_cast<uintptr_t>(col) % 8 == 0) {
+            const int tgrid = (int) (nrb < (int64_t) ctx->sm_count * 3 ? nrb : (int64_t) ctx->sm_count * 3);
+            const int rc = launch_tma_kernel(ndot, tgrid, st, rows, nnz, rpb, nrb, reinterpret_cast<const double *>(entry),
+                                             colp, rowptr, k_base, reinterpret_cast<const double *>(x_shifted),
+                                             reinterpret_cast<double *>(y), reinterpret_cast<const double *>(w), rs,
+                                             reinterpret_cast<double *>(o0), reinterpret_cast<double *>(o1));
+            if (rc != 0) return rc;
+        } else if (vec && impl != 2)
+            launch_pipe_kernel<T>(ndot, grid, st, rows, rpb, nrb, entry, colp, rowptr, k_base, x_shifted, y, w, rs, o0, o1);
+        else if (vec)
             launch_stream_kernel<T, true>(ndot, grid, st, rows, rpb, nrb, entry, colp, rowptr, k_base, x_shifted, y, w, rs, o0, o1);
         else
             launch_stream_kernel<T, false>(ndot, grid, st, rows, rpb, nrb, entry, colp, rowptr, k_base, x_shifted, y, w, rs, o0, o1);
