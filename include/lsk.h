@@ -120,6 +120,12 @@ enum lsk_scalar_op {
 /* *out = op(*a, *b); b is ignored (may be NULL) for the unary ops */
 int lsk_scalar_op_f64(lsk_ctx *ctx, lsk_stream s, int op, const double *a, const double *b, double *out);
 int lsk_scalar_op_f32(lsk_ctx *ctx, lsk_stream s, int op, const float *a, const float *b, float *out);
+/* residual_norm_squared.push_back(...) (src/CGSolver.hpp:53) with a device-side length, so that a
+ * recorded trace (CUDA graph) can be replayed: hist[*count % capacity] = *value; ++*count; and, when
+ * `also` is not NULL, *also = *value.  The history is a circular buffer (the reference's TODO at
+ * src/CGSolver.hpp:25-26). */
+int lsk_scalar_append_f64(lsk_ctx *ctx, lsk_stream s, const double *value, double *hist, int64_t capacity,
+                          int64_t *count, double *also);
 
 /* ------------------------------------------------------------------------------------------------
  * CSR mat-vec -- replaces CSRMatvecTask::cuda_task_body (src/CSRMatrixTasks.cu:14-156) together
@@ -212,6 +218,74 @@ int lsk_bicg_p_update_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, const double *r
 int lsk_bicg_tail_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, const double *alpha, const double *ru,
                       const double *uu, const double *p, const double *u, const double *rt,
                       double *x, double *r, double *rho_next);
+
+
+/* ------------------------------------------------------------------------------------------------
+ * Set-up side: the integer work that runs once before the hot path,
+ * moved to the GPU.  All results are exact integers; parity with the oracle is bit-exact.
+ * ---------------------------------------------------------------------------------------------- */
+
+#define LSK_MAX_DIM 3
+#define LSK_MAX_STENCIL 64
+
+/* A stencil on a dense DIM-dimensional grid, as FillLinearizedCSRStencilTask receives it
+ * (src/StencilGenerator.hpp:100-137): `shape[d]` points per dimension (bounds.lo = 0), `noff`
+ * offsets with their entries ALREADY SORTED the way the task sorts them
+ * (src/StencilGenerator.cpp:408-433; lsk_stencil_sort does it), order 0 = ROW_MAJOR, 1 = COLUMN_MAJOR. */
+typedef struct {
+    int dim;
+    int order;
+    int noff;
+    int64_t shape[LSK_MAX_DIM];
+    int64_t offsets[LSK_MAX_STENCIL][LSK_MAX_DIM];
+    double values[LSK_MAX_STENCIL];
+} lsk_stencil;
+
+/* host-only helpers: the sort of the fill tasks, and calculate_stencil_size
+ * (src/StencilGenerator.hpp:270-323, closed form: sum over offsets of prod_d max(0, shape_d - |o_d|)) */
+int lsk_stencil_sort(lsk_stencil *st);
+int64_t lsk_stencil_size(const lsk_stencil *st);
+
+/* number of non-zeros in rows [r_lo, r_hi] (inclusive, linearised): *out is a DEVICE int64 */
+int lsk_stencil_count_f64(lsk_ctx *ctx, lsk_stream s, const lsk_stencil *st, int64_t r_lo, int64_t r_hi,
+                          int64_t *out);
+/* FillLinearizedCSRStencilTask::task_body (src/StencilGenerator.cpp:380-543) for the slab of rows
+ * [r_lo, r_hi]: k_first = global k of the slab's first non-zero (= count of rows [0, r_lo)).
+ * Writes entry/col for k in [k_first, k_first + slab_nnz) at entry[0..], and rowptr[0..rows) with
+ * inclusive GLOBAL-k rects.  scratch: rows + 1 device int64 (row start offsets). */
+int lsk_stencil_fill_csr_f64(lsk_ctx *ctx, lsk_stream s, const lsk_stencil *st, int64_t r_lo, int64_t r_hi,
+                             int64_t k_first, double *entry, int64_t *col, lsk_rect *rowptr,
+                             int64_t *scratch);
+/* row[k - k_base] = r for every k in rowptr[r - r_lo]  (CSR -> COO row field, as
+ * FillLinearizedCOOStencilTask writes it, src/StencilGenerator.cpp:160-243) */
+int lsk_csr_expand_rows(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t r_lo, const lsk_rect *rowptr,
+                        int64_t k_base, int64_t *row);
+
+/* Dependent partitioning (Legion/Realm operations called at src/CSRMatrix.cpp:68-155 and
+ * src/COOMatrix.cpp:56-141), on device-resident fields.  "span" results are 3 DEVICE int64:
+ * {min, max, count}; min > max when empty.  "flags" results are one byte per point of the
+ * parent space window, 1 = member. */
+/* image_range over rowptr (src/CSRMatrix.cpp:89-109): union of `rows` rects */
+int lsk_rect_span_i64(lsk_ctx *ctx, lsk_stream s, int64_t rows, const lsk_rect *rowptr, int64_t *out3);
+int lsk_image_range_flags(lsk_ctx *ctx, lsk_stream s, int64_t rows, const lsk_rect *rowptr,
+                          int64_t k_lo, int64_t k_n, uint8_t *kflags);
+/* image of a point field over a kernel piece (src/CSRMatrix.cpp:112-132): values field[0..n) */
+int lsk_minmax_i64(lsk_ctx *ctx, lsk_stream s, int64_t n, const int64_t *field, int64_t *out3);
+int lsk_image_flags(lsk_ctx *ctx, lsk_stream s, int64_t n, const int64_t *field, const uint8_t *kflags,
+                    int64_t out_lo, int64_t out_n, uint8_t *out_flags);
+/* preimage of a point field (src/COOMatrix.cpp:77-96): { k : lo <= field[k] <= hi }, k = k_base + i */
+int lsk_preimage_span_i64(lsk_ctx *ctx, lsk_stream s, int64_t n, const int64_t *field, int64_t lo,
+                          int64_t hi, int64_t k_base, int64_t *out3);
+int lsk_preimage_flags(lsk_ctx *ctx, lsk_stream s, int64_t n, const int64_t *field, int64_t lo,
+                       int64_t hi, uint8_t *kflags);
+/* preimage_range (src/CSRMatrix.cpp:135-155): rows whose rect meets the kernel piece kflags
+ * (kflags[i] describes k = k_lo + i) */
+int lsk_preimage_range_flags(lsk_ctx *ctx, lsk_stream s, int64_t rows, const lsk_rect *rowptr,
+                             int64_t k_lo, int64_t k_n, const uint8_t *kflags, uint8_t *rflags);
+/* create_equal_partition (host arithmetic): piece i of `pieces` over [0, n) */
+int lsk_equal_partition(int64_t n, int pieces, int64_t *lo, int64_t *hi);
+/* BlockingShardingFunctor::shard (src/LegionSolversMapper.cpp:140-151) */
+int lsk_shard(int64_t point, int64_t volume, int64_t total_shards);
 
 #ifdef __cplusplus
 }

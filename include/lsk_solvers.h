@@ -1,0 +1,116 @@
+/*
+ * lsk_solvers.h -- C ABI of the C++ host layer (legionsolvers_b200/host/*.hpp): the planner-level
+ * API of the reference (PartitionedVector, CSRMatrix / COOMatrix, SquarePlanner, CGSolver,
+ * BiCGStabSolver, GMRESSolver) as opaque handles, for callers that are not C++ (the Python tests
+ * and bench.py drive everything through this file and lsk.h).
+ *
+ * Conventions: plain C types; 0 = success, otherwise a status from lsk.h; after a failure
+ * lsk_last_error() describes it (thread-local).  Handles are created and destroyed explicitly;
+ * destroy solvers before planners, planners before vectors / matrices, everything before the runtime.
+ * "global" host arrays are indexed by GLOBAL row; a rank reads / writes only the rows it owns.
+ */
+#ifndef LSK_SOLVERS_H
+#define LSK_SOLVERS_H
+
+#include "lsk.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lsk_runtime lsk_runtime;
+typedef struct lsk_vector lsk_vector;
+typedef struct lsk_matrix lsk_matrix;
+typedef struct lsk_planner lsk_planner;
+typedef struct lsk_solver lsk_solver;
+
+const char *lsk_last_error(void);
+
+/* ---- runtime: one per process / GPU (replaces Legion::Runtime + mapper for this path) ------------ */
+/* external_stream: a cudaStream_t to enqueue on, or NULL for a private stream */
+int lsk_rt_create(int device, int rank, int nranks, void *external_stream, lsk_runtime **out);
+int lsk_rt_destroy(lsk_runtime *rt);
+/* NCCL bootstrap: rank 0 calls lsk_rt_unique_id, ships the 128 bytes to every rank, all call comm_init */
+int lsk_rt_unique_id(void *out128);
+int lsk_rt_comm_init(lsk_runtime *rt, const void *uid128);
+lsk_ctx *lsk_rt_ctx(lsk_runtime *rt);
+void *lsk_rt_stream(lsk_runtime *rt);
+int lsk_rt_fence(lsk_runtime *rt);                 /* issue_execution_fence */
+uint64_t lsk_rt_kernel_launches(lsk_runtime *rt);  /* graph replays included */
+/* Legion begin_trace / end_trace (test/BenchmarkStencil.cpp:219-241): first use of an id records the
+ * enclosed launches into a CUDA graph, later uses replay it */
+int lsk_rt_begin_trace(lsk_runtime *rt, int trace_id);
+int lsk_rt_end_trace(lsk_runtime *rt, int trace_id);
+
+/* ---- PartitionedVector<double> (src/PartitionedVector.hpp) --------------------------------------------- */
+int lsk_vector_create(lsk_runtime *rt, const char *name, int64_t volume, int pieces, lsk_vector **out);
+int lsk_vector_destroy(lsk_vector *v);
+int lsk_vector_owned_range(lsk_vector *v, int64_t *lo, int64_t *hi);
+int lsk_vector_constant_fill(lsk_vector *v, double value);
+int lsk_vector_assign(lsk_vector *dst, const lsk_vector *src);           /* operator= (IndexCopy) */
+int lsk_vector_scal(lsk_vector *v, double alpha);
+int lsk_vector_axpy(lsk_vector *y, double alpha, const lsk_vector *x);   /* y.axpy(alpha, x) */
+int lsk_vector_xpay(lsk_vector *y, double alpha, const lsk_vector *x);   /* y.xpay(alpha, x) */
+int lsk_vector_dot(const lsk_vector *v, const lsk_vector *w, double *out); /* synchronises (get_value) */
+int lsk_vector_copy_from_host(lsk_vector *v, const double *global);
+int lsk_vector_copy_to_host(const lsk_vector *v, double *global);
+
+/* ---- matrices (src/CSRMatrix.hpp, src/COOMatrix.hpp) ------------------------------------------------------ */
+/* upload the slab rows [r_lo, r_hi] / non-zeros [k_lo, k_hi] this rank needs; arrays start at the slab */
+int lsk_csr_create(lsk_runtime *rt, int64_t rows, int64_t cols, int64_t nnz_global, int64_t r_lo, int64_t r_hi,
+                   int64_t k_lo, int64_t k_hi, const double *entry, const int64_t *col, const lsk_rect *rowptr,
+                   lsk_matrix **out);
+int lsk_coo_create(lsk_runtime *rt, int64_t rows, int64_t cols, int64_t nnz_global, int64_t k_lo, int64_t k_hi,
+                   const double *entry, const int64_t *row, const int64_t *col, lsk_matrix **out);
+/* create_linearized_csr_stencil_matrix (src/StencilGenerator.hpp:533-643), filled on the GPU */
+int lsk_csr_create_stencil(lsk_runtime *rt, const lsk_stencil *stencil, int pieces, lsk_matrix **out);
+/* the BenchmarkStencil matrices: dim_flag 1, 2, 3, 4 (= 27-point) (test/BenchmarkStencil.cpp:33-131) */
+int lsk_benchmark_stencil(int dim_flag, int64_t nx, int64_t ny, int64_t nz, lsk_stencil *out);
+int lsk_matrix_destroy(lsk_matrix *m);
+/* rows, cols, nnz_global, slab r_lo, r_hi, k_lo, k_hi, is_csr */
+int lsk_matrix_info(const lsk_matrix *m, int64_t *out8);
+/* copy the slab back (generator parity tests): third array is rowptr (CSR) or row (COO) */
+int lsk_matrix_slab_to_host(const lsk_matrix *m, double *entry, int64_t *col, void *rowptr_or_row);
+/* device pointers of the slab fields: entry, col, rowptr-or-row (for direct lsk.h kernel calls) */
+int lsk_matrix_device_fields(const lsk_matrix *m, void **entry, void **col, void **rowptr_or_row);
+
+/* ---- SquarePlanner<double> (src/SquarePlanner.hpp) ------------------------------------------------------------ */
+int lsk_planner_create(lsk_runtime *rt, lsk_planner **out);
+int lsk_planner_destroy(lsk_planner *pl);
+int lsk_planner_add_sol_vector(lsk_planner *pl, lsk_vector *v);
+int lsk_planner_add_rhs_vector(lsk_planner *pl, lsk_vector *v);
+int lsk_planner_add_row_partitioned_matrix(lsk_planner *pl, const lsk_matrix *m, int domain_index, int range_index);
+int lsk_planner_allocate_workspace(lsk_planner *pl, int num_vectors);
+/* which: 0 = canonical partition of space `index`, 1 = kernel partition of block `index`,
+ * 2 = ghost partition of block `index`; bounds are inclusive; only local colours are meaningful for 1, 2 */
+int lsk_planner_partition_bounds(lsk_planner *pl, int which, int index, int color, int64_t *lo, int64_t *hi);
+int lsk_planner_local_colors(lsk_planner *pl, int space, int *first, int *end);
+uint64_t lsk_planner_halo_bytes_per_matvec(lsk_planner *pl);
+/* vector-id operations (0 SOL, 1 RHS, 2.. workspace); scalars given by value */
+int lsk_planner_zero_fill(lsk_planner *pl, int vec);
+int lsk_planner_copy(lsk_planner *pl, int dst, int src);
+int lsk_planner_scal(lsk_planner *pl, int dst, double alpha);
+int lsk_planner_axpy(lsk_planner *pl, int dst, double alpha, int src);
+int lsk_planner_xpay(lsk_planner *pl, int dst, double alpha, int src);
+int lsk_planner_dot(lsk_planner *pl, int v, int w, double *out); /* synchronises */
+int lsk_planner_matvec(lsk_planner *pl, int dst, int src);
+/* fused dst = A src with out_yw = dst . vec(w) (and out_yy = dst . dst if not NULL); synchronises */
+int lsk_planner_matvec_dot(lsk_planner *pl, int dst, int src, int w, double *out_yw, double *out_yy);
+int lsk_planner_vector_to_host(lsk_planner *pl, int vec, int space, double *global);
+int lsk_planner_vector_from_host(lsk_planner *pl, int vec, int space, const double *global);
+
+/* ---- solvers (src/CGSolver.hpp, src/BiCGStabSolver.hpp, src/GMRESSolver.hpp) -------------------------------------- */
+enum lsk_solver_kind { LSK_SOLVER_CG = 1, LSK_SOLVER_BICGSTAB = 2, LSK_SOLVER_GMRES = 3 }; /* BenchmarkStencil -solver */
+/* fused = 0: the reference's call sequence, one launch per planner call; 1: fewest-pass form */
+int lsk_solver_create(lsk_planner *pl, int kind, int restart, int fused, lsk_solver **out);
+int lsk_solver_destroy(lsk_solver *s);
+int lsk_solver_step(lsk_solver *s);
+/* which: CG 0 = residual_norm_squared; BiCGStab 0 = rho, 1 = alpha, 2 = omega; GMRES 0 = the
+ * (restart+1) x restart inner_products table, row-major.  Copies up to `cap` values (oldest first),
+ * *n = number available.  Synchronises. */
+int lsk_solver_history(lsk_solver *s, int which, double *out, int64_t cap, int64_t *n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSK_SOLVERS_H */

@@ -81,6 +81,7 @@ def _declare(L: C.CDLL) -> None:
     L.lsk_fill_f32.argtypes = [vp, vp, i64, flt, vp]
     L.lsk_fill_dev_f64.argtypes = [vp, vp, i64, vp, vp]
     L.lsk_copy_f64.argtypes = [vp, vp, i64, vp, vp]
+    L.lsk_scalar_append_f64.argtypes = [vp, vp, vp, vp, i64, vp, vp]
     L.lsk_csr_spmv_pick.argtypes = [i64, i64]
     L.lsk_cg_update_f64.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp]
     L.lsk_axpy_dot_f64.argtypes = [vp, vp, i64, ci, vp, vp, vp, vp, vp, vp, vp, vp]

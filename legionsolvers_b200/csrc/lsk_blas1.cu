@@ -332,6 +332,15 @@ __global__ void scalar_op_kernel(int op, const T *a, const T *b, T *out) {
     *out = r;
 }
 
+__global__ void scalar_append_kernel(const double *value, double *hist, long long capacity, long long *count,
+                                     double *also) {
+    const double v = *value;
+    const long long n = *count;
+    hist[n % capacity] = v;
+    *count = n + 1;
+    if (also) *also = v;
+}
+
 template <typename T>
 static int scalar_op(lsk_ctx *ctx, lsk_stream s, int op, const T *a, const T *b, T *out) {
     if (!ctx || !out || op < 0 || op > LSK_OP_COPY) return LSK_E_INVALID;
@@ -438,6 +447,13 @@ int lsk_scalar_op_f64(lsk_ctx *ctx, lsk_stream s, int op, const double *a, const
 }
 int lsk_scalar_op_f32(lsk_ctx *ctx, lsk_stream s, int op, const float *a, const float *b, float *out) {
     return scalar_op<float>(ctx, s, op, a, b, out);
+}
+
+int lsk_scalar_append_f64(lsk_ctx *ctx, lsk_stream s, const double *value, double *hist, int64_t capacity,
+                          int64_t *count, double *also) {
+    if (!ctx || !value || !hist || !count || capacity <= 0) return LSK_E_INVALID;
+    scalar_append_kernel<<<1, 1, 0, (cudaStream_t) s>>>(value, hist, capacity, reinterpret_cast<long long *>(count), also);
+    return after_launch(ctx);
 }
 
 int lsk_cg_update_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, const double *rr_old, const double *pq,

@@ -1,0 +1,179 @@
+// Runtime.cpp -- see Runtime.hpp.
+#include "Runtime.hpp"
+
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstring>
+#include <sstream>
+
+namespace LegionSolvers {
+
+Runtime::Runtime(int device, int rank, int nranks, void *external_stream)
+    : device_(device), rank_(rank), nranks_(nranks) {
+    if (nranks < 1 || rank < 0 || rank >= nranks) throw std::runtime_error("Runtime: bad rank / nranks");
+    const int rc = lsk_ctx_create(device, &ctx_);
+    if (rc != 0) fail(rc, "lsk_ctx_create");
+    check_cuda(cudaSetDevice(device), "cudaSetDevice");
+    if (external_stream) {
+        stream_ = static_cast<cudaStream_t>(external_stream);
+    } else {
+        check_cuda(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate");
+        own_stream_ = true;
+    }
+    (void) new_slot();  // first arena chunk up front, so that traces never have to grow it
+}
+
+Runtime::~Runtime() {
+    cudaSetDevice(device_);
+    cudaStreamSynchronize(stream_);
+    for (auto &kv : traces_)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    if (comm_) ncclCommDestroy(reinterpret_cast<ncclComm_t>(comm_));
+    for (void *p : allocations_) cudaFree(p);
+    for (double *p : arena_chunks_) cudaFree(p);
+    if (own_stream_) cudaStreamDestroy(stream_);
+    lsk_ctx_destroy(ctx_);
+}
+
+void Runtime::fail(int status, const char *what) const {
+    std::ostringstream os;
+    os << "[LegionSolvers] " << what << " failed on rank " << rank_ << ": " << lsk_error_string(status) << " ("
+       << status << ")";
+    throw std::runtime_error(os.str());
+}
+
+// ---- communication ---------------------------------------------------------------------------------
+static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is passed through the C ABI as 128 bytes");
+
+void Runtime::comm_unique_id(void *out128) {
+    ncclUniqueId id;
+    if (ncclGetUniqueId(&id) != ncclSuccess) throw std::runtime_error("ncclGetUniqueId failed");
+    std::memcpy(out128, &id, sizeof(id));
+}
+
+void Runtime::comm_init(const void *uid128) {
+    if (nranks_ == 1) return;
+    ncclUniqueId id;
+    std::memcpy(&id, uid128, sizeof(id));
+    check_cuda(cudaSetDevice(device_), "cudaSetDevice");
+    ncclComm_t c;
+    if (ncclCommInitRank(&c, nranks_, id, rank_) != ncclSuccess) fail(LSK_E_NCCL, "ncclCommInitRank");
+    comm_ = reinterpret_cast<ncclComm *>(c);
+}
+
+#define LSK_NCCL(expr, what)                              \
+    do {                                                  \
+        if ((expr) != ncclSuccess) fail(LSK_E_NCCL, what); \
+    } while (0)
+
+void Runtime::allreduce_sum(double *slots, int count) {
+    if (nranks_ == 1 || mode_ == Mode::Replay) return;
+    if (!comm_) fail(LSK_E_NCCL, "allreduce_sum without comm_init");
+    LSK_NCCL(ncclAllReduce(slots, slots, (size_t) count, ncclDouble, ncclSum, reinterpret_cast<ncclComm_t>(comm_), stream_),
+             "ncclAllReduce");
+}
+
+void Runtime::allgather_i64(const int64_t *send_dev, int64_t *recv_dev, int count_per_rank) {
+    if (nranks_ == 1) {
+        check_cuda(cudaMemcpyAsync(recv_dev, send_dev, sizeof(int64_t) * (size_t) count_per_rank,
+                                   cudaMemcpyDeviceToDevice, stream_), "allgather copy");
+        return;
+    }
+    if (!comm_) fail(LSK_E_NCCL, "allgather without comm_init");
+    LSK_NCCL(ncclAllGather(send_dev, recv_dev, (size_t) count_per_rank, ncclInt64, reinterpret_cast<ncclComm_t>(comm_), stream_),
+             "ncclAllGather");
+}
+
+void Runtime::group_start() {
+    if (nranks_ > 1 && mode_ != Mode::Replay) LSK_NCCL(ncclGroupStart(), "ncclGroupStart");
+}
+void Runtime::group_end() {
+    if (nranks_ > 1 && mode_ != Mode::Replay) LSK_NCCL(ncclGroupEnd(), "ncclGroupEnd");
+}
+void Runtime::send(const void *ptr, size_t bytes, int peer) {
+    if (mode_ == Mode::Replay) return;
+    LSK_NCCL(ncclSend(ptr, bytes, ncclChar, peer, reinterpret_cast<ncclComm_t>(comm_), stream_), "ncclSend");
+}
+void Runtime::recv(void *ptr, size_t bytes, int peer) {
+    if (mode_ == Mode::Replay) return;
+    LSK_NCCL(ncclRecv(ptr, bytes, ncclChar, peer, reinterpret_cast<ncclComm_t>(comm_), stream_), "ncclRecv");
+}
+
+// ---- memory ----------------------------------------------------------------------------------------------
+void *Runtime::alloc(size_t bytes) {
+    void *p = nullptr;
+    check_cuda(cudaSetDevice(device_), "cudaSetDevice");
+    check_cuda(cudaMalloc(&p, bytes ? bytes : 1), "cudaMalloc");
+    allocations_.push_back(p);
+    return p;
+}
+
+void Runtime::free(void *p) {
+    if (!p) return;
+    auto it = std::find(allocations_.begin(), allocations_.end(), p);
+    if (it != allocations_.end()) {
+        allocations_.erase(it);
+        cudaStreamSynchronize(stream_);
+        cudaFree(p);
+    }
+}
+
+double *Runtime::new_slot() {
+    if (mode_ == Mode::Replay) return arena_chunks_.empty() ? nullptr : arena_chunks_.front();  // value unused on replay
+    if (arena_chunks_.empty() || arena_used_ == kArenaChunk) {
+        if (mode_ == Mode::Capture) fail(LSK_E_CAPACITY, "scalar arena growth inside a trace");
+        double *chunk = nullptr;
+        check_cuda(cudaMalloc(&chunk, sizeof(double) * kArenaChunk), "cudaMalloc(arena)");
+        check_cuda(cudaMemset(chunk, 0, sizeof(double) * kArenaChunk), "cudaMemset(arena)");
+        arena_chunks_.push_back(chunk);
+        arena_used_ = 0;
+    }
+    return arena_chunks_.back() + arena_used_++;
+}
+
+// ---- tracing ---------------------------------------------------------------------------------------------
+void Runtime::begin_trace(int id) {
+    if (mode_ != Mode::Eager) fail(LSK_E_INVALID, "begin_trace: traces do not nest");
+    active_trace_ = id;
+    if (traces_.count(id)) {
+        mode_ = Mode::Replay;
+        return;
+    }
+    check_cuda(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
+    capture_mark_ = lsk_ctx_launch_count(ctx_);
+    mode_ = Mode::Capture;
+}
+
+void Runtime::end_trace(int id) {
+    if (mode_ == Mode::Eager || id != active_trace_) fail(LSK_E_INVALID, "end_trace without matching begin_trace");
+    if (mode_ == Mode::Capture) {
+        cudaGraph_t graph = nullptr;
+        mode_ = Mode::Eager;
+        check_cuda(cudaStreamEndCapture(stream_, &graph), "cudaStreamEndCapture");
+        Trace t;
+        t.kernels = lsk_ctx_launch_count(ctx_) - capture_mark_;
+        check_cuda(cudaGraphInstantiate(&t.exec, graph, 0), "cudaGraphInstantiate");
+        cudaGraphDestroy(graph);
+        traces_[id] = t;
+    }
+    mode_ = Mode::Eager;
+    active_trace_ = -1;
+    const Trace &t = traces_[id];
+    check_cuda(cudaGraphLaunch(t.exec, stream_), "cudaGraphLaunch");
+    // launches made while capturing were counted by the context but only run now; replays add theirs
+    static_cast<void>(0);
+    replayed_kernels_ += t.kernels;
+}
+
+void Runtime::fence() { check_cuda(cudaStreamSynchronize(stream_), "cudaStreamSynchronize"); }
+
+uint64_t Runtime::kernel_launches() const {
+    // the capture pass itself is counted once by lsk_ctx and once by the graph launch at end_trace:
+    // subtract one copy per recorded trace so each executed kernel is counted exactly once
+    uint64_t captured_once = 0;
+    for (const auto &kv : traces_) captured_once += kv.second.kernels;
+    return lsk_ctx_launch_count(ctx_) + replayed_kernels_ - captured_once;
+}
+
+}  // namespace LegionSolvers
