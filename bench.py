@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of the Krylov inner loop on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3]
+
+Metric (BASELINE.json): CG iterations / second, fp64 CSR, 3-D 7-point Laplacian 256^3 (config C3),
+with the SpMV HBM GB/s of the dominant kernel reported in `roofline`.  The matrix is the reference's
+own benchmark matrix (BenchmarkStencil -dim 3 -nx 256 -ny 256 -nz 256), generated on the GPU by
+the same StencilGenerator rules; b = 1, x0 = 0, exactly the BenchmarkStencil / Test06 set-up.
+
+A STEP is one replay of a recorded trace of `iters_per_step` CG iterations (BenchmarkStencil's
+`-pt`): `--steps 10` with the default 20 iterations per step is the reference protocol's 200 timed
+iterations after warm-up traces.  `value` is the whole-job rate with everything resident in HBM;
+`e2e` is the same rate through the host-buffer API (per step: H2D of the right-hand side from pinned
+memory, a fresh solve of `iters_per_step` iterations, D2H of the solution and the residual history).
+
+At N > 1 (launched under torchrun) the FIXED 256^3 problem is row-partitioned over the N GPUs --
+strong scaling -- with the ghost-x halo exchange and the dot-product all-reduces on NCCL.
+
+`--impl reference` times the reference's CPU task variants (the oracle restatement; the reference
+itself needs Legion and cannot be built here) on the host cores, on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (dim_flag, (nx, ny, nz), description)
+    "c3": (3, (256, 256, 256), "BenchmarkStencil -dim 3: 3-D 7-point Laplacian 256^3, fp64 CSR, CG"),
+    "c2": (2, (8192, 8192, 1), "BenchmarkStencil -dim 2: 2-D 5-point Laplacian 8192^2, fp64 CSR, CG"),
+    "c4": (4, (192, 192, 192), "BenchmarkStencil -dim 4: 3-D 27-point stencil 192^3, fp64 CSR, CG"),
+    "c1": (2, (256, 256, 1), "2-D 5-point Laplacian 256^2 (the CPU-runnable parity case)"),
+    "tiny": (3, (48, 48, 48), "3-D 7-point Laplacian 48^3 (smoke)"),
+}
+METRIC = "cg_iterations_per_second"
+UNIT = "it/s"
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks during the timed region (pynvml; the recipe's nvidia-smi line, in-process)
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {
+        0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+        0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+        0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting",
+    }
+
+    def __init__(self, device_index: int, period_s: float = 0.05):
+        self.samples, self.reasons, self.power = [], set(), []
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.period = period_s
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                    self.nv, "nvmlDeviceGetCurrentClocksEventReasons") else self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+                self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def start(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "power_w_max": max(self.power) if self.power else None, "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference arm / cpu_baseline: the reference's CPU task variants on the host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_run(dim_flag, shape, threads, its_warm, its_timed, steps=1):
+    """CG on the oracle (restated CPU task bodies, one piece per host thread -- one Legion CPU processor
+    per piece).  Returns (iterations/s, list of per-step seconds, description of the sample)."""
+    from oracle import oracle as orc
+
+    off, val = orc.benchmark_stencil(dim_flag)
+    dims = shape[:3] if dim_flag >= 3 else shape[:dim_flag]
+    m = orc.stencil_csr(dims, off, val)
+    orc.set_threads(threads)
+    pl = orc.Planner([m.n_rows], [threads])
+    pl.fill(1, 1.0)
+    pl.add_matrix(m)
+    cg = orc.CGSolver(pl)
+    for _ in range(its_warm):
+        cg.step()
+    per_step = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        for _ in range(its_timed):
+            cg.step()
+        per_step.append(time.perf_counter() - t0)
+    total = sum(per_step)
+    sample = (f"{steps} x {its_timed} CG iterations of the FULL {'x'.join(map(str, dims))} system after {its_warm} warm-up "
+              f"iterations, {threads} pieces on {threads} host threads (reference-equivalent linear-time CSR body)")
+    return steps * its_timed / total, per_step, sample
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0  # under torchrun only rank 0 runs the CPU arm
+    dim_flag, shape, desc = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, 64))
+    its = max(1, args.ref_iters_per_step)
+    rate, per_step, sample = cpu_reference_run(dim_flag, shape, threads, its_warm=max(1, args.warmup),
+                                               its_timed=its, steps=args.steps)
+    ms = 1e3 * sum(per_step) / len(per_step)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "iters_per_step": its, "spaces": 1, "pieces": threads,
+                   "note": "reference CPU task variants restated in C (oracle/): the reference needs Legion and cannot be built here"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+
+    from legionsolvers_b200 import _abi
+    from legionsolvers_b200 import solvers as S
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: legionsolvers_b200 has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks")
+        args.gpus = world
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+
+        dist = dist_
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    dim_flag, shape, desc = WORKLOADS[args.workload]
+    ipt = args.iters_per_step
+    stream = torch.cuda.current_stream().cuda_stream
+    rt = S.Runtime(device=local_rank, rank=rank, nranks=world, stream=stream)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(S.Runtime.unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, src=0)
+        rt.comm_init(bytes(uid.cpu().numpy().tobytes()))
+
+    # ---- problem set-up, all on the GPU: BenchmarkStencil's matrix, b = 1, x0 = 0 -------------------
+    t_setup = time.perf_counter()
+    st = S.benchmark_stencil(dim_flag, *shape)
+    n = shape[0] * shape[1] * shape[2]
+    pieces = world  # -vp = total GPUs (bench_all.py:206-208)
+    mat = S.CSRMatrix.stencil(rt, st, pieces)
+    sol = S.PartitionedVector(rt, "sol", n, pieces)
+    rhs = S.PartitionedVector(rt, "rhs", n, pieces)
+    sol.zero_fill()
+    rhs.constant_fill(1.0)
+    pl = S.SquarePlanner(rt)
+    pl.add_sol_vector(sol)
+    pl.add_rhs_vector(rhs)
+    pl.add_row_partitioned_matrix(mat, 0, 0)
+    cg = S.CGSolver(pl, fused=not args.unfused)
+    rt.fence()
+    setup_s = time.perf_counter() - t_setup
+    nnz = mat.nnz
+    own_lo, own_hi = sol.owned_range()
+    n_local = own_hi - own_lo + 1
+    nnz_local = mat.slab_k_hi - mat.slab_k_lo + 1
+
+    TRACE = 51  # the reference's trace id (test/BenchmarkStencil.cpp:218)
+
+    def step():
+        rt.begin_trace(TRACE)
+        for _ in range(ipt):
+            cg.step()
+        rt.end_trace(TRACE)
+
+    # ---- warm-up, then EXACTLY K timed steps between barriers, CUDA events on the launching stream ---
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = rt.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    elapsed_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = rt.kernel_launches - launches0
+    clocks = sampler.stop()
+    ms_per_step = elapsed_ms / args.steps
+    value = args.steps * ipt / (elapsed_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel: the fused CSR SpMV + p.Ap, timed alone on the same stream ----
+    L = _abi.lib()
+    e_ptr, c_ptr, rp_ptr = mat.device_fields()
+    g_lo, g_hi = pl.ghost_bounds(0, pl.local_colors(0)[0])
+    xg = torch.rand(g_hi - g_lo + 1, dtype=torch.float64, device="cuda")
+    yv = torch.zeros(n_local, dtype=torch.float64, device="cuda")
+    dslot = torch.zeros(1, dtype=torch.float64, device="cuda")
+    x_shifted = xg.data_ptr() - g_lo * 8
+    w_ptr = xg.data_ptr() + (own_lo - g_lo) * 8
+
+    def spmv():
+        _abi.check(L.lsk_csr_spmv_f64(rt.ctx, stream, n_local, nnz_local, e_ptr, c_ptr, rp_ptr, mat.slab_k_lo, x_shifted,
+                                      yv.data_ptr(), w_ptr, dslot.data_ptr(), None, 0), "lsk_csr_spmv_f64")
+
+    for _ in range(5):
+        spmv()
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 50
+    s0.record()
+    for _ in range(reps):
+        spmv()
+    s1.record()
+    torch.cuda.synchronize()
+    spmv_ms = s0.elapsed_time(s1) / reps
+    spmv_bytes = 16 * nnz_local + 32 * n_local  # 16/nnz + rowptr 16 + x 8 + y 8 per row
+    achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
+    peaks_file = ROOT / "MEASURED_PEAKS.json"
+    if peaks_file.exists():
+        peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    traffic = None
+    tf = ROOT / "profiles" / "spmv_traffic.json"
+    if tf.exists() and args.workload == "c3" and world == 1:
+        traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
+    # solver-iteration roofline: fused minimum 16 nnz + 104 N bytes per iteration
+    iter_bytes = 16 * nnz_local + 104 * n_local
+    iter_frac = (iter_bytes * value / 1e9) / peak
+
+    # ---- end to end through the host-buffer API ------------------------------------------------------
+    b_host = torch.ones(n, dtype=torch.float64).pin_memory()
+    x_host = torch.zeros(n, dtype=torch.float64).pin_memory()
+    b_np, x_np = b_host.numpy(), x_host.numpy()
+    e2e_steps = max(2, min(args.steps, 5))
+    TRACE_E2E = 52
+
+    def e2e_step():
+        pl.vector_from_numpy(1, 0, b_np)          # H2D: this step's right-hand side (owned rows)
+        pl.zero_fill(0)
+        cg.reset()
+        rt.begin_trace(TRACE_E2E)
+        for _ in range(ipt):
+            cg.step()
+        rt.end_trace(TRACE_E2E)
+        S._check(_abi.lib().lsk_planner_vector_to_host(pl.h, 0, 0, x_np.ctypes.data), "vector_to_host")  # D2H: solution
+        return cg.residual_norm_squared               # D2H: residual history (synchronises)
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        hist = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = e2e_steps * ipt / e2e_s
+    rr_final = float(hist[-1])
+
+    # ---- CPU baseline on the box's host cores (rank 0, N = 1 only), bounded sample ---------------------
+    cpu_baseline = None
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        threads = max(1, min(cores, 64))
+        its = 6 if n >= 1 << 24 else 20
+        rate, _, sample = cpu_reference_run(dim_flag, shape, threads, its_warm=2, its_timed=its)
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": desc, "unknowns": n, "nnz": nnz, "iters_per_step": ipt, "spaces": 1, "pieces": pieces,
+                "solver": "CGSolver fused (3 HBM passes / iteration)" if not args.unfused else "CGSolver unfused (reference call sequence)",
+                "trace": "CUDA graph replay of iters_per_step iterations", "rhs": "b = 1, x0 = 0 (BenchmarkStencil)",
+                "l2": "working set per GPU exceeds the 126 MB L2 (matrix streamed once per iteration)",
+                "halo_bytes_per_matvec_rank0": pl.halo_bytes_per_matvec, "setup_seconds": round(setup_s, 3),
+                "residual_norm_squared_last": rr_final,
+                "iteration_roofline": {"bytes_per_iteration_per_gpu": iter_bytes, "frac_of_peak": iter_frac},
+            },
+            "roofline": {"bound": "hbm", "kernel": "csr_tma_kernel<1> (fused CSR SpMV + p.Ap)", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms},
+            "spmv_gbs": achieved,
+            "cpu_baseline": cpu_baseline,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n_local,
+                    "d2h_bytes_per_step": 8 * n_local + 8 * (ipt + 1), "steps": e2e_steps,
+                    "what": "per step: H2D rhs (pinned) -> reset -> iters_per_step CG iterations -> D2H solution + residual history"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    barrier()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c3")
+    ap.add_argument("--iters-per-step", type=int, default=20, help="CG iterations per recorded trace (BenchmarkStencil -pt)")
+    ap.add_argument("--ref-iters-per-step", type=int, default=2, help="CPU reference arm: iterations per step (bounded sample)")
+    ap.add_argument("--unfused", action="store_true", help="run the reference's unfused call sequence on the GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

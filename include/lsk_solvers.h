@@ -105,6 +105,8 @@ enum lsk_solver_kind { LSK_SOLVER_CG = 1, LSK_SOLVER_BICGSTAB = 2, LSK_SOLVER_GM
 int lsk_solver_create(lsk_planner *pl, int kind, int restart, int fused, lsk_solver **out);
 int lsk_solver_destroy(lsk_solver *s);
 int lsk_solver_step(lsk_solver *s);
+/* CG only: start a new solve from the current RHS (re-runs the constructor's P <- RHS, R <- RHS, rr0) */
+int lsk_solver_reset(lsk_solver *s);
 /* which: CG 0 = residual_norm_squared; BiCGStab 0 = rho, 1 = alpha, 2 = omega; GMRES 0 = the
  * (restart+1) x restart inner_products table, row-major.  Copies up to `cap` values (oldest first),
  * *n = number available.  Synchronises. */

@@ -133,6 +133,10 @@ public:
             return lsk_scalar_append_f64(rt->ctx(), rt->stream(), v, hist.ptr, capacity, count.ptr, a);
         });
     }
+    void clear() {
+        int64_t *c = count.ptr;
+        rt->enqueue("history clear", [&] { return (int) cudaMemsetAsync(c, 0, sizeof(int64_t), rt->stream()); });
+    }
     int64_t size() const {
         int64_t n = 0;
         rt->check_cuda(cudaMemcpyAsync(&n, count.ptr, sizeof(n), cudaMemcpyDeviceToHost, rt->stream()), "history size");

@@ -34,6 +34,12 @@ public:
           negative_one(planner_.get_runtime(), static_cast<T>(-1)), fused(fused_), rr_cur(planner_.get_runtime()),
           rr_new(planner_.get_runtime()), p_norm(planner_.get_runtime()) {
         planner.allocate_workspace(3);
+        reset();
+    }
+
+    // start a new solve with the current RHS (and SOL taken as 0, like the constructor)
+    void reset() {
+        residual_norm_squared.clear();
         planner.copy(P, RHS);
         planner.copy(R, RHS);
         planner.dot_into(R, R, rr_cur);

@@ -389,6 +389,13 @@ int lsk_solver_step(lsk_solver *s) {
         else s->gmres->step();
     });
 }
+int lsk_solver_reset(lsk_solver *s) {
+    REQUIRE(s);
+    return guard([&] {
+        if (!s->cg) s->rt->fail(LSK_E_INVALID, "reset is implemented for CGSolver");
+        s->cg->reset();
+    });
+}
 int lsk_solver_history(lsk_solver *s, int which, double *out, int64_t cap, int64_t *n) {
     REQUIRE(s && n);
     return guard([&] {

@@ -333,6 +333,10 @@ class CGSolver(_Solver):
     def __init__(self, planner, fused=True):
         super().__init__(planner, 0, fused)
 
+    def reset(self):
+        """Start a new solve from the current RHS (SOL taken as 0, like the constructor)."""
+        _check(_abi.lib().lsk_solver_reset(self.h), "reset")
+
     @property
     def residual_norm_squared(self) -> np.ndarray:
         return self._history(0)
