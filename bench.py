@@ -200,7 +200,12 @@ def run_ours(args):
 
     dim_flag, shape, desc = WORKLOADS[args.workload]
     ipt = args.iters_per_step
-    stream = torch.cuda.current_stream().cuda_stream
+    # everything (our kernels, NCCL, the timing events) goes on ONE explicit non-default stream: torch's
+    # default stream has handle 0, which the runtime would read as "create a private stream"
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
     rt = S.Runtime(device=local_rank, rank=rank, nranks=world, stream=stream)
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")

@@ -1,0 +1,129 @@
+"""N > 1: (gpu) torchrun with 2 ranks on 2 GPUs when the box has them; (cpu) world_size-2 gloo tests
+of the host-side logic of the same path: partition -> ghost intervals -> halo plan -> SpMV/CG."""
+import json
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.mark.gpu
+def test_two_gpu_cg_bicgstab_gmres_parity():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29511", str(ROOT / "tests" / "mp_worker.py")]
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    lines = [json.loads(l) for l in proc.stdout.splitlines() if l.startswith("{")]
+    assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
+    assert len(lines) == 2 and all(l["ok"] for l in lines), lines
+    assert lines[0]["results"]["cg_7pt"]["halo_bytes"] == 20 * 16 * 8  # one ny*nz plane from the single neighbour
+
+
+# ---- CPU: the host logic of the N > 1 path over gloo, world_size = 2 ---------------------------------------
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    sys.path.insert(0, str(ROOT))
+    from oracle import oracle as orc
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        off, val = orc.benchmark_stencil(3)
+        shape = (8, 6, 5)
+        m = orc.stencil_csr(shape, off, val)
+        n, pieces = m.n_rows, world
+        lo, hi = orc.equal_partition(n, pieces)
+        # blocked sharding: colour c -> rank c / ceil(P / world)
+        mine = [c for c in range(pieces) if orc.shard(c, pieces, world) == rank]
+        assert mine == [rank]
+        pl = orc.Planner([n], [pieces])
+        b = pl.add_matrix(m)
+        own_lo, own_hi = int(lo[rank]), int(hi[rank])
+        g_lo, g_hi = pl.ghost_bounds(b, rank)
+        # every rank learns every rank's owned rows and ghost interval (the planner's all-gather)
+        mine_t = torch.tensor([own_lo, own_hi, g_lo, g_hi], dtype=torch.int64)
+        allr = [torch.zeros(4, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(allr, mine_t)
+        allr = [tuple(int(v) for v in t) for t in allr]
+        # halo plan, same arithmetic as SquarePlanner::add_row_partitioned_matrix
+        moves = []
+        for q_ in range(world):
+            if q_ == rank:
+                continue
+            qo_lo, qo_hi, qg_lo, qg_hi = allr[q_]
+            recv_lo = max(g_lo, qo_lo); recv_n = max(0, min(g_hi, qo_hi) - recv_lo + 1)
+            send_lo = max(qg_lo, own_lo); send_n = max(0, min(qg_hi, own_hi) - send_lo + 1)
+            moves.append((q_, send_lo, send_n, recv_lo, recv_n))
+        # run 12 CG iterations with a DISTRIBUTED x: each rank holds only [g_lo, g_hi] of p
+        x_full = np.zeros(n); r = np.ones(n); p = np.ones(n); qv = np.zeros(n)
+        own = slice(own_lo, own_hi + 1)
+        rr = torch.tensor([float(r[own] @ r[own])], dtype=torch.float64)
+        dist.all_reduce(rr)
+        hist = [float(rr)]
+        for _ in range(12):
+            # halo exchange of p
+            reqs = []
+            for (q_, s_lo, s_n, r_lo, r_n) in moves:
+                if s_n:
+                    reqs.append(dist.isend(torch.from_numpy(p[s_lo:s_lo + s_n].copy()), q_))
+            for (q_, s_lo, s_n, r_lo, r_n) in moves:
+                if r_n:
+                    buf = torch.zeros(r_n, dtype=torch.float64)
+                    dist.recv(buf, q_)
+                    p[r_lo:r_lo + r_n] = buf.numpy()
+            for rq in reqs:
+                rq.wait()
+            pg = np.full(n, np.nan); pg[g_lo:g_hi + 1] = p[g_lo:g_hi + 1]  # poison everything outside the ghost piece
+            qv[own] = 0.0
+            k_lo, k_hi = pl.kernel_bounds(b, rank)
+            orc.csr_matvec(m, pg, qv, k=(k_lo, k_hi), r=(own_lo, own_hi), cols=(g_lo, g_hi))
+            pq = torch.tensor([float(p[own] @ qv[own])], dtype=torch.float64); dist.all_reduce(pq)
+            alpha = hist[-1] / float(pq)
+            x_full[own] += alpha * p[own]; r[own] -= alpha * qv[own]
+            rn = torch.tensor([float(r[own] @ r[own])], dtype=torch.float64); dist.all_reduce(rn)
+            p[own] = r[own] + (float(rn) / hist[-1]) * p[own]
+            hist.append(float(rn))
+        # single-process oracle on the same system
+        opl = orc.Planner([n], [pieces]); opl.fill(1, 1.0); opl.add_matrix(m)
+        ocg = orc.CGSolver(opl)
+        for _ in range(12):
+            ocg.step()
+        want = ocg.residual_norm_squared
+        err = float(np.max(np.abs(np.array(hist) - want) / want))
+        xerr = float(np.max(np.abs(x_full[own] - opl.vector(0)[own])))
+        q.put((rank, err, xerr, moves, (g_lo, g_hi)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_halo_plan_and_cg():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29533
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, e0, x0, m0, g0), (r1, e1, x1, m1, g1) = out
+    assert e0 <= 1e-12 and e1 <= 1e-12 and x0 <= 1e-12 and x1 <= 1e-12
+    # plans are consistent: what rank 0 sends to 1 is what rank 1 receives from 0, and vice versa
+    (_, s0_lo, s0_n, r0_lo, r0_n), = m0
+    (_, s1_lo, s1_n, r1_lo, r1_n), = m1
+    assert (s0_lo, s0_n) == (r1_lo, r1_n) and (s1_lo, s1_n) == (r0_lo, r0_n)
+    # 3-D 7-point, row-major: the halo is exactly one ny*nz plane each way
+    assert s0_n == s1_n == 6 * 5
+    assert g0 == (0, 4 * 30 + 30 - 1) and g1 == (4 * 30 - 30, 8 * 30 - 1)
