@@ -351,6 +351,10 @@ def run_ours(args):
                 "trace": "CUDA graph replay of iters_per_step iterations", "rhs": "b = 1, x0 = 0 (BenchmarkStencil)",
                 "l2": "working set per GPU exceeds the 126 MB L2 (matrix streamed once per iteration)",
                 "halo_bytes_per_matvec_rank0": pl.halo_bytes_per_matvec, "setup_seconds": round(setup_s, 3),
+                "collectives": ("none (1 GPU)" if world == 1 else
+                                "peer memory over NVLink (CUDA IPC): 1 halo-exchange kernel + 2 all-reduce kernels / iteration"
+                                if rt.uses_peer_memory else "NCCL: grouped send/recv halo + 2 ncclAllReduce / iteration"),
+                "comm_error": rt.comm_error() if world > 1 else 0,
                 "residual_norm_squared_last": rr_final,
                 "iteration_roofline": {"bytes_per_iteration_per_gpu": iter_bytes, "frac_of_peak": iter_frac},
             },

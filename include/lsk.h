@@ -287,6 +287,45 @@ int lsk_equal_partition(int64_t n, int pieces, int64_t *lo, int64_t *hi);
 /* BlockingShardingFunctor::shard (src/LegionSolversMapper.cpp:140-151) */
 int lsk_shard(int64_t point, int64_t volume, int64_t total_shards);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Collectives over NVLink / NVSwitch PEER MEMORY (one process per GPU, windows mapped with CUDA IPC).
+ * The Krylov path has exactly two exchange steps: the ghost-x halo before a
+ * mat-vec and the sum of per-rank dot partials.  Both are latency-bound (<= 512 KB, 8 bytes), so they
+ * are single small kernels that store straight into the peers' memory and spin on epoch flags --
+ * a few microseconds instead of one NCCL launch each.  Every rank must call them the same number of
+ * times in the same order (SPMD), on the stream that orders them with the producers / consumers.
+ *
+ * `lsk_peers.window[r]` is rank r's comm window (lsk_comm_window_bytes() bytes of zeroed device
+ * memory, cudaMalloc'ed) as mapped INTO THE CALLING PROCESS; window[rank] is the local one.
+ * ---------------------------------------------------------------------------------------------- */
+#define LSK_MAX_RANKS 16
+typedef struct {
+    int rank, nranks;
+    void *window[LSK_MAX_RANKS];
+} lsk_peers;
+size_t lsk_comm_window_bytes(void);
+/* slots[0..count) (count <= 2) := sum over ranks, identical bits on every rank (rank-order sum) */
+int lsk_allreduce_sum_f64(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, double *slots, int count);
+/* one halo move: copy n doubles from local `src` to `dst`, an address inside peer `peer`'s memory
+ * as mapped into this process (n == 0: nothing to send, but a receive from that peer is expected
+ * when `expect` is non-zero) */
+typedef struct {
+    int peer;
+    int expect;        /* non-zero: this peer also sends to me in this exchange */
+    const double *src;
+    double *dst;
+    int64_t n;
+} lsk_halo_move;
+#define LSK_MAX_HALO_MOVES 32
+/* neighbour exchange with barrier semantics: when the kernel completes on this stream, every
+ * peer's data destined for this rank has landed and this rank's data has been delivered.  A
+ * ready-handshake precedes the stores, so a fast peer never overwrites ghost values still in use. */
+int lsk_halo_exchange_f64(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, const lsk_halo_move *moves,
+                          int nmoves);
+/* non-zero if a spin-wait in one of the collectives gave up (protocol violation / dead peer) */
+int lsk_comm_error(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, int *host_out);
+
 #ifdef __cplusplus
 }
 #endif

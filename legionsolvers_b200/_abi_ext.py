@@ -38,11 +38,17 @@ def declare(L) -> None:
     L.lsk_equal_partition.argtypes = [i64, ci, vp, vp]
     L.lsk_shard.argtypes = [i64, i64, i64]
 
+    L.lsk_comm_window_bytes.restype = C.c_size_t
+    L.lsk_allreduce_sum_f64.argtypes = [vp, vp, vp, vp, ci]
+    L.lsk_halo_exchange_f64.argtypes = [vp, vp, vp, vp, ci]
+    L.lsk_comm_error.argtypes = [vp, vp, vp, vp]
     L.lsk_last_error.restype = C.c_char_p
     L.lsk_rt_create.argtypes = [ci, ci, ci, vp, C.POINTER(vp)]
     L.lsk_rt_destroy.argtypes = [vp]
     L.lsk_rt_unique_id.argtypes = [vp]
     L.lsk_rt_comm_init.argtypes = [vp, vp]
+    L.lsk_rt_uses_peer_memory.argtypes = [vp]
+    L.lsk_rt_comm_error.argtypes = [vp, C.POINTER(ci)]
     L.lsk_rt_ctx.argtypes = [vp]
     L.lsk_rt_ctx.restype = vp
     L.lsk_rt_stream.argtypes = [vp]

@@ -1,0 +1,175 @@
+// lsk_comm.cu -- the two collectives of the Krylov path over NVLink / NVSwitch peer memory.
+//
+// One process per GPU; each rank's comm window and its vectors' buffers are mapped into every peer
+// with CUDA IPC (host side: host/Runtime.cpp).  Stores to a mapped peer address travel over NVLink
+// through the NVSwitch and land in the peer's L2 / HBM; visibility is ordered with
+// __threadfence_system() before the epoch-flag store, and the reader polls the flag in its OWN
+// memory with volatile (L1-bypassing) loads.  Epochs are monotonic device-side counters, so the
+// kernels can be recorded in a CUDA graph and replayed without patching arguments.
+#include "lsk_common.cuh"
+
+namespace lsk {
+
+struct CommWindow {
+    // ---- written by PEERS (remote stores) -------------------------------------------------------
+    double ar_val[2][LSK_MAX_RANKS][kMaxRed];          // all-reduce contributions, by epoch parity and source rank
+    unsigned long long ar_flag[LSK_MAX_RANKS];         // epoch of the latest contribution from each source
+    unsigned long long halo_ready[LSK_MAX_RANKS];      // peer r is ready to RECEIVE my data of this epoch
+    unsigned long long halo_done[LSK_MAX_RANKS];       // peer r's data of this epoch has landed here
+    // ---- local state ----------------------------------------------------------------------------------
+    unsigned long long ar_epoch;
+    unsigned long long halo_epoch;
+    unsigned int halo_ticket;
+    int error;
+};
+
+constexpr long long kSpinLimit = 400LL * 1000 * 1000;  // ~ seconds; then give up instead of hanging the GPU
+
+__device__ __forceinline__ bool spin_until(const volatile unsigned long long *flag, unsigned long long want, int *err) {
+    long long n = 0;
+    while (*flag < want) {
+        if (++n > kSpinLimit) {
+            *err = 1;
+            return false;
+        }
+    }
+    return true;
+}
+
+// ---- all-reduce: one CTA, thread r talks to rank r ----------------------------------------------------
+__global__ void __launch_bounds__(32) allreduce_kernel(lsk_peers peers, double *slots, int count) {
+    CommWindow *me = static_cast<CommWindow *>(peers.window[peers.rank]);
+    const int r = threadIdx.x;
+    const unsigned long long e = me->ar_epoch + 1;
+    const int par = (int) (e & 1);
+    if (r < peers.nranks) {
+        CommWindow *dst = static_cast<CommWindow *>(peers.window[r]);
+        for (int j = 0; j < count; ++j) dst->ar_val[par][peers.rank][j] = slots[j];
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long *>(&dst->ar_flag[peers.rank]) = e;
+        spin_until(&me->ar_flag[r], e, &me->error);
+    }
+    __syncwarp();
+    __threadfence_system();
+    if (r == 0) {
+        for (int j = 0; j < count; ++j) {
+            double sum = 0.0;
+            for (int q = 0; q < peers.nranks; ++q) sum += *reinterpret_cast<volatile double *>(&me->ar_val[par][q][j]);
+            slots[j] = sum;  // same rank order everywhere: identical bits on every rank
+        }
+        me->ar_epoch = e;
+    }
+}
+
+// ---- halo exchange -------------------------------------------------------------------------------------
+struct HaloArgs {
+    int nmoves;
+    lsk_halo_move m[LSK_MAX_HALO_MOVES];
+};
+
+__global__ void __launch_bounds__(kBlock) halo_exchange_kernel(lsk_peers peers, HaloArgs a) {
+    CommWindow *me = static_cast<CommWindow *>(peers.window[peers.rank]);
+    __shared__ bool s_last;
+    const unsigned long long e = me->halo_epoch + 1;  // written only by the last CTA, after everyone read it
+    // 1. tell every peer I receive from that my ghost region may be overwritten (all my earlier kernels
+    //    on this stream -- the readers of the previous ghost values -- have completed)
+    if (blockIdx.x == 0 && threadIdx.x < a.nmoves && a.m[threadIdx.x].expect) {
+        CommWindow *dst = static_cast<CommWindow *>(peers.window[a.m[threadIdx.x].peer]);
+        *reinterpret_cast<volatile unsigned long long *>(&dst->halo_ready[peers.rank]) = e;
+    }
+    // 2. wait until every peer I send to is ready
+    if (threadIdx.x < a.nmoves && a.m[threadIdx.x].n > 0) spin_until(&me->halo_ready[a.m[threadIdx.x].peer], e, &me->error);
+    __syncthreads();
+    // 3. store my boundary values straight into the peers' ghost regions
+    for (int i = 0; i < a.nmoves; ++i) {
+        const double *src = a.m[i].src;
+        double *dst = a.m[i].dst;
+        const int64_t n = a.m[i].n;
+        const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+        const int64_t tid = (int64_t) blockIdx.x * kBlock + threadIdx.x, stride = (int64_t) gridDim.x * kBlock;
+        if (vec) {
+            const int64_t n2 = n >> 1;
+            for (int64_t k = tid; k < n2; k += stride)
+                reinterpret_cast<double2 *>(dst)[k] = reinterpret_cast<const double2 *>(src)[k];
+            if (tid == 0 && (n & 1)) dst[n - 1] = src[n - 1];
+        } else {
+            for (int64_t k = tid; k < n; k += stride) dst[k] = src[k];
+        }
+    }
+    // 4. the last CTA to finish publishes "done" to the peers, waits for theirs, and closes the epoch
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(&me->halo_ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence_system();
+    if (threadIdx.x < a.nmoves) {
+        const lsk_halo_move &mv = a.m[threadIdx.x];
+        if (mv.n > 0) {
+            CommWindow *dst = static_cast<CommWindow *>(peers.window[mv.peer]);
+            *reinterpret_cast<volatile unsigned long long *>(&dst->halo_done[peers.rank]) = e;
+        }
+        if (mv.expect) spin_until(&me->halo_done[mv.peer], e, &me->error);
+    }
+    __syncthreads();
+    __threadfence_system();
+    if (threadIdx.x == 0) {
+        me->halo_epoch = e;
+        me->halo_ticket = 0u;
+    }
+}
+
+}  // namespace lsk
+
+using namespace lsk;
+
+extern "C" {
+
+size_t lsk_comm_window_bytes(void) { return (sizeof(CommWindow) + 255) & ~size_t(255); }
+
+static bool peers_ok(const lsk_peers *p) {
+    if (!p || p->nranks < 1 || p->nranks > LSK_MAX_RANKS || p->rank < 0 || p->rank >= p->nranks) return false;
+    for (int r = 0; r < p->nranks; ++r)
+        if (!p->window[r]) return false;
+    return true;
+}
+
+int lsk_allreduce_sum_f64(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, double *slots, int count) {
+    if (!ctx || !slots || count < 1 || count > kMaxRed || !peers_ok(peers)) return LSK_E_INVALID;
+    if (peers->nranks > 32) return LSK_E_INVALID;
+    allreduce_kernel<<<1, 32, 0, (cudaStream_t) s>>>(*peers, slots, count);
+    return after_launch(ctx);
+}
+
+int lsk_halo_exchange_f64(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, const lsk_halo_move *moves, int nmoves) {
+    if (!ctx || !peers_ok(peers) || nmoves < 0 || nmoves > LSK_MAX_HALO_MOVES || (nmoves > 0 && !moves)) return LSK_E_INVALID;
+    if (nmoves == 0) return 0;
+    HaloArgs a;
+    a.nmoves = nmoves;
+    int64_t total = 0;
+    for (int i = 0; i < nmoves; ++i) {
+        a.m[i] = moves[i];
+        if (moves[i].peer < 0 || moves[i].peer >= peers->nranks || moves[i].n < 0) return LSK_E_INVALID;
+        if (moves[i].n > 0 && (!moves[i].src || !moves[i].dst)) return LSK_E_INVALID;
+        total += moves[i].n;
+    }
+    // enough CTAs to keep NVLink busy for a few hundred KB, few enough that the epilogue stays cheap
+    int grid = (int) ((total + 4 * kBlock - 1) / (4 * kBlock));
+    if (grid < 1) grid = 1;
+    if (grid > 32) grid = 32;
+    halo_exchange_kernel<<<grid, kBlock, 0, (cudaStream_t) s>>>(*peers, a);
+    return after_launch(ctx);
+}
+
+int lsk_comm_error(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, int *host_out) {
+    if (!ctx || !peers_ok(peers) || !host_out) return LSK_E_INVALID;
+    const CommWindow *me = static_cast<const CommWindow *>(peers->window[peers->rank]);
+    LSK_RETURN_IF_CUDA(cudaMemcpyAsync(host_out, &me->error, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t) s));
+    LSK_RETURN_IF_CUDA(cudaStreamSynchronize((cudaStream_t) s));
+    return 0;
+}
+
+}  // extern "C"

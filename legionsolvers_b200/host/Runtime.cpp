@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 #include <sstream>
 
 namespace LegionSolvers {
@@ -29,7 +30,9 @@ Runtime::~Runtime() {
     cudaStreamSynchronize(stream_);
     for (auto &kv : traces_)
         if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    for (void *p : ipc_opened_) cudaIpcCloseMemHandle(p);
     if (comm_) ncclCommDestroy(reinterpret_cast<ncclComm_t>(comm_));
+    if (window_) cudaFree(window_);
     for (void *p : allocations_) cudaFree(p);
     for (double *p : arena_chunks_) cudaFree(p);
     if (own_stream_) cudaStreamDestroy(stream_);
@@ -60,6 +63,95 @@ void Runtime::comm_init(const void *uid128) {
     ncclComm_t c;
     if (ncclCommInitRank(&c, nranks_, id, rank_) != ncclSuccess) fail(LSK_E_NCCL, "ncclCommInitRank");
     comm_ = reinterpret_cast<ncclComm *>(c);
+    // Peer-memory windows for the latency-bound collectives.  LSK_COMM=nccl keeps everything on NCCL.
+    const char *mode = std::getenv("LSK_COMM");
+    if (mode && std::string(mode) == "nccl") return;
+    if (nranks_ > LSK_MAX_RANKS) return;
+    const size_t wbytes = lsk_comm_window_bytes();
+    check_cuda(cudaMalloc(&window_, wbytes), "cudaMalloc(comm window)");
+    check_cuda(cudaMemset(window_, 0, wbytes), "cudaMemset(comm window)");
+    try {
+        const Exported ex = export_allocation(window_, 0, 0);
+        peers_.rank = rank_;
+        peers_.nranks = nranks_;
+        for (int r = 0; r < nranks_; ++r) peers_.window[r] = ex.base[(size_t) r];
+        p2p_ = true;
+    } catch (const std::exception &) {
+        p2p_ = false;  // no IPC / no peer access: stay on NCCL
+    }
+    // all ranks must agree (a rank falling back alone would deadlock the others)
+    DeviceBuffer<int64_t> flag(this, 1), all(this, (size_t) nranks_);
+    const int64_t ok = p2p_ ? 1 : 0;
+    check_cuda(cudaMemcpyAsync(flag.ptr, &ok, sizeof(ok), cudaMemcpyHostToDevice, stream_), "p2p vote");
+    allgather_i64(flag.ptr, all.ptr, 1);
+    std::vector<int64_t> votes((size_t) nranks_);
+    check_cuda(cudaMemcpyAsync(votes.data(), all.ptr, sizeof(int64_t) * votes.size(), cudaMemcpyDeviceToHost, stream_), "p2p vote");
+    fence();
+    for (int64_t v : votes) p2p_ = p2p_ && (v == 1);
+}
+
+Runtime::Exported Runtime::export_allocation(void *raw, int64_t tag0, int64_t tag1) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle travels as 8 int64");
+    constexpr int W = 10;  // 8 words of handle + 2 tags
+    int64_t mine[W];
+    cudaIpcMemHandle_t h;
+    const cudaError_t ge = cudaIpcGetMemHandle(&h, raw);
+    std::memset(mine, 0, sizeof(mine));
+    if (ge == cudaSuccess) std::memcpy(mine, &h, sizeof(h));
+    else (void) cudaGetLastError();
+    mine[8] = tag0;
+    mine[9] = tag1;
+    DeviceBuffer<int64_t> send(this, W), recv(this, (size_t) W * nranks_);
+    check_cuda(cudaMemcpyAsync(send.ptr, mine, sizeof(mine), cudaMemcpyHostToDevice, stream_), "export H2D");
+    allgather_i64(send.ptr, recv.ptr, W);
+    std::vector<int64_t> all((size_t) W * nranks_);
+    check_cuda(cudaMemcpyAsync(all.data(), recv.ptr, sizeof(int64_t) * all.size(), cudaMemcpyDeviceToHost, stream_), "export D2H");
+    fence();
+    Exported ex;
+    ex.base.assign((size_t) nranks_, nullptr);
+    ex.tag0.assign((size_t) nranks_, 0);
+    ex.tag1.assign((size_t) nranks_, 0);
+    bool ok = (ge == cudaSuccess);
+    for (int r = 0; r < nranks_; ++r) {
+        ex.tag0[(size_t) r] = all[(size_t) r * W + 8];
+        ex.tag1[(size_t) r] = all[(size_t) r * W + 9];
+        if (r == rank_) {
+            ex.base[(size_t) r] = static_cast<char *>(raw);
+            continue;
+        }
+        cudaIpcMemHandle_t ph;
+        std::memcpy(&ph, &all[(size_t) r * W], sizeof(ph));
+        const std::string key(reinterpret_cast<const char *>(&ph), sizeof(ph));
+        auto hit = ipc_cache_.find(key);
+        if (hit != ipc_cache_.end()) {  // the peer re-exported an allocation that is already mapped here
+            ex.base[(size_t) r] = static_cast<char *>(hit->second);
+            continue;
+        }
+        void *mapped = nullptr;
+        const cudaError_t oe = cudaIpcOpenMemHandle(&mapped, ph, cudaIpcMemLazyEnablePeerAccess);
+        if (oe != cudaSuccess) {
+            (void) cudaGetLastError();
+            ok = false;
+            continue;
+        }
+        ipc_opened_.push_back(mapped);
+        ipc_cache_[key] = mapped;
+        ex.base[(size_t) r] = static_cast<char *>(mapped);
+    }
+    if (!ok) throw std::runtime_error("[LegionSolvers] CUDA IPC export failed (no peer access between ranks?)");
+    return ex;
+}
+
+void Runtime::halo_exchange_p2p(const lsk_halo_move *moves, int nmoves) {
+    enqueue("halo exchange", [&] { return lsk_halo_exchange_f64(ctx_, stream_, &peers_, moves, nmoves); });
+}
+
+int Runtime::comm_error() {
+    if (!p2p_) return 0;
+    int e = 0;
+    const int rc = lsk_comm_error(ctx_, stream_, &peers_, &e);
+    if (rc != 0) fail(rc, "lsk_comm_error");
+    return e;
 }
 
 #define LSK_NCCL(expr, what)                              \
@@ -69,6 +161,10 @@ void Runtime::comm_init(const void *uid128) {
 
 void Runtime::allreduce_sum(double *slots, int count) {
     if (nranks_ == 1 || mode_ == Mode::Replay) return;
+    if (p2p_) {
+        enqueue("allreduce", [&] { return lsk_allreduce_sum_f64(ctx_, stream_, &peers_, slots, count); });
+        return;
+    }
     if (!comm_) fail(LSK_E_NCCL, "allreduce_sum without comm_init");
     LSK_NCCL(ncclAllReduce(slots, slots, (size_t) count, ncclDouble, ncclSum, reinterpret_cast<ncclComm_t>(comm_), stream_),
              "ncclAllReduce");

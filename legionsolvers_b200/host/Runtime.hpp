@@ -51,6 +51,17 @@ public:
     void comm_init(const void *uid128);
     bool has_comm() const { return comm_ != nullptr; }
     void allreduce_sum(double *slots, int count);  // in place, stream-ordered; no-op on one rank
+    // ---- peer memory (CUDA IPC over NVLink): the low-latency path of the two collectives -----------
+    struct Exported {            // one cudaMalloc'ed allocation mapped into every peer
+        std::vector<char *> base;     // base[r] = rank r's allocation as mapped here (base[rank] = local)
+        std::vector<int64_t> tag0, tag1;  // two user values per rank (e.g. byte offset of element 0, buf_lo)
+    };
+    bool p2p() const { return p2p_; }
+    const lsk_peers &peers() const { return peers_; }
+    // COLLECTIVE (every rank, same order): export `raw` and map everybody else's
+    Exported export_allocation(void *raw, int64_t tag0, int64_t tag1);
+    void halo_exchange_p2p(const lsk_halo_move *moves, int nmoves);
+    int comm_error();
     void allgather_i64(const int64_t *send_dev, int64_t *recv_dev, int count_per_rank);
     void group_start();
     void group_end();
@@ -96,6 +107,11 @@ private:
     cudaStream_t stream_ = nullptr;
     bool own_stream_ = false;
     ncclComm *comm_ = nullptr;
+    bool p2p_ = false;
+    lsk_peers peers_{};
+    void *window_ = nullptr;
+    std::vector<void *> ipc_opened_;
+    std::map<std::string, void *> ipc_cache_;
     Mode mode_ = Mode::Eager;
     int active_trace_ = -1;
     uint64_t capture_mark_ = 0;

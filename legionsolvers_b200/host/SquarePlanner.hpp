@@ -98,6 +98,23 @@ class SquarePlanner {
 
     void exchange_halo(const Block &b, const PartitionedVector<T> &v) {
         if (b.halo.empty()) return;
+        if constexpr (std::is_same<T, double>::value) {
+            if (rt->p2p() && v.exported() && b.halo.size() <= LSK_MAX_HALO_MOVES) {
+                // one kernel: ready-handshake, P2P stores into the peers' ghost regions, epoch flags
+                lsk_halo_move moves[LSK_MAX_HALO_MOVES];
+                int n = 0;
+                for (const HaloMove &m : b.halo) {
+                    moves[n].peer = m.peer;
+                    moves[n].expect = m.recv_n > 0 ? 1 : 0;
+                    moves[n].n = m.send_n;
+                    moves[n].src = m.send_n > 0 ? v.ptr(m.send_lo) : nullptr;
+                    moves[n].dst = m.send_n > 0 ? v.peer_ptr(m.peer, m.send_lo) : nullptr;
+                    ++n;
+                }
+                rt->halo_exchange_p2p(moves, n);
+                return;
+            }
+        }
         rt->group_start();
         for (const HaloMove &m : b.halo) {
             if (m.send_n > 0) rt->send(v.ptr(m.send_lo), (size_t) m.send_n * sizeof(T), m.peer);
@@ -204,9 +221,10 @@ public:
         if (g_hi >= g_lo) {
             space_need[domain_index].first = std::min(space_need[domain_index].first, g_lo);
             space_need[domain_index].second = std::max(space_need[domain_index].second, g_hi);
-            sol_vectors[domain_index].ensure_range(g_lo, g_hi);
-            rhs_vectors[domain_index].ensure_range(g_lo, g_hi);
         }
+        // (ensure_range is collective in multi-rank mode: called on every rank, empty range or not)
+        sol_vectors[domain_index].ensure_range(g_lo, g_hi);
+        rhs_vectors[domain_index].ensure_range(g_lo, g_hi);
         row_partitioned_matrices.push_back(std::move(b));
     }
 

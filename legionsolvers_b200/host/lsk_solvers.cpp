@@ -87,6 +87,11 @@ int lsk_rt_comm_init(lsk_runtime *rt, const void *uid128) {
     REQUIRE(rt && uid128);
     return guard([&] { rt->rt->comm_init(uid128); });
 }
+int lsk_rt_uses_peer_memory(lsk_runtime *rt) { return (rt && rt->rt->p2p()) ? 1 : 0; }
+int lsk_rt_comm_error(lsk_runtime *rt, int *out) {
+    REQUIRE(rt && out);
+    return guard([&] { *out = rt->rt->comm_error(); });
+}
 lsk_ctx *lsk_rt_ctx(lsk_runtime *rt) { return rt ? rt->rt->ctx() : nullptr; }
 void *lsk_rt_stream(lsk_runtime *rt) { return rt ? (void *) rt->rt->stream() : nullptr; }
 int lsk_rt_fence(lsk_runtime *rt) {

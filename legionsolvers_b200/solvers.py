@@ -70,6 +70,15 @@ class Runtime:
         _check(_abi.lib().lsk_rt_comm_init(self.h, C.create_string_buffer(uid, 128)), "lsk_rt_comm_init")
 
     @property
+    def uses_peer_memory(self) -> bool:
+        return bool(_abi.lib().lsk_rt_uses_peer_memory(self.h))
+
+    def comm_error(self) -> int:
+        out = C.c_int()
+        _check(_abi.lib().lsk_rt_comm_error(self.h, C.byref(out)), "lsk_rt_comm_error")
+        return out.value
+
+    @property
     def ctx(self) -> int:
         return _abi.lib().lsk_rt_ctx(self.h)
 

@@ -14,17 +14,31 @@ ROOT = Path(__file__).resolve().parents[1]
 
 
 @pytest.mark.gpu
-def test_two_gpu_cg_bicgstab_gmres_parity():
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+@pytest.mark.parametrize("comm", ["peer-memory", "nccl"])
+def test_multi_gpu_cg_bicgstab_gmres_parity(comm):
+    """Every rank checks generator slab, partitions, solver histories and its owned solution rows against
+    the single-process oracle; once with the peer-memory collectives (CUDA IPC over NVLink), once on NCCL."""
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    world = 4 if ngpu >= 4 else 2
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29511", str(ROOT / "tests" / "mp_worker.py")]
-    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    if comm == "nccl":
+        env["LSK_COMM"] = "nccl"
+    else:
+        env.pop("LSK_COMM", None)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
+           "127.0.0.1", "--master-port", "29511" if comm == "nccl" else "29512", str(ROOT / "tests" / "mp_worker.py")]
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
     lines = [json.loads(l) for l in proc.stdout.splitlines() if l.startswith("{")]
     assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
-    assert len(lines) == 2 and all(l["ok"] for l in lines), lines
-    assert lines[0]["results"]["cg_7pt"]["halo_bytes"] == 20 * 16 * 8  # one ny*nz plane from the single neighbour
+    assert len(lines) == world and all(l["ok"] for l in lines), lines
+    assert all(l["results"]["_comm"]["error"] == 0 for l in lines)
+    if comm == "nccl":
+        assert not any(l["results"]["_comm"]["peer_memory"] for l in lines)
+    by_rank = {l["rank"]: l for l in lines}
+    # 3-D 7-point, row-major: rank 0 receives exactly one ny*nz plane from its single neighbour
+    assert by_rank[0]["results"]["cg_7pt"]["halo_bytes"] == 20 * 16 * 8
 
 
 # ---- CPU: the host logic of the N > 1 path over gloo, world_size = 2 ---------------------------------------
