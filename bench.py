@@ -199,6 +199,9 @@ def run_ours(args):
         return float(t.item())
 
     dim_flag, shape, desc = WORKLOADS[args.workload]
+    if args.shape:
+        shape = tuple(int(v) for v in args.shape.split(","))
+        desc += f" [grid overridden to {shape}]"
     ipt = args.iters_per_step
     # everything (our kernels, NCCL, the timing events) goes on ONE explicit non-default stream: torch's
     # default stream has handle 0, which the runtime would read as "create a private stream"
@@ -351,9 +354,7 @@ def run_ours(args):
                 "trace": "CUDA graph replay of iters_per_step iterations", "rhs": "b = 1, x0 = 0 (BenchmarkStencil)",
                 "l2": "working set per GPU exceeds the 126 MB L2 (matrix streamed once per iteration)",
                 "halo_bytes_per_matvec_rank0": pl.halo_bytes_per_matvec, "setup_seconds": round(setup_s, 3),
-                "collectives": ("none (1 GPU)" if world == 1 else
-                                "peer memory over NVLink (CUDA IPC): 1 halo-exchange kernel + 2 all-reduce kernels / iteration"
-                                if rt.uses_peer_memory else "NCCL: grouped send/recv halo + 2 ncclAllReduce / iteration"),
+                "collectives": "none (1 GPU)" if world == 1 else rt.collectives,
                 "comm_error": rt.comm_error() if world > 1 else 0,
                 "residual_norm_squared_last": rr_final,
                 "iteration_roofline": {"bytes_per_iteration_per_gpu": iter_bytes, "frac_of_peak": iter_frac},
@@ -385,6 +386,7 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c3")
     ap.add_argument("--iters-per-step", type=int, default=20, help="CG iterations per recorded trace (BenchmarkStencil -pt)")
     ap.add_argument("--ref-iters-per-step", type=int, default=2, help="CPU reference arm: iterations per step (bounded sample)")
+    ap.add_argument("--shape", type=str, default=None, help="developer override nx,ny,nz of the workload's grid")
     ap.add_argument("--unfused", action="store_true", help="run the reference's unfused call sequence on the GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -323,6 +323,20 @@ typedef struct {
  * ready-handshake precedes the stores, so a fast peer never overwrites ghost values still in use. */
 int lsk_halo_exchange_f64(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, const lsk_halo_move *moves,
                           int nmoves);
+/* FUSED forms: no launch of their own.
+ * lsk_ctx_set_peers(ctx, peers): from now on EVERY reducing kernel launched through ctx (dot, dot2,
+ * cg_update, axpy_dot, bicg_tail, the fused SpMV dots) finishes with the cross-rank sum in the tail of
+ * its last CTA: the value it writes is already the global one.  Every rank must then launch the same
+ * reducing kernels in the same order.  NULL switches back to rank-local reductions. */
+int lsk_ctx_set_peers(lsk_ctx *ctx, const lsk_peers *peers);
+/* XpayTask fused with the halo push of its result: y = fma(alpha, y, x), and the elements of y that lie
+ * in moves[i].src[0..n) (sub-ranges of y) are also stored to moves[i].dst in the neighbour's memory;
+ * when the kernel completes every rank's ghosts of y are current.  There is NO ready-handshake: the
+ * caller guarantees that the neighbours' readers of the previous ghost values finished before this
+ * launch (in CG an all-reduce of p.Ap separates them).  Needs lsk_ctx_set_peers.  nmoves <= 4. */
+int lsk_xpay_halo_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, int n_terms, const double *f0, const double *f1,
+                      const double *f2, const double *f3, const double *x, double *y, const lsk_halo_move *moves,
+                      int nmoves);
 /* non-zero if a spin-wait in one of the collectives gave up (protocol violation / dead peer) */
 int lsk_comm_error(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, int *host_out);
 

@@ -33,8 +33,8 @@ int lsk_rt_destroy(lsk_runtime *rt);
 /* NCCL bootstrap: rank 0 calls lsk_rt_unique_id, ships the 128 bytes to every rank, all call comm_init */
 int lsk_rt_unique_id(void *out128);
 int lsk_rt_comm_init(lsk_runtime *rt, const void *uid128);
-/* 1 if the halo exchange and the scalar all-reduce run over CUDA-IPC peer memory (NVLink), 0 if on NCCL
- * (LSK_COMM=nccl, or no peer access) */
+/* 0: collectives on NCCL (LSK_COMM=nccl, or no peer access); 1: stand-alone peer-memory kernels (CUDA IPC
+ * over NVLink); 2: peer-memory collectives FUSED into the producing kernels' tails (one piece per rank) */
 int lsk_rt_uses_peer_memory(lsk_runtime *rt);
 /* non-zero if a peer-memory collective gave up waiting (synchronises) */
 int lsk_rt_comm_error(lsk_runtime *rt, int *out);

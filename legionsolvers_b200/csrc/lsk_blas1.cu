@@ -17,7 +17,8 @@ namespace lsk {
 // ---------------------------------------------------------------------------------------------------
 template <typename F>
 __global__ void __launch_bounds__(kBlock)
-stream_kernel(F f, int64_t n, int64_t head, int64_t npacks, double *partials, unsigned int *ticket) {
+stream_kernel(F f, int64_t n, int64_t head, int64_t npacks, double *partials, unsigned int *ticket,
+              const lsk_peers *peers) {
     using T = typename F::T;
     constexpr int NRED = F::NRED;
     constexpr int EPP = PackOf<T>::N;
@@ -38,7 +39,7 @@ stream_kernel(F f, int64_t n, int64_t head, int64_t npacks, double *partials, un
     if constexpr (NRED > 0) {
         T *out[NRED];
         f.outs(out);
-        grid_reduce_finish<NRED, T>(acc, partials, ticket, out);
+        grid_reduce_finish<NRED, T>(acc, partials, ticket, out, peers);
     }
 }
 
@@ -71,10 +72,98 @@ static int launch_stream(lsk_ctx *ctx, lsk_stream s, F f, int64_t n, Span sp) {
     if (n == 0 && F::NRED == 0) return 0;
     const int64_t items = sp.npacks > 0 ? sp.npacks : n;
     const int grid = stream_grid(ctx, items > 0 ? items : 1, 8);
-    RedScratch rs = {nullptr, nullptr};
+    RedScratch rs = {nullptr, nullptr, nullptr};
     if (F::NRED > 0) rs = next_scratch(ctx);
-    stream_kernel<F><<<grid, kBlock, 0, (cudaStream_t) s>>>(f, n, sp.head, sp.npacks, rs.partials, rs.ticket);
+    stream_kernel<F><<<grid, kBlock, 0, (cudaStream_t) s>>>(f, n, sp.head, sp.npacks, rs.partials, rs.ticket,
+                                                            F::NRED > 0 ? ctx->d_peers : nullptr);
     return after_launch(ctx);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// xpay fused with the halo push of its result (the p = r + beta p of CG feeds the next mat-vec):
+// elements that fall in a send range are also stored straight into the neighbour's ghost region over
+// NVLink; the last CTA publishes the epoch to the neighbours and waits for theirs, so when the kernel
+// completes the ghosts of y are current on every rank -- no separate exchange launch.
+// ---------------------------------------------------------------------------------------------------
+struct HaloSpec {
+    int nmoves;
+    lsk_halo_move m[4];
+    int64_t lo[4];  // send range start as an element index into y
+};
+
+__global__ void __launch_bounds__(kBlock)
+xpay_halo_kernel(Alpha<double> al, const double *__restrict__ x, double *__restrict__ y, int64_t n, int64_t head,
+                 int64_t npacks, HaloSpec h, const lsk_peers *peers) {
+    const double a = fold_alpha(al);
+    const int64_t tid = (int64_t) blockIdx.x * kBlock + threadIdx.x;
+    const int64_t stride = (int64_t) gridDim.x * kBlock;
+    auto mirror = [&](int64_t i, double v) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (q < h.nmoves && i >= h.lo[q] && i < h.lo[q] + h.m[q].n) h.m[q].dst[i - h.lo[q]] = v;
+    };
+    for (int64_t p = tid; p < npacks; p += stride) {
+        const int64_t i = head + p * 4;
+        const Pack32 px = ld256(x + i);
+        Pack32 py = ld256(y + i);
+        double v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            v[e] = fma_rn(a, PackOf<double>::get(py, e), PackOf<double>::get(px, e));
+            PackOf<double>::set(py, e, v[e]);
+        }
+        st256(y + i, py);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (q < h.nmoves && i + 4 > h.lo[q] && i < h.lo[q] + h.m[q].n) {
+                double *d = h.m[q].dst + (i - h.lo[q]);
+                const bool inside = (i >= h.lo[q]) && (i + 4 <= h.lo[q] + h.m[q].n);
+                if (inside && (reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+                    reinterpret_cast<double2 *>(d)[0] = make_double2(v[0], v[1]);
+                    reinterpret_cast<double2 *>(d)[1] = make_double2(v[2], v[3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (i + e >= h.lo[q] && i + e < h.lo[q] + h.m[q].n) d[e] = v[e];
+                }
+            }
+        }
+    }
+    const int64_t tail0 = head + npacks * 4;
+    const int64_t nedge = head + (n - tail0);
+    for (int64_t e = tid; e < nedge; e += stride) {
+        const int64_t i = e < head ? e : tail0 + (e - head);
+        const double v = fma_rn(a, y[i], x[i]);
+        y[i] = v;
+        mirror(i, v);
+    }
+    // ---- epilogue: last CTA closes the exchange epoch
+    CommWindow *me = static_cast<CommWindow *>(peers->window[peers->rank]);
+    __shared__ bool s_last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(&me->halo_ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence_system();
+    const unsigned long long e = me->halo_epoch + 1;
+    if (threadIdx.x < h.nmoves) {
+        const lsk_halo_move &mv = h.m[threadIdx.x];
+        if (mv.n > 0) {
+            CommWindow *dst = static_cast<CommWindow *>(peers->window[mv.peer]);
+            *reinterpret_cast<volatile unsigned long long *>(&dst->halo_done[peers->rank]) = e;
+        }
+        if (mv.expect) spin_until(&me->halo_done[mv.peer], e, &me->error);
+    }
+    __syncthreads();
+    __threadfence_system();
+    if (threadIdx.x == 0) {
+        me->halo_epoch = e;
+        me->halo_ticket = 0u;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -404,6 +493,27 @@ int lsk_axpy_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, int nt, const double *f0
 int lsk_xpay_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, int nt, const double *f0, const double *f1,
                  const double *f2, const double *f3, const double *x, double *y) {
     return do_xpay<double>(ctx, s, n, make_alpha(nt, f0, f1, f2, f3), x, y);
+}
+int lsk_xpay_halo_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, int nt, const double *f0, const double *f1,
+                      const double *f2, const double *f3, const double *x, double *y, const lsk_halo_move *moves,
+                      int nmoves) {
+    Alpha<double> al = make_alpha(nt, f0, f1, f2, f3);
+    if (!ctx || n < 0 || !alpha_ok(al) || (n > 0 && (!x || !y)) || nmoves < 0 || nmoves > 4 || (nmoves > 0 && !moves))
+        return LSK_E_INVALID;
+    if (!ctx->d_peers) return LSK_E_INVALID;  // needs lsk_ctx_set_peers
+    HaloSpec h;
+    h.nmoves = nmoves;
+    for (int i = 0; i < nmoves; ++i) {
+        h.m[i] = moves[i];
+        if (moves[i].n < 0 || (moves[i].n > 0 && (!moves[i].dst || moves[i].src < y || moves[i].src + moves[i].n > y + n)))
+            return LSK_E_INVALID;
+        h.lo[i] = moves[i].n > 0 ? (int64_t) (moves[i].src - y) : 0;
+    }
+    const Span sp = plan_span<double>(n, {x, y});
+    const int64_t items = sp.npacks > 0 ? sp.npacks : n;
+    const int grid = stream_grid(ctx, items > 0 ? items : 1, 8);
+    xpay_halo_kernel<<<grid, kBlock, 0, (cudaStream_t) s>>>(al, x, y, n, sp.head, sp.npacks, h, ctx->d_peers);
+    return after_launch(ctx);
 }
 int lsk_dot_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, const double *v, const double *w, double *out) {
     return do_dot<double>(ctx, s, n, v, w, out);

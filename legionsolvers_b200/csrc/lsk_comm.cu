@@ -10,55 +10,13 @@
 
 namespace lsk {
 
-struct CommWindow {
-    // ---- written by PEERS (remote stores) -------------------------------------------------------
-    double ar_val[2][LSK_MAX_RANKS][kMaxRed];          // all-reduce contributions, by epoch parity and source rank
-    unsigned long long ar_flag[LSK_MAX_RANKS];         // epoch of the latest contribution from each source
-    unsigned long long halo_ready[LSK_MAX_RANKS];      // peer r is ready to RECEIVE my data of this epoch
-    unsigned long long halo_done[LSK_MAX_RANKS];       // peer r's data of this epoch has landed here
-    // ---- local state ----------------------------------------------------------------------------------
-    unsigned long long ar_epoch;
-    unsigned long long halo_epoch;
-    unsigned int halo_ticket;
-    int error;
-};
-
-constexpr long long kSpinLimit = 400LL * 1000 * 1000;  // ~ seconds; then give up instead of hanging the GPU
-
-__device__ __forceinline__ bool spin_until(const volatile unsigned long long *flag, unsigned long long want, int *err) {
-    long long n = 0;
-    while (*flag < want) {
-        if (++n > kSpinLimit) {
-            *err = 1;
-            return false;
-        }
-    }
-    return true;
-}
-
 // ---- all-reduce: one CTA, thread r talks to rank r ----------------------------------------------------
 __global__ void __launch_bounds__(32) allreduce_kernel(lsk_peers peers, double *slots, int count) {
-    CommWindow *me = static_cast<CommWindow *>(peers.window[peers.rank]);
-    const int r = threadIdx.x;
-    const unsigned long long e = me->ar_epoch + 1;
-    const int par = (int) (e & 1);
-    if (r < peers.nranks) {
-        CommWindow *dst = static_cast<CommWindow *>(peers.window[r]);
-        for (int j = 0; j < count; ++j) dst->ar_val[par][peers.rank][j] = slots[j];
-        __threadfence_system();
-        *reinterpret_cast<volatile unsigned long long *>(&dst->ar_flag[peers.rank]) = e;
-        spin_until(&me->ar_flag[r], e, &me->error);
-    }
-    __syncwarp();
-    __threadfence_system();
-    if (r == 0) {
-        for (int j = 0; j < count; ++j) {
-            double sum = 0.0;
-            for (int q = 0; q < peers.nranks; ++q) sum += *reinterpret_cast<volatile double *>(&me->ar_val[par][q][j]);
-            slots[j] = sum;  // same rank order everywhere: identical bits on every rank
-        }
-        me->ar_epoch = e;
-    }
+    double v[kMaxRed];
+    for (int j = 0; j < kMaxRed; ++j) v[j] = j < count ? slots[j] : 0.0;
+    allreduce_warp(peers, v, count);
+    if (threadIdx.x == 0)
+        for (int j = 0; j < count; ++j) slots[j] = v[j];
 }
 
 // ---- halo exchange -------------------------------------------------------------------------------------

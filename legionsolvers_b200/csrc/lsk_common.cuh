@@ -30,6 +30,7 @@ struct lsk_ctx {
     double *consts;            // {1.0, -1.0, 0.0}
     int cursor;                // next scratch set
     unsigned long long launches;
+    lsk_peers *d_peers;        // device copy of the peer windows; non-null = reducing kernels all-reduce in their tail
 };
 
 namespace lsk {
@@ -37,6 +38,7 @@ namespace lsk {
 struct RedScratch {
     double *partials;      // [kMaxRed][kMaxPartials]
     unsigned int *ticket;
+    const lsk_peers *peers;  // non-null: finish the reduction with a cross-rank sum
 };
 
 inline RedScratch next_scratch(lsk_ctx *ctx) {
@@ -45,6 +47,7 @@ inline RedScratch next_scratch(lsk_ctx *ctx) {
     RedScratch r;
     r.partials = ctx->partials + (size_t) set * kMaxRed * kMaxPartials;
     r.ticket = ctx->tickets + set;
+    r.peers = ctx->d_peers;
     return r;
 }
 
@@ -173,6 +176,61 @@ struct PackOf<long long> {
     __device__ static __forceinline__ long long get(const Pack32 &p, int i) { return (long long) p.q[i]; }
 };
 
+// ---- peer-memory collectives (see lsk_comm.cu) --------------------------------------------------------
+struct CommWindow {
+    // written by PEERS (remote stores over NVLink)
+    double ar_val[2][LSK_MAX_RANKS][kMaxRed];          // all-reduce contributions, by epoch parity and source rank
+    unsigned long long ar_flag[LSK_MAX_RANKS];         // epoch of the latest contribution from each source
+    unsigned long long halo_ready[LSK_MAX_RANKS];      // peer r may overwrite... is ready to RECEIVE this epoch
+    unsigned long long halo_done[LSK_MAX_RANKS];       // peer r's data of this epoch has landed here
+    // local state
+    unsigned long long ar_epoch;
+    unsigned long long halo_epoch;
+    unsigned int halo_ticket;
+    int error;
+};
+
+constexpr long long kSpinLimit = 400LL * 1000 * 1000;  // then give up instead of hanging the GPU
+
+__device__ __forceinline__ bool spin_until(const volatile unsigned long long *flag, unsigned long long want, int *err) {
+    long long n = 0;
+    while (*flag < want) {
+        if (++n > kSpinLimit) {
+            *err = 1;
+            return false;
+        }
+    }
+    return true;
+}
+
+// Cross-rank sum of `count` values, executed by ONE warp (all 32 lanes call it): lane r stores this
+// rank's values into rank r's window, publishes the epoch, waits for rank r's contribution; lane 0
+// then adds the contributions in rank order (identical bits on every rank) and returns them in v[].
+__device__ __forceinline__ void allreduce_warp(const lsk_peers &peers, double *v, int count) {
+    CommWindow *me = static_cast<CommWindow *>(peers.window[peers.rank]);
+    const int r = threadIdx.x & 31;
+    const unsigned long long e = me->ar_epoch + 1;
+    const int par = (int) (e & 1);
+    if (r < peers.nranks) {
+        CommWindow *dst = static_cast<CommWindow *>(peers.window[r]);
+        for (int j = 0; j < count; ++j) dst->ar_val[par][peers.rank][j] = v[j];
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long *>(&dst->ar_flag[peers.rank]) = e;
+        spin_until(&me->ar_flag[r], e, &me->error);
+    }
+    __syncwarp();
+    __threadfence_system();
+    if (r == 0) {
+        for (int j = 0; j < count; ++j) {
+            double sum = 0.0;
+            for (int q = 0; q < peers.nranks; ++q) sum += *reinterpret_cast<volatile double *>(&me->ar_val[par][q][j]);
+            v[j] = sum;
+        }
+        me->ar_epoch = e;
+    }
+    __syncwarp();
+}
+
 // ---- deterministic reductions ----------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -202,8 +260,10 @@ __device__ __forceinline__ double block_sum(double v, double *smem /*[kWarps]*/)
 // Accumulation is fp64 for both entry types; the result is narrowed on the final store.
 template <int NRED, typename T>
 __device__ __forceinline__ void grid_reduce_finish(const double (&acc)[NRED], double *partials,
-                                                   unsigned int *ticket, T *const (&out)[NRED]) {
+                                                   unsigned int *ticket, T *const (&out)[NRED],
+                                                   const lsk_peers *peers = nullptr) {
     __shared__ double s_red[kWarps];
+    __shared__ double s_tot[NRED];
     __shared__ bool s_last;
 #pragma unroll
     for (int j = 0; j < NRED; ++j) {
@@ -224,9 +284,29 @@ __device__ __forceinline__ void grid_reduce_finish(const double (&acc)[NRED], do
         const volatile double *pj = partials + (size_t) j * kMaxPartials;
         for (unsigned int i = threadIdx.x; i < gridDim.x; i += kBlock) v += pj[i];
         v = block_sum(v, s_red);
-        if (threadIdx.x == 0 && out[j] != nullptr) *out[j] = (T) v;
+        if (threadIdx.x == 0) s_tot[j] = v;
     }
-    if (threadIdx.x == 0) *ticket = 0u;  // ready for the next launch on this scratch set
+    __syncthreads();
+    if (peers != nullptr && peers->nranks > 1) {
+        // fused all-reduce: the cross-rank sum rides in the tail of the producing kernel (no extra launch)
+        if (threadIdx.x < 32) {
+            double v[NRED];
+#pragma unroll
+            for (int j = 0; j < NRED; ++j) v[j] = s_tot[j];
+            allreduce_warp(*peers, v, NRED);
+            if (threadIdx.x == 0) {
+#pragma unroll
+                for (int j = 0; j < NRED; ++j) s_tot[j] = v[j];
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int j = 0; j < NRED; ++j)
+            if (out[j] != nullptr) *out[j] = (T) s_tot[j];
+        *ticket = 0u;  // ready for the next launch on this scratch set
+    }
 }
 
 #endif  // __CUDACC__

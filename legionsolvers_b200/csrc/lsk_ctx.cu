@@ -44,6 +44,7 @@ int lsk_ctx_create(int device, lsk_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     ctx->cursor = 0;
     ctx->launches = 0;
+    ctx->d_peers = nullptr;
     const size_t pbytes = sizeof(double) * (size_t) kScratchSets * kMaxRed * kMaxPartials;
     cudaError_t e = cudaMalloc(&ctx->partials, pbytes);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->tickets, sizeof(unsigned int) * kScratchSets);
@@ -66,7 +67,25 @@ int lsk_ctx_destroy(lsk_ctx *ctx) {
     if (ctx->partials) cudaFree(ctx->partials);
     if (ctx->tickets) cudaFree(ctx->tickets);
     if (ctx->consts) cudaFree(ctx->consts);
+    if (ctx->d_peers) cudaFree(ctx->d_peers);
     delete ctx;
+    return 0;
+}
+
+int lsk_ctx_set_peers(lsk_ctx *ctx, const lsk_peers *peers) {
+    if (!ctx) return LSK_E_INVALID;
+    LSK_RETURN_IF_CUDA(cudaSetDevice(ctx->device));
+    if (!peers) {
+        if (ctx->d_peers) {
+            LSK_RETURN_IF_CUDA(cudaDeviceSynchronize());
+            cudaFree(ctx->d_peers);
+            ctx->d_peers = nullptr;
+        }
+        return 0;
+    }
+    if (peers->nranks < 1 || peers->nranks > LSK_MAX_RANKS || peers->rank < 0 || peers->rank >= peers->nranks) return LSK_E_INVALID;
+    if (!ctx->d_peers) LSK_RETURN_IF_CUDA(cudaMalloc(&ctx->d_peers, sizeof(lsk_peers)));
+    LSK_RETURN_IF_CUDA(cudaMemcpy(ctx->d_peers, peers, sizeof(lsk_peers), cudaMemcpyHostToDevice));
     return 0;
 }
 

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(kBlock, 4)
 csr_stream_kernel(int64_t rows, int rpb, int64_t n_row_blocks, const T *__restrict__ entry,
                   const long long *__restrict__ col, const lsk_rect *__restrict__ rowptr, int64_t k_base,
                   const T *__restrict__ x, T *__restrict__ y, const T *__restrict__ dot_w,
-                  double *partials, unsigned int *ticket, T *out_yw, T *out_yy) {
+                  double *partials, unsigned int *ticket, T *out_yw, T *out_yy, const lsk_peers *peers) {
     __shared__ __align__(16) T s_prod[kTile];
     __shared__ long long s_lo[kWarps], s_hi[kWarps];
     const int tid = threadIdx.x;
@@ -184,7 +184,7 @@ csr_stream_kernel(int64_t rows, int rpb, int64_t n_row_blocks, const T *__restri
         T *out[NDOT];
         out[0] = out_yw;
         if constexpr (NDOT >= 2) out[NDOT - 1] = out_yy;
-        grid_reduce_finish<NDOT, T>(dacc, partials, ticket, out);
+        grid_reduce_finish<NDOT, T>(dacc, partials, ticket, out, peers);
     }
 }
 
@@ -202,7 +202,7 @@ csr_stream_pipe_kernel(int64_t rows, int rpb, int64_t n_row_blocks, const T *__r
                        const long long *__restrict__ col, const lsk_rect *__restrict__ rowptr,
                        int64_t k_base, const T *__restrict__ x, T *__restrict__ y,
                        const T *__restrict__ dot_w, double *partials, unsigned int *ticket, T *out_yw,
-                       T *out_yy) {
+                       T *out_yy, const lsk_peers *peers) {
     constexpr int U = kTile / (4 * kBlock);
     __shared__ __align__(16) T s_prod[kTile];
     __shared__ long long s_lo[kWarps], s_hi[kWarps];
@@ -339,7 +339,7 @@ csr_stream_pipe_kernel(int64_t rows, int rpb, int64_t n_row_blocks, const T *__r
         T *out[NDOT];
         out[0] = out_yw;
         if constexpr (NDOT >= 2) out[NDOT - 1] = out_yy;
-        grid_reduce_finish<NDOT, T>(dacc, partials, ticket, out);
+        grid_reduce_finish<NDOT, T>(dacc, partials, ticket, out, peers);
     }
 }
 
@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(kBlock, 3)
 csr_tma_kernel(int64_t rows, int64_t nnz, int rpb, int64_t n_row_blocks, const double *__restrict__ entry,
                const long long *__restrict__ col, const lsk_rect *__restrict__ rowptr, int64_t k_base,
                const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ dot_w,
-               double *partials, unsigned int *ticket, double *out_yw, double *out_yy) {
+               double *partials, unsigned int *ticket, double *out_yw, double *out_yy, const lsk_peers *peers) {
     constexpr int S = 2;  // stages: 2 x (16 KB col + 16 KB entry) = 64 KB dynamic shared memory
     extern __shared__ __align__(128) unsigned char s_dyn[];
     long long (*s_col)[kTile] = reinterpret_cast<long long (*)[kTile]>(s_dyn);
@@ -555,7 +555,7 @@ csr_tma_kernel(int64_t rows, int64_t nnz, int rpb, int64_t n_row_blocks, const d
         double *out[NDOT];
         out[0] = out_yw;
         if constexpr (NDOT >= 2) out[NDOT - 1] = out_yy;
-        grid_reduce_finish<NDOT, double>(dacc, partials, ticket, out);
+        grid_reduce_finish<NDOT, double>(dacc, partials, ticket, out, peers);
     }
 }
 
@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(kBlock)
 csr_vector_kernel(int64_t rows, const T *__restrict__ entry, const long long *__restrict__ col,
                   const lsk_rect *__restrict__ rowptr, int64_t k_base, const T *__restrict__ x,
                   T *__restrict__ y, const T *__restrict__ dot_w, double *partials, unsigned int *ticket,
-                  T *out_yw, T *out_yy) {
+                  T *out_yw, T *out_yy, const lsk_peers *peers) {
     constexpr int RPC = kBlock / V;  // rows per CTA pass
     const int sub = threadIdx.x % V;
     double dacc[NDOT > 0 ? NDOT : 1];
@@ -598,7 +598,7 @@ csr_vector_kernel(int64_t rows, const T *__restrict__ entry, const long long *__
         T *out[NDOT];
         out[0] = out_yw;
         if constexpr (NDOT >= 2) out[NDOT - 1] = out_yy;
-        grid_reduce_finish<NDOT, T>(dacc, partials, ticket, out);
+        grid_reduce_finish<NDOT, T>(dacc, partials, ticket, out, peers);
     }
 }
 
@@ -671,11 +671,11 @@ static void launch_stream_kernel(int ndot, int grid, cudaStream_t st, int64_t ro
                                  int64_t k_base, const T *x, T *y, const T *dot_w, RedScratch rs, T *o0,
                                  T *o1) {
     if (ndot == 0)
-        csr_stream_kernel<T, VEC, 0><<<grid, kBlock, 0, st>>>(rows, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1);
+        csr_stream_kernel<T, VEC, 0><<<grid, kBlock, 0, st>>>(rows, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers);
     else if (ndot == 1)
-        csr_stream_kernel<T, VEC, 1><<<grid, kBlock, 0, st>>>(rows, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1);
+        csr_stream_kernel<T, VEC, 1><<<grid, kBlock, 0, st>>>(rows, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers);
     else
-        csr_stream_kernel<T, VEC, 2><<<grid, kBlock, 0, st>>>(rows, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1);
+        csr_stream_kernel<T, VEC, 2><<<grid, kBlock, 0, st>>>(rows, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers);
 }
 
 template <typename T>
@@ -683,11 +683,11 @@ static void launch_pipe_kernel(int ndot, int grid, cudaStream_t st, int64_t rows
                                const T *entry, const long long *col, const lsk_rect *rowptr, int64_t k_base,
                                const T *x, T *y, const T *dot_w, RedScratch rs, T *o0, T *o1) {
     if (ndot == 0)
-        csr_stream_pipe_kernel<T, 0><<<grid, kBlock, 0, st>>>(rows, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1);
+        csr_stream_pipe_kernel<T, 0><<<grid, kBlock, 0, st>>>(rows, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers);
     else if (ndot == 1)
-        csr_stream_pipe_kernel<T, 1><<<grid, kBlock, 0, st>>>(rows, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1);
+        csr_stream_pipe_kernel<T, 1><<<grid, kBlock, 0, st>>>(rows, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers);
     else
-        csr_stream_pipe_kernel<T, 2><<<grid, kBlock, 0, st>>>(rows, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1);
+        csr_stream_pipe_kernel<T, 2><<<grid, kBlock, 0, st>>>(rows, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers);
 }
 
 constexpr size_t kTmaSmem = (size_t) 2 * kTile * (sizeof(long long) + sizeof(double));
@@ -703,11 +703,11 @@ static int launch_tma_kernel(int ndot, int grid, cudaStream_t st, int64_t rows, 
         configured = true;
     }
     if (ndot == 0)
-        csr_tma_kernel<0><<<grid, kBlock, kTmaSmem, st>>>(rows, nnz, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1);
+        csr_tma_kernel<0><<<grid, kBlock, kTmaSmem, st>>>(rows, nnz, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers);
     else if (ndot == 1)
-        csr_tma_kernel<1><<<grid, kBlock, kTmaSmem, st>>>(rows, nnz, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1);
+        csr_tma_kernel<1><<<grid, kBlock, kTmaSmem, st>>>(rows, nnz, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers);
     else
-        csr_tma_kernel<2><<<grid, kBlock, kTmaSmem, st>>>(rows, nnz, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1);
+        csr_tma_kernel<2><<<grid, kBlock, kTmaSmem, st>>>(rows, nnz, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers);
     return 0;
 }
 
@@ -716,11 +716,11 @@ static void launch_vector_kernel(int ndot, int grid, cudaStream_t st, int64_t ro
                                  const long long *col, const lsk_rect *rowptr, int64_t k_base, const T *x,
                                  T *y, const T *dot_w, RedScratch rs, T *o0, T *o1) {
     if (ndot == 0)
-        csr_vector_kernel<T, V, 0><<<grid, kBlock, 0, st>>>(rows, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1);
+        csr_vector_kernel<T, V, 0><<<grid, kBlock, 0, st>>>(rows, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers);
     else if (ndot == 1)
-        csr_vector_kernel<T, V, 1><<<grid, kBlock, 0, st>>>(rows, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1);
+        csr_vector_kernel<T, V, 1><<<grid, kBlock, 0, st>>>(rows, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers);
     else
-        csr_vector_kernel<T, V, 2><<<grid, kBlock, 0, st>>>(rows, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1);
+        csr_vector_kernel<T, V, 2><<<grid, kBlock, 0, st>>>(rows, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers);
 }
 
 template <typename T>
@@ -745,7 +745,7 @@ static int csr_spmv(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const
     if (variant == LSK_SPMV_AUTO) variant = pick_variant(rows, nnz);
     const cudaStream_t st = (cudaStream_t) s;
     const long long *colp = reinterpret_cast<const long long *>(col);
-    RedScratch rs = {nullptr, nullptr};
+    RedScratch rs = {nullptr, nullptr, nullptr};
     if (ndot > 0) rs = next_scratch(ctx);
 
     if (variant == LSK_SPMV_STREAM) {

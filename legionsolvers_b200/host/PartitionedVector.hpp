@@ -273,7 +273,9 @@ public:
             const T *b = part.ptr();
             rt->enqueue("dot fold", [&] { return ScalarKernels<T>::op(rt->ctx(), rt->stream(), LSK_OP_ADD, o, b, o); });
         }
-        if (std::is_same<T, double>::value) rt->allreduce_sum(reinterpret_cast<double *>(out.ptr()), 1);
+        if (rt->fused_collectives()) {  // the dot kernel's tail already summed across ranks
+            if (p.end_color - p.first_color != 1) rt->fail(LSK_E_INVALID, "fused reductions need exactly one local piece per rank");
+        } else if (std::is_same<T, double>::value) rt->allreduce_sum(reinterpret_cast<double *>(out.ptr()), 1);
         else if (rt->nranks() > 1) rt->fail(LSK_E_INVALID, "multi-rank dot is instantiated for fp64");
     }
 

@@ -146,6 +146,17 @@ void Runtime::halo_exchange_p2p(const lsk_halo_move *moves, int nmoves) {
     enqueue("halo exchange", [&] { return lsk_halo_exchange_f64(ctx_, stream_, &peers_, moves, nmoves); });
 }
 
+void Runtime::set_fused_collectives(bool on) {
+    if (on && !p2p_) return;
+    if (on == fused_) return;
+    if (mode_ != Mode::Eager) fail(LSK_E_INVALID, "set_fused_collectives inside a trace");
+    const char *mode = std::getenv("LSK_COMM");
+    if (on && mode && std::string(mode) == "p2p-unfused") return;  // developer A/B switch: standalone collective kernels
+    const int rc = lsk_ctx_set_peers(ctx_, on ? &peers_ : nullptr);
+    if (rc != 0) fail(rc, "lsk_ctx_set_peers");
+    fused_ = on;
+}
+
 int Runtime::comm_error() {
     if (!p2p_) return 0;
     int e = 0;
@@ -161,6 +172,7 @@ int Runtime::comm_error() {
 
 void Runtime::allreduce_sum(double *slots, int count) {
     if (nranks_ == 1 || mode_ == Mode::Replay) return;
+    if (fused_) fail(LSK_E_INVALID, "stand-alone all-reduce while reductions are fused (would double count)");
     if (p2p_) {
         enqueue("allreduce", [&] { return lsk_allreduce_sum_f64(ctx_, stream_, &peers_, slots, count); });
         return;

@@ -61,6 +61,11 @@ public:
     // COLLECTIVE (every rank, same order): export `raw` and map everybody else's
     Exported export_allocation(void *raw, int64_t tag0, int64_t tag1);
     void halo_exchange_p2p(const lsk_halo_move *moves, int nmoves);
+    // Fused collectives: every reducing kernel finishes with the cross-rank sum in its own tail, and
+    // lsk_xpay_halo_f64 may be used.  Valid only while every rank launches exactly the same reducing
+    // kernels (one local piece per rank); the planner switches it on when that holds.
+    void set_fused_collectives(bool on);
+    bool fused_collectives() const { return fused_; }
     int comm_error();
     void allgather_i64(const int64_t *send_dev, int64_t *recv_dev, int count_per_rank);
     void group_start();
@@ -108,6 +113,7 @@ private:
     bool own_stream_ = false;
     ncclComm *comm_ = nullptr;
     bool p2p_ = false;
+    bool fused_ = false;
     lsk_peers peers_{};
     void *window_ = nullptr;
     std::vector<void *> ipc_opened_;

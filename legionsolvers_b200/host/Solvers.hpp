@@ -44,6 +44,9 @@ public:
         planner.copy(R, RHS);
         planner.dot_into(R, R, rr_cur);
         residual_norm_squared.push_back(rr_cur);
+        // when the xpay pushes P's boundary itself, every step ends with current ghosts; make it START so too,
+        // so that the launch sequence of a step is the same from the first one on (traces are replayed)
+        if (fused && planner.halo_push_is_fused()) planner.refresh_halo(P);
     }
 
     // step (src/CGSolver.hpp:46-55)
@@ -51,7 +54,7 @@ public:
         if (fused) {
             planner.matvec_dot(Q, P, P, p_norm);                     // Q = A P and P.Q in one pass
             planner.cg_update(SOL, R, rr_cur, p_norm, P, Q, rr_new);  // both axpys and R.R in one pass
-            planner.xpay(P, rr_new, rr_cur, R);
+            planner.xpay_halo(P, rr_new, rr_cur, R);                  // P's boundary goes to the neighbours' ghosts
         } else {
             planner.matvec(Q, P);
             planner.dot_into(P, Q, p_norm);

@@ -40,6 +40,8 @@ class SquarePlanner {
     std::vector<std::pair<int64_t, int64_t>> space_need;  // ghost range every vector of a space must hold
     std::vector<std::vector<Scalar<T>>> piece_partials;   // [slot set][space-major local piece]
     uint64_t halo_bytes_per_matvec = 0;
+    std::set<std::size_t> halo_fresh;  // vector ids whose ghost values are current on every rank
+    void mark_dirty(std::size_t vec_idx) { halo_fresh.erase(vec_idx); }
 
     void register_space(size_t idx, const PartitionedVector<T> &v) {
         if (canonical_index_partitions.size() > idx) {
@@ -64,6 +66,10 @@ class SquarePlanner {
             } else {
                 rt->enqueue("fold", [&] { return ScalarKernels<T>::op(rt->ctx(), rt->stream(), LSK_OP_ADD, o, p, o); });
             }
+        }
+        if (rt->fused_collectives()) {  // the producing kernel's tail already summed across ranks
+            if (parts.size() != 1) rt->fail(LSK_E_INVALID, "fused reductions need exactly one local piece per rank");
+            return;
         }
         if constexpr (std::is_same<T, double>::value) rt->allreduce_sum(o, 1);
         else if (rt->nranks() > 1) rt->fail(LSK_E_INVALID, "multi-rank reductions are instantiated for fp64");
@@ -163,6 +169,55 @@ public:
                 workspace_vectors[j][i].ensure_range(space_need[i].first, space_need[i].second);
             }
         }
+        // one space, one piece per rank: every reducing kernel is launched identically on every rank, so
+        // the all-reduces can ride in the kernels' tails and the halo push in the producing xpay
+        rt->set_fused_collectives(rt->p2p() && get_num_spaces() == 1 && canonical_index_partitions[0]->pieces == rt->nranks());
+    }
+
+    // bring the ghost values of vector `vec_idx` up to date on every rank (stand-alone exchange)
+    void refresh_halo(std::size_t vec_idx) {
+        std::set<size_t> done;
+        for (const Block &b : row_partitioned_matrices)
+            if (done.insert(b.domain_index).second) exchange_halo(b, get_vector(vec_idx, b.domain_index));
+        halo_fresh.insert(vec_idx);
+    }
+
+    // true when xpay_halo pushes the boundary itself (then a step that ends with it leaves the ghosts current)
+    bool halo_push_is_fused() const {
+        return std::is_same<T, double>::value && rt->fused_collectives() && row_partitioned_matrices.size() == 1 &&
+               row_partitioned_matrices[0].halo.size() <= 4;
+    }
+
+    // xpay (2 scalars) whose result is the source of the next mat-vec: when the collectives are fused, the
+    // boundary values are pushed into the neighbours' ghost regions by the same kernel
+    void xpay_halo(std::size_t dst, Scalar<T> numer, Scalar<T> denom, std::size_t src) {
+        if constexpr (std::is_same<T, double>::value) {
+            const Block *blk = row_partitioned_matrices.size() == 1 ? &row_partitioned_matrices[0] : nullptr;
+            if (rt->fused_collectives() && blk && blk->halo.size() <= 4 && get_vector(dst, 0).exported()) {
+                PartitionedVector<T> &y = get_vector(dst, 0);
+                const PartitionedVector<T> &x = get_vector(src, 0);
+                const IndexPartition &p = *canonical_index_partitions[0];
+                lsk_halo_move moves[4];
+                int n = 0;
+                for (const HaloMove &m : blk->halo) {
+                    moves[n].peer = m.peer;
+                    moves[n].expect = m.recv_n > 0 ? 1 : 0;
+                    moves[n].n = m.send_n;
+                    moves[n].src = m.send_n > 0 ? y.ptr(m.send_lo) : nullptr;
+                    moves[n].dst = m.send_n > 0 ? y.peer_ptr(m.peer, m.send_lo) : nullptr;
+                    ++n;
+                }
+                const int64_t lo = p.own_lo(), cnt = p.own_hi() - p.own_lo() + 1;
+                const T *xs = x.ptr(lo);
+                T *ys = y.ptr(lo);
+                rt->enqueue("xpay_halo", [&] {
+                    return lsk_xpay_halo_f64(rt->ctx(), rt->stream(), cnt, 2, numer.ptr(), denom.ptr(), nullptr, nullptr, xs, ys, moves, n);
+                });
+                halo_fresh.insert(dst);
+                return;
+            }
+        }
+        xpay(dst, numer, denom, src);
     }
 
     // add_row_partitioned_matrix (:209-235): kernel partition from the range partition, ghost
@@ -237,27 +292,35 @@ public:
 
     // ---- the reference's vector-id operations (:248-338) --------------------------------------------------
     void zero_fill(std::size_t vec_idx) {
+        mark_dirty(vec_idx);
         for (std::size_t i = 0; i < get_num_spaces(); ++i) get_vector(vec_idx, i).zero_fill();
     }
     void copy(std::size_t dst, std::size_t src) {
+        mark_dirty(dst);
         for (std::size_t i = 0; i < get_num_spaces(); ++i) get_vector(dst, i) = get_vector(src, i);
     }
     void scal(std::size_t dst, Scalar<T> alpha) {
+        mark_dirty(dst);
         for (std::size_t i = 0; i < get_num_spaces(); ++i) get_vector(dst, i).scal(alpha);
     }
     void axpy(std::size_t dst, Scalar<T> alpha, std::size_t src) {
+        mark_dirty(dst);
         for (std::size_t i = 0; i < get_num_spaces(); ++i) get_vector(dst, i).axpy(alpha, get_vector(src, i));
     }
     void axpy(std::size_t dst, Scalar<T> numer, Scalar<T> denom, std::size_t src) {
+        mark_dirty(dst);
         for (std::size_t i = 0; i < get_num_spaces(); ++i) get_vector(dst, i).axpy(numer, denom, get_vector(src, i));
     }
     void axpy(std::size_t dst, Scalar<T> n1, Scalar<T> n2, Scalar<T> denom, std::size_t src) {
+        mark_dirty(dst);
         for (std::size_t i = 0; i < get_num_spaces(); ++i) get_vector(dst, i).axpy(n1, n2, denom, get_vector(src, i));
     }
     void xpay(std::size_t dst, Scalar<T> alpha, std::size_t src) {
+        mark_dirty(dst);
         for (std::size_t i = 0; i < get_num_spaces(); ++i) get_vector(dst, i).xpay(alpha, get_vector(src, i));
     }
     void xpay(std::size_t dst, Scalar<T> numer, Scalar<T> denom, std::size_t src) {
+        mark_dirty(dst);
         for (std::size_t i = 0; i < get_num_spaces(); ++i) get_vector(dst, i).xpay(numer, denom, get_vector(src, i));
     }
     // dot (:331-338): per-space dots chained with AddScalarTask
@@ -305,6 +368,8 @@ public:
     void cg_update(std::size_t sol, std::size_t r, const Scalar<T> &rr_old, const Scalar<T> &pq, std::size_t p, std::size_t q,
                    const Scalar<T> &rr_new) {
         static_assert(std::is_same<T, double>::value, "fused passes are instantiated for fp64");
+        mark_dirty(sol);
+        mark_dirty(r);
         std::vector<T *> parts = partial_slots(0, rr_new);
         for_each_local_piece([&](size_t s, int, int64_t lo, int64_t n, size_t flat) {
             const T *pp = get_vector(p, s).ptr(lo), *qq = get_vector(q, s).ptr(lo);
@@ -319,6 +384,7 @@ public:
         T *f[4] = {nullptr, nullptr, nullptr, nullptr};
         int nt = 0;
         for (const Scalar<T> &t : terms) f[nt++] = t.ptr();
+        mark_dirty(dst);
         std::vector<T *> parts = partial_slots(0, out);
         for_each_local_piece([&](size_t s, int, int64_t lo, int64_t n, size_t flat) {
             const T *xs = get_vector(src, s).ptr(lo), *ws = get_vector(w_idx, s).ptr(lo);
@@ -330,6 +396,7 @@ public:
     void bicg_p_update(std::size_t p, const Scalar<T> &rho_new, const Scalar<T> &rho_old, const Scalar<T> &alpha, const Scalar<T> &omega,
                        std::size_t v, std::size_t r) {
         static_assert(std::is_same<T, double>::value, "fused passes are instantiated for fp64");
+        mark_dirty(p);
         for_each_local_piece([&](size_t s, int, int64_t lo, int64_t n, size_t) {
             const T *vv = get_vector(v, s).ptr(lo), *rr = get_vector(r, s).ptr(lo);
             T *pp = get_vector(p, s).ptr(lo);
@@ -341,6 +408,8 @@ public:
     void bicg_tail(std::size_t sol, std::size_t r, const Scalar<T> &alpha, const Scalar<T> &ru, const Scalar<T> &uu, std::size_t p,
                    std::size_t u, std::size_t rt_idx, const Scalar<T> &rho_next) {
         static_assert(std::is_same<T, double>::value, "fused passes are instantiated for fp64");
+        mark_dirty(sol);
+        mark_dirty(r);
         std::vector<T *> parts = partial_slots(0, rho_next);
         for_each_local_piece([&](size_t s, int, int64_t lo, int64_t n, size_t flat) {
             const T *pp = get_vector(p, s).ptr(lo), *uu_v = get_vector(u, s).ptr(lo), *rtv = get_vector(rt_idx, s).ptr(lo);
@@ -355,6 +424,8 @@ public:
 private:
     void matvec_impl(std::size_t dst_idx, std::size_t src_idx, const Scalar<T> *yw, const Scalar<T> *yy, std::size_t w_idx) {
         const size_t S = get_num_spaces();
+        mark_dirty(dst_idx);
+        const bool src_fresh = halo_fresh.count(src_idx) != 0;
         std::vector<bool> overwritten(S, false);
         for (const Block &b : row_partitioned_matrices)
             if (b.matrix->overwrites_output()) overwritten[b.range_index] = true;
@@ -364,7 +435,7 @@ private:
         std::vector<T *> parts_yw, parts_yy;
         auto run = [&](const Block &b) {
             PartitionedVector<T> &src = get_vector(src_idx, b.domain_index);
-            if (exchanged.insert(b.domain_index).second) exchange_halo(b, src);
+            if (!src_fresh && exchanged.insert(b.domain_index).second) exchange_halo(b, src);
             if (yw) {
                 const IndexPartition &range = *canonical_index_partitions[b.range_index];
                 MatvecFusion<T> fz;

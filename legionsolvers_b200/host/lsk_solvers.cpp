@@ -87,7 +87,10 @@ int lsk_rt_comm_init(lsk_runtime *rt, const void *uid128) {
     REQUIRE(rt && uid128);
     return guard([&] { rt->rt->comm_init(uid128); });
 }
-int lsk_rt_uses_peer_memory(lsk_runtime *rt) { return (rt && rt->rt->p2p()) ? 1 : 0; }
+int lsk_rt_uses_peer_memory(lsk_runtime *rt) {
+    if (!rt || !rt->rt->p2p()) return 0;
+    return rt->rt->fused_collectives() ? 2 : 1;
+}
 int lsk_rt_comm_error(lsk_runtime *rt, int *out) {
     REQUIRE(rt && out);
     return guard([&] { *out = rt->rt->comm_error(); });

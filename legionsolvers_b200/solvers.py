@@ -71,7 +71,12 @@ class Runtime:
 
     @property
     def uses_peer_memory(self) -> bool:
-        return bool(_abi.lib().lsk_rt_uses_peer_memory(self.h))
+        return _abi.lib().lsk_rt_uses_peer_memory(self.h) > 0
+
+    @property
+    def collectives(self) -> str:
+        return {0: "nccl", 1: "peer-memory kernels", 2: "peer-memory, fused into producer kernels"}[
+            _abi.lib().lsk_rt_uses_peer_memory(self.h)]
 
     def comm_error(self) -> int:
         out = C.c_int()

@@ -95,12 +95,17 @@ def main():
         results[name] = {"hist_err": err, "tol": tol, "x_err": xerr, "gen": bool(ok_gen), "part": bool(ok_part),
                          "halo_bytes": pl.halo_bytes_per_matvec, "n_hist": int(np.size(got))}
     comm_err = rt.comm_error()
-    results["_comm"] = {"peer_memory": rt.uses_peer_memory, "error": comm_err, "hist_err": 0.0, "tol": 1.0, "x_err": 0.0,
+    results["_comm"] = {"peer_memory": rt.uses_peer_memory, "mode": rt.collectives, "error": comm_err, "hist_err": 0.0, "tol": 1.0, "x_err": 0.0,
                         "gen": comm_err == 0, "part": True}
     ok = all(r["hist_err"] <= r["tol"] and r["x_err"] <= 1e-8 and r["gen"] and r["part"] for r in results.values())
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    print(json.dumps({"rank": rank, "ok": ok, "results": results}), flush=True)
+    out_dir = os.environ.get("LSK_MP_OUT")
+    payload = json.dumps({"rank": rank, "ok": ok, "results": results})
+    if out_dir:  # one file per rank: stdout of concurrent ranks can interleave
+        Path(out_dir, f"rank{rank}.json").write_text(payload)
+    else:
+        print(payload, flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if int(flag.item()) == 1 else 1)

@@ -29,9 +29,13 @@ def test_multi_gpu_cg_bicgstab_gmres_parity(comm):
         env.pop("LSK_COMM", None)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
            "127.0.0.1", "--master-port", "29511" if comm == "nccl" else "29512", str(ROOT / "tests" / "mp_worker.py")]
-    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
-    lines = [json.loads(l) for l in proc.stdout.splitlines() if l.startswith("{")]
-    assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as tmp:
+        env["LSK_MP_OUT"] = tmp
+        proc = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+        lines = [json.loads(f.read_text()) for f in sorted(Path(tmp).glob("rank*.json"))]
+    assert proc.returncode == 0, (lines, proc.stdout[-3000:] + proc.stderr[-3000:])
     assert len(lines) == world and all(l["ok"] for l in lines), lines
     assert all(l["results"]["_comm"]["error"] == 0 for l in lines)
     if comm == "nccl":
