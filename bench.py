@@ -250,10 +250,17 @@ def run_ours(args):
     # ---- warm-up, then EXACTLY K timed steps between barriers, CUDA events on the launching stream ---
     for _ in range(max(args.warmup, 3)):
         step()
+    # keep warming until the clocks have had ~0.4 s under load (short multi-GPU steps would otherwise be
+    # timed on a GPU still ramping up from idle)
+    t_w = time.perf_counter()
+    while time.perf_counter() - t_w < 0.4:
+        step()
+        rt.fence()
     barrier()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, period_s=0.02)
     sampler.start()
     launches0 = rt.kernel_launches
+    cs0 = rt.comm_stats() if world > 1 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
@@ -263,6 +270,16 @@ def run_ours(args):
     elapsed_ms = max_over_ranks(ev0.elapsed_time(ev1))
     launches = rt.kernel_launches - launches0
     clocks = sampler.stop()
+    comm_us = None
+    if world > 1:
+        cs1 = rt.comm_stats()
+        its_timed = args.steps * ipt
+        mine = torch.tensor([(cs1["ar_ns"] - cs0["ar_ns"]) / 1e3 / its_timed, (cs1["halo_ns"] - cs0["halo_ns"]) / 1e3 / its_timed],
+                            dtype=torch.float64, device="cuda")
+        allv = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        comm_us = {"allreduce_us_per_iteration_by_rank": [round(float(v[0]), 2) for v in allv],
+                   "halo_close_us_per_iteration_by_rank": [round(float(v[1]), 2) for v in allv]}
     ms_per_step = elapsed_ms / args.steps
     value = args.steps * ipt / (elapsed_ms * 1e-3)
 
@@ -356,6 +373,7 @@ def run_ours(args):
                 "halo_bytes_per_matvec_rank0": pl.halo_bytes_per_matvec, "setup_seconds": round(setup_s, 3),
                 "collectives": "none (1 GPU)" if world == 1 else rt.collectives,
                 "comm_error": rt.comm_error() if world > 1 else 0,
+                "time_inside_collectives": comm_us,
                 "residual_norm_squared_last": rr_final,
                 "iteration_roofline": {"bytes_per_iteration_per_gpu": iter_bytes, "frac_of_peak": iter_frac},
             },
@@ -380,7 +398,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c3")

@@ -337,6 +337,9 @@ int lsk_ctx_set_peers(lsk_ctx *ctx, const lsk_peers *peers);
 int lsk_xpay_halo_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, int n_terms, const double *f0, const double *f1,
                       const double *f2, const double *f3, const double *x, double *y, const lsk_halo_move *moves,
                       int nmoves);
+/* accounting kept in the comm window: {all-reduce calls, ns inside them, halo closes, ns inside them}
+ * (time between entering the collective and leaving it, on the thread that closes it).  Synchronises. */
+int lsk_comm_stats(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, uint64_t *host_out4);
 /* non-zero if a spin-wait in one of the collectives gave up (protocol violation / dead peer) */
 int lsk_comm_error(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, int *host_out);
 

@@ -36,6 +36,8 @@ int lsk_rt_comm_init(lsk_runtime *rt, const void *uid128);
 /* 0: collectives on NCCL (LSK_COMM=nccl, or no peer access); 1: stand-alone peer-memory kernels (CUDA IPC
  * over NVLink); 2: peer-memory collectives FUSED into the producing kernels' tails (one piece per rank) */
 int lsk_rt_uses_peer_memory(lsk_runtime *rt);
+/* lsk_comm_stats of this runtime's window (zeros when not on peer memory) */
+int lsk_rt_comm_stats(lsk_runtime *rt, uint64_t *out4);
 /* non-zero if a peer-memory collective gave up waiting (synchronises) */
 int lsk_rt_comm_error(lsk_runtime *rt, int *out);
 lsk_ctx *lsk_rt_ctx(lsk_runtime *rt);

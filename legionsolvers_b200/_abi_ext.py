@@ -51,6 +51,8 @@ def declare(L) -> None:
     L.lsk_rt_comm_init.argtypes = [vp, vp]
     L.lsk_rt_uses_peer_memory.argtypes = [vp]
     L.lsk_rt_comm_error.argtypes = [vp, C.POINTER(ci)]
+    L.lsk_rt_comm_stats.argtypes = [vp, vp]
+    L.lsk_comm_stats.argtypes = [vp, vp, vp, vp]
     L.lsk_rt_ctx.argtypes = [vp]
     L.lsk_rt_ctx.restype = vp
     L.lsk_rt_stream.argtypes = [vp]

@@ -97,10 +97,14 @@ xpay_halo_kernel(Alpha<double> al, const double *__restrict__ x, double *__restr
     const double a = fold_alpha(al);
     const int64_t tid = (int64_t) blockIdx.x * kBlock + threadIdx.x;
     const int64_t stride = (int64_t) gridDim.x * kBlock;
+    bool remote = false;
     auto mirror = [&](int64_t i, double v) {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-            if (q < h.nmoves && i >= h.lo[q] && i < h.lo[q] + h.m[q].n) h.m[q].dst[i - h.lo[q]] = v;
+            if (q < h.nmoves && i >= h.lo[q] && i < h.lo[q] + h.m[q].n) {
+                h.m[q].dst[i - h.lo[q]] = v;
+                remote = true;
+            }
     };
     for (int64_t p = tid; p < npacks; p += stride) {
         const int64_t i = head + p * 4;
@@ -117,6 +121,7 @@ xpay_halo_kernel(Alpha<double> al, const double *__restrict__ x, double *__restr
         for (int q = 0; q < 4; ++q) {
             if (q < h.nmoves && i + 4 > h.lo[q] && i < h.lo[q] + h.m[q].n) {
                 double *d = h.m[q].dst + (i - h.lo[q]);
+                remote = true;
                 const bool inside = (i >= h.lo[q]) && (i + 4 <= h.lo[q] + h.m[q].n);
                 if (inside && (reinterpret_cast<uintptr_t>(d) & 15) == 0) {
                     reinterpret_cast<double2 *>(d)[0] = make_double2(v[0], v[1]);
@@ -140,14 +145,16 @@ xpay_halo_kernel(Alpha<double> al, const double *__restrict__ x, double *__restr
     // ---- epilogue: last CTA closes the exchange epoch
     CommWindow *me = static_cast<CommWindow *>(peers->window[peers->rank]);
     __shared__ bool s_last;
-    __threadfence_system();
+    if (remote) __threadfence_system();  // my stores into the neighbours' memory are visible there
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence();
         const unsigned int t = atomicAdd(&me->halo_ticket, 1u);
         s_last = (t == gridDim.x - 1);
     }
     __syncthreads();
     if (!s_last) return;
+    const unsigned long long t_halo0 = global_ns();
     __threadfence_system();
     const unsigned long long e = me->halo_epoch + 1;
     if (threadIdx.x < h.nmoves) {
@@ -163,6 +170,8 @@ xpay_halo_kernel(Alpha<double> al, const double *__restrict__ x, double *__restr
     if (threadIdx.x == 0) {
         me->halo_epoch = e;
         me->halo_ticket = 0u;
+        me->halo_calls += 1;
+        me->halo_wait_ns += global_ns() - t_halo0;
     }
 }
 

@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(kBlock) halo_exchange_kernel(lsk_peers peers, 
     }
     __syncthreads();
     if (!s_last) return;
+    const unsigned long long t_halo0 = global_ns();
     __threadfence_system();
     if (threadIdx.x < a.nmoves) {
         const lsk_halo_move &mv = a.m[threadIdx.x];
@@ -77,6 +78,8 @@ __global__ void __launch_bounds__(kBlock) halo_exchange_kernel(lsk_peers peers, 
     if (threadIdx.x == 0) {
         me->halo_epoch = e;
         me->halo_ticket = 0u;
+        me->halo_calls += 1;
+        me->halo_wait_ns += global_ns() - t_halo0;
     }
 }
 
@@ -120,6 +123,14 @@ int lsk_halo_exchange_f64(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, co
     if (grid > 32) grid = 32;
     halo_exchange_kernel<<<grid, kBlock, 0, (cudaStream_t) s>>>(*peers, a);
     return after_launch(ctx);
+}
+
+int lsk_comm_stats(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, uint64_t *host_out4) {
+    if (!ctx || !peers_ok(peers) || !host_out4) return LSK_E_INVALID;
+    const CommWindow *me = static_cast<const CommWindow *>(peers->window[peers->rank]);
+    LSK_RETURN_IF_CUDA(cudaMemcpyAsync(host_out4, &me->ar_calls, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, (cudaStream_t) s));
+    LSK_RETURN_IF_CUDA(cudaStreamSynchronize((cudaStream_t) s));
+    return 0;
 }
 
 int lsk_comm_error(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, int *host_out) {

@@ -179,8 +179,8 @@ struct PackOf<long long> {
 // ---- peer-memory collectives (see lsk_comm.cu) --------------------------------------------------------
 struct CommWindow {
     // written by PEERS (remote stores over NVLink)
-    double ar_val[2][LSK_MAX_RANKS][kMaxRed];          // all-reduce contributions, by epoch parity and source rank
-    unsigned long long ar_flag[LSK_MAX_RANKS];         // epoch of the latest contribution from each source
+    unsigned long long ar_pkt[2][LSK_MAX_RANKS][kMaxRed][2];  // all-reduce packets {32 data bits | epoch << 32},
+                                                               // by epoch parity, source rank, value, half
     unsigned long long halo_ready[LSK_MAX_RANKS];      // peer r may overwrite... is ready to RECEIVE this epoch
     unsigned long long halo_done[LSK_MAX_RANKS];       // peer r's data of this epoch has landed here
     // local state
@@ -188,7 +188,15 @@ struct CommWindow {
     unsigned long long halo_epoch;
     unsigned int halo_ticket;
     int error;
+    // accounting (cheap, always on): time spent inside the collectives by the thread that closes them
+    unsigned long long ar_calls, ar_wait_ns, halo_calls, halo_wait_ns;
 };
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 constexpr long long kSpinLimit = 400LL * 1000 * 1000;  // then give up instead of hanging the GPU
 
@@ -203,30 +211,53 @@ __device__ __forceinline__ bool spin_until(const volatile unsigned long long *fl
     return true;
 }
 
-// Cross-rank sum of `count` values, executed by ONE warp (all 32 lanes call it): lane r stores this
-// rank's values into rank r's window, publishes the epoch, waits for rank r's contribution; lane 0
-// then adds the contributions in rank order (identical bits on every rank) and returns them in v[].
+// Cross-rank sum of `count` values, executed by ONE warp (all 32 lanes call it).  LL-style protocol: a
+// double travels as two 8-byte packets {32 data bits, 32-bit epoch}; an aligned 8-byte store is atomic, so
+// the packet both delivers the data and signals its arrival -- no fence, no separate flag, one NVLink
+// one-way latency.  Lane r stores this rank's packets into rank r's window and polls rank r's packets in
+// its own window; lane 0 then adds the contributions in rank order (identical bits on every rank).
+// Slots alternate with the epoch's parity: a peer can run at most one reduction ahead.
 __device__ __forceinline__ void allreduce_warp(const lsk_peers &peers, double *v, int count) {
     CommWindow *me = static_cast<CommWindow *>(peers.window[peers.rank]);
     const int r = threadIdx.x & 31;
     const unsigned long long e = me->ar_epoch + 1;
+    const unsigned long long tag = (e & 0xffffffffull) << 32;
     const int par = (int) (e & 1);
+    const unsigned long long t0 = (r == 0) ? global_ns() : 0ull;
+    double got[kMaxRed];
     if (r < peers.nranks) {
         CommWindow *dst = static_cast<CommWindow *>(peers.window[r]);
-        for (int j = 0; j < count; ++j) dst->ar_val[par][peers.rank][j] = v[j];
-        __threadfence_system();
-        *reinterpret_cast<volatile unsigned long long *>(&dst->ar_flag[peers.rank]) = e;
-        spin_until(&me->ar_flag[r], e, &me->error);
-    }
-    __syncwarp();
-    __threadfence_system();
-    if (r == 0) {
         for (int j = 0; j < count; ++j) {
-            double sum = 0.0;
-            for (int q = 0; q < peers.nranks; ++q) sum += *reinterpret_cast<volatile double *>(&me->ar_val[par][q][j]);
-            v[j] = sum;
+            const unsigned long long bits = (unsigned long long) __double_as_longlong(v[j]);
+            volatile unsigned long long *pk = &dst->ar_pkt[par][peers.rank][j][0];
+            pk[0] = tag | (bits & 0xffffffffull);
+            pk[1] = tag | (bits >> 32);
         }
+        for (int j = 0; j < count; ++j) {
+            const volatile unsigned long long *pk = &me->ar_pkt[par][r][j][0];
+            unsigned long long a, b;
+            long long n = 0;
+            do {
+                a = pk[0];
+                b = pk[1];
+                if (++n > kSpinLimit) {
+                    me->error = 1;
+                    break;
+                }
+            } while ((a >> 32) != (tag >> 32) || (b >> 32) != (tag >> 32));
+            got[j] = __longlong_as_double((long long) ((a & 0xffffffffull) | (b << 32)));
+        }
+    }
+    // rank-order sum: lane 0 collects lane q's value
+    for (int j = 0; j < count; ++j) {
+        double sum = 0.0;
+        for (int q = 0; q < peers.nranks; ++q) sum += __shfl_sync(0xffffffffu, got[j], q);
+        v[j] = sum;
+    }
+    if (r == 0) {
         me->ar_epoch = e;
+        me->ar_calls += 1;
+        me->ar_wait_ns += global_ns() - t0;
     }
     __syncwarp();
 }

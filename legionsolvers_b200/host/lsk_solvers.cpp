@@ -91,6 +91,15 @@ int lsk_rt_uses_peer_memory(lsk_runtime *rt) {
     if (!rt || !rt->rt->p2p()) return 0;
     return rt->rt->fused_collectives() ? 2 : 1;
 }
+int lsk_rt_comm_stats(lsk_runtime *rt, uint64_t *out4) {
+    REQUIRE(rt && out4);
+    return guard([&] {
+        out4[0] = out4[1] = out4[2] = out4[3] = 0;
+        if (!rt->rt->p2p()) return;
+        const int rc = lsk_comm_stats(rt->rt->ctx(), rt->rt->stream(), &rt->rt->peers(), out4);
+        if (rc != 0) rt->rt->fail(rc, "lsk_comm_stats");
+    });
+}
 int lsk_rt_comm_error(lsk_runtime *rt, int *out) {
     REQUIRE(rt && out);
     return guard([&] { *out = rt->rt->comm_error(); });

@@ -78,6 +78,12 @@ class Runtime:
         return {0: "nccl", 1: "peer-memory kernels", 2: "peer-memory, fused into producer kernels"}[
             _abi.lib().lsk_rt_uses_peer_memory(self.h)]
 
+    def comm_stats(self) -> dict:
+        """{ar_calls, ar_ns, halo_calls, halo_ns}: time spent inside the peer-memory collectives."""
+        out = (C.c_uint64 * 4)()
+        _check(_abi.lib().lsk_rt_comm_stats(self.h, out), "lsk_rt_comm_stats")
+        return {"ar_calls": out[0], "ar_ns": out[1], "halo_calls": out[2], "halo_ns": out[3]}
+
     def comm_error(self) -> int:
         out = C.c_int()
         _check(_abi.lib().lsk_rt_comm_error(self.h, C.byref(out)), "lsk_rt_comm_error")
