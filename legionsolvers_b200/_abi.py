@@ -41,12 +41,15 @@ def declared_symbols() -> list[str]:
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        if not Path(LIB_PATH).exists():
+        import os
+
+        path = Path(os.environ.get("LSK_LIB_PATH", LIB_PATH))  # developer switch: alternative build of the same library
+        if not path.exists():
             raise RuntimeError(
                 f"{LIB_PATH} is missing: build it with `python -m legionsolvers_b200.build` "
                 "(or __graft_entry__.build()). legionsolvers_b200 has no CPU fallback."
             )
-        L = C.CDLL(str(LIB_PATH), mode=C.RTLD_GLOBAL)
+        L = C.CDLL(str(path), mode=C.RTLD_GLOBAL)
         _declare(L)
         _lib = L
     return _lib

@@ -53,14 +53,15 @@ def is_stale() -> bool:
     return any(d.stat().st_mtime > t for d in _deps())
 
 
-def build_library(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not is_stale():
+def build_library(force: bool = False, verbose: bool = False, defines: list[str] | None = None, out: Path | None = None) -> Path:
+    """defines / out: developer experiments (extra -D flags into an alternative .so)."""
+    if out is None and not force and not is_stale():
         return LIB_PATH
     LIB_DIR.mkdir(exist_ok=True)
     env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
     host_cxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
     cmd = [_nvcc(), *NVCC_FLAGS, "-ccbin", host_cxx, "-I", str(INCLUDE), "-I", str(CSRC), "-I", str(HOST),
-           "-shared", "-o", str(LIB_PATH), *map(str, sources()), "-lnccl", "-lcudart"]
+           "-shared", "-o", str(out or LIB_PATH), *[f"-D{d}" for d in (defines or [])], *map(str, sources()), "-lnccl", "-lcudart"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     proc = subprocess.run(cmd, capture_output=True, text=True, env=env)
@@ -68,7 +69,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
         raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
     if verbose:
         print(proc.stderr)
-    return LIB_PATH
+    return out or LIB_PATH
 
 
 if __name__ == "__main__":

@@ -19,6 +19,13 @@
 namespace lsk {
 
 constexpr int kTile = 2048;  // products staged per tile: 16 KB (fp64) of shared memory per CTA
+#ifndef LSK_TMA_TILE
+#define LSK_TMA_TILE 2048
+#endif
+#ifndef LSK_TMA_MINB
+#define LSK_TMA_MINB 3
+#endif
+constexpr int kTmaTile = LSK_TMA_TILE;  // non-zeros per TMA stage (col + entry: 16 B each)
 
 // ---- small load helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ void load4_stream(const double *p, double (&v)[4]) {
@@ -389,15 +396,15 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 }
 
 template <int NDOT>
-__global__ void __launch_bounds__(kBlock, 3)
+__global__ void __launch_bounds__(kBlock, LSK_TMA_MINB)
 csr_tma_kernel(int64_t rows, int64_t nnz, int rpb, int64_t n_row_blocks, const double *__restrict__ entry,
                const long long *__restrict__ col, const lsk_rect *__restrict__ rowptr, int64_t k_base,
                const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ dot_w,
                double *partials, unsigned int *ticket, double *out_yw, double *out_yy, const lsk_peers *peers) {
     constexpr int S = 2;  // stages: 2 x (16 KB col + 16 KB entry) = 64 KB dynamic shared memory
     extern __shared__ __align__(128) unsigned char s_dyn[];
-    long long (*s_col)[kTile] = reinterpret_cast<long long (*)[kTile]>(s_dyn);
-    double (*s_ent)[kTile] = reinterpret_cast<double (*)[kTile]>(s_dyn + (size_t) S * kTile * sizeof(long long));
+    long long (*s_col)[kTmaTile] = reinterpret_cast<long long (*)[kTmaTile]>(s_dyn);
+    double (*s_ent)[kTmaTile] = reinterpret_cast<double (*)[kTmaTile]>(s_dyn + (size_t) S * kTmaTile * sizeof(long long));
     __shared__ __align__(8) uint64_t s_full[S];
     __shared__ long long s_lo[2][kWarps], s_hi[2][kWarps];
     const int tid = threadIdx.x;
@@ -447,10 +454,10 @@ csr_tma_kernel(int64_t rows, int64_t nnz, int rpb, int64_t n_row_blocks, const d
     };
     // tiles start where `col` (and the congruent `entry`) are 16-byte aligned
     auto tile_start = [&](long long jb) { return jb - (long long) ((reinterpret_cast<uintptr_t>(col + jb) >> 3) & 1); };
-    // thread 0: copy elements [t0, t0 + kTile) /\ [jb, je) of both arrays into stage s
+    // thread 0: copy elements [t0, t0 + kTmaTile) /\ [jb, je) of both arrays into stage s
     auto issue_tile = [&](int s, long long t0, long long jb, long long je) {
         long long a = t0 > jb ? t0 : jb;                       // first needed element
-        long long b = (t0 + kTile) < je ? (t0 + kTile) : je;   // one past the last
+        long long b = (t0 + kTmaTile) < je ? (t0 + kTmaTile) : je;   // one past the last
         if (b < a) b = a;
         // bulk part: 16-byte aligned on both ends, never outside [0, nnz)
         long long A = a + ((reinterpret_cast<uintptr_t>(col + a) >> 3) & 1);
@@ -487,7 +494,7 @@ csr_tma_kernel(int64_t rows, int64_t nnz, int rpb, int64_t n_row_blocks, const d
     double acc = 0.0;
 
     while (rb < n_row_blocks) {
-        const bool last_tile = (t0 + kTile >= je);
+        const bool last_tile = (t0 + kTmaTile >= je);
         if (last_tile) publish_span(pb, nlo, nhi1);
         // one barrier per tile: (i) stage^1, consumed last iteration, may now be overwritten;
         // (ii) the next block's span is published; (iii) ragged elements stored by thread 0 are visible
@@ -498,15 +505,21 @@ csr_tma_kernel(int64_t rows, int64_t nnz, int rpb, int64_t n_row_blocks, const d
             pb ^= 1;
         }
         if (tid == 0) {
-            if (!last_tile) issue_tile(stage ^ 1, t0 + kTile, jb, je);
+            if (!last_tile) issue_tile(stage ^ 1, t0 + kTmaTile, jb, je);
             else if (rb + G < n_row_blocks) issue_tile(stage ^ 1, tile_start(njb), njb, nje);
         }
         // ---- consume this tile: thread-per-row, products added in ascending k
+        // the fused dot's w[r] is requested now, so that its latency hides behind the gathers below
+        double wv = 0.0;
+        if constexpr (NDOT >= 1) {
+            const int64_t r = rb * rpb + tid;
+            if (last_tile && tid < rpb && r < rows) wv = __ldg(dot_w + r);
+        }
         mbar_wait(&s_full[stage], (phases >> stage) & 1u);
         phases ^= (1u << stage);
         {
             const long long a = lo > t0 ? lo : t0;
-            const long long b = hi1 < t0 + kTile ? hi1 : t0 + kTile;
+            const long long b = hi1 < t0 + kTmaTile ? hi1 : t0 + kTmaTile;
             const long long *sc = s_col[stage];
             const double *se = s_ent[stage];
             // up to kChunk gathers in flight per thread; the adds stay in ascending k
@@ -535,7 +548,7 @@ csr_tma_kernel(int64_t rows, int64_t nnz, int rpb, int64_t n_row_blocks, const d
             const int64_t r = rb * rpb + tid;
             if (tid < rpb && r < rows) {
                 y[r] = acc;
-                if constexpr (NDOT >= 1) dacc[0] = fma(acc, __ldg(dot_w + r), dacc[0]);
+                if constexpr (NDOT >= 1) dacc[0] = fma(acc, wv, dacc[0]);
                 if constexpr (NDOT >= 2) dacc[NDOT - 1] = fma(acc, acc, dacc[NDOT - 1]);
             }
             acc = 0.0;
@@ -547,7 +560,7 @@ csr_tma_kernel(int64_t rows, int64_t nnz, int rpb, int64_t n_row_blocks, const d
             t0 = tile_start(jb);
             load_rect(rb + G, nlo, nhi1);
         } else {
-            t0 += kTile;
+            t0 += kTmaTile;
         }
         stage ^= 1;
     }
@@ -690,7 +703,7 @@ static void launch_pipe_kernel(int ndot, int grid, cudaStream_t st, int64_t rows
         csr_stream_pipe_kernel<T, 2><<<grid, kBlock, 0, st>>>(rows, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers);
 }
 
-constexpr size_t kTmaSmem = (size_t) 2 * kTile * (sizeof(long long) + sizeof(double));
+constexpr size_t kTmaSmem = (size_t) 2 * kTmaTile * (sizeof(long long) + sizeof(double));
 
 static int launch_tma_kernel(int ndot, int grid, cudaStream_t st, int64_t rows, int64_t nnz, int rpb, int64_t nrb,
                              const double *entry, const long long *col, const lsk_rect *rowptr, int64_t k_base,
@@ -770,8 +783,14 @@ static int csr_spmv(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const
         const bool par = (((reinterpret_cast<uintptr_t>(entry) >> 3) & 1) == ((reinterpret_cast<uintptr_t>(col) >> 3) & 1));
         if (std::is_same<T, double>::value && par && impl == 0 && reinterpret_cast<uintptr_t>(entry) % 8 == 0 &&
             reinterpret_cast<uintptr_t>(col) % 8 == 0) {
-            const int tgrid = (int) (nrb < (int64_t) ctx->sm_count * 3 ? nrb : (int64_t) ctx->sm_count * 3);
-            const int rc = launch_tma_kernel(ndot, tgrid, st, rows, nnz, rpb, nrb, reinterpret_cast<const double *>(entry),
+            int trpb = (int) ((double) kTmaTile / (mean < 1.0 ? 1.0 : mean));
+            trpb = (trpb / 32) * 32;
+            if (trpb < 32) trpb = 32;
+            if (trpb > kBlock) trpb = kBlock;
+            const int64_t tnrb = rows > 0 ? (rows + trpb - 1) / trpb : 1;
+            const int64_t tcap = (int64_t) ctx->sm_count * LSK_TMA_MINB;
+            const int tgrid = (int) (tnrb < tcap ? tnrb : tcap);
+            const int rc = launch_tma_kernel(ndot, tgrid, st, rows, nnz, trpb, tnrb, reinterpret_cast<const double *>(entry),
                                              colp, rowptr, k_base, reinterpret_cast<const double *>(x_shifted),
                                              reinterpret_cast<double *>(y), reinterpret_cast<const double *>(w), rs,
                                              reinterpret_cast<double *>(o0), reinterpret_cast<double *>(o1));
