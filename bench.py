@@ -266,6 +266,7 @@ def run_ours(args):
     sampler.start()
     launches0 = rt.kernel_launches
     cs0 = rt.comm_stats() if world > 1 else None
+    ph0 = rt.cg_phase_stats() if getattr(cg, "persistent", False) else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
@@ -287,6 +288,11 @@ def run_ours(args):
                    "halo_close_us_per_iteration_by_rank": [round(float(v[1]), 2) for v in allv]}
     ms_per_step = elapsed_ms / args.steps
     value = args.steps * ipt / (elapsed_ms * 1e-3)
+    phase_us = None
+    if ph0 is not None:
+        ph1 = rt.cg_phase_stats()
+        its = max(1, ph1["iterations"] - ph0["iterations"])
+        phase_us = {k[:-3] + "_us_per_iteration": round((ph1[k] - ph0[k]) / 1e3 / its, 2) for k in ("matvec_ns", "update_ns", "direction_ns")}
 
     # ---- roofline of the dominant kernel: the fused CSR SpMV + p.Ap, timed alone on the same stream ----
     L = _abi.lib()
@@ -390,13 +396,16 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": desc, "unknowns": n, "nnz": nnz, "iters_per_step": ipt, "spaces": 1, "pieces": pieces,
-                "solver": "CGSolver fused (3 HBM passes / iteration)" if not args.unfused else "CGSolver unfused (reference call sequence)",
+                "solver": ("CGSolver persistent kernel (3 HBM passes / iteration, grid barriers instead of kernel boundaries, one launch per step)"
+                           if getattr(cg, "persistent", False) else "CGSolver fused (3 HBM passes / iteration)" if not args.unfused
+                           else "CGSolver unfused (reference call sequence)"),
                 "trace": "CUDA graph replay of iters_per_step iterations", "rhs": "b = 1, x0 = 0 (BenchmarkStencil)",
                 "l2": "working set per GPU exceeds the 126 MB L2 (matrix streamed once per iteration)",
                 "halo_bytes_per_matvec_rank0": pl.halo_bytes_per_matvec, "setup_seconds": round(setup_s, 3),
                 "collectives": "none (1 GPU)" if world == 1 else rt.collectives,
                 "comm_error": rt.comm_error() if world > 1 else 0,
                 "time_inside_collectives": comm_us,
+                "persistent_kernel_phases_rank0": phase_us,
                 "residual_norm_squared_last": rr_final,
                 "iteration_roofline": {"bytes_per_iteration_per_gpu": iter_bytes, "frac_of_peak": iter_frac},
             },

@@ -337,6 +337,50 @@ int lsk_ctx_set_peers(lsk_ctx *ctx, const lsk_peers *peers);
 int lsk_xpay_halo_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, int n_terms, const double *f0, const double *f1,
                       const double *f2, const double *f3, const double *x, double *y, const lsk_halo_move *moves,
                       int nmoves);
+/* ------------------------------------------------------------------------------------------------
+ * The whole CG step as one persistent kernel -- CGSolver::step (src/CGSolver.hpp:46-55) `niter` times:
+ *     q = A p;  pq = p.q;  x = fma(rr/pq, p, x);  r = fma((-1*rr)/pq, q, r);  rr' = r.r;
+ *     p = fma(rr'/rr, p, r);  history.push_back(rr');  rr = rr'
+ * on one CSR piece per GPU, with grid barriers between the phases instead of kernel boundaries.  With
+ * lsk_ctx_set_peers in effect the two dot products are summed across ranks inside the grid barrier
+ * and the boundary of p is stored into the neighbours' ghost regions (`moves`, as for
+ * lsk_xpay_halo_f64); consumers wait per ghost access, so no rank ever waits at a halo barrier.
+ * Element-wise arithmetic is identical to the leaf-task sequence.  Preconditions: the ghosts of p are
+ * current at entry (they are again at exit); entry/col 16-byte aligned at the same elements.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int64_t rows, nnz;            /* this rank's rows and their non-zeros (the kernel piece) */
+    const double *entry;          /* as for lsk_csr_spmv_f64 */
+    const int64_t *col;
+    const lsk_rect *rowptr;
+    int64_t k_base;
+    double *p_shifted;            /* P, indexable by GLOBAL column id: owned rows and ghost interval */
+    int64_t own_lo;               /* global index of the first owned row (P's owned piece = p_shifted + own_lo) */
+    double *q, *x, *r;            /* Q, SOL, R: owned pieces */
+    double *rr_cur, *rr_new, *p_norm;   /* device scalars of the solver (read: rr_cur; written: all three) */
+    double *history;              /* residual_norm_squared: circular, like lsk_scalar_append_f64 */
+    int64_t history_capacity;
+    int64_t *history_count;
+    const lsk_halo_move *moves;   /* boundary sub-ranges of P's owned piece to push; NULL / 0 on one rank */
+    int nmoves;                   /* <= 4 */
+    const uint8_t *ghost_blocks;  /* optional (several ranks): lsk_cg_row_blocks() flags from lsk_cg_ghost_blocks; only
+                                     flagged row blocks pay the per-gather ghost test.  NULL = test everywhere */
+} lsk_cg_problem;
+/* number of row blocks the kernel cuts `rows` into, and the flags "row block references a column outside the
+ * owned rows [own_lo, own_lo + rows)" (one byte per row block, computed once per matrix piece) */
+int64_t lsk_cg_row_blocks(int64_t rows, int64_t nnz);
+int lsk_cg_ghost_blocks(lsk_ctx *ctx, lsk_stream s, const lsk_cg_problem *pb, uint8_t *flags);
+/* 1 if lsk_cg_steps_f64 can run this problem (alignment, move count), 0 = use the leaf-task sequence */
+int lsk_cg_steps_supported(const lsk_cg_problem *pb);
+int lsk_cg_steps_f64(lsk_ctx *ctx, lsk_stream s, const lsk_cg_problem *pb, int niter);
+/* accounting kept by the persistent kernel: ns that CTA 0 spent in {mat-vec + p.q sync, x/r update + r.r sync,
+ * p update + halo sync} and the number of iterations, accumulated since context creation.  Synchronises. */
+int lsk_cg_phase_stats(lsk_ctx *ctx, lsk_stream s, uint64_t *host_out4);
+/* non-zero if a grid barrier or ghost wait of a persistent kernel gave up.  Synchronises. */
+int lsk_ctx_error(lsk_ctx *ctx, lsk_stream s, int *host_out);
+/* bytes of the grid-barrier block a context holds (internal; exported for the context) */
+size_t lsk_gridsync_bytes(void);
+
 /* accounting kept in the comm window: {all-reduce calls, ns inside them, halo closes, ns inside them}
  * (time between entering the collective and leaving it, on the thread that closes it).  Synchronises. */
 int lsk_comm_stats(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, uint64_t *host_out4);

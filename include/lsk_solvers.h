@@ -111,7 +111,11 @@ enum lsk_solver_kind { LSK_SOLVER_CG = 1, LSK_SOLVER_BICGSTAB = 2, LSK_SOLVER_GM
 /* fused = 0: the reference's call sequence, one launch per planner call; 1: fewest-pass form */
 int lsk_solver_create(lsk_planner *pl, int kind, int restart, int fused, lsk_solver **out);
 int lsk_solver_destroy(lsk_solver *s);
+/* CGSolver on one CSR piece per GPU defers: consecutive steps are issued as ONE persistent-kernel launch
+ * (lsk_cg_steps_f64) when anything else touches the stream -- a fence, a history read, the end of a trace. */
 int lsk_solver_step(lsk_solver *s);
+/* 1 if the solver's step runs as a persistent kernel (lsk_cg_steps_f64), 0 = one launch per pass */
+int lsk_solver_persistent(lsk_solver *s);
 /* CG only: start a new solve from the current RHS (re-runs the constructor's P <- RHS, R <- RHS, rr0) */
 int lsk_solver_reset(lsk_solver *s);
 /* which: CG 0 = residual_norm_squared; BiCGStab 0 = rho, 1 = alpha, 2 = omega; GMRES 0 = the

@@ -55,6 +55,18 @@ def lib() -> C.CDLL:
     return _lib
 
 
+class HaloMove(C.Structure):  # lsk_halo_move
+    _fields_ = [("peer", ci), ("expect", ci), ("src", vp), ("dst", vp), ("n", i64)]
+
+
+class CgProblem(C.Structure):  # lsk_cg_problem
+    _fields_ = [("rows", i64), ("nnz", i64), ("entry", vp), ("col", vp), ("rowptr", vp), ("k_base", i64),
+                ("p_shifted", vp), ("own_lo", i64), ("q", vp), ("x", vp), ("r", vp),
+                ("rr_cur", vp), ("rr_new", vp), ("p_norm", vp),
+                ("history", vp), ("history_capacity", i64), ("history_count", vp),
+                ("moves", C.POINTER(HaloMove)), ("nmoves", ci), ("ghost_blocks", vp)]
+
+
 def check(status: int, where: str) -> None:
     if status != 0:
         raise LskError(status, where)
@@ -91,6 +103,14 @@ def _declare(L: C.CDLL) -> None:
     L.lsk_dot2_f64.argtypes = [vp, vp, i64, vp, vp, vp, vp]
     L.lsk_bicg_p_update_f64.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp]
     L.lsk_bicg_tail_f64.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.lsk_cg_steps_supported.argtypes = [C.POINTER(CgProblem)]
+    L.lsk_cg_steps_f64.argtypes = [vp, vp, C.POINTER(CgProblem), ci]
+    L.lsk_cg_row_blocks.argtypes = [i64, i64]
+    L.lsk_cg_row_blocks.restype = i64
+    L.lsk_cg_ghost_blocks.argtypes = [vp, vp, C.POINTER(CgProblem), vp]
+    L.lsk_ctx_error.argtypes = [vp, vp, C.POINTER(ci)]
+    L.lsk_cg_phase_stats.argtypes = [vp, vp, C.POINTER(u64)]
+    L.lsk_gridsync_bytes.restype = C.c_size_t
     # optional groups are declared by the modules that own them (setup / solvers / comm)
     from . import _abi_ext
 

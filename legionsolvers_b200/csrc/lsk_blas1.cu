@@ -85,12 +85,6 @@ static int launch_stream(lsk_ctx *ctx, lsk_stream s, F f, int64_t n, Span sp) {
 // NVLink; the last CTA publishes the epoch to the neighbours and waits for theirs, so when the kernel
 // completes the ghosts of y are current on every rank -- no separate exchange launch.
 // ---------------------------------------------------------------------------------------------------
-struct HaloSpec {
-    int nmoves;
-    lsk_halo_move m[4];
-    int64_t lo[4];  // send range start as an element index into y
-};
-
 __global__ void __launch_bounds__(kBlock)
 xpay_halo_kernel(Alpha<double> al, const double *__restrict__ x, double *__restrict__ y, int64_t n, int64_t head,
                  int64_t npacks, HaloSpec h, const lsk_peers *peers) {

@@ -1,0 +1,556 @@
+// lsk_cg.cu -- the whole CG step (src/CGSolver.hpp:46-55) as ONE persistent kernel.
+//
+// The three HBM passes of the fused CG iteration are launch- and latency-bound once the problem is
+// strong-scaled over 8 GPUs (a 256^3 slab is ~80 us of memory traffic per iteration, but three kernel
+// boundaries, two dependent all-reduces and a halo exchange cost ~40 us more).  This kernel keeps one
+// co-resident wave of CTAs alive for `niter` complete iterations:
+//
+//   phase A   q = A p          (the TMA-staged thread-per-row mat-vec of lsk_spmv_tma.cuh) + p.q partial
+//   sync 1    grid barrier; its LAST ARRIVER folds the partials (fixed order) and, on several GPUs,
+//             exchanges the rank sums over NVLink peer memory (LL packets), then releases the grid
+//   phase B   x = fma(rr/pq, p, x);  r = fma((-1*rr)/pq, q, r);  r.r partial      (:50-52)
+//   sync 2    same as sync 1 for r.r
+//   phase C   p = fma(rr_new/rr, p, r)                                             (:54)
+//             boundary elements are also stored into the neighbours' ghost regions
+//   sync 3    grid barrier; the last arriver publishes "my halo of this iteration has landed" to the
+//             neighbours.  Nobody waits here: in the next phase A only the threads that actually gather
+//             a ghost column wait for the neighbour's flag (and then read through L2).
+//
+// Element-wise arithmetic is the reference's (same fma / rounded multiply per element as the
+// 3-kernel fused path and the oracle); scalars never leave the device; the residual history is
+// appended by the kernel.  Matrix tiles come through the async proxy (TMA) and are read-only; the
+// vectors are re-read on the coherent path after each grid barrier (fence + bar.sync, the
+// cooperative-groups grid.sync protocol).
+#include <stdlib.h>
+
+#include "lsk_common.cuh"
+#include "lsk_spmv_tma.cuh"
+
+namespace lsk {
+
+struct GridSync {
+    unsigned int count;
+    unsigned int gen;
+    int error;
+    int pad;
+    double bcast;
+    unsigned long long phase_ns[4];  // accounting: time CTA 0 spent in phase A / B / C (incl. the barrier that ends it), iterations
+    double partials[kMaxPartials];
+};
+
+// ---- TMA-streamed vector phases ---------------------------------------------------------------------------
+// The BLAS-1 phases run on the mat-vec's CTA shape (3 x 256 threads per SM, ~80 registers), which cannot keep
+// enough register-staged loads in flight to saturate HBM.  So they stream too: the 64 KB shared-memory ring
+// of the mat-vec becomes 4 stages of 16 KB, each holding one chunk of every input vector, filled by
+// cp.async.bulk three chunks ahead; threads read the chunk from shared memory, compute, and store results
+// straight from registers.
+constexpr int kVecStages = 4;
+constexpr int kVecStageBytes = 16384;
+
+struct VecRing {
+    unsigned char *smem;   // kVecStages x kVecStageBytes
+    uint64_t *bar;         // kVecStages mbarriers
+    uint32_t phases;       // bit s = parity to wait for on stage s
+};
+
+// Streams elements [head, head + nelem) of NIN congruent (32-byte aligned at `head`) arrays through the ring in
+// chunks of CH = 16 KB / (8 NIN); chunk c belongs to CTA c % gridDim.x.  f(i, v) receives, for two consecutive
+// elements i and i + 1, the inputs v[a][0..1] of each array.
+// `last_first`: this CTA's LAST chunk is processed first (then 0, 1, ...): phase C uses it so that the chunks whose
+// results are also stored into the neighbours' memory -- the two ends of the vector -- are issued early and their
+// NVLink traffic overlaps the rest of the phase.
+template <int NIN, class F>
+__device__ __forceinline__ void vec_stream(VecRing &ring, const double *const (&in)[NIN], int64_t head, int64_t nelem, bool last_first, F f) {
+    constexpr int CH = kVecStageBytes / (8 * NIN);
+    const int64_t nchunks = (nelem + CH - 1) / CH;
+    const int64_t G = gridDim.x;
+    const int64_t mine = nchunks > (int64_t) blockIdx.x ? (nchunks - 1 - blockIdx.x) / G + 1 : 0;  // chunks of this CTA
+    const int64_t rot = (last_first && mine > 0) ? mine - 1 : 0;
+    auto chunk_of = [&](int64_t k) -> int64_t {  // k-th chunk in processing order
+        int64_t kk = k + rot;
+        if (kk >= mine) kk -= mine;
+        return (int64_t) blockIdx.x + kk * G;
+    };
+    auto issue = [&](int64_t k) {  // thread 0: k-th chunk of this CTA into stage k % kVecStages
+        const int s = (int) (k % kVecStages);
+        const int64_t e0 = chunk_of(k) * CH;
+        const int64_t cnt = nelem - e0 < CH ? nelem - e0 : CH;
+        const uint32_t bytes = (uint32_t) cnt * 8u;
+        mbar_expect_tx(&ring.bar[s], NIN * bytes);
+#pragma unroll
+        for (int a = 0; a < NIN; ++a)
+            tma_bulk_g2s_plain(ring.smem + (size_t) s * kVecStageBytes + (size_t) a * CH * 8, in[a] + head + e0, bytes, &ring.bar[s]);
+    };
+    if (threadIdx.x == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int64_t k = 0; k < kVecStages - 1 && k < mine; ++k) issue(k);
+    }
+    for (int64_t k = 0; k < mine; ++k) {
+        const int s = (int) (k % kVecStages);
+        // stage (k - 1) % kVecStages was consumed in the previous iteration, which ended with a CTA barrier
+        if (threadIdx.x == 0 && k + kVecStages - 1 < mine) issue(k + kVecStages - 1);
+        mbar_wait(&ring.bar[s], (ring.phases >> s) & 1u);
+        ring.phases ^= (1u << s);
+        const int64_t e0 = chunk_of(k) * CH;
+        const int cnt = (int) (nelem - e0 < CH ? nelem - e0 : CH);
+        const unsigned char *st = ring.smem + (size_t) s * kVecStageBytes;
+#pragma unroll
+        for (int u = 0; u < CH / (2 * kBlock); ++u) {
+            const int j = u * 2 * kBlock + 2 * (int) threadIdx.x;
+            if (j < cnt) {  // cnt is a multiple of 4, j is even: both elements exist
+                double v[NIN][2];
+#pragma unroll
+                for (int a = 0; a < NIN; ++a) {
+                    const double2 t = *reinterpret_cast<const double2 *>(st + (size_t) a * CH * 8 + (size_t) j * 8);
+                    v[a][0] = t.x;
+                    v[a][1] = t.y;
+                }
+                f(head + e0 + j, v);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+struct CgArgs {
+    TmaSpmvArgs mv;          // x = P shifted to global column 0, y = Q, dot_w = P (owned piece)
+    double *p, *q, *x, *r;   // owned pieces
+    int64_t n, head, npacks; // 256-bit body shared by the four vectors
+    double *rr_cur, *rr_new, *p_norm;
+    double *hist;
+    long long hist_cap;
+    long long *hist_count;
+    int niter;
+    GridSync *gs;
+    const lsk_peers *peers;  // device copy; null on one rank
+    HaloSpec halo;           // what to push (send side) and whom to expect data from
+    long long own_lo;
+    const unsigned char *ghost_blocks;  // per row block: references a ghost column (null = unknown)
+};
+
+// one thread per row: flags[row / rpb] = 1 if the row references a column outside [own_lo, own_lo + own_n)
+__global__ void __launch_bounds__(kBlock) ghost_blocks_kernel(int64_t rows, int rpb, const lsk_rect *__restrict__ rowptr,
+                                                              int64_t k_base, const long long *__restrict__ col, long long own_lo,
+                                                              unsigned long long own_n, unsigned char *flags) {
+    for (int64_t r = (int64_t) blockIdx.x * kBlock + threadIdx.x; r < rows; r += (int64_t) gridDim.x * kBlock) {
+        const longlong2 rc = __ldg(reinterpret_cast<const longlong2 *>(rowptr + r));
+        bool ghost = false;
+        for (long long k = rc.x - k_base; k <= rc.y - k_base; ++k)
+            ghost |= ((unsigned long long) (__ldg(col + k) - own_lo) >= own_n);
+        if (ghost) flags[r / rpb] = 1;
+    }
+}
+
+__device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int *p) {
+    return *reinterpret_cast<const volatile unsigned int *>(p);
+}
+
+// Grid barrier (all CTAs co-resident: cooperative launch).  REDUCE: returns the sum of `v` over all
+// threads of all CTAs -- and over all ranks when `peers` is set -- identical bits in every thread.
+// `tail()` is executed by every thread of the last-arriving CTA after all CTAs have arrived and before
+// anybody is released.  Returns through `err` whether a spin-wait anywhere has given up.
+template <bool REDUCE, class Tail>
+__device__ __forceinline__ double grid_sync(GridSync *gs, const lsk_peers *peers, double v, bool &err, Tail tail) {
+    __shared__ double s_red[kWarps];
+    __shared__ double s_val;
+    __shared__ unsigned int s_gen;
+    __shared__ int s_last, s_err;
+    const unsigned int G = gridDim.x;
+    if constexpr (REDUCE) {
+        const double b = block_sum(v, s_red);
+        if (threadIdx.x == 0) *reinterpret_cast<volatile double *>(&gs->partials[blockIdx.x]) = b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int g = ld_volatile_u32(&gs->gen);  // cannot advance before this CTA arrives
+        __threadfence();
+        const unsigned int t = atomicAdd(&gs->count, 1u);
+        s_last = (t == G - 1);
+        s_gen = g;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        double tot = 0.0;
+        if constexpr (REDUCE) {
+            const volatile double *pj = gs->partials;
+            double acc = 0.0;
+            for (unsigned int i = threadIdx.x; i < G; i += kBlock) acc += pj[i];
+            tot = block_sum(acc, s_red);  // every lane of warp 0 holds it
+            if (peers != nullptr && peers->nranks > 1 && threadIdx.x < 32) {
+                double w[kMaxRed];
+                w[0] = tot;
+                allreduce_warp(*peers, w, 1);
+                tot = w[0];
+            }
+        }
+        tail();
+        if (threadIdx.x == 0) {
+            if constexpr (REDUCE) *reinterpret_cast<volatile double *>(&gs->bcast) = tot;
+            *reinterpret_cast<volatile unsigned int *>(&gs->count) = 0u;
+            __threadfence();
+            *reinterpret_cast<volatile unsigned int *>(&gs->gen) = s_gen + 1u;
+        }
+    } else if (threadIdx.x == 0) {
+        unsigned int polls = 0;
+        unsigned long long t_start = 0;
+        while (ld_volatile_u32(&gs->gen) == s_gen) {
+            if (spin_expired(polls, t_start)) {
+                gs->error = 1;
+                break;
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if constexpr (REDUCE) s_val = *reinterpret_cast<volatile double *>(&gs->bcast);
+        s_err = *reinterpret_cast<volatile int *>(&gs->error);
+    }
+    __syncthreads();
+    err = (s_err != 0);
+    return REDUCE ? s_val : 0.0;
+}
+
+// The mat-vec phase as a REAL call: the tile loop needs every register 3 CTAs/SM allow (80), so whatever the
+// surrounding kernel keeps live across the phase is saved once at the call instead of spilling inside the loop.
+struct MatvecPhaseShared {
+    uint64_t full[kTmaStages];
+    long long lo[2][kWarps], hi[2][kWarps];
+};
+template <bool GATED>
+__device__ __noinline__ double matvec_phase(const TmaSpmvArgs *mv, TmaSpmvState *st, unsigned char *s_dyn, MatvecPhaseShared *sh,
+                                            const GhostGate *gate) {
+    double dacc[1] = {0.0};
+    const TmaSpmvArgs a = *mv;
+    TmaSpmvState s = *st;
+    csr_tma_run<1, true, GATED>(a, s, s_dyn, sh->full, sh->lo, sh->hi, dacc, gate);
+    *st = s;
+    return dacc[0];
+}
+
+__global__ void __launch_bounds__(kBlock, LSK_TMA_MINB) cg_persistent_kernel(CgArgs a) {
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    __shared__ __align__(8) MatvecPhaseShared s_mv;
+    __shared__ __align__(8) uint64_t s_vbar[kVecStages];
+    TmaSpmvState st;
+    csr_tma_init(st, s_mv.full);
+    VecRing ring;
+    ring.smem = s_dyn;
+    ring.bar = s_vbar;
+    ring.phases = 0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kVecStages; ++s) mbar_init(&s_vbar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+
+    GridSync *gs = a.gs;
+    const lsk_peers *peers = a.peers;
+    const bool multi = (peers != nullptr && peers->nranks > 1);
+    CommWindow *me = multi ? static_cast<CommWindow *>(peers->window[peers->rank]) : nullptr;
+    const unsigned long long halo_base = multi ? *reinterpret_cast<volatile unsigned long long *>(&me->halo_epoch) : 0ull;
+    // state that only one thread (or only the rare ghost path) needs lives in shared memory, not in registers:
+    // the mat-vec phase runs at the register limit of 3 CTAs per SM
+    __shared__ GhostGate gate;
+    __shared__ long long s_hcount;
+    __shared__ unsigned long long s_tmark;
+    const bool scribe = (blockIdx.x == 0 && threadIdx.x == 0);
+    if (threadIdx.x == 0) {
+        gate.own_lo = a.own_lo;
+        gate.own_n = (unsigned long long) a.n;
+        gate.blocks = a.ghost_blocks;
+        gate.nflags = 0;
+        gate.want = halo_base;
+        gate.error = &gs->error;
+        if (multi) {
+            for (int q = 0; q < a.halo.nmoves; ++q)
+                if (a.halo.m[q].expect) gate.flag[gate.nflags++] = &me->halo_done[a.halo.m[q].peer];
+        }
+        s_hcount = scribe ? *reinterpret_cast<volatile long long *>(a.hist_count) : 0;
+        s_tmark = global_ns();
+    }
+    __syncthreads();
+
+    double rr = *reinterpret_cast<volatile double *>(a.rr_cur);
+    double pq = 0.0;
+    bool err = false;
+    int done = 0;
+
+    auto lap = [&](int which) {  // accounting by one thread: time since the previous lap goes to phase `which`
+        if (scribe) {
+            const unsigned long long now = global_ns();
+            gs->phase_ns[which] += now - s_tmark;
+            s_tmark = now;
+        }
+    };
+    // ragged edges of the vectors (outside the 32-byte aligned body): elements [0, head) and [tail0, n)
+    auto for_each_edge = [&](auto &&body) {
+        const int64_t tail0 = a.head + a.npacks * 4;
+        const int64_t nedge = a.head + (a.n - tail0);
+        for (int64_t e = (int64_t) blockIdx.x * kBlock + threadIdx.x; e < nedge; e += (int64_t) gridDim.x * kBlock)
+            body(e < a.head ? e : tail0 + (e - a.head));
+    };
+    for (int it = 0; it < a.niter; ++it) {
+        // ---- phase A: q = A p, partial p.q -------------------------------------------------------------
+        if (threadIdx.x == 0) gate.want = halo_base + (unsigned long long) it;  // published by the mat-vec's first CTA barrier
+        const double pq_part = multi ? matvec_phase<true>(&a.mv, &st, s_dyn, &s_mv, &gate)
+                                     : matvec_phase<false>(&a.mv, &st, s_dyn, &s_mv, nullptr);
+        pq = grid_sync<true>(gs, peers, pq_part, err, [] {});
+        lap(0);
+        if (err) break;
+
+        // ---- phase B: x += (rr/pq) p;  r += ((-1*rr)/pq) q;  partial r.r -------------------------------------
+        const double a1 = div_rn(rr, pq);
+        const double a2 = div_rn(mul_rn(-1.0, rr), pq);
+        double racc = 0.0;
+        {
+            const double *const in[4] = {a.p, a.q, a.x, a.r};
+            vec_stream<4>(ring, in, a.head, a.npacks * 4, false, [&](int64_t i, const double (&v)[4][2]) {
+                const double x0 = fma_rn(a1, v[0][0], v[2][0]), x1 = fma_rn(a1, v[0][1], v[2][1]);
+                const double r0 = fma_rn(a2, v[1][0], v[3][0]), r1 = fma_rn(a2, v[1][1], v[3][1]);
+                *reinterpret_cast<double2 *>(a.x + i) = make_double2(x0, x1);
+                *reinterpret_cast<double2 *>(a.r + i) = make_double2(r0, r1);
+                racc = fma(r0, r0, racc);
+                racc = fma(r1, r1, racc);
+            });
+        }
+        for_each_edge([&](int64_t i) {
+            a.x[i] = fma_rn(a1, ld_f64(a.p + i), a.x[i]);
+            const double rn = fma_rn(a2, ld_f64(a.q + i), a.r[i]);
+            a.r[i] = rn;
+            racc = fma(rn, rn, racc);
+        });
+        const double rr_new = grid_sync<true>(gs, peers, racc, err, [] {});
+        lap(1);
+        if (err) break;
+
+        // ---- phase C: p = fma(rr_new/rr, p, r), boundary mirrored into the neighbours' ghosts -------------
+        const double beta = div_rn(rr_new, rr);
+        bool remote = false;
+        {
+            const double *const in[2] = {a.p, a.r};
+            vec_stream<2>(ring, in, a.head, a.npacks * 4, multi, [&](int64_t i, const double (&v)[2][2]) {
+                const double p0 = fma_rn(beta, v[0][0], v[1][0]), p1 = fma_rn(beta, v[0][1], v[1][1]);
+                *reinterpret_cast<double2 *>(a.p + i) = make_double2(p0, p1);
+                if (multi) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (q < a.halo.nmoves && i + 2 > a.halo.lo[q] && i < a.halo.lo[q] + a.halo.m[q].n) {
+                            double *d = a.halo.m[q].dst + (i - a.halo.lo[q]);
+                            remote = true;
+                            const bool inside = (i >= a.halo.lo[q]) && (i + 2 <= a.halo.lo[q] + a.halo.m[q].n);
+                            if (inside && (reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+                                *reinterpret_cast<double2 *>(d) = make_double2(p0, p1);
+                            } else {
+                                if (i >= a.halo.lo[q] && i < a.halo.lo[q] + a.halo.m[q].n) d[0] = p0;
+                                if (i + 1 >= a.halo.lo[q] && i + 1 < a.halo.lo[q] + a.halo.m[q].n) d[1] = p1;
+                            }
+                        }
+                    }
+                }
+            });
+        }
+        for_each_edge([&](int64_t i) {
+            const double v = fma_rn(beta, ld_f64(a.p + i), ld_f64(a.r + i));
+            a.p[i] = v;
+            if (multi) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (q < a.halo.nmoves && i >= a.halo.lo[q] && i < a.halo.lo[q] + a.halo.m[q].n) {
+                        a.halo.m[q].dst[i - a.halo.lo[q]] = v;
+                        remote = true;
+                    }
+            }
+        });
+        if (remote) __threadfence_system();  // my stores into the neighbours' memory are visible there
+        const bool final_it = (it + 1 == a.niter);
+        const unsigned long long e_now = halo_base + (unsigned long long) it + 1ull;
+        grid_sync<false>(gs, peers, 0.0, err, [&] {
+            if (!multi) return;
+            // every CTA's remote stores are fenced and ordered before its arrival: publish the epoch
+            const unsigned long long t0 = global_ns();
+            __threadfence_system();
+            if (threadIdx.x < a.halo.nmoves) {
+                const lsk_halo_move &mv = a.halo.m[threadIdx.x];
+                if (mv.n > 0) {
+                    CommWindow *dst = static_cast<CommWindow *>(peers->window[mv.peer]);
+                    *reinterpret_cast<volatile unsigned long long *>(&dst->halo_done[peers->rank]) = e_now;
+                }
+                // leaving the kernel: the ghosts must be current for whatever runs next on this stream
+                if (final_it && mv.expect) spin_until(&me->halo_done[mv.peer], e_now, &gs->error);
+            }
+            __syncthreads();
+            if (final_it) {
+                __threadfence_system();
+                if (threadIdx.x == 0) {
+                    me->halo_epoch = e_now;
+                    me->halo_calls += (unsigned long long) a.niter;
+                    me->halo_wait_ns += global_ns() - t0;
+                }
+            }
+        });
+        lap(2);
+        if (scribe) {
+            a.hist[s_hcount % a.hist_cap] = rr_new;  // residual_norm_squared.push_back (src/CGSolver.hpp:53)
+            ++s_hcount;
+            gs->phase_ns[3] += 1ull;
+        }
+        rr = rr_new;
+        ++done;
+        if (err) break;
+    }
+    if (scribe) {
+        *a.hist_count = s_hcount;
+        if (done > 0) {
+            *a.rr_cur = rr;
+            *a.rr_new = rr;
+            *a.p_norm = pq;
+        }
+        if (multi && gs->error) me->error = 1;
+    }
+    if (err && multi && done < a.niter && blockIdx.x == 0 && threadIdx.x == 0) {
+        // a wait gave up: keep the epoch arithmetic of later launches consistent anyway
+        me->halo_epoch = halo_base + (unsigned long long) a.niter;
+    }
+}
+
+}  // namespace lsk
+
+using namespace lsk;
+
+extern "C" {
+
+int lsk_cg_steps_supported(const lsk_cg_problem *pb) {
+    if (!pb || pb->rows <= 0 || pb->nnz <= 0 || !pb->entry || !pb->col || !pb->rowptr) return 0;
+    const uintptr_t e = reinterpret_cast<uintptr_t>(pb->entry), c = reinterpret_cast<uintptr_t>(pb->col);
+    if (e % 8 != 0 || c % 8 != 0 || ((e >> 3) & 1) != ((c >> 3) & 1)) return 0;  // TMA tiles: col/entry 16-byte aligned together
+    if (pb->nmoves < 0 || pb->nmoves > 4) return 0;
+    static const char *off = getenv("LSK_CG_PERSISTENT");
+    if (off && off[0] == '0') return 0;
+    return 1;
+}
+
+int lsk_cg_steps_f64(lsk_ctx *ctx, lsk_stream s, const lsk_cg_problem *pb, int niter) {
+    if (!ctx || !pb || niter < 0) return LSK_E_INVALID;
+    if (niter == 0) return 0;
+    if (!lsk_cg_steps_supported(pb)) return LSK_E_INVALID;
+    if (!pb->p_shifted || !pb->q || !pb->x || !pb->r || !pb->rr_cur || !pb->rr_new || !pb->p_norm || !pb->history ||
+        !pb->history_count || pb->history_capacity <= 0)
+        return LSK_E_INVALID;
+    if (pb->nmoves > 0 && (!pb->moves || !ctx->d_peers)) return LSK_E_INVALID;
+    LSK_RETURN_IF_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->cg_blocks_per_sm == 0) {
+        LSK_RETURN_IF_CUDA(cudaFuncSetAttribute(cg_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kTmaSmem));
+        int nb = 0;
+        LSK_RETURN_IF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cg_persistent_kernel, kBlock, kTmaSmem));
+        if (nb < 1) return LSK_E_CAPACITY;
+        if (nb > LSK_TMA_MINB) nb = LSK_TMA_MINB;
+        ctx->cg_blocks_per_sm = nb;
+    }
+    CgArgs a;
+    a.mv.rows = pb->rows;
+    a.mv.nnz = pb->nnz;
+    a.mv.rpb = tma_rows_per_block(pb->rows, pb->nnz);
+    a.mv.n_row_blocks = (pb->rows + a.mv.rpb - 1) / a.mv.rpb;
+    a.mv.entry = pb->entry;
+    a.mv.col = reinterpret_cast<const long long *>(pb->col);
+    a.mv.rowptr = pb->rowptr;
+    a.mv.k_base = pb->k_base;
+    a.mv.x = pb->p_shifted;
+    a.mv.y = pb->q;
+    a.p = pb->p_shifted + pb->own_lo;
+    a.mv.dot_w = a.p;
+    a.q = pb->q;
+    a.x = pb->x;
+    a.r = pb->r;
+    a.n = pb->rows;
+    // 256-bit body shared by the four vectors (scalar edges otherwise)
+    const uintptr_t m0 = mod32(a.p);
+    const bool congruent = m0 % 8 == 0 && mod32(a.q) == m0 && mod32(a.x) == m0 && mod32(a.r) == m0;
+    if (congruent) {
+        int64_t head = (int64_t) ((32 - m0) % 32) / 8;
+        if (head > a.n) head = a.n;
+        a.head = head;
+        a.npacks = (a.n - head) / 4;
+    } else {
+        a.head = a.n;
+        a.npacks = 0;
+    }
+    a.rr_cur = pb->rr_cur;
+    a.rr_new = pb->rr_new;
+    a.p_norm = pb->p_norm;
+    a.hist = pb->history;
+    a.hist_cap = pb->history_capacity;
+    a.hist_count = reinterpret_cast<long long *>(pb->history_count);
+    a.niter = niter;
+    a.gs = static_cast<GridSync *>(ctx->gridsync);
+    a.peers = ctx->d_peers;  // non-null = several ranks: the dot products are summed across them inside the grid barrier
+    a.own_lo = pb->own_lo;
+    a.ghost_blocks = pb->ghost_blocks;
+    a.halo.nmoves = pb->nmoves;
+    for (int i = 0; i < 4; ++i) {
+        a.halo.lo[i] = 0;
+        a.halo.m[i].peer = 0; a.halo.m[i].expect = 0; a.halo.m[i].src = nullptr; a.halo.m[i].dst = nullptr; a.halo.m[i].n = 0;
+    }
+    for (int i = 0; i < pb->nmoves; ++i) {
+        const lsk_halo_move &m = pb->moves[i];
+        if (m.n < 0 || (m.n > 0 && (!m.dst || m.src < a.p || m.src + m.n > a.p + a.n))) return LSK_E_INVALID;
+        a.halo.m[i] = m;
+        a.halo.lo[i] = m.n > 0 ? (int64_t) (m.src - a.p) : 0;
+    }
+    int64_t cap = (int64_t) ctx->sm_count * ctx->cg_blocks_per_sm;
+    if (cap > kMaxPartials) cap = kMaxPartials;
+    const int grid = (int) (a.mv.n_row_blocks < cap ? a.mv.n_row_blocks : cap);
+
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned) grid);
+    cfg.blockDim = dim3(kBlock);
+    cfg.dynamicSmemBytes = kTmaSmem;
+    cfg.stream = (cudaStream_t) s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    static const char *coop = getenv("LSK_CG_COOPERATIVE");  // developer switch: "0" = plain launch (grid <= one wave anyway)
+    cfg.attrs = attr;
+    cfg.numAttrs = (coop && coop[0] == '0') ? 0 : 1;
+    LSK_RETURN_IF_CUDA(cudaLaunchKernelEx(&cfg, cg_persistent_kernel, a));
+    return after_launch(ctx);
+}
+
+int64_t lsk_cg_row_blocks(int64_t rows, int64_t nnz) {
+    if (rows <= 0) return 0;
+    const int rpb = tma_rows_per_block(rows, nnz);
+    return (rows + rpb - 1) / rpb;
+}
+
+int lsk_cg_ghost_blocks(lsk_ctx *ctx, lsk_stream s, const lsk_cg_problem *pb, uint8_t *flags) {
+    if (!ctx || !pb || !flags || pb->rows <= 0 || !pb->rowptr || !pb->col) return LSK_E_INVALID;
+    const int rpb = tma_rows_per_block(pb->rows, pb->nnz);
+    const int64_t nrb = (pb->rows + rpb - 1) / rpb;
+    LSK_RETURN_IF_CUDA(cudaMemsetAsync(flags, 0, (size_t) nrb, (cudaStream_t) s));
+    const int grid = stream_grid(ctx, pb->rows, 8);
+    ghost_blocks_kernel<<<grid, kBlock, 0, (cudaStream_t) s>>>(pb->rows, rpb, pb->rowptr, pb->k_base,
+                                                              reinterpret_cast<const long long *>(pb->col), pb->own_lo,
+                                                              (unsigned long long) pb->rows, flags);
+    return after_launch(ctx);
+}
+
+int lsk_ctx_error(lsk_ctx *ctx, lsk_stream s, int *host_out) {
+    if (!ctx || !host_out) return LSK_E_INVALID;
+    const GridSync *gs = static_cast<const GridSync *>(ctx->gridsync);
+    LSK_RETURN_IF_CUDA(cudaMemcpyAsync(host_out, &gs->error, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t) s));
+    LSK_RETURN_IF_CUDA(cudaStreamSynchronize((cudaStream_t) s));
+    return 0;
+}
+
+int lsk_cg_phase_stats(lsk_ctx *ctx, lsk_stream s, uint64_t *host_out4) {
+    if (!ctx || !host_out4) return LSK_E_INVALID;
+    const GridSync *gs = static_cast<const GridSync *>(ctx->gridsync);
+    LSK_RETURN_IF_CUDA(cudaMemcpyAsync(host_out4, gs->phase_ns, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, (cudaStream_t) s));
+    LSK_RETURN_IF_CUDA(cudaStreamSynchronize((cudaStream_t) s));
+    return 0;
+}
+
+size_t lsk_gridsync_bytes(void) { return sizeof(GridSync); }
+
+}  // extern "C"

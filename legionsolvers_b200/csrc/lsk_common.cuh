@@ -31,6 +31,8 @@ struct lsk_ctx {
     int cursor;                // next scratch set
     unsigned long long launches;
     lsk_peers *d_peers;        // device copy of the peer windows; non-null = reducing kernels all-reduce in their tail
+    void *gridsync;            // lsk::GridSync: grid barrier + partials of the persistent solver kernels
+    int cg_blocks_per_sm;      // occupancy of the persistent CG kernel (0 = not queried yet)
 };
 
 namespace lsk {
@@ -198,12 +200,25 @@ __device__ __forceinline__ unsigned long long global_ns() {
     return t;
 }
 
-constexpr long long kSpinLimit = 400LL * 1000 * 1000;  // then give up instead of hanging the GPU
+constexpr unsigned long long kSpinLimitNs = 4ull * 1000 * 1000 * 1000;  // 4 s, then give up instead of hanging the GPU
+
+// true once a spin loop that started at `t_start` (0 = not started yet) has used up its time budget;
+// the clock is read only every 1024 polls
+__device__ __forceinline__ bool spin_expired(unsigned int &polls, unsigned long long &t_start) {
+    if ((++polls & 1023u) != 0) return false;
+    const unsigned long long now = global_ns();
+    if (t_start == 0) {
+        t_start = now;
+        return false;
+    }
+    return now - t_start > kSpinLimitNs;
+}
 
 __device__ __forceinline__ bool spin_until(const volatile unsigned long long *flag, unsigned long long want, int *err) {
-    long long n = 0;
+    unsigned int polls = 0;
+    unsigned long long t_start = 0;
     while (*flag < want) {
-        if (++n > kSpinLimit) {
+        if (spin_expired(polls, t_start)) {
             *err = 1;
             return false;
         }
@@ -236,11 +251,12 @@ __device__ __forceinline__ void allreduce_warp(const lsk_peers &peers, double *v
         for (int j = 0; j < count; ++j) {
             const volatile unsigned long long *pk = &me->ar_pkt[par][r][j][0];
             unsigned long long a, b;
-            long long n = 0;
+            unsigned int polls = 0;
+            unsigned long long t_start = 0;
             do {
                 a = pk[0];
                 b = pk[1];
-                if (++n > kSpinLimit) {
+                if (spin_expired(polls, t_start)) {
                     me->error = 1;
                     break;
                 }
@@ -261,6 +277,13 @@ __device__ __forceinline__ void allreduce_warp(const lsk_peers &peers, double *v
     }
     __syncwarp();
 }
+
+// boundary sub-ranges of a vector y that are mirrored into the neighbours' ghost regions (xpay_halo, CG kernel)
+struct HaloSpec {
+    int nmoves;
+    lsk_halo_move m[4];
+    int64_t lo[4];  // send range start as an element index into y
+};
 
 // ---- deterministic reductions ----------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {

@@ -15,17 +15,11 @@
 #include <type_traits>
 
 #include "lsk_common.cuh"
+#include "lsk_spmv_tma.cuh"
 
 namespace lsk {
 
 constexpr int kTile = 2048;  // products staged per tile: 16 KB (fp64) of shared memory per CTA
-#ifndef LSK_TMA_TILE
-#define LSK_TMA_TILE 2048
-#endif
-#ifndef LSK_TMA_MINB
-#define LSK_TMA_MINB 3
-#endif
-constexpr int kTmaTile = LSK_TMA_TILE;  // non-zeros per TMA stage (col + entry: 16 B each)
 
 // ---- small load helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ void load4_stream(const double *p, double (&v)[4]) {
@@ -38,35 +32,12 @@ __device__ __forceinline__ void load4_stream(const float *p, float (&v)[4]) {
                  : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
                  : "l"(p));
 }
-__device__ __forceinline__ double load1_stream(const double *p) {
-    return __longlong_as_double((long long) ld64_stream(p));
-}
-__device__ __forceinline__ float load1_stream(const float *p) { return __uint_as_float(ld32_stream(p)); }
-__device__ __forceinline__ long long load1_stream(const long long *p) { return (long long) ld64_stream(p); }
-
 __device__ __forceinline__ void store4_shared(double *s, const double (&v)[4]) {
     *reinterpret_cast<double2 *>(s) = make_double2(v[0], v[1]);
     *reinterpret_cast<double2 *>(s + 2) = make_double2(v[2], v[3]);
 }
 __device__ __forceinline__ void store4_shared(float *s, const float (&v)[4]) {
     *reinterpret_cast<float4 *>(s) = make_float4(v[0], v[1], v[2], v[3]);
-}
-
-__device__ __forceinline__ long long warp_min_ll(long long v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const long long t = __shfl_xor_sync(0xffffffffu, v, o);
-        v = t < v ? t : v;
-    }
-    return v;
-}
-__device__ __forceinline__ long long warp_max_ll(long long v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const long long t = __shfl_xor_sync(0xffffffffu, v, o);
-        v = t > v ? t : v;
-    }
-    return v;
 }
 
 // ===================================================================================================
@@ -364,206 +335,18 @@ csr_stream_pipe_kernel(int64_t rows, int rpb, int64_t n_row_blocks, const T *__r
 // (conflict-free for odd lengths).  Each thread adds its rounded products in ascending k in a
 // register: bit-identical to the reference CPU body, no product staging, one barrier per tile.
 // ===================================================================================================
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-    return (uint32_t) __cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar,
-                                             uint64_t policy) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-        : "memory");
-}
-
 template <int NDOT>
 __global__ void __launch_bounds__(kBlock, LSK_TMA_MINB)
-csr_tma_kernel(int64_t rows, int64_t nnz, int rpb, int64_t n_row_blocks, const double *__restrict__ entry,
-               const long long *__restrict__ col, const lsk_rect *__restrict__ rowptr, int64_t k_base,
-               const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ dot_w,
-               double *partials, unsigned int *ticket, double *out_yw, double *out_yy, const lsk_peers *peers) {
-    constexpr int S = 2;  // stages: 2 x (16 KB col + 16 KB entry) = 64 KB dynamic shared memory
+csr_tma_kernel(TmaSpmvArgs a, double *partials, unsigned int *ticket, double *out_yw, double *out_yy, const lsk_peers *peers) {
     extern __shared__ __align__(128) unsigned char s_dyn[];
-    long long (*s_col)[kTmaTile] = reinterpret_cast<long long (*)[kTmaTile]>(s_dyn);
-    double (*s_ent)[kTmaTile] = reinterpret_cast<double (*)[kTmaTile]>(s_dyn + (size_t) S * kTmaTile * sizeof(long long));
-    __shared__ __align__(8) uint64_t s_full[S];
+    __shared__ __align__(8) uint64_t s_full[kTmaStages];
     __shared__ long long s_lo[2][kWarps], s_hi[2][kWarps];
-    const int tid = threadIdx.x;
-    const int64_t G = gridDim.x;
     double dacc[NDOT > 0 ? NDOT : 1];
 #pragma unroll
     for (int j = 0; j < (NDOT > 0 ? NDOT : 1); ++j) dacc[j] = 0.0;
-
-    uint64_t policy = 0;
-    if (tid == 0) {
-        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-#pragma unroll
-        for (int s = 0; s < S; ++s) mbar_init(&s_full[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-
-    auto load_rect = [&](int64_t rb, long long &lo, long long &hi1) {
-        lo = LLONG_MAX;
-        hi1 = LLONG_MIN;
-        if (rb < n_row_blocks) {
-            const int64_t r = rb * rpb + tid;
-            if (tid < rpb && r < rows) {
-                const longlong2 rc = __ldg(reinterpret_cast<const longlong2 *>(rowptr + r));
-                if (rc.y >= rc.x) {
-                    lo = rc.x - k_base;
-                    hi1 = rc.y + 1 - k_base;
-                }
-            }
-        }
-    };
-    auto publish_span = [&](int pb, long long lo, long long hi1) {
-        const long long wl = warp_min_ll(lo), wh = warp_max_ll(hi1);
-        if ((tid & 31) == 0) {
-            s_lo[pb][tid >> 5] = wl;
-            s_hi[pb][tid >> 5] = wh;
-        }
-    };
-    auto read_span = [&](int pb, long long &jb, long long &je) {
-        jb = s_lo[pb][0];
-        je = s_hi[pb][0];
-#pragma unroll
-        for (int w = 1; w < kWarps; ++w) {
-            jb = s_lo[pb][w] < jb ? s_lo[pb][w] : jb;
-            je = s_hi[pb][w] > je ? s_hi[pb][w] : je;
-        }
-        if (je <= jb) jb = je = 0;
-    };
-    // tiles start where `col` (and the congruent `entry`) are 16-byte aligned
-    auto tile_start = [&](long long jb) { return jb - (long long) ((reinterpret_cast<uintptr_t>(col + jb) >> 3) & 1); };
-    // thread 0: copy elements [t0, t0 + kTmaTile) /\ [jb, je) of both arrays into stage s
-    auto issue_tile = [&](int s, long long t0, long long jb, long long je) {
-        long long a = t0 > jb ? t0 : jb;                       // first needed element
-        long long b = (t0 + kTmaTile) < je ? (t0 + kTmaTile) : je;   // one past the last
-        if (b < a) b = a;
-        // bulk part: 16-byte aligned on both ends, never outside [0, nnz)
-        long long A = a + ((reinterpret_cast<uintptr_t>(col + a) >> 3) & 1);
-        long long B = b - ((reinterpret_cast<uintptr_t>(col + b) >> 3) & 1);
-        if (B < A) B = A;
-        const uint32_t bytes = (uint32_t) (B - A) * 8u;
-        mbar_expect_tx(&s_full[s], 2u * bytes);
-        if (bytes) {
-            tma_bulk_g2s(&s_col[s][A - t0], col + A, bytes, &s_full[s], policy);
-            tma_bulk_g2s(&s_ent[s][A - t0], entry + A, bytes, &s_full[s], policy);
-        }
-        // ragged single elements at either end (generic proxy; visible after the next CTA barrier)
-        if (a < A && a < b) {
-            s_col[s][a - t0] = load1_stream(col + a);
-            s_ent[s][a - t0] = load1_stream(entry + a);
-        }
-        if (B < b && B >= A && !(a < A && B == a)) {
-            s_col[s][B - t0] = load1_stream(col + B);
-            s_ent[s][B - t0] = load1_stream(entry + B);
-        }
-    };
-
-    int64_t rb = blockIdx.x;
-    long long lo, hi1, jb, je, nlo, nhi1;
-    load_rect(rb, lo, hi1);
-    publish_span(0, lo, hi1);
-    __syncthreads();  // also publishes the mbarrier inits
-    read_span(0, jb, je);
-    long long t0 = tile_start(jb);
-    int stage = 0, pb = 1;
-    uint32_t phases = 0;  // bit s = parity to wait for on stage s
-    if (tid == 0) issue_tile(0, t0, jb, je);
-    load_rect(rb + G, nlo, nhi1);
-    double acc = 0.0;
-
-    while (rb < n_row_blocks) {
-        const bool last_tile = (t0 + kTmaTile >= je);
-        if (last_tile) publish_span(pb, nlo, nhi1);
-        // one barrier per tile: (i) stage^1, consumed last iteration, may now be overwritten;
-        // (ii) the next block's span is published; (iii) ragged elements stored by thread 0 are visible
-        __syncthreads();
-        long long njb = 0, nje = 0;
-        if (last_tile) {
-            read_span(pb, njb, nje);
-            pb ^= 1;
-        }
-        if (tid == 0) {
-            if (!last_tile) issue_tile(stage ^ 1, t0 + kTmaTile, jb, je);
-            else if (rb + G < n_row_blocks) issue_tile(stage ^ 1, tile_start(njb), njb, nje);
-        }
-        // ---- consume this tile: thread-per-row, products added in ascending k
-        // the fused dot's w[r] is requested now, so that its latency hides behind the gathers below
-        double wv = 0.0;
-        if constexpr (NDOT >= 1) {
-            const int64_t r = rb * rpb + tid;
-            if (last_tile && tid < rpb && r < rows) wv = __ldg(dot_w + r);
-        }
-        mbar_wait(&s_full[stage], (phases >> stage) & 1u);
-        phases ^= (1u << stage);
-        {
-            const long long a = lo > t0 ? lo : t0;
-            const long long b = hi1 < t0 + kTmaTile ? hi1 : t0 + kTmaTile;
-            const long long *sc = s_col[stage];
-            const double *se = s_ent[stage];
-            // up to kChunk gathers in flight per thread; the adds stay in ascending k
-            constexpr int kChunk = 8;
-            long long j = a;
-            for (; j + kChunk <= b; j += kChunk) {  // full chunks: no predication
-                const int o = (int) (j - t0);
-                double xv[kChunk];
-#pragma unroll
-                for (int e = 0; e < kChunk; ++e) xv[e] = __ldg(x + sc[o + e]);
-#pragma unroll
-                for (int e = 0; e < kChunk; ++e) acc = add_rn(acc, mul_rn(se[o + e], xv[e]));
-            }
-            if (j < b) {  // 1..kChunk-1 left
-                const int o = (int) (j - t0);
-                const int rem = (int) (b - j);
-                double xv[kChunk - 1];
-#pragma unroll
-                for (int e = 0; e < kChunk - 1; ++e) xv[e] = (e < rem) ? __ldg(x + sc[o + e]) : 0.0;
-#pragma unroll
-                for (int e = 0; e < kChunk - 1; ++e)
-                    if (e < rem) acc = add_rn(acc, mul_rn(se[o + e], xv[e]));
-            }
-        }
-        if (last_tile) {
-            const int64_t r = rb * rpb + tid;
-            if (tid < rpb && r < rows) {
-                y[r] = acc;
-                if constexpr (NDOT >= 1) dacc[0] = fma(acc, wv, dacc[0]);
-                if constexpr (NDOT >= 2) dacc[NDOT - 1] = fma(acc, acc, dacc[NDOT - 1]);
-            }
-            acc = 0.0;
-            rb += G;
-            lo = nlo;
-            hi1 = nhi1;
-            jb = njb;
-            je = nje;
-            t0 = tile_start(jb);
-            load_rect(rb + G, nlo, nhi1);
-        } else {
-            t0 += kTmaTile;
-        }
-        stage ^= 1;
-    }
+    TmaSpmvState st;
+    csr_tma_init(st, s_full);
+    csr_tma_run<NDOT, false, false>(a, st, s_dyn, s_full, s_lo, s_hi, dacc, nullptr);
     if constexpr (NDOT > 0) {
         double *out[NDOT];
         out[0] = out_yw;
@@ -703,8 +486,6 @@ static void launch_pipe_kernel(int ndot, int grid, cudaStream_t st, int64_t rows
         csr_stream_pipe_kernel<T, 2><<<grid, kBlock, 0, st>>>(rows, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers);
 }
 
-constexpr size_t kTmaSmem = (size_t) 2 * kTmaTile * (sizeof(long long) + sizeof(double));
-
 static int launch_tma_kernel(int ndot, int grid, cudaStream_t st, int64_t rows, int64_t nnz, int rpb, int64_t nrb,
                              const double *entry, const long long *col, const lsk_rect *rowptr, int64_t k_base,
                              const double *x, double *y, const double *dot_w, RedScratch rs, double *o0, double *o1) {
@@ -715,12 +496,15 @@ static int launch_tma_kernel(int ndot, int grid, cudaStream_t st, int64_t rows, 
         LSK_RETURN_IF_CUDA(cudaFuncSetAttribute(csr_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kTmaSmem));
         configured = true;
     }
+    TmaSpmvArgs a;
+    a.rows = rows; a.nnz = nnz; a.rpb = rpb; a.n_row_blocks = nrb; a.entry = entry; a.col = col; a.rowptr = rowptr;
+    a.k_base = k_base; a.x = x; a.y = y; a.dot_w = dot_w;
     if (ndot == 0)
-        csr_tma_kernel<0><<<grid, kBlock, kTmaSmem, st>>>(rows, nnz, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers);
+        csr_tma_kernel<0><<<grid, kBlock, kTmaSmem, st>>>(a, rs.partials, rs.ticket, o0, o1, rs.peers);
     else if (ndot == 1)
-        csr_tma_kernel<1><<<grid, kBlock, kTmaSmem, st>>>(rows, nnz, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers);
+        csr_tma_kernel<1><<<grid, kBlock, kTmaSmem, st>>>(a, rs.partials, rs.ticket, o0, o1, rs.peers);
     else
-        csr_tma_kernel<2><<<grid, kBlock, kTmaSmem, st>>>(rows, nnz, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers);
+        csr_tma_kernel<2><<<grid, kBlock, kTmaSmem, st>>>(a, rs.partials, rs.ticket, o0, o1, rs.peers);
     return 0;
 }
 

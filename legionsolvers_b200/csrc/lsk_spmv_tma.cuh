@@ -1,0 +1,432 @@
+// lsk_spmv_tma.cuh -- the TMA-staged, thread-per-row CSR mat-vec as a device-side building block.
+//
+// Used by csr_tma_kernel (lsk_spmv.cu: one mat-vec per launch) and by the persistent CG kernel
+// (lsk_cg.cu: the mat-vec phase of every iteration).  See lsk_spmv.cu for the design notes: the
+// CTA's contiguous run of (col, entry) is copied global->shared by the TMA engine
+// (cp.async.bulk, mbarrier completion, L2 evict-first, two stages), threads own ROWS and add their
+// rounded products in ascending k in a register -- bit-identical to the reference CPU body
+// (src/CSRMatrixTasks.cpp:73-91).
+#pragma once
+
+#include <limits.h>
+
+#include "lsk_common.cuh"
+
+namespace lsk {
+
+#ifndef LSK_TMA_TILE
+#define LSK_TMA_TILE 2048
+#endif
+#ifndef LSK_TMA_MINB
+#define LSK_TMA_MINB 3
+#endif
+constexpr int kTmaTile = LSK_TMA_TILE;  // non-zeros per TMA stage (col + entry: 16 B each)
+constexpr int kTmaStages = 2;           // 2 x (16 KB col + 16 KB entry) = 64 KB dynamic shared memory
+constexpr size_t kTmaSmem = (size_t) kTmaStages * kTmaTile * (sizeof(long long) + sizeof(double));
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ double load1_stream(const double *p) {
+    return __longlong_as_double((long long) ld64_stream(p));
+}
+__device__ __forceinline__ float load1_stream(const float *p) { return __uint_as_float(ld32_stream(p)); }
+__device__ __forceinline__ long long load1_stream(const long long *p) { return (long long) ld64_stream(p); }
+
+__device__ __forceinline__ long long warp_min_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = t < v ? t : v;
+    }
+    return v;
+}
+__device__ __forceinline__ long long warp_max_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = t > v ? t : v;
+    }
+    return v;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t) __cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar,
+                                             uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
+// same, default L2 policy (vectors, which should stay L2-resident)
+__device__ __forceinline__ void tma_bulk_g2s_plain(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// one rowptr rect (16 bytes), streamed once per mat-vec: no L1 allocation, evict-first in L2, so that the
+// solver's vectors keep the L2
+__device__ __forceinline__ longlong2 ld_rect_stream(const lsk_rect *p) {
+    longlong2 r;
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.b64 {%0, %1}, [%2], %3;"
+                 : "=l"(r.x), "=l"(r.y)
+                 : "l"(p), "l"(policy));
+    return r;
+}
+
+// weak, L1-cacheable load on the COHERENT path (never LDG.CONSTANT): for vectors that the same kernel
+// also writes in another phase, made visible by a grid barrier (fence + L1 invalidation)
+__device__ __forceinline__ double ld_f64(const double *p) {
+    double v;
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+// L2 load (bypasses L1): ghost values stored by a peer GPU while this kernel runs
+__device__ __forceinline__ double ld_f64_cg(const double *p) {
+    double v;
+    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+struct TmaSpmvArgs {
+    int64_t rows, nnz;
+    int rpb;                 // rows per row block (<= kBlock, one thread per row)
+    int64_t n_row_blocks;
+    const double *entry;     // element 0 <-> k = k_base
+    const long long *col;
+    const lsk_rect *rowptr;  // inclusive rects of GLOBAL k
+    int64_t k_base;
+    const double *x;         // shifted to global column 0
+    double *y;
+    const double *dot_w;     // NDOT >= 1
+};
+
+// Ghost columns (outside [own_lo, own_lo + own_n)) are written by peer GPUs during the kernel: a thread
+// that meets one waits until every peer it receives from has published epoch `want`, then reads
+// through L2.  Everything else is local and already ordered by the grid barrier.
+struct GhostGate {
+    long long own_lo;
+    unsigned long long own_n;
+    const unsigned char *blocks;  // optional: blocks[rb] != 0 <=> row block rb references a ghost column
+                                  // (computed once at plan time); null = check every chunk
+    int nflags;
+    const volatile unsigned long long *flag[4];
+    unsigned long long want;
+    int *error;
+};
+
+static __device__ __noinline__ void ghost_gate_wait(const GhostGate &g) {
+    for (int q = 0; q < g.nflags; ++q) spin_until(g.flag[q], g.want, g.error);
+    __threadfence_system();
+}
+
+struct TmaSpmvState {
+    uint64_t policy;   // thread 0 only
+    uint32_t phases;   // bit s = parity to wait for on stage s (persists across runs)
+};
+
+// Call once per kernel, by all threads, before the first csr_tma_run (which starts with a CTA barrier).
+__device__ __forceinline__ void csr_tma_init(TmaSpmvState &st, uint64_t *s_full) {
+    st.policy = 0;
+    st.phases = 0;
+    if (threadIdx.x == 0) {
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(st.policy));
+#pragma unroll
+        for (int s = 0; s < kTmaStages; ++s) mbar_init(&s_full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+}
+
+// One mat-vec over the row blocks blockIdx.x, blockIdx.x + gridDim.x, ...
+//   NDOT      0: y only; 1: dacc[0] += y.w; 2: also dacc[1] += y.y
+//   COHERENT  false: x is read-only for the kernel's lifetime (LDG.CONSTANT path)
+//             true : x was written earlier in this kernel (plain ld.global)
+//   GATED     (needs COHERENT) ghost columns are guarded by `gate`; row blocks that reference none (per
+//             gate->blocks) take the same straight-line gather loop as the ungated kernel
+template <int NDOT, bool COHERENT, bool GATED>
+__device__ __forceinline__ void csr_tma_run(const TmaSpmvArgs &a, TmaSpmvState &st, unsigned char *s_dyn, uint64_t *s_full,
+                                            long long (*s_lo)[kWarps], long long (*s_hi)[kWarps],
+                                            double (&dacc)[NDOT > 0 ? NDOT : 1], const GhostGate *gate) {
+    constexpr int S = kTmaStages;
+    long long (*s_col)[kTmaTile] = reinterpret_cast<long long (*)[kTmaTile]>(s_dyn);
+    double (*s_ent)[kTmaTile] = reinterpret_cast<double (*)[kTmaTile]>(s_dyn + (size_t) S * kTmaTile * sizeof(long long));
+    const int tid = threadIdx.x;
+    const int64_t G = gridDim.x;
+    const int64_t rows = a.rows, n_row_blocks = a.n_row_blocks;
+    const int rpb = a.rpb;
+    const double *__restrict__ entry = a.entry;
+    const long long *__restrict__ col = a.col;
+    const lsk_rect *__restrict__ rowptr = a.rowptr;
+    const int64_t k_base = a.k_base;
+    const double *x = a.x;
+    const uint64_t policy = st.policy;
+    bool ghost_ok = false;
+    // copies in registers: `gate` itself escapes to a non-inlined call
+    static_assert(COHERENT || !GATED, "a gate needs the coherent path");
+    // the gate's fields are re-read from (shared) memory where they are needed -- only flagged row blocks do --
+    // instead of occupying registers across the whole tile loop
+    auto block_checked = [&](int64_t rb) -> bool {
+        if constexpr (!GATED) return false;
+        const unsigned char *blk_flags = gate->blocks;
+        if (blk_flags == nullptr) return true;
+        return rb < n_row_blocks ? (__ldg(blk_flags + rb) != 0) : false;
+    };
+
+    // ghost-aware gather (COHERENT only): the slow path of a chunk that contains a ghost column
+    auto gather_checked = [&](long long c, long long own_lo, unsigned long long own_n) -> double {
+        if ((unsigned long long) (c - own_lo) >= own_n) {
+            if (!ghost_ok) {
+                ghost_gate_wait(*gate);
+                ghost_ok = true;
+            }
+            return ld_f64_cg(x + c);
+        }
+        return ld_f64(x + c);
+    };
+
+    auto load_rect = [&](int64_t rb, long long &lo, long long &hi1) {
+        lo = LLONG_MAX;
+        hi1 = LLONG_MIN;
+        if (rb < n_row_blocks) {
+            const int64_t r = rb * rpb + tid;
+            if (tid < rpb && r < rows) {
+                const longlong2 rc = ld_rect_stream(rowptr + r);
+                if (rc.y >= rc.x) {
+                    lo = rc.x - k_base;
+                    hi1 = rc.y + 1 - k_base;
+                }
+            }
+        }
+    };
+    auto publish_span = [&](int pb, long long lo, long long hi1) {
+        const long long wl = warp_min_ll(lo), wh = warp_max_ll(hi1);
+        if ((tid & 31) == 0) {
+            s_lo[pb][tid >> 5] = wl;
+            s_hi[pb][tid >> 5] = wh;
+        }
+    };
+    auto read_span = [&](int pb, long long &jb, long long &je) {
+        jb = s_lo[pb][0];
+        je = s_hi[pb][0];
+#pragma unroll
+        for (int w = 1; w < kWarps; ++w) {
+            jb = s_lo[pb][w] < jb ? s_lo[pb][w] : jb;
+            je = s_hi[pb][w] > je ? s_hi[pb][w] : je;
+        }
+        if (je <= jb) jb = je = 0;
+    };
+    // tiles start where `col` (and the congruent `entry`) are 16-byte aligned
+    auto tile_start = [&](long long jb) { return jb - (long long) ((reinterpret_cast<uintptr_t>(col + jb) >> 3) & 1); };
+    // thread 0: copy elements [t0, t0 + kTmaTile) /\ [jb, je) of both arrays into stage s
+    auto issue_tile = [&](int s, long long t0, long long jb, long long je) {
+        long long a0 = t0 > jb ? t0 : jb;                             // first needed element
+        long long b0 = (t0 + kTmaTile) < je ? (t0 + kTmaTile) : je;   // one past the last
+        if (b0 < a0) b0 = a0;
+        // bulk part: 16-byte aligned on both ends, never outside [0, nnz)
+        long long A = a0 + ((reinterpret_cast<uintptr_t>(col + a0) >> 3) & 1);
+        long long B = b0 - ((reinterpret_cast<uintptr_t>(col + b0) >> 3) & 1);
+        if (B < A) B = A;
+        const uint32_t bytes = (uint32_t) (B - A) * 8u;
+        mbar_expect_tx(&s_full[s], 2u * bytes);
+        if (bytes) {
+            tma_bulk_g2s(&s_col[s][A - t0], col + A, bytes, &s_full[s], policy);
+            tma_bulk_g2s(&s_ent[s][A - t0], entry + A, bytes, &s_full[s], policy);
+        }
+        // ragged single elements at either end (generic proxy; visible after the next CTA barrier)
+        if (a0 < A && a0 < b0) {
+            s_col[s][a0 - t0] = load1_stream(col + a0);
+            s_ent[s][a0 - t0] = load1_stream(entry + a0);
+        }
+        if (B < b0 && B >= A && !(a0 < A && B == a0)) {
+            s_col[s][B - t0] = load1_stream(col + B);
+            s_ent[s][B - t0] = load1_stream(entry + B);
+        }
+    };
+
+    uint32_t phases = st.phases;
+    // This CTA's row blocks are blockIdx.x + kk * G, kk = 0 .. mine-1.  GATED kernels walk them starting from the
+    // middle (kk = mine/2, wrapping): the first and last row blocks of a banded matrix are the ones that read
+    // ghost columns, and by mid-phase the neighbours' halo has long arrived -- nobody stalls at the phase start.
+    int64_t rb_start = blockIdx.x;
+    if constexpr (GATED) {
+        const int64_t mine = n_row_blocks > (int64_t) blockIdx.x ? (n_row_blocks - 1 - blockIdx.x) / G + 1 : 0;
+        rb_start += (mine / 2) * G;
+    }
+    auto next_rb = [&](int64_t r) -> int64_t {  // successor in walking order; n_row_blocks = none
+        int64_t n = r + G;
+        if constexpr (GATED) {
+            if (n >= n_row_blocks) n = blockIdx.x;
+            if (n == rb_start) n = n_row_blocks;
+        }
+        return n;
+    };
+    int64_t rb = rb_start < n_row_blocks ? rb_start : n_row_blocks;
+    int64_t rb_next = rb < n_row_blocks ? next_rb(rb) : n_row_blocks;
+    long long lo, hi1, jb, je, nlo, nhi1;
+    load_rect(rb, lo, hi1);
+    publish_span(0, lo, hi1);
+    __syncthreads();  // also publishes the mbarrier inits (first run) / retires the previous run's tiles
+    read_span(0, jb, je);
+    long long t0 = tile_start(jb);
+    int stage = 0, pb = 1;
+    if (tid == 0 && rb < n_row_blocks) issue_tile(0, t0, jb, je);
+    load_rect(rb_next, nlo, nhi1);
+    bool checked = block_checked(rb), nchecked = block_checked(rb_next);
+    double acc = 0.0;
+
+    while (rb < n_row_blocks) {
+        const bool last_tile = (t0 + kTmaTile >= je);
+        if (last_tile) publish_span(pb, nlo, nhi1);
+        // one barrier per tile: (i) stage^1, consumed last iteration, may now be overwritten;
+        // (ii) the next block's span is published; (iii) ragged elements stored by thread 0 are visible
+        __syncthreads();
+        long long njb = 0, nje = 0;
+        if (last_tile) {
+            read_span(pb, njb, nje);
+            pb ^= 1;
+        }
+        if (tid == 0) {
+            if (!last_tile) issue_tile(stage ^ 1, t0 + kTmaTile, jb, je);
+            else if (rb_next < n_row_blocks) issue_tile(stage ^ 1, tile_start(njb), njb, nje);
+        }
+        // ---- consume this tile: thread-per-row, products added in ascending k
+        // the fused dot's w[r] is requested now, so that its latency hides behind the gathers below
+        double wv = 0.0;
+        if constexpr (NDOT >= 1) {
+            const int64_t r = rb * rpb + tid;
+            if (last_tile && tid < rpb && r < rows) wv = COHERENT ? ld_f64(a.dot_w + r) : __ldg(a.dot_w + r);
+        }
+        mbar_wait(&s_full[stage], (phases >> stage) & 1u);
+        phases ^= (1u << stage);
+        {
+            const long long ka = lo > t0 ? lo : t0;
+            const long long kb = hi1 < t0 + kTmaTile ? hi1 : t0 + kTmaTile;
+            const long long *sc = s_col[stage];
+            const double *se = s_ent[stage];
+            // up to kChunk gathers in flight per thread; the adds stay in ascending k
+            constexpr int kChunk = 8;
+            long long j = ka;
+            for (; j + kChunk <= kb; j += kChunk) {  // full chunks: no predication
+                const int o = (int) (j - t0);
+                double xv[kChunk];
+                if (GATED && checked) {
+                    const long long own_lo = gate->own_lo;
+                    const unsigned long long own_n = gate->own_n;
+                    long long c[kChunk];
+                    bool any_ghost = false;
+#pragma unroll
+                    for (int e = 0; e < kChunk; ++e) {
+                        c[e] = sc[o + e];
+                        any_ghost |= ((unsigned long long) (c[e] - own_lo) >= own_n);
+                    }
+                    if (any_ghost) {  // rare: one branch per chunk keeps the common path straight-line
+#pragma unroll
+                        for (int e = 0; e < kChunk; ++e) xv[e] = gather_checked(c[e], own_lo, own_n);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < kChunk; ++e) xv[e] = ld_f64(x + c[e]);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < kChunk; ++e) xv[e] = COHERENT ? ld_f64(x + sc[o + e]) : __ldg(x + sc[o + e]);
+                }
+#pragma unroll
+                for (int e = 0; e < kChunk; ++e) acc = add_rn(acc, mul_rn(se[o + e], xv[e]));
+            }
+            if (j < kb) {  // 1..kChunk-1 left
+                const int o = (int) (j - t0);
+                const int rem = (int) (kb - j);
+                double xv[kChunk - 1];
+                if (GATED && checked) {
+                    const long long own_lo = gate->own_lo;
+                    const unsigned long long own_n = gate->own_n;
+                    long long c[kChunk - 1];
+                    bool any_ghost = false;
+#pragma unroll
+                    for (int e = 0; e < kChunk - 1; ++e) {
+                        c[e] = (e < rem) ? sc[o + e] : own_lo;
+                        any_ghost |= ((unsigned long long) (c[e] - own_lo) >= own_n);
+                    }
+                    if (any_ghost) {
+#pragma unroll
+                        for (int e = 0; e < kChunk - 1; ++e) xv[e] = (e < rem) ? gather_checked(c[e], own_lo, own_n) : 0.0;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < kChunk - 1; ++e) xv[e] = (e < rem) ? ld_f64(x + c[e]) : 0.0;
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < kChunk - 1; ++e)
+                        xv[e] = (e < rem) ? (COHERENT ? ld_f64(x + sc[o + e]) : __ldg(x + sc[o + e])) : 0.0;
+                }
+#pragma unroll
+                for (int e = 0; e < kChunk - 1; ++e)
+                    if (e < rem) acc = add_rn(acc, mul_rn(se[o + e], xv[e]));
+            }
+        }
+        if (last_tile) {
+            const int64_t r = rb * rpb + tid;
+            if (tid < rpb && r < rows) {
+                a.y[r] = acc;
+                if constexpr (NDOT >= 1) dacc[0] = fma(acc, wv, dacc[0]);
+                if constexpr (NDOT >= 2) dacc[NDOT - 1] = fma(acc, acc, dacc[NDOT - 1]);
+            }
+            acc = 0.0;
+            rb = rb_next;
+            rb_next = rb < n_row_blocks ? next_rb(rb) : n_row_blocks;
+            lo = nlo;
+            hi1 = nhi1;
+            jb = njb;
+            je = nje;
+            t0 = tile_start(jb);
+            load_rect(rb_next, nlo, nhi1);
+            checked = nchecked;
+            nchecked = block_checked(rb_next);
+        } else {
+            t0 += kTmaTile;
+        }
+        stage ^= 1;
+    }
+    st.phases = phases;
+    // stage parity: a run may end after an odd number of tiles; the next run starts at stage 0 again, which
+    // is safe because every issued tile has been waited for (no copy in flight) and `phases` is per stage
+}
+
+// rows per row block so that one block's non-zeros fill about one tile
+inline int tma_rows_per_block(int64_t rows, int64_t nnz) {
+    const double mean = rows > 0 ? (double) nnz / (double) rows : 1.0;
+    int rpb = (int) ((double) kTmaTile / (mean < 1.0 ? 1.0 : mean));
+    rpb = (rpb / 32) * 32;
+    if (rpb < 32) rpb = 32;
+    if (rpb > kBlock) rpb = kBlock;
+    return rpb;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace lsk

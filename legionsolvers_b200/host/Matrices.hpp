@@ -49,6 +49,9 @@ public:
     virtual void matvec(PartitionedVector<T> &dst, const PartitionedVector<T> &src, const IntervalPartition &kernel_partition,
                         const IntervalPartition &ghost_partition, const MatvecFusion<T> *fusion = nullptr) const = 0;
     virtual bool overwrites_output() const = 0;  // CSR: beta = 0; COO: beta = 1 (reference GPU variants)
+    // CSR fields of the piece of colour c (rows r_lo.., kernel piece kp), for kernels that take the whole
+    // problem (lsk_cg_steps_f64); false = not a CSR matrix of this entry type
+    virtual bool csr_piece(int /*c*/, int64_t /*r_lo*/, const IntervalPartition & /*kp*/, lsk_cg_problem * /*out*/) const { return false; }
 
     IntervalPartition domain_partition_from_range_partition(int64_t domain_volume,
                                                             const IndexPartition &range_partition) const override {
@@ -167,6 +170,21 @@ public:
             gp.hi[(size_t) c] = std::min<int64_t>(domain_volume - 1, s.mx);
         }
         return gp;
+    }
+
+    bool csr_piece(int c, int64_t r_lo, const IntervalPartition &kp, lsk_cg_problem *out) const override {
+        if constexpr (!std::is_same<T, double>::value) {
+            return false;
+        } else {
+            const int64_t k_lo = kp.lo[(size_t) c], nk = kp.hi[(size_t) c] - k_lo + 1;
+            if (nk <= 0 || r_lo < slab_r_lo) return false;
+            out->nnz = nk;
+            out->entry = entry.ptr + (k_lo - slab_k_lo);
+            out->col = col.ptr + (k_lo - slab_k_lo);
+            out->rowptr = rowptr.ptr + (r_lo - slab_r_lo);
+            out->k_base = k_lo;
+            return true;
+        }
     }
 
     // CSRMatrix::matvec (src/CSRMatrix.cpp:158-214): one CSRMatvecTask per piece of dst with regions

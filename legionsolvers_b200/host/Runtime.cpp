@@ -26,6 +26,7 @@ Runtime::Runtime(int device, int rank, int nranks, void *external_stream)
 }
 
 Runtime::~Runtime() {
+    has_deferred_ = false;
     cudaSetDevice(device_);
     cudaStreamSynchronize(stream_);
     for (auto &kv : traces_)
@@ -158,11 +159,14 @@ void Runtime::set_fused_collectives(bool on) {
 }
 
 int Runtime::comm_error() {
-    if (!p2p_) return 0;
-    int e = 0;
-    const int rc = lsk_comm_error(ctx_, stream_, &peers_, &e);
+    flush_deferred();
+    int e = 0, g = 0;
+    int rc = lsk_ctx_error(ctx_, stream_, &g);
+    if (rc != 0) fail(rc, "lsk_ctx_error");
+    if (!p2p_) return g;
+    rc = lsk_comm_error(ctx_, stream_, &peers_, &e);
     if (rc != 0) fail(rc, "lsk_comm_error");
-    return e;
+    return e | g;
 }
 
 #define LSK_NCCL(expr, what)                              \
@@ -171,6 +175,7 @@ int Runtime::comm_error() {
     } while (0)
 
 void Runtime::allreduce_sum(double *slots, int count) {
+    flush_deferred();
     if (nranks_ == 1 || mode_ == Mode::Replay) return;
     if (fused_) fail(LSK_E_INVALID, "stand-alone all-reduce while reductions are fused (would double count)");
     if (p2p_) {
@@ -183,6 +188,7 @@ void Runtime::allreduce_sum(double *slots, int count) {
 }
 
 void Runtime::allgather_i64(const int64_t *send_dev, int64_t *recv_dev, int count_per_rank) {
+    flush_deferred();
     if (nranks_ == 1) {
         check_cuda(cudaMemcpyAsync(recv_dev, send_dev, sizeof(int64_t) * (size_t) count_per_rank,
                                    cudaMemcpyDeviceToDevice, stream_), "allgather copy");
@@ -194,6 +200,7 @@ void Runtime::allgather_i64(const int64_t *send_dev, int64_t *recv_dev, int coun
 }
 
 void Runtime::group_start() {
+    flush_deferred();
     if (nranks_ > 1 && mode_ != Mode::Replay) LSK_NCCL(ncclGroupStart(), "ncclGroupStart");
 }
 void Runtime::group_end() {
@@ -219,6 +226,7 @@ void *Runtime::alloc(size_t bytes) {
 
 void Runtime::free(void *p) {
     if (!p) return;
+    flush_deferred();
     auto it = std::find(allocations_.begin(), allocations_.end(), p);
     if (it != allocations_.end()) {
         allocations_.erase(it);
@@ -242,6 +250,7 @@ double *Runtime::new_slot() {
 
 // ---- tracing ---------------------------------------------------------------------------------------------
 void Runtime::begin_trace(int id) {
+    flush_deferred();  // work deferred before the trace does not belong to it
     if (mode_ != Mode::Eager) fail(LSK_E_INVALID, "begin_trace: traces do not nest");
     active_trace_ = id;
     if (traces_.count(id)) {
@@ -254,6 +263,7 @@ void Runtime::begin_trace(int id) {
 }
 
 void Runtime::end_trace(int id) {
+    flush_deferred();  // work deferred inside the trace is recorded (or, on replay, skipped) now
     if (mode_ == Mode::Eager || id != active_trace_) fail(LSK_E_INVALID, "end_trace without matching begin_trace");
     if (mode_ == Mode::Capture) {
         cudaGraph_t graph = nullptr;
@@ -274,7 +284,10 @@ void Runtime::end_trace(int id) {
     replayed_kernels_ += t.kernels;
 }
 
-void Runtime::fence() { check_cuda(cudaStreamSynchronize(stream_), "cudaStreamSynchronize"); }
+void Runtime::fence() {
+    flush_deferred();
+    check_cuda(cudaStreamSynchronize(stream_), "cudaStreamSynchronize");
+}
 
 uint64_t Runtime::kernel_launches() const {
     // the capture pass itself is counted once by lsk_ctx and once by the graph launch at end_trace:

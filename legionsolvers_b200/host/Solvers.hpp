@@ -34,11 +34,17 @@ public:
           negative_one(planner_.get_runtime(), static_cast<T>(-1)), fused(fused_), rr_cur(planner_.get_runtime()),
           rr_new(planner_.get_runtime()), p_norm(planner_.get_runtime()) {
         planner.allocate_workspace(3);
+        if (fused) {
+            lsk_cg_problem pb{};
+            lsk_halo_move moves[4];
+            persistent = planner.cg_problem(SOL, R, P, Q, &pb, moves);
+        }
         reset();
     }
 
     // start a new solve with the current RHS (and SOL taken as 0, like the constructor)
     void reset() {
+        planner.get_runtime()->flush_deferred();
         residual_norm_squared.clear();
         planner.copy(P, RHS);
         planner.copy(R, RHS);
@@ -46,11 +52,18 @@ public:
         residual_norm_squared.push_back(rr_cur);
         // when the xpay pushes P's boundary itself, every step ends with current ghosts; make it START so too,
         // so that the launch sequence of a step is the same from the first one on (traces are replayed)
-        if (fused && planner.halo_push_is_fused()) planner.refresh_halo(P);
+        if (fused && (persistent || planner.halo_push_is_fused())) planner.refresh_halo(P);
     }
 
     // step (src/CGSolver.hpp:46-55)
     void step() {
+        if (persistent) {
+            // deferred: consecutive steps are issued as ONE persistent-kernel launch when anything else
+            // touches the stream (Runtime::defer)
+            ++pending;
+            planner.get_runtime()->defer(this, [this] { flush(); });
+            return;
+        }
         if (fused) {
             planner.matvec_dot(Q, P, P, p_norm);                     // Q = A P and P.Q in one pass
             planner.cg_update(SOL, R, rr_cur, p_norm, P, Q, rr_new);  // both axpys and R.R in one pass
@@ -64,6 +77,21 @@ public:
             planner.xpay(P, rr_new, rr_cur, R);
         }
         residual_norm_squared.push_back(rr_new, &rr_cur);  // append, and rr_cur <- rr_new for the next step
+    }
+
+    ~CGSolver() { planner.get_runtime()->drop_deferred(this); }
+    CGSolver(const CGSolver &) = delete;
+    CGSolver &operator=(const CGSolver &) = delete;
+
+    bool is_persistent() const { return persistent; }
+
+private:
+    bool persistent = false;  // the whole step runs as lsk_cg_steps_f64
+    int pending = 0;
+    void flush() {
+        const int n = pending;
+        pending = 0;
+        if (n > 0) planner.cg_steps(SOL, R, P, Q, rr_cur, rr_new, p_norm, residual_norm_squared, n);
     }
 };
 

@@ -40,6 +40,7 @@ class SquarePlanner {
     std::vector<std::pair<int64_t, int64_t>> space_need;  // ghost range every vector of a space must hold
     std::vector<std::vector<Scalar<T>>> piece_partials;   // [slot set][space-major local piece]
     uint64_t halo_bytes_per_matvec = 0;
+    DeviceBuffer<uint8_t> cg_ghost_blocks;  // lsk_cg_ghost_blocks flags of the (single) CSR block, see cg_problem
     std::set<std::size_t> halo_fresh;  // vector ids whose ghost values are current on every rank
     void mark_dirty(std::size_t vec_idx) { halo_fresh.erase(vec_idx); }
 
@@ -218,6 +219,79 @@ public:
             }
         }
         xpay(dst, numer, denom, src);
+    }
+
+    // ---- the whole CG step as one persistent kernel (lsk_cg_steps_f64) ------------------------------------
+    // Possible when this rank holds ONE piece of ONE space whose only operator is a CSR block, and (on
+    // several ranks) the collectives run over peer memory with P's buffer mapped into the neighbours.
+    bool cg_problem(std::size_t sol, std::size_t r, std::size_t p, std::size_t q, lsk_cg_problem *pb, lsk_halo_move (&moves)[4]) {
+        if constexpr (!std::is_same<T, double>::value) {
+            return false;
+        } else {
+            if (get_num_spaces() != 1 || row_partitioned_matrices.size() != 1 || total_local_pieces() != 1) return false;
+            const Block &blk = row_partitioned_matrices[0];
+            if (blk.domain_index != 0 || blk.range_index != 0) return false;
+            const IndexPartition &part = *canonical_index_partitions[0];
+            const int c = part.first_color;
+            const int64_t lo = part.lo[(size_t) c], n = part.piece_size(c);
+            if (n <= 0) return false;
+            if (!blk.matrix->csr_piece(c, lo, blk.kernel_partition, pb)) return false;
+            PartitionedVector<T> &vp = get_vector(p, 0);
+            if (rt->nranks() > 1) {
+                if (!rt->fused_collectives() || blk.halo.size() > 4) return false;
+                if (!blk.halo.empty() && !vp.exported()) return false;
+            }
+            pb->rows = n;
+            pb->p_shifted = vp.shifted();
+            pb->own_lo = lo;
+            pb->q = get_vector(q, 0).ptr(lo);
+            pb->x = get_vector(sol, 0).ptr(lo);
+            pb->r = get_vector(r, 0).ptr(lo);
+            int nm = 0;
+            for (const HaloMove &m : blk.halo) {
+                moves[nm].peer = m.peer;
+                moves[nm].expect = m.recv_n > 0 ? 1 : 0;
+                moves[nm].n = m.send_n;
+                moves[nm].src = m.send_n > 0 ? vp.ptr(m.send_lo) : nullptr;
+                moves[nm].dst = m.send_n > 0 ? vp.peer_ptr(m.peer, m.send_lo) : nullptr;
+                ++nm;
+            }
+            pb->moves = nm > 0 ? moves : nullptr;
+            pb->nmoves = nm;
+            pb->ghost_blocks = nullptr;
+            if (!lsk_cg_steps_supported(pb)) return false;
+            if (nm > 0) {
+                // which row blocks reference ghost columns: computed once (outside any trace), so that only
+                // those pay the per-gather ghost test inside the kernel
+                if (cg_ghost_blocks.count == 0 && !rt->capturing() && !rt->replaying()) {
+                    cg_ghost_blocks = DeviceBuffer<uint8_t>(rt, (size_t) lsk_cg_row_blocks(pb->rows, pb->nnz));
+                    uint8_t *flags = cg_ghost_blocks.ptr;
+                    rt->enqueue("cg ghost blocks", [&] { return lsk_cg_ghost_blocks(rt->ctx(), rt->stream(), pb, flags); });
+                }
+                if (cg_ghost_blocks.count == (size_t) lsk_cg_row_blocks(pb->rows, pb->nnz)) pb->ghost_blocks = cg_ghost_blocks.ptr;
+            }
+            return true;
+        }
+    }
+    // `niter` CG steps; P's ghosts must be current at entry (they are at exit)
+    void cg_steps(std::size_t sol, std::size_t r, std::size_t p, std::size_t q, const Scalar<T> &rr_cur, const Scalar<T> &rr_new,
+                  const Scalar<T> &p_norm, const ScalarHistory &history, int niter) {
+        if constexpr (std::is_same<T, double>::value) {
+            lsk_cg_problem pb{};
+            lsk_halo_move moves[4];
+            if (!cg_problem(sol, r, p, q, &pb, moves)) rt->fail(LSK_E_INVALID, "cg_steps: problem not eligible");
+            pb.rr_cur = rr_cur.ptr();
+            pb.rr_new = rr_new.ptr();
+            pb.p_norm = p_norm.ptr();
+            pb.history = history.data();
+            pb.history_capacity = history.get_capacity();
+            pb.history_count = history.count_ptr();
+            mark_dirty(sol);
+            mark_dirty(r);
+            mark_dirty(q);
+            rt->enqueue("cg_steps", [&] { return lsk_cg_steps_f64(rt->ctx(), rt->stream(), &pb, niter); });
+            halo_fresh.insert(p);
+        }
     }
 
     // add_row_partitioned_matrix (:209-235): kernel partition from the range partition, ghost

@@ -282,8 +282,10 @@ int lsk_planner_create(lsk_runtime *rt, lsk_planner **out) {
     });
 }
 int lsk_planner_destroy(lsk_planner *pl) {
+    if (!pl) return 0;
+    const int rc = guard([&] { pl->rt->flush_deferred(); });
     delete pl;
-    return 0;
+    return rc;
 }
 int lsk_planner_add_sol_vector(lsk_planner *pl, lsk_vector *v) {
     REQUIRE(pl && v);
@@ -395,9 +397,12 @@ int lsk_solver_create(lsk_planner *pl, int kind, int restart, int fused, lsk_sol
     });
 }
 int lsk_solver_destroy(lsk_solver *s) {
+    if (!s) return 0;
+    const int rc = guard([&] { s->rt->flush_deferred(); });  // deferred steps of this solver still happen
     delete s;
-    return 0;
+    return rc;
 }
+int lsk_solver_persistent(lsk_solver *s) { return (s && s->cg && s->cg->is_persistent()) ? 1 : 0; }
 int lsk_solver_step(lsk_solver *s) {
     REQUIRE(s);
     return guard([&] {

@@ -84,6 +84,14 @@ class Runtime:
         _check(_abi.lib().lsk_rt_comm_stats(self.h, out), "lsk_rt_comm_stats")
         return {"ar_calls": out[0], "ar_ns": out[1], "halo_calls": out[2], "halo_ns": out[3]}
 
+    def cg_phase_stats(self) -> dict:
+        """Accounting of the persistent CG kernel (CTA 0's view): ns in {mat-vec + p.q sync, x/r update + r.r
+        sync, p update + halo sync} and iterations, accumulated since the runtime was created.  Synchronises."""
+        self.fence()
+        out = (C.c_uint64 * 4)()
+        _check(_abi.lib().lsk_cg_phase_stats(self.ctx, self.stream, out), "lsk_cg_phase_stats")
+        return {"matvec_ns": out[0], "update_ns": out[1], "direction_ns": out[2], "iterations": out[3]}
+
     def comm_error(self) -> int:
         out = C.c_int()
         _check(_abi.lib().lsk_rt_comm_error(self.h, C.byref(out)), "lsk_rt_comm_error")
@@ -352,6 +360,11 @@ class CGSolver(_Solver):
 
     def __init__(self, planner, fused=True):
         super().__init__(planner, 0, fused)
+
+    @property
+    def persistent(self) -> bool:
+        """True when step() runs as the persistent CG kernel (steps are deferred and batched per launch)."""
+        return bool(_abi.lib().lsk_solver_persistent(self.h))
 
     def reset(self):
         """Start a new solve from the current RHS (SOL taken as 0, like the constructor)."""

@@ -373,5 +373,20 @@ def test_kernel_launch_accounting(rt, oracle):
         cg.step()
         rt.end_trace(tid)
     rt.fence()
-    # fused CG step on one piece: spmv+dot, cg_update, xpay, history append = 4 kernels
-    assert rt.kernel_launches - before == 5 * 4
+    # one piece of one CSR block: the whole step is one persistent-kernel launch
+    assert cg.persistent
+    assert rt.kernel_launches - before == 5 * 1
+    # the leaf-task form of the fused step on 4 local pieces
+    pl4, _, _, _ = build_system(rt, oracle, m, 4)
+    cg4 = CGSolver(pl4, fused=True)
+    assert not cg4.persistent
+    rt.fence()
+    before = rt.kernel_launches
+    tid = new_trace_id()
+    for _ in range(5):
+        rt.begin_trace(tid)
+        cg4.step()
+        rt.end_trace(tid)
+    rt.fence()
+    # per step: 4 pieces x (spmv+dot, cg_update, xpay) + 2 colour-order folds of 4 partials (copy + 3 adds) + append
+    assert rt.kernel_launches - before == 5 * (4 * 3 + 2 * 4 + 1)

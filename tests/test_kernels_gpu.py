@@ -479,3 +479,91 @@ def test_cg_golden_history_through_leaf_kernels(ctx, oracle):
     got = hist.cpu().numpy()
     assert list(got) == [100.0, 4900.0, 4704.0, 4512.0, 4324.0, 4140.0, 3960.0, 3784.0, 3612.0, 3444.0, 3280.0]
     assert ctx.launch_count > 0
+
+
+# ---- the persistent CG kernel (lsk_cg_steps_f64) -------------------------------------------------------------------
+def _cg_state(oracle, m, rhs_val=1.0, cap=64):
+    from legionsolvers_b200 import kernels as K
+
+    n = m.n_rows
+    z = lambda: torch.zeros(n, dtype=torch.float64, device="cuda")  # noqa: E731
+    st = dict(entry=dev(m.entry), col=dev(m.col), rowptr=K.rect_tensor(m.rowptr), x=z(), r=z(), p=z(), q=z(),
+              rr_cur=torch.zeros(1, dtype=torch.float64, device="cuda"), rr_new=torch.zeros(1, dtype=torch.float64, device="cuda"),
+              pq=torch.zeros(1, dtype=torch.float64, device="cuda"), hist=torch.zeros(cap, dtype=torch.float64, device="cuda"),
+              count=torch.zeros(1, dtype=torch.int64, device="cuda"))
+    st["r"].fill_(rhs_val); st["p"].fill_(rhs_val)
+    st["rr_cur"].fill_(float(n) * rhs_val * rhs_val)
+    return st
+
+
+def _cg_steps(ctx, st, niter):
+    ctx.cg_steps(st["entry"], st["col"], st["rowptr"], 0, st["p"], 0, st["q"], st["x"], st["r"], st["rr_cur"], st["rr_new"],
+                 st["pq"], st["hist"], st["count"], niter)
+
+
+def test_cg_steps_golden_history(ctx, oracle):
+    """Test06CSRSolveCG's system (1-D Laplacian n = 100) through the persistent kernel: the reference's
+    golden residual history (exact integers), one launch of 10 iterations and ten launches of one."""
+    m = oracle.laplacian_1d_csr(100)
+    want = [4900.0, 4704.0, 4512.0, 4324.0, 4140.0, 3960.0, 3784.0, 3612.0, 3444.0, 3280.0]
+    for split in ([10], [1] * 10, [3, 7]):
+        st = _cg_state(oracle, m)
+        for k in split:
+            _cg_steps(ctx, st, k)
+        torch.cuda.synchronize()
+        assert ctx.error() == 0
+        assert int(st["count"].item()) == 10
+        assert list(st["hist"][:10].cpu().numpy()) == want
+        assert st["rr_cur"].item() == want[-1] and st["rr_new"].item() == want[-1]
+
+
+@pytest.mark.parametrize("dim_flag,shape,its", [(2, (256, 256), 60), (3, (40, 40, 40), 50), (4, (24, 24, 24), 30), (3, (96, 96, 96), 25)])
+def test_cg_steps_vs_oracle_and_leaf_sequence(ctx, oracle, dim_flag, shape, its):
+    """Residual history within 1e-10 of the oracle's CG (north_star tolerance); vectors agree with the
+    oracle to 1e-10 and p.q is the last p.Ap.  Grids above one wave of CTAs exercise the multi-block path."""
+    off, val = oracle.benchmark_stencil(dim_flag)
+    m = oracle.stencil_csr(shape, off, val)
+    n = m.n_rows
+    st = _cg_state(oracle, m, cap=its)
+    _cg_steps(ctx, st, its)
+    torch.cuda.synchronize()
+    assert ctx.error() == 0
+    opl = oracle.Planner([n], [1]); opl.fill(1, 1.0); opl.add_matrix(m)
+    ocg = oracle.CGSolver(opl)
+    for _ in range(its):
+        ocg.step()
+    want = ocg.residual_norm_squared[1:]
+    got = st["hist"].cpu().numpy()
+    live = want >= 1e-12 * want[0]
+    assert np.max(np.abs(got[live] - want[live]) / want[live]) <= 1e-10
+    xo = opl.vector(0)
+    assert np.max(np.abs(st["x"].cpu().numpy() - xo)) <= 1e-10 * np.max(np.abs(xo))
+    ro = opl.vector(4)
+    assert np.max(np.abs(st["r"].cpu().numpy() - ro)) <= 1e-9 * max(np.max(np.abs(ro)), 1e-300) + 1e-12
+
+
+def test_cg_steps_misaligned_vectors_and_odd_k(ctx, oracle):
+    """Vectors at different 8-byte residues mod 32 (scalar edge path), entry/col starting at an odd element."""
+    from legionsolvers_b200 import kernels as K
+
+    off, val = oracle.benchmark_stencil(3)
+    m = oracle.stencil_csr((17, 13, 11), off, val)
+    n, nnz, its = m.n_rows, m.nnz, 12
+    buf = lambda o: torch.zeros(n + 8, dtype=torch.float64, device="cuda")[o:o + n]  # noqa: E731
+    ebuf = torch.zeros(nnz + 4, dtype=torch.float64, device="cuda"); cbuf = torch.zeros(nnz + 4, dtype=torch.int64, device="cuda")
+    entry, col = ebuf[1:1 + nnz], cbuf[1:1 + nnz]
+    entry.copy_(dev(m.entry)); col.copy_(dev(m.col))
+    st = _cg_state(oracle, m, cap=its)
+    st.update(entry=entry, col=col, x=buf(1), r=buf(2), p=buf(3), q=buf(0))
+    st["r"].fill_(1.0); st["p"].fill_(1.0)
+    _cg_steps(ctx, st, its)
+    torch.cuda.synchronize()
+    assert ctx.error() == 0
+    opl = oracle.Planner([n], [1]); opl.fill(1, 1.0); opl.add_matrix(m)
+    ocg = oracle.CGSolver(opl)
+    for _ in range(its):
+        ocg.step()
+    want = ocg.residual_norm_squared[1:]
+    assert np.max(np.abs(st["hist"].cpu().numpy() - want) / want) <= 1e-10
+    xo = opl.vector(0)
+    assert np.max(np.abs(st["x"].cpu().numpy() - xo)) <= 1e-10 * np.max(np.abs(xo))
