@@ -373,9 +373,9 @@ int lsk_cg_ghost_blocks(lsk_ctx *ctx, lsk_stream s, const lsk_cg_problem *pb, ui
 /* 1 if lsk_cg_steps_f64 can run this problem (alignment, move count), 0 = use the leaf-task sequence */
 int lsk_cg_steps_supported(const lsk_cg_problem *pb);
 int lsk_cg_steps_f64(lsk_ctx *ctx, lsk_stream s, const lsk_cg_problem *pb, int niter);
-/* accounting kept by the persistent kernel: ns that CTA 0 spent in {mat-vec + p.q sync, x/r update + r.r sync,
- * p update + halo sync} and the number of iterations, accumulated since context creation.  Synchronises. */
-int lsk_cg_phase_stats(lsk_ctx *ctx, lsk_stream s, uint64_t *host_out4);
+/* accounting kept by the persistent kernel: ns that CTA 0 spent in {mat-vec, its p.q barrier, x/r update, its r.r
+ * barrier, p update, its halo barrier} and the number of iterations, accumulated since context creation.  Synchronises. */
+int lsk_cg_phase_stats(lsk_ctx *ctx, lsk_stream s, uint64_t *host_out7);
 /* non-zero if a grid barrier or ghost wait of a persistent kernel gave up.  Synchronises. */
 int lsk_ctx_error(lsk_ctx *ctx, lsk_stream s, int *host_out);
 /* bytes of the grid-barrier block a context holds (internal; exported for the context) */

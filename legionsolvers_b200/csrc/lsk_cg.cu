@@ -29,13 +29,12 @@
 namespace lsk {
 
 struct GridSync {
-    unsigned int count;
-    unsigned int gen;
+    unsigned int gen;    // generation of the last completed barrier (read at kernel start, written back at its end)
     int error;
-    int pad;
-    double bcast;
-    unsigned long long phase_ns[4];  // accounting: time CTA 0 spent in phase A / B / C (incl. the barrier that ends it), iterations
-    double partials[kMaxPartials];
+    unsigned long long release[2];   // root -> everybody: LL packets {32 data bits | generation << 32}
+    unsigned long long work[4];      // dynamic work counters of the phases (A, B, C); reset by CTA 0 in the barrier that ends the phase
+    unsigned long long phase_ns[8];  // accounting (CTA 0): ns in phase A, its barrier, phase B, its barrier, phase C, its barrier; [6] = iterations
+    unsigned long long slots[kMaxPartials][2];  // CTA i -> root: its partial sum as two LL packets
 };
 
 // ---- TMA-streamed vector phases ---------------------------------------------------------------------------
@@ -50,50 +49,73 @@ constexpr int kVecStageBytes = 16384;
 struct VecRing {
     unsigned char *smem;   // kVecStages x kVecStageBytes
     uint64_t *bar;         // kVecStages mbarriers
+    long long *chunk;      // [kVecStages] (shared): chunk held by each stage, -1 = none left
     uint32_t phases;       // bit s = parity to wait for on stage s
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // Streams elements [head, head + nelem) of NIN congruent (32-byte aligned at `head`) arrays through the ring in
-// chunks of CH = 16 KB / (8 NIN); chunk c belongs to CTA c % gridDim.x.  f(i, v) receives, for two consecutive
-// elements i and i + 1, the inputs v[a][0..1] of each array.
-// `last_first`: this CTA's LAST chunk is processed first (then 0, 1, ...): phase C uses it so that the chunks whose
-// results are also stored into the neighbours' memory -- the two ends of the vector -- are issued early and their
-// NVLink traffic overlaps the rest of the phase.
-template <int NIN, class F>
-__device__ __forceinline__ void vec_stream(VecRing &ring, const double *const (&in)[NIN], int64_t head, int64_t nelem, bool last_first, F f) {
+// chunks of CH = 16 KB / (8 NIN).  Chunks are handed out DYNAMICALLY from a global counter: SMs do not all get the
+// same share of the memory system, and with a static split the slow ones finish ~7 % after the fast ones while
+// HBM idles; first come, first served keeps it saturated to the end of the phase.  Thread 0 grabs three chunks
+// ahead (the atomic's latency hides behind the chunks in flight), publishes the chunk id of a stage in shared
+// memory before arming its mbarrier, and everybody learns it after the wait.  Grabbed index g maps to chunk
+// (g + rot) % nchunks, so a phase can have a chosen range of chunks taken first.
+// begin(i0, cnt) is called by every thread once per chunk (elements i0 .. i0 + cnt - 1) before its pairs;
+// f(i, v) receives, for two consecutive elements i and i + 1, the inputs v[a][0..1] of each array.
+template <int NIN, class B, class F>
+__device__ __forceinline__ void vec_stream(VecRing &ring, const double *const (&in)[NIN], int64_t head, int64_t nelem,
+                                           unsigned long long *counter, int64_t rot, B begin, F f) {
     constexpr int CH = kVecStageBytes / (8 * NIN);
     const int64_t nchunks = (nelem + CH - 1) / CH;
-    const int64_t G = gridDim.x;
-    const int64_t mine = nchunks > (int64_t) blockIdx.x ? (nchunks - 1 - blockIdx.x) / G + 1 : 0;  // chunks of this CTA
-    const int64_t rot = (last_first && mine > 0) ? mine - 1 : 0;
-    auto chunk_of = [&](int64_t k) -> int64_t {  // k-th chunk in processing order
-        int64_t kk = k + rot;
-        if (kk >= mine) kk -= mine;
-        return (int64_t) blockIdx.x + kk * G;
-    };
-    auto issue = [&](int64_t k) {  // thread 0: k-th chunk of this CTA into stage k % kVecStages
-        const int s = (int) (k % kVecStages);
-        const int64_t e0 = chunk_of(k) * CH;
-        const int64_t cnt = nelem - e0 < CH ? nelem - e0 : CH;
-        const uint32_t bytes = (uint32_t) cnt * 8u;
-        mbar_expect_tx(&ring.bar[s], NIN * bytes);
+    auto issue = [&](int s, int64_t g) {  // thread 0: grabbed index g into stage s
+        if (g < nchunks) {
+            int64_t c = g + rot;
+            if (c >= nchunks) c -= nchunks;
+            ring.chunk[s] = c;
+            const int64_t e0 = c * CH;
+            const int64_t cnt = nelem - e0 < CH ? nelem - e0 : CH;
+            const uint32_t bytes = (uint32_t) cnt * 8u;
+            mbar_expect_tx(&ring.bar[s], NIN * bytes);
 #pragma unroll
-        for (int a = 0; a < NIN; ++a)
-            tma_bulk_g2s_plain(ring.smem + (size_t) s * kVecStageBytes + (size_t) a * CH * 8, in[a] + head + e0, bytes, &ring.bar[s]);
+            for (int a = 0; a < NIN; ++a)
+                tma_bulk_g2s_plain(ring.smem + (size_t) s * kVecStageBytes + (size_t) a * CH * 8, in[a] + head + e0, bytes, &ring.bar[s]);
+        } else {
+            ring.chunk[s] = -1;
+            mbar_arrive(&ring.bar[s]);  // completes the stage's phase with no bytes
+        }
     };
+    auto grab = [&](long long prev) -> long long {  // thread 0; stops asking once the work has run out
+        return prev < nchunks ? (long long) atomicAdd(counter, 1ull) : prev;
+    };
+    long long pend = 0;
     if (threadIdx.x == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (int64_t k = 0; k < kVecStages - 1 && k < mine; ++k) issue(k);
+        for (int s = 0; s < kVecStages - 1; ++s) {
+            pend = grab(pend);
+            issue(s, pend);
+        }
+        pend = grab(pend);
     }
-    for (int64_t k = 0; k < mine; ++k) {
+    int64_t k = 0;
+    for (;; ++k) {
         const int s = (int) (k % kVecStages);
         // stage (k - 1) % kVecStages was consumed in the previous iteration, which ended with a CTA barrier
-        if (threadIdx.x == 0 && k + kVecStages - 1 < mine) issue(k + kVecStages - 1);
+        if (threadIdx.x == 0) {
+            issue((int) ((k + kVecStages - 1) % kVecStages), pend);
+            pend = grab(pend);
+        }
         mbar_wait(&ring.bar[s], (ring.phases >> s) & 1u);
         ring.phases ^= (1u << s);
-        const int64_t e0 = chunk_of(k) * CH;
+        const long long c = ring.chunk[s];
+        if (c < 0) break;  // uniform: the stages issued after this one are empty as well
+        const int64_t e0 = c * CH;
         const int cnt = (int) (nelem - e0 < CH ? nelem - e0 : CH);
         const unsigned char *st = ring.smem + (size_t) s * kVecStageBytes;
+        begin(head + e0, cnt);
 #pragma unroll
         for (int u = 0; u < CH / (2 * kBlock); ++u) {
             const int j = u * 2 * kBlock + 2 * (int) threadIdx.x;
@@ -110,6 +132,13 @@ __device__ __forceinline__ void vec_stream(VecRing &ring, const double *const (&
         }
         __syncthreads();
     }
+    // retire the (empty) stages that were armed ahead, so that every mbarrier's parity matches ring.phases again
+    for (int64_t j = k + 1; j < k + kVecStages; ++j) {
+        const int s = (int) (j % kVecStages);
+        mbar_wait(&ring.bar[s], (ring.phases >> s) & 1u);
+        ring.phases ^= (1u << s);
+    }
+    __syncthreads();
 }
 
 struct CgArgs {
@@ -145,38 +174,77 @@ __device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int *p) {
     return *reinterpret_cast<const volatile unsigned int *>(p);
 }
 
-// Grid barrier (all CTAs co-resident: cooperative launch).  REDUCE: returns the sum of `v` over all
-// threads of all CTAs -- and over all ranks when `peers` is set -- identical bits in every thread.
-// `tail()` is executed by every thread of the last-arriving CTA after all CTAs have arrived and before
-// anybody is released.  Returns through `err` whether a spin-wait anywhere has given up.
+// ---- grid barrier with the reduction riding on it ---------------------------------------------------------------
+// All CTAs are co-resident (cooperative launch).  Gather-broadcast through CTA 0 with LL packets -- an aligned
+// 8-byte word carries 32 data bits and the barrier generation, so data and arrival are ONE store and one poll:
+//   every CTA:  block sum -> thread 0: fence (release), 2 packet stores into its slot, then polls `release`
+//   CTA 0:      its 256 threads poll the slots of all other CTAs (values arrive in registers), fixed-order sum,
+//               [cross-rank sum over NVLink], tail(), fence, 2 packet stores to `release`
+// No atomics, no second pass over partials, no separate flag: ~3 us of critical path instead of ~7 for the
+// counter-based barrier.  Results are bitwise reproducible for a given grid size.
+__device__ __forceinline__ void ll_store(unsigned long long *pk, double v, unsigned int tag) {
+    const unsigned long long bits = (unsigned long long) __double_as_longlong(v);
+    const unsigned long long t = (unsigned long long) tag << 32;
+    *reinterpret_cast<volatile unsigned long long *>(pk) = t | (bits & 0xffffffffull);
+    *reinterpret_cast<volatile unsigned long long *>(pk + 1) = t | (bits >> 32);
+}
+// false = gave up
+__device__ __forceinline__ bool ll_poll(const unsigned long long *pk, unsigned int tag, double &v) {
+    const volatile unsigned long long *p = pk;
+    unsigned long long a, b;
+    unsigned int polls = 0;
+    unsigned long long t_start = 0;
+    for (;;) {
+        a = p[0];
+        b = p[1];
+        if ((unsigned int) (a >> 32) == tag && (unsigned int) (b >> 32) == tag) break;
+        if (spin_expired(polls, t_start)) return false;
+    }
+    v = __longlong_as_double((long long) ((a & 0xffffffffull) | (b << 32)));
+    return true;
+}
+
+// REDUCE: returns the sum of `v` over all threads of all CTAs -- and over all ranks when `peers` is set -- identical
+// bits in every thread.  `tail()` is executed by every thread of CTA 0 after all CTAs have arrived and before anybody
+// is released.  `gen` is the caller's running generation counter (same value in every thread of the grid).
 template <bool REDUCE, class Tail>
-__device__ __forceinline__ double grid_sync(GridSync *gs, const lsk_peers *peers, double v, bool &err, Tail tail) {
+__device__ __forceinline__ double grid_sync(GridSync *gs, unsigned int &gen, const lsk_peers *peers, double v, bool &err, Tail tail) {
     __shared__ double s_red[kWarps];
     __shared__ double s_val;
-    __shared__ unsigned int s_gen;
-    __shared__ int s_last, s_err;
+    __shared__ int s_err;
     const unsigned int G = gridDim.x;
-    if constexpr (REDUCE) {
-        const double b = block_sum(v, s_red);
-        if (threadIdx.x == 0) *reinterpret_cast<volatile double *>(&gs->partials[blockIdx.x]) = b;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int g = ld_volatile_u32(&gs->gen);  // cannot advance before this CTA arrives
-        __threadfence();
-        const unsigned int t = atomicAdd(&gs->count, 1u);
-        s_last = (t == G - 1);
-        s_gen = g;
-    }
-    __syncthreads();
-    if (s_last) {
-        __threadfence();
-        double tot = 0.0;
+    const unsigned int tag = ++gen;
+    double b = 0.0;
+    if constexpr (REDUCE) b = block_sum(v, s_red);  // valid in warp 0
+    if (threadIdx.x == 0) s_err = 0;
+    __syncthreads();  // every thread's writes of the phase are ordered before thread 0's fence below
+    if (blockIdx.x != 0) {
+        if (threadIdx.x == 0) {
+            __threadfence();
+            ll_store(gs->slots[blockIdx.x], b, tag);
+            double r = 0.0;
+            if (!ll_poll(gs->release, tag, r)) {
+                gs->error = 1;
+                s_err = 1;
+            }
+            __threadfence();
+            s_val = r;
+        }
+    } else {
+        double acc = (threadIdx.x == 0) ? b : 0.0;  // CTA 0's own partial takes the place of slot 0
+        bool ok = true;
+        for (unsigned int i = threadIdx.x; i < G; i += kBlock) {
+            if (i == 0) continue;
+            double x = 0.0;
+            ok = ll_poll(gs->slots[i], tag, x) && ok;
+            if constexpr (REDUCE) acc += x;
+        }
+        if (!ok) {
+            gs->error = 1;
+            s_err = 1;
+        }
+        double tot = block_sum(acc, s_red);  // its barriers also mean: every CTA has arrived
         if constexpr (REDUCE) {
-            const volatile double *pj = gs->partials;
-            double acc = 0.0;
-            for (unsigned int i = threadIdx.x; i < G; i += kBlock) acc += pj[i];
-            tot = block_sum(acc, s_red);  // every lane of warp 0 holds it
             if (peers != nullptr && peers->nranks > 1 && threadIdx.x < 32) {
                 double w[kMaxRed];
                 w[0] = tot;
@@ -184,47 +252,42 @@ __device__ __forceinline__ double grid_sync(GridSync *gs, const lsk_peers *peers
                 tot = w[0];
             }
         }
+        __threadfence();  // acquire side of the arrivals observed by this thread, before the tail acts on them
         tail();
         if (threadIdx.x == 0) {
-            if constexpr (REDUCE) *reinterpret_cast<volatile double *>(&gs->bcast) = tot;
-            *reinterpret_cast<volatile unsigned int *>(&gs->count) = 0u;
             __threadfence();
-            *reinterpret_cast<volatile unsigned int *>(&gs->gen) = s_gen + 1u;
+            ll_store(gs->release, tot, tag);
+            s_val = tot;
         }
-    } else if (threadIdx.x == 0) {
-        unsigned int polls = 0;
-        unsigned long long t_start = 0;
-        while (ld_volatile_u32(&gs->gen) == s_gen) {
-            if (spin_expired(polls, t_start)) {
-                gs->error = 1;
-                break;
-            }
-        }
-    }
-    if (threadIdx.x == 0) {
-        __threadfence();
-        if constexpr (REDUCE) s_val = *reinterpret_cast<volatile double *>(&gs->bcast);
-        s_err = *reinterpret_cast<volatile int *>(&gs->error);
     }
     __syncthreads();
     err = (s_err != 0);
     return REDUCE ? s_val : 0.0;
 }
 
-// The mat-vec phase as a REAL call: the tile loop needs every register 3 CTAs/SM allow (80), so whatever the
-// surrounding kernel keeps live across the phase is saved once at the call instead of spilling inside the loop.
+// The mat-vec phase.  Measured: as a real (noinline) call it needs no spills but runs 9 % slower -- behind a call the
+// shared-memory ring is reached through generic pointers -- so it is inlined and the kernel around it keeps its
+// live state small instead (rarely used state lives in shared memory).
 struct MatvecPhaseShared {
     uint64_t full[kTmaStages];
     long long lo[2][kWarps], hi[2][kWarps];
+    long long rbq[2];
 };
-template <bool GATED>
-__device__ __noinline__ double matvec_phase(const TmaSpmvArgs *mv, TmaSpmvState *st, unsigned char *s_dyn, MatvecPhaseShared *sh,
-                                            const GhostGate *gate) {
+template <bool GATED, int PART>
+__device__ __forceinline__ double matvec_phase(const TmaSpmvArgs &mv, TmaSpmvState &st, unsigned char *s_dyn, MatvecPhaseShared *sh,
+                                               const GhostGate *gate, TmaCursor &cur, unsigned long long *counter) {
     double dacc[1] = {0.0};
-    const TmaSpmvArgs a = *mv;
-    TmaSpmvState s = *st;
-    csr_tma_run<1, true, GATED>(a, s, s_dyn, sh->full, sh->lo, sh->hi, dacc, gate);
-    *st = s;
+    TmaDynamic dyn;
+    dyn.counter = counter;
+    dyn.s_rbq = sh->rbq;
+    // several ranks: start from the middle of the slab, so that the row blocks at its two ends -- the ones that read
+    // ghost columns -- come up when the neighbours' halo has long arrived
+    dyn.rot = GATED ? mv.n_row_blocks / 2 : 0;
+    // Measured on the 256^3 system: dynamic hand-out shortens the tail of the phase (10 -> 5 us) but the walk itself
+    // gets 12 us slower; the static strided walk wins for the mat-vec (it is not limited by per-SM memory share
+    // the way the vector phases are), so DYN stays off here.
+    constexpr bool kDynamicMatvec = false;
+    csr_tma_run<1, true, GATED, PART, kDynamicMatvec>(mv, st, s_dyn, sh->full, sh->lo, sh->hi, dacc, gate, &cur, &dyn);
     return dacc[0];
 }
 
@@ -232,11 +295,13 @@ __global__ void __launch_bounds__(kBlock, LSK_TMA_MINB) cg_persistent_kernel(CgA
     extern __shared__ __align__(128) unsigned char s_dyn[];
     __shared__ __align__(8) MatvecPhaseShared s_mv;
     __shared__ __align__(8) uint64_t s_vbar[kVecStages];
+    __shared__ long long s_vchunk[kVecStages];
     TmaSpmvState st;
     csr_tma_init(st, s_mv.full);
     VecRing ring;
     ring.smem = s_dyn;
     ring.bar = s_vbar;
+    ring.chunk = s_vchunk;
     ring.phases = 0;
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -256,8 +321,6 @@ __global__ void __launch_bounds__(kBlock, LSK_TMA_MINB) cg_persistent_kernel(CgA
     __shared__ unsigned long long s_tmark;
     const bool scribe = (blockIdx.x == 0 && threadIdx.x == 0);
     if (threadIdx.x == 0) {
-        gate.own_lo = a.own_lo;
-        gate.own_n = (unsigned long long) a.n;
         gate.blocks = a.ghost_blocks;
         gate.nflags = 0;
         gate.want = halo_base;
@@ -273,6 +336,7 @@ __global__ void __launch_bounds__(kBlock, LSK_TMA_MINB) cg_persistent_kernel(CgA
 
     double rr = *reinterpret_cast<volatile double *>(a.rr_cur);
     double pq = 0.0;
+    unsigned int gen = *reinterpret_cast<volatile unsigned int *>(&gs->gen);  // written back by the scribe at the end
     bool err = false;
     int done = 0;
 
@@ -290,13 +354,26 @@ __global__ void __launch_bounds__(kBlock, LSK_TMA_MINB) cg_persistent_kernel(CgA
         for (int64_t e = (int64_t) blockIdx.x * kBlock + threadIdx.x; e < nedge; e += (int64_t) gridDim.x * kBlock)
             body(e < a.head ? e : tail0 + (e - a.head));
     };
+    TmaCursor cur;
+    if (multi) matvec_phase<true, 1>(a.mv, st, s_dyn, &s_mv, &gate, cur, &gs->work[0]);
+    else matvec_phase<false, 1>(a.mv, st, s_dyn, &s_mv, nullptr, cur, &gs->work[0]);
     for (int it = 0; it < a.niter; ++it) {
         // ---- phase A: q = A p, partial p.q -------------------------------------------------------------
         if (threadIdx.x == 0) gate.want = halo_base + (unsigned long long) it;  // published by the mat-vec's first CTA barrier
-        const double pq_part = multi ? matvec_phase<true>(&a.mv, &st, s_dyn, &s_mv, &gate)
-                                     : matvec_phase<false>(&a.mv, &st, s_dyn, &s_mv, nullptr);
-        pq = grid_sync<true>(gs, peers, pq_part, err, [] {});
+        // (its prologue -- first rects, first matrix tile in flight -- ran before the previous grid barrier)
+#ifdef LSK_EXP_NO_PREFETCH
+        if (it > 0) {
+            if (multi) matvec_phase<true, 1>(a.mv, st, s_dyn, &s_mv, &gate, cur, &gs->work[0]);
+            else matvec_phase<false, 1>(a.mv, st, s_dyn, &s_mv, nullptr, cur, &gs->work[0]);
+        }
+#endif
+        const double pq_part = multi ? matvec_phase<true, 2>(a.mv, st, s_dyn, &s_mv, &gate, cur, &gs->work[0])
+                                     : matvec_phase<false, 2>(a.mv, st, s_dyn, &s_mv, nullptr, cur, &gs->work[0]);
         lap(0);
+        pq = grid_sync<true>(gs, gen, peers, pq_part, err, [&] {
+            if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long *>(&gs->work[0]) = 0ull;  // everybody is done with phase A
+        });
+        lap(1);
         if (err) break;
 
         // ---- phase B: x += (rr/pq) p;  r += ((-1*rr)/pq) q;  partial r.r -------------------------------------
@@ -305,7 +382,7 @@ __global__ void __launch_bounds__(kBlock, LSK_TMA_MINB) cg_persistent_kernel(CgA
         double racc = 0.0;
         {
             const double *const in[4] = {a.p, a.q, a.x, a.r};
-            vec_stream<4>(ring, in, a.head, a.npacks * 4, false, [&](int64_t i, const double (&v)[4][2]) {
+            vec_stream<4>(ring, in, a.head, a.npacks * 4, &gs->work[1], 0, [](int64_t, int) {}, [&](int64_t i, const double (&v)[4][2]) {
                 const double x0 = fma_rn(a1, v[0][0], v[2][0]), x1 = fma_rn(a1, v[0][1], v[2][1]);
                 const double r0 = fma_rn(a2, v[1][0], v[3][0]), r1 = fma_rn(a2, v[1][1], v[3][1]);
                 *reinterpret_cast<double2 *>(a.x + i) = make_double2(x0, x1);
@@ -320,8 +397,11 @@ __global__ void __launch_bounds__(kBlock, LSK_TMA_MINB) cg_persistent_kernel(CgA
             a.r[i] = rn;
             racc = fma(rn, rn, racc);
         });
-        const double rr_new = grid_sync<true>(gs, peers, racc, err, [] {});
-        lap(1);
+        lap(2);
+        const double rr_new = grid_sync<true>(gs, gen, peers, racc, err, [&] {
+            if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long *>(&gs->work[1]) = 0ull;  // everybody is done with phase B
+        });
+        lap(3);
         if (err) break;
 
         // ---- phase C: p = fma(rr_new/rr, p, r), boundary mirrored into the neighbours' ghosts -------------
@@ -329,10 +409,28 @@ __global__ void __launch_bounds__(kBlock, LSK_TMA_MINB) cg_persistent_kernel(CgA
         bool remote = false;
         {
             const double *const in[2] = {a.p, a.r};
-            vec_stream<2>(ring, in, a.head, a.npacks * 4, multi, [&](int64_t i, const double (&v)[2][2]) {
+            bool chunk_halo = false;  // this chunk overlaps a range that is mirrored into a neighbour (uniform per chunk)
+            auto begin = [&](int64_t i0, int cnt) {
+                chunk_halo = false;
+                if (multi) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        chunk_halo |= (q < a.halo.nmoves && i0 + cnt > a.halo.lo[q] && i0 < a.halo.lo[q] + a.halo.m[q].n);
+                }
+            };
+            // chunks from the first one that overlaps a send range not at the start of the vector are taken first:
+            // their results also travel over NVLink, which then overlaps the rest of the phase
+            int64_t rot = 0;
+            if (multi) {
+                int64_t first = -1;
+                for (int q = 0; q < a.halo.nmoves; ++q)
+                    if (a.halo.m[q].n > 0 && a.halo.lo[q] > a.head && (first < 0 || a.halo.lo[q] < first)) first = a.halo.lo[q];
+                if (first >= 0) rot = (first - a.head) / (kVecStageBytes / 16);
+            }
+            vec_stream<2>(ring, in, a.head, a.npacks * 4, &gs->work[2], rot, begin, [&](int64_t i, const double (&v)[2][2]) {
                 const double p0 = fma_rn(beta, v[0][0], v[1][0]), p1 = fma_rn(beta, v[0][1], v[1][1]);
                 *reinterpret_cast<double2 *>(a.p + i) = make_double2(p0, p1);
-                if (multi) {
+                if (chunk_halo) {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         if (q < a.halo.nmoves && i + 2 > a.halo.lo[q] && i < a.halo.lo[q] + a.halo.m[q].n) {
@@ -364,8 +462,19 @@ __global__ void __launch_bounds__(kBlock, LSK_TMA_MINB) cg_persistent_kernel(CgA
         });
         if (remote) __threadfence_system();  // my stores into the neighbours' memory are visible there
         const bool final_it = (it + 1 == a.niter);
+        // the ring is free again: start the next mat-vec's first matrix tile now, so that it lands during the barrier
+#ifdef LSK_EXP_NO_PREFETCH
+        if (false) {
+#else
+        if (!final_it) {
+#endif
+            if (multi) matvec_phase<true, 1>(a.mv, st, s_dyn, &s_mv, &gate, cur, &gs->work[0]);
+            else matvec_phase<false, 1>(a.mv, st, s_dyn, &s_mv, nullptr, cur, &gs->work[0]);
+        }
         const unsigned long long e_now = halo_base + (unsigned long long) it + 1ull;
-        grid_sync<false>(gs, peers, 0.0, err, [&] {
+        lap(4);
+        grid_sync<false>(gs, gen, peers, 0.0, err, [&] {
+            if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long *>(&gs->work[2]) = 0ull;  // everybody is done with phase C
             if (!multi) return;
             // every CTA's remote stores are fenced and ordered before its arrival: publish the epoch
             const unsigned long long t0 = global_ns();
@@ -389,17 +498,18 @@ __global__ void __launch_bounds__(kBlock, LSK_TMA_MINB) cg_persistent_kernel(CgA
                 }
             }
         });
-        lap(2);
+        lap(5);
         if (scribe) {
             a.hist[s_hcount % a.hist_cap] = rr_new;  // residual_norm_squared.push_back (src/CGSolver.hpp:53)
             ++s_hcount;
-            gs->phase_ns[3] += 1ull;
+            gs->phase_ns[6] += 1ull;
         }
         rr = rr_new;
         ++done;
         if (err) break;
     }
     if (scribe) {
+        gs->gen = gen;  // every CTA has left the last barrier's arrival side; nobody reads gen again in this launch
         *a.hist_count = s_hcount;
         if (done > 0) {
             *a.rr_cur = rr;
@@ -543,10 +653,10 @@ int lsk_ctx_error(lsk_ctx *ctx, lsk_stream s, int *host_out) {
     return 0;
 }
 
-int lsk_cg_phase_stats(lsk_ctx *ctx, lsk_stream s, uint64_t *host_out4) {
-    if (!ctx || !host_out4) return LSK_E_INVALID;
+int lsk_cg_phase_stats(lsk_ctx *ctx, lsk_stream s, uint64_t *host_out7) {
+    if (!ctx || !host_out7) return LSK_E_INVALID;
     const GridSync *gs = static_cast<const GridSync *>(ctx->gridsync);
-    LSK_RETURN_IF_CUDA(cudaMemcpyAsync(host_out4, gs->phase_ns, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, (cudaStream_t) s));
+    LSK_RETURN_IF_CUDA(cudaMemcpyAsync(host_out7, gs->phase_ns, 7 * sizeof(uint64_t), cudaMemcpyDeviceToHost, (cudaStream_t) s));
     LSK_RETURN_IF_CUDA(cudaStreamSynchronize((cudaStream_t) s));
     return 0;
 }

@@ -102,9 +102,13 @@ __device__ __forceinline__ longlong2 ld_rect_stream(const lsk_rect *p) {
 // weak, L1-cacheable load on the COHERENT path (never LDG.CONSTANT): for vectors that the same kernel
 // also writes in another phase, made visible by a grid barrier (fence + L1 invalidation)
 __device__ __forceinline__ double ld_f64(const double *p) {
+#ifdef LSK_EXP_NC_GATHER
+    return __ldg(p);
+#else
     double v;
     asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
+#endif
 }
 // L2 load (bypasses L1): ghost values stored by a peer GPU while this kernel runs
 __device__ __forceinline__ double ld_f64_cg(const double *p) {
@@ -126,14 +130,13 @@ struct TmaSpmvArgs {
     const double *dot_w;     // NDOT >= 1
 };
 
-// Ghost columns (outside [own_lo, own_lo + own_n)) are written by peer GPUs during the kernel: a thread
-// that meets one waits until every peer it receives from has published epoch `want`, then reads
-// through L2.  Everything else is local and already ordered by the grid barrier.
+// Ghost columns (outside the owned rows) are written by peer GPUs while the kernel runs.  Before a CTA
+// consumes a row block that references one (blocks[rb] != 0, computed once at plan time; null = every block),
+// its thread 0 waits until every peer this rank receives from has published epoch `want`, then fences at
+// system scope -- MEMBAR.SC.SYS + CCTL.IVALL, which also drops every L1 line of the SM -- and the CTA barrier
+// of the tile loop releases the other threads, which then gather ghosts like any other column.
 struct GhostGate {
-    long long own_lo;
-    unsigned long long own_n;
-    const unsigned char *blocks;  // optional: blocks[rb] != 0 <=> row block rb references a ghost column
-                                  // (computed once at plan time); null = check every chunk
+    const unsigned char *blocks;
     int nflags;
     const volatile unsigned long long *flag[4];
     unsigned long long want;
@@ -168,10 +171,28 @@ __device__ __forceinline__ void csr_tma_init(TmaSpmvState &st, uint64_t *s_full)
 //             true : x was written earlier in this kernel (plain ld.global)
 //   GATED     (needs COHERENT) ghost columns are guarded by `gate`; row blocks that reference none (per
 //             gate->blocks) take the same straight-line gather loop as the ungated kernel
-template <int NDOT, bool COHERENT, bool GATED>
+//   PART      0: the whole mat-vec.  1: only the prologue -- the rects of this CTA's first two row blocks are
+//             loaded into `cur` and the TMA copy of its first tile is started (the matrix is constant, so a
+//             persistent kernel does this BEFORE the grid barrier that precedes the mat-vec).  2: the rest.
+//   DYN       row blocks are handed out first come, first served from a global counter instead of the static
+//             blockIdx.x + k * gridDim.x walk: SMs do not all get the same share of the memory system, and with a
+//             static split HBM idles while the slow ones finish.  Thread 0 grabs two blocks ahead (the atomic's
+//             latency hides behind a whole block) and broadcasts the id through shared memory one CTA barrier
+//             before it is needed.  Grabbed index g maps to row block (g + rot) % n_row_blocks.
+struct TmaCursor {
+    long long lo, hi1, nlo, nhi1;
+    long long rb, rb_next, pend;
+};
+struct TmaDynamic {
+    unsigned long long *counter;  // global, zero at the start of the mat-vec
+    long long *s_rbq;             // shared, 2 entries
+    long long rot;
+};
+template <int NDOT, bool COHERENT, bool GATED, int PART = 0, bool DYN = false>
 __device__ __forceinline__ void csr_tma_run(const TmaSpmvArgs &a, TmaSpmvState &st, unsigned char *s_dyn, uint64_t *s_full,
                                             long long (*s_lo)[kWarps], long long (*s_hi)[kWarps],
-                                            double (&dacc)[NDOT > 0 ? NDOT : 1], const GhostGate *gate) {
+                                            double (&dacc)[NDOT > 0 ? NDOT : 1], const GhostGate *gate,
+                                            TmaCursor *cur = nullptr, const TmaDynamic *dyn = nullptr) {
     constexpr int S = kTmaStages;
     long long (*s_col)[kTmaTile] = reinterpret_cast<long long (*)[kTmaTile]>(s_dyn);
     double (*s_ent)[kTmaTile] = reinterpret_cast<double (*)[kTmaTile]>(s_dyn + (size_t) S * kTmaTile * sizeof(long long));
@@ -185,28 +206,12 @@ __device__ __forceinline__ void csr_tma_run(const TmaSpmvArgs &a, TmaSpmvState &
     const int64_t k_base = a.k_base;
     const double *x = a.x;
     const uint64_t policy = st.policy;
-    bool ghost_ok = false;
-    // copies in registers: `gate` itself escapes to a non-inlined call
-    static_assert(COHERENT || !GATED, "a gate needs the coherent path");
-    // the gate's fields are re-read from (shared) memory where they are needed -- only flagged row blocks do --
-    // instead of occupying registers across the whole tile loop
+    bool ghost_ok = false;  // thread 0: the gate has been passed in this run
     auto block_checked = [&](int64_t rb) -> bool {
         if constexpr (!GATED) return false;
         const unsigned char *blk_flags = gate->blocks;
         if (blk_flags == nullptr) return true;
         return rb < n_row_blocks ? (__ldg(blk_flags + rb) != 0) : false;
-    };
-
-    // ghost-aware gather (COHERENT only): the slow path of a chunk that contains a ghost column
-    auto gather_checked = [&](long long c, long long own_lo, unsigned long long own_n) -> double {
-        if ((unsigned long long) (c - own_lo) >= own_n) {
-            if (!ghost_ok) {
-                ghost_gate_wait(*gate);
-                ghost_ok = true;
-            }
-            return ld_f64_cg(x + c);
-        }
-        return ld_f64(x + c);
     };
 
     auto load_rect = [&](int64_t rb, long long &lo, long long &hi1) {
@@ -215,7 +220,11 @@ __device__ __forceinline__ void csr_tma_run(const TmaSpmvArgs &a, TmaSpmvState &
         if (rb < n_row_blocks) {
             const int64_t r = rb * rpb + tid;
             if (tid < rpb && r < rows) {
+#ifdef LSK_EXP_RECT_LDG
+                const longlong2 rc = __ldg(reinterpret_cast<const longlong2 *>(rowptr + r));
+#else
                 const longlong2 rc = ld_rect_stream(rowptr + r);
+#endif
                 if (rc.y >= rc.x) {
                     lo = rc.x - k_base;
                     hi1 = rc.y + 1 - k_base;
@@ -273,11 +282,11 @@ __device__ __forceinline__ void csr_tma_run(const TmaSpmvArgs &a, TmaSpmvState &
     // middle (kk = mine/2, wrapping): the first and last row blocks of a banded matrix are the ones that read
     // ghost columns, and by mid-phase the neighbours' halo has long arrived -- nobody stalls at the phase start.
     int64_t rb_start = blockIdx.x;
-    if constexpr (GATED) {
+    if constexpr (GATED && !DYN) {
         const int64_t mine = n_row_blocks > (int64_t) blockIdx.x ? (n_row_blocks - 1 - blockIdx.x) / G + 1 : 0;
         rb_start += (mine / 2) * G;
     }
-    auto next_rb = [&](int64_t r) -> int64_t {  // successor in walking order; n_row_blocks = none
+    auto next_rb = [&](int64_t r) -> int64_t {  // static walk: successor; n_row_blocks = none
         int64_t n = r + G;
         if constexpr (GATED) {
             if (n >= n_row_blocks) n = blockIdx.x;
@@ -285,23 +294,70 @@ __device__ __forceinline__ void csr_tma_run(const TmaSpmvArgs &a, TmaSpmvState &
         }
         return n;
     };
-    int64_t rb = rb_start < n_row_blocks ? rb_start : n_row_blocks;
-    int64_t rb_next = rb < n_row_blocks ? next_rb(rb) : n_row_blocks;
+    auto dyn_map = [&](long long g) -> int64_t {  // grabbed index -> row block
+        if (g >= n_row_blocks) return n_row_blocks;
+        long long c = g + dyn->rot;
+        if (c >= n_row_blocks) c -= n_row_blocks;
+        return c;
+    };
+    auto dyn_grab = [&](long long prev) -> long long {  // thread 0; stops asking once the work has run out
+        return prev < n_row_blocks ? (long long) atomicAdd(dyn->counter, 1ull) : prev;
+    };
+    int64_t rb, rb_next;
+    long long pend = 0;  // DYN, thread 0: grabbed index of the block after rb_next
+    int par = 0;
+    if constexpr (DYN) {
+        if constexpr (PART != 2) {
+            if (tid == 0) dyn->s_rbq[0] = (long long) atomicAdd(dyn->counter, 2ull);
+            __syncthreads();
+            const long long g0 = dyn->s_rbq[0];
+            rb = dyn_map(g0);
+            rb_next = dyn_map(g0 + 1);
+            if (tid == 0) pend = dyn_grab(g0 + 1);
+        }
+    } else {
+        rb = rb_start < n_row_blocks ? rb_start : n_row_blocks;
+        rb_next = rb < n_row_blocks ? next_rb(rb) : n_row_blocks;
+    }
     long long lo, hi1, jb, je, nlo, nhi1;
-    load_rect(rb, lo, hi1);
-    publish_span(0, lo, hi1);
-    __syncthreads();  // also publishes the mbarrier inits (first run) / retires the previous run's tiles
-    read_span(0, jb, je);
-    long long t0 = tile_start(jb);
+    long long t0;
+    if constexpr (PART != 2) {
+        load_rect(rb, lo, hi1);
+        publish_span(0, lo, hi1);
+        __syncthreads();  // also publishes the mbarrier inits (first run) / retires the previous run's tiles
+        read_span(0, jb, je);
+        t0 = tile_start(jb);
+        if (tid == 0 && rb < n_row_blocks) issue_tile(0, t0, jb, je);
+        load_rect(rb_next, nlo, nhi1);
+        if constexpr (PART == 1) {
+            cur->lo = lo; cur->hi1 = hi1; cur->nlo = nlo; cur->nhi1 = nhi1;
+            if constexpr (DYN) { cur->rb = rb; cur->rb_next = rb_next; cur->pend = pend; }
+            return;
+        }
+    } else {
+        lo = cur->lo; hi1 = cur->hi1; nlo = cur->nlo; nhi1 = cur->nhi1;
+        if constexpr (DYN) { rb = cur->rb; rb_next = cur->rb_next; pend = cur->pend; }
+        read_span(0, jb, je);  // still published: nothing has touched s_lo / s_hi since the prologue
+        t0 = tile_start(jb);
+    }
     int stage = 0, pb = 1;
-    if (tid == 0 && rb < n_row_blocks) issue_tile(0, t0, jb, je);
-    load_rect(rb_next, nlo, nhi1);
     bool checked = block_checked(rb), nchecked = block_checked(rb_next);
+    bool new_block = true;
     double acc = 0.0;
 
     while (rb < n_row_blocks) {
         const bool last_tile = (t0 + kTmaTile >= je);
         if (last_tile) publish_span(pb, nlo, nhi1);
+        if constexpr (DYN) {
+            if (new_block && tid == 0) dyn->s_rbq[par] = pend;  // read by everybody at the end of this block
+            new_block = false;
+        }
+        if constexpr (GATED) {
+            if (checked && tid == 0 && !ghost_ok) {  // released to the other threads by the barrier below
+                ghost_gate_wait(*gate);
+                ghost_ok = true;
+            }
+        }
         // one barrier per tile: (i) stage^1, consumed last iteration, may now be overwritten;
         // (ii) the next block's span is published; (iii) ragged elements stored by thread 0 are visible
         __syncthreads();
@@ -334,27 +390,8 @@ __device__ __forceinline__ void csr_tma_run(const TmaSpmvArgs &a, TmaSpmvState &
             for (; j + kChunk <= kb; j += kChunk) {  // full chunks: no predication
                 const int o = (int) (j - t0);
                 double xv[kChunk];
-                if (GATED && checked) {
-                    const long long own_lo = gate->own_lo;
-                    const unsigned long long own_n = gate->own_n;
-                    long long c[kChunk];
-                    bool any_ghost = false;
 #pragma unroll
-                    for (int e = 0; e < kChunk; ++e) {
-                        c[e] = sc[o + e];
-                        any_ghost |= ((unsigned long long) (c[e] - own_lo) >= own_n);
-                    }
-                    if (any_ghost) {  // rare: one branch per chunk keeps the common path straight-line
-#pragma unroll
-                        for (int e = 0; e < kChunk; ++e) xv[e] = gather_checked(c[e], own_lo, own_n);
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < kChunk; ++e) xv[e] = ld_f64(x + c[e]);
-                    }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < kChunk; ++e) xv[e] = COHERENT ? ld_f64(x + sc[o + e]) : __ldg(x + sc[o + e]);
-                }
+                for (int e = 0; e < kChunk; ++e) xv[e] = COHERENT ? ld_f64(x + sc[o + e]) : __ldg(x + sc[o + e]);
 #pragma unroll
                 for (int e = 0; e < kChunk; ++e) acc = add_rn(acc, mul_rn(se[o + e], xv[e]));
             }
@@ -362,28 +399,9 @@ __device__ __forceinline__ void csr_tma_run(const TmaSpmvArgs &a, TmaSpmvState &
                 const int o = (int) (j - t0);
                 const int rem = (int) (kb - j);
                 double xv[kChunk - 1];
-                if (GATED && checked) {
-                    const long long own_lo = gate->own_lo;
-                    const unsigned long long own_n = gate->own_n;
-                    long long c[kChunk - 1];
-                    bool any_ghost = false;
 #pragma unroll
-                    for (int e = 0; e < kChunk - 1; ++e) {
-                        c[e] = (e < rem) ? sc[o + e] : own_lo;
-                        any_ghost |= ((unsigned long long) (c[e] - own_lo) >= own_n);
-                    }
-                    if (any_ghost) {
-#pragma unroll
-                        for (int e = 0; e < kChunk - 1; ++e) xv[e] = (e < rem) ? gather_checked(c[e], own_lo, own_n) : 0.0;
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < kChunk - 1; ++e) xv[e] = (e < rem) ? ld_f64(x + c[e]) : 0.0;
-                    }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < kChunk - 1; ++e)
-                        xv[e] = (e < rem) ? (COHERENT ? ld_f64(x + sc[o + e]) : __ldg(x + sc[o + e])) : 0.0;
-                }
+                for (int e = 0; e < kChunk - 1; ++e)
+                    xv[e] = (e < rem) ? (COHERENT ? ld_f64(x + sc[o + e]) : __ldg(x + sc[o + e])) : 0.0;
 #pragma unroll
                 for (int e = 0; e < kChunk - 1; ++e)
                     if (e < rem) acc = add_rn(acc, mul_rn(se[o + e], xv[e]));
@@ -398,7 +416,15 @@ __device__ __forceinline__ void csr_tma_run(const TmaSpmvArgs &a, TmaSpmvState &
             }
             acc = 0.0;
             rb = rb_next;
-            rb_next = rb < n_row_blocks ? next_rb(rb) : n_row_blocks;
+            if constexpr (DYN) {
+                const long long g2 = dyn->s_rbq[par];
+                par ^= 1;
+                rb_next = dyn_map(g2);
+                if (tid == 0) pend = dyn_grab(g2);
+                new_block = true;
+            } else {
+                rb_next = rb < n_row_blocks ? next_rb(rb) : n_row_blocks;
+            }
             lo = nlo;
             hi1 = nhi1;
             jb = njb;

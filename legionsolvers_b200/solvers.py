@@ -85,12 +85,13 @@ class Runtime:
         return {"ar_calls": out[0], "ar_ns": out[1], "halo_calls": out[2], "halo_ns": out[3]}
 
     def cg_phase_stats(self) -> dict:
-        """Accounting of the persistent CG kernel (CTA 0's view): ns in {mat-vec + p.q sync, x/r update + r.r
-        sync, p update + halo sync} and iterations, accumulated since the runtime was created.  Synchronises."""
+        """Accounting of the persistent CG kernel (CTA 0's view): ns in the three phases and in the grid barrier
+        that ends each, and iterations, accumulated since the runtime was created.  Synchronises."""
         self.fence()
-        out = (C.c_uint64 * 4)()
+        out = (C.c_uint64 * 7)()
         _check(_abi.lib().lsk_cg_phase_stats(self.ctx, self.stream, out), "lsk_cg_phase_stats")
-        return {"matvec_ns": out[0], "update_ns": out[1], "direction_ns": out[2], "iterations": out[3]}
+        return {"matvec_ns": out[0], "matvec_sync_ns": out[1], "update_ns": out[2], "update_sync_ns": out[3],
+                "direction_ns": out[4], "direction_sync_ns": out[5], "iterations": out[6]}
 
     def comm_error(self) -> int:
         out = C.c_int()
