@@ -232,7 +232,7 @@ def run_ours(args):
     pl.add_rhs_vector(rhs)
     pl.add_row_partitioned_matrix(mat, 0, 0)
     if args.solver == "cg":
-        cg = S.CGSolver(pl, fused=not args.unfused)
+        cg = S.CGSolver(pl, fused=not args.unfused, persistent=True if args.persistent else None)
     elif args.solver == "bicgstab":
         cg = S.BiCGStabSolver(pl, fused=not args.unfused)
     else:
@@ -293,6 +293,11 @@ def run_ours(args):
         ph1 = rt.cg_phase_stats()
         its = max(1, ph1["iterations"] - ph0["iterations"])
         phase_us = {k[:-3] + "_us_per_iteration": round((ph1[k] - ph0[k]) / 1e3 / its, 2) for k in ph1 if k.endswith("_ns")}
+        if dist is not None:  # every rank's CTA-0 view, in the order of the keys above
+            mine_ph = torch.tensor(list(phase_us.values()), dtype=torch.float64, device="cuda")
+            all_ph = [torch.zeros_like(mine_ph) for _ in range(world)]
+            dist.all_gather(all_ph, mine_ph)
+            phase_us = {"keys": list(phase_us.keys()), "by_rank": [[round(float(x), 2) for x in v] for v in all_ph]}
 
     # ---- roofline of the dominant kernel: the fused CSR SpMV + p.Ap, timed alone on the same stream ----
     L = _abi.lib()
@@ -319,6 +324,12 @@ def run_ours(args):
     s1.record()
     torch.cuda.synchronize()
     spmv_ms = s0.elapsed_time(s1) / reps
+    spmv_ms_by_rank = None
+    if dist is not None:  # the same kernel on every rank's slab: tells a slow GPU from a slow collective
+        mine_ms = torch.tensor([spmv_ms], dtype=torch.float64, device="cuda")
+        all_ms = [torch.zeros_like(mine_ms) for _ in range(world)]
+        dist.all_gather(all_ms, mine_ms)
+        spmv_ms_by_rank = [round(float(v[0]), 5) for v in all_ms]
     spmv_bytes = 16 * nnz_local + 32 * n_local  # 16/nnz + rowptr 16 + x 8 + y 8 per row
     achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
     peaks_file = ROOT / "MEASURED_PEAKS.json"
@@ -405,7 +416,8 @@ def run_ours(args):
                 "collectives": "none (1 GPU)" if world == 1 else rt.collectives,
                 "comm_error": rt.comm_error() if world > 1 else 0,
                 "time_inside_collectives": comm_us,
-                "persistent_kernel_phases_rank0": phase_us,
+                "persistent_kernel_phases": phase_us,
+                "spmv_ms_per_launch_by_rank": spmv_ms_by_rank,
                 "residual_norm_squared_last": rr_final,
                 "iteration_roofline": {"bytes_per_iteration_per_gpu": iter_bytes, "frac_of_peak": iter_frac},
             },
@@ -440,6 +452,8 @@ def main():
                     help="cg is the headline; bicgstab / gmres (restart 10, as BenchmarkStencil) are reported for the other configs")
     ap.add_argument("--shape", type=str, default=None, help="developer override nx,ny,nz of the workload's grid")
     ap.add_argument("--unfused", action="store_true", help="run the reference's unfused call sequence on the GPU")
+    ap.add_argument("--persistent", action="store_true",
+                    help="CG as one persistent kernel per step (default: three leaf kernels per iteration, ~2 %% faster; also LSK_CG_PERSISTENT=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

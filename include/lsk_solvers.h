@@ -108,7 +108,9 @@ int lsk_planner_vector_from_host(lsk_planner *pl, int vec, int space, const doub
 
 /* ---- solvers (src/CGSolver.hpp, src/BiCGStabSolver.hpp, src/GMRESSolver.hpp) -------------------------------------- */
 enum lsk_solver_kind { LSK_SOLVER_CG = 1, LSK_SOLVER_BICGSTAB = 2, LSK_SOLVER_GMRES = 3 }; /* BenchmarkStencil -solver */
-/* fused = 0: the reference's call sequence, one launch per planner call; 1: fewest-pass form */
+/* fused = 0: the reference's call sequence, one launch per planner call; 1: fewest-pass form (leaf kernels);
+ * 2 (CG): fewest-pass form as ONE persistent kernel per batch of steps (lsk_cg_steps_f64) when the problem is
+ * eligible -- one CSR block, one piece per GPU -- else as 1 */
 int lsk_solver_create(lsk_planner *pl, int kind, int restart, int fused, lsk_solver **out);
 int lsk_solver_destroy(lsk_solver *s);
 /* CGSolver on one CSR piece per GPU defers: consecutive steps are issued as ONE persistent-kernel launch

@@ -535,8 +535,6 @@ int lsk_cg_steps_supported(const lsk_cg_problem *pb) {
     const uintptr_t e = reinterpret_cast<uintptr_t>(pb->entry), c = reinterpret_cast<uintptr_t>(pb->col);
     if (e % 8 != 0 || c % 8 != 0 || ((e >> 3) & 1) != ((c >> 3) & 1)) return 0;  // TMA tiles: col/entry 16-byte aligned together
     if (pb->nmoves < 0 || pb->nmoves > 4) return 0;
-    static const char *off = getenv("LSK_CG_PERSISTENT");
-    if (off && off[0] == '0') return 0;
     return 1;
 }
 

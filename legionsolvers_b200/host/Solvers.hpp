@@ -29,12 +29,14 @@ private:
 
 public:
     // constructor (src/CGSolver.hpp:32-44): workspace(3); P <- RHS; R <- RHS (x0 = 0 assumed); rr0 = R.R
-    explicit CGSolver(SquarePlanner<T> &planner_, bool fused_ = true, int64_t history_capacity = 1 << 16)
+    // `use_persistent`: run the whole step as the persistent kernel (lsk_cg_steps_f64) when the problem is eligible.
+    // Off by default: on the 256^3 benchmark the three leaf kernels are ~2 % faster at 1, 2 and 8 GPUs.
+    explicit CGSolver(SquarePlanner<T> &planner_, bool fused_ = true, int64_t history_capacity = 1 << 16, bool use_persistent = false)
         : planner(planner_), residual_norm_squared(planner_.get_runtime(), history_capacity),
           negative_one(planner_.get_runtime(), static_cast<T>(-1)), fused(fused_), rr_cur(planner_.get_runtime()),
           rr_new(planner_.get_runtime()), p_norm(planner_.get_runtime()) {
         planner.allocate_workspace(3);
-        if (fused) {
+        if (fused && use_persistent) {
             lsk_cg_problem pb{};
             lsk_halo_move moves[4];
             persistent = planner.cg_problem(SOL, R, P, Q, &pb, moves);

@@ -387,7 +387,7 @@ int lsk_solver_create(lsk_planner *pl, int kind, int restart, int fused, lsk_sol
         auto h = std::make_unique<lsk_solver>();
         h->rt = pl->rt;
         h->kind = kind;
-        if (kind == LSK_SOLVER_CG) h->cg = std::make_unique<CGSolver<double>>(*pl->pl, fused != 0);
+        if (kind == LSK_SOLVER_CG) h->cg = std::make_unique<CGSolver<double>>(*pl->pl, fused != 0, int64_t(1) << 16, fused == 2);
         else if (kind == LSK_SOLVER_BICGSTAB) h->bicg = std::make_unique<BiCGStabSolver<double>>(*pl->pl, fused != 0);
         else if (kind == LSK_SOLVER_GMRES) {
             if (restart <= 0) pl->rt->fail(LSK_E_INVALID, "GMRES restart");

@@ -7,6 +7,7 @@ into liblsk.so.  numpy arrays are host staging only.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -359,8 +360,12 @@ class _Solver:
 class CGSolver(_Solver):
     KIND = SOLVER_CG
 
-    def __init__(self, planner, fused=True):
-        super().__init__(planner, 0, fused)
+    def __init__(self, planner, fused=True, persistent=None):
+        """persistent: run the step as the persistent CG kernel when eligible (None: LSK_CG_PERSISTENT=1 in the
+        environment switches it on; the default is the leaf-kernel form, which is ~2 % faster on the benchmark)."""
+        if persistent is None:
+            persistent = os.environ.get("LSK_CG_PERSISTENT", "0") == "1"
+        super().__init__(planner, 0, 2 if (fused and persistent) else int(bool(fused)))
 
     @property
     def persistent(self) -> bool:

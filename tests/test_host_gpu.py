@@ -247,15 +247,17 @@ CG_CASES = [
 
 
 @pytest.mark.parametrize("name,dim_flag,shape,pieces,spaces,its", CG_CASES, ids=[c[0] for c in CG_CASES])
-@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("fused", [True, False, "persistent"])
 def test_cg_history_vs_oracle(rt, oracle, name, dim_flag, shape, pieces, spaces, its, fused):
-    """CG residual histories within 1e-10 relative (north_star tolerance), solution within 1e-10."""
+    """CG residual histories within 1e-10 relative (north_star tolerance), solution within 1e-10.
+    "persistent" = the whole step as one persistent kernel where eligible (one piece of one CSR block)."""
     from legionsolvers_b200.solvers import CGSolver
 
     off, val = oracle.benchmark_stencil(dim_flag)
     m = oracle.stencil_csr(shape, off, val)
     pl, opl, _, _ = build_system(rt, oracle, m, pieces, spaces=spaces)
-    cg, ocg = CGSolver(pl, fused=fused), oracle.CGSolver(opl)
+    cg, ocg = CGSolver(pl, fused=bool(fused), persistent=(fused == "persistent")), oracle.CGSolver(opl)
+    assert cg.persistent == (fused == "persistent" and pieces == 1 and spaces == 1)
     tid = new_trace_id()
     for i in range(its):
         rt.begin_trace(tid)
@@ -364,7 +366,7 @@ def test_kernel_launch_accounting(rt, oracle):
     off, val = oracle.benchmark_stencil(3)
     m = oracle.stencil_csr((16, 16, 16), off, val)
     pl, _, _, _ = build_system(rt, oracle, m, 1)
-    cg = CGSolver(pl, fused=True)
+    cg = CGSolver(pl, fused=True, persistent=True)
     rt.fence()
     before = rt.kernel_launches
     tid = new_trace_id()
@@ -376,9 +378,22 @@ def test_kernel_launch_accounting(rt, oracle):
     # one piece of one CSR block: the whole step is one persistent-kernel launch
     assert cg.persistent
     assert rt.kernel_launches - before == 5 * 1
-    # the leaf-task form of the fused step on 4 local pieces
+    # the leaf-kernel form of the fused step: spmv+dot, cg_update, xpay, history append
+    pl1, _, _, _ = build_system(rt, oracle, m, 1)
+    cg1 = CGSolver(pl1, fused=True, persistent=False)
+    assert not cg1.persistent
+    rt.fence()
+    before = rt.kernel_launches
+    tid = new_trace_id()
+    for _ in range(5):
+        rt.begin_trace(tid)
+        cg1.step()
+        rt.end_trace(tid)
+    rt.fence()
+    assert rt.kernel_launches - before == 5 * 4
+    # ... and on 4 local pieces
     pl4, _, _, _ = build_system(rt, oracle, m, 4)
-    cg4 = CGSolver(pl4, fused=True)
+    cg4 = CGSolver(pl4, fused=True, persistent=True)
     assert not cg4.persistent
     rt.fence()
     before = rt.kernel_launches
