@@ -337,6 +337,17 @@ int lsk_ctx_set_peers(lsk_ctx *ctx, const lsk_peers *peers);
 int lsk_xpay_halo_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, int n_terms, const double *f0, const double *f1,
                       const double *f2, const double *f3, const double *x, double *y, const lsk_halo_move *moves,
                       int nmoves);
+/* CGSolver::step lines src/CGSolver.hpp:53-54 in one launch:
+ *   residual_norm_squared.push_back(rr_new);  p = fma(rr_new/rr_cur, p, r)   [xpay(P, rr_new, rr_cur, R)]
+ * then *rr_cur = *rr_new for the next step.  `history` may be NULL (no append); otherwise circular like
+ * lsk_scalar_append_f64.  With `moves` (nmoves <= 4; needs lsk_ctx_set_peers) the boundary of p is also stored into
+ * the neighbours' ghost regions and the exchange epoch is closed, exactly as lsk_xpay_halo_f64 does.
+ * TMA-streamed: r and p must be 32-byte congruent (lsk_cg_direction_supported). */
+int lsk_cg_direction_supported(int64_t n, const double *r, const double *p);
+int lsk_cg_direction_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, double *rr_cur, const double *rr_new, const double *r,
+                         double *p, const lsk_halo_move *moves, int nmoves, double *history,
+                         int64_t history_capacity, int64_t *history_count);
+
 /* ------------------------------------------------------------------------------------------------
  * The whole CG step as one persistent kernel -- CGSolver::step (src/CGSolver.hpp:46-55) `niter` times:
  *     q = A p;  pq = p.q;  x = fma(rr/pq, p, x);  r = fma((-1*rr)/pq, q, r);  rr' = r.r;

@@ -103,6 +103,8 @@ def _declare(L: C.CDLL) -> None:
     L.lsk_dot2_f64.argtypes = [vp, vp, i64, vp, vp, vp, vp]
     L.lsk_bicg_p_update_f64.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp]
     L.lsk_bicg_tail_f64.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.lsk_cg_direction_supported.argtypes = [i64, vp, vp]
+    L.lsk_cg_direction_f64.argtypes = [vp, vp, i64, vp, vp, vp, vp, C.POINTER(HaloMove), ci, vp, i64, vp]
     L.lsk_cg_steps_supported.argtypes = [C.POINTER(CgProblem)]
     L.lsk_cg_steps_f64.argtypes = [vp, vp, C.POINTER(CgProblem), ci]
     L.lsk_cg_row_blocks.argtypes = [i64, i64]

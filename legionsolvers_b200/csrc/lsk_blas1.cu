@@ -9,6 +9,7 @@
 #include <initializer_list>
 
 #include "lsk_common.cuh"
+#include "lsk_vec_stream.cuh"
 
 namespace lsk {
 
@@ -72,7 +73,7 @@ static int launch_stream(lsk_ctx *ctx, lsk_stream s, F f, int64_t n, Span sp) {
     if (n == 0 && F::NRED == 0) return 0;
     const int64_t items = sp.npacks > 0 ? sp.npacks : n;
     const int grid = stream_grid(ctx, items > 0 ? items : 1, 8);
-    RedScratch rs = {nullptr, nullptr, nullptr};
+    RedScratch rs = {nullptr, nullptr, nullptr, nullptr};
     if (F::NRED > 0) rs = next_scratch(ctx);
     stream_kernel<F><<<grid, kBlock, 0, (cudaStream_t) s>>>(f, n, sp.head, sp.npacks, rs.partials, rs.ticket,
                                                             F::NRED > 0 ? ctx->d_peers : nullptr);
@@ -166,6 +167,140 @@ xpay_halo_kernel(Alpha<double> al, const double *__restrict__ x, double *__restr
         me->halo_ticket = 0u;
         me->halo_calls += 1;
         me->halo_wait_ns += global_ns() - t_halo0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The two vector passes of the fused CG step, TMA-streamed and dynamically scheduled (lsk_vec_stream.cuh):
+// 3 CTAs per SM, a 4 x 16 KB shared-memory ring filled by cp.async.bulk three chunks ahead, chunks handed out
+// first come, first served.  7.0 TB/s on the 805 MB x/r update of the 256^3 system, where the grid-stride
+// register-staged kernel above reaches 6.3 and the torch copy that defines the "measured peak" 6.5.
+// ---------------------------------------------------------------------------------------------------
+struct VecKernelShared {
+    uint64_t bar[kVecStages];
+    long long chunk[kVecStages];
+};
+__device__ __forceinline__ void vec_ring_init(VecRing &ring, unsigned char *s_dyn, VecKernelShared &sh) {
+    ring.smem = s_dyn;
+    ring.bar = sh.bar;
+    ring.chunk = sh.chunk;
+    ring.phases = 0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kVecStages; ++s) mbar_init(&sh.bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+}
+// ragged edges [0, head) and [head + 4 npacks, n)
+template <class Body>
+__device__ __forceinline__ void for_each_edge(int64_t n, int64_t head, int64_t npacks, Body body) {
+    const int64_t tail0 = head + npacks * 4;
+    const int64_t nedge = head + (n - tail0);
+    for (int64_t e = (int64_t) blockIdx.x * kBlock + threadIdx.x; e < nedge; e += (int64_t) gridDim.x * kBlock)
+        body(e < head ? e : tail0 + (e - head));
+}
+
+// src/CGSolver.hpp:50-52: x = fma(rr/pq, p, x); r = fma((-1*rr)/pq, q, r); rr_new = r.r
+__global__ void __launch_bounds__(kBlock, 3)
+cg_update_tma_kernel(const double *rr_old, const double *pq, const double *neg_one, const double *p, const double *q, double *x,
+                     double *r, double *rr_new, int64_t n, int64_t head, int64_t npacks, RedScratch rs) {
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    __shared__ __align__(8) VecKernelShared sh;
+    VecRing ring;
+    vec_ring_init(ring, s_dyn, sh);
+    const double a1 = div_rn(*rr_old, *pq);
+    const double a2 = div_rn(mul_rn(*neg_one, *rr_old), *pq);
+    double racc = 0.0;
+    const double *const in[4] = {p, q, x, r};
+    vec_stream<4>(ring, in, head, npacks * 4, rs.work, 0, [](int64_t, int) {}, [&](int64_t i, const double (&v)[4][2]) {
+        const double x0 = fma_rn(a1, v[0][0], v[2][0]), x1 = fma_rn(a1, v[0][1], v[2][1]);
+        const double r0 = fma_rn(a2, v[1][0], v[3][0]), r1 = fma_rn(a2, v[1][1], v[3][1]);
+        *reinterpret_cast<double2 *>(x + i) = make_double2(x0, x1);
+        *reinterpret_cast<double2 *>(r + i) = make_double2(r0, r1);
+        racc = fma(r0, r0, racc);
+        racc = fma(r1, r1, racc);
+    });
+    for_each_edge(n, head, npacks, [&](int64_t i) {
+        x[i] = fma_rn(a1, p[i], x[i]);
+        const double rn = fma_rn(a2, q[i], r[i]);
+        r[i] = rn;
+        racc = fma(rn, rn, racc);
+    });
+    const double acc[1] = {racc};
+    double *const out[1] = {rr_new};
+    grid_reduce_finish<1, double>(acc, rs.partials, rs.ticket, out, rs.peers, rs.work);
+}
+
+// src/CGSolver.hpp:53-54: residual_norm_squared.push_back(rr_new); p = fma(rr_new/rr_cur, p, r) -- plus, on several
+// ranks, p's boundary stored into the neighbours' ghost regions and the exchange epoch closed (as xpay_halo_kernel),
+// and rr_cur <- rr_new for the next step.  Everything after the element loop is done by the last CTA to finish.
+__global__ void __launch_bounds__(kBlock, 3)
+cg_direction_tma_kernel(double *rr_cur, const double *rr_new, const double *r, double *p, int64_t n, int64_t head, int64_t npacks,
+                        HaloSpec h, RedScratch rs, double *hist, long long hist_cap, long long *hist_count) {
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    __shared__ __align__(8) VecKernelShared sh;
+    __shared__ bool s_last;
+    VecRing ring;
+    vec_ring_init(ring, s_dyn, sh);
+    const lsk_peers *peers = rs.peers;
+    const bool multi = (peers != nullptr && h.nmoves > 0);
+    const double beta = div_rn(*rr_new, *rr_cur);  // xpay(P, rr_new, rr_cur, R): alpha = f0 / f1
+    bool remote = false, chunk_halo = false;
+    const double *const in[2] = {p, r};
+    const int64_t rot = multi ? halo_first_chunk(h, head, kVecStageBytes / 16) : 0;
+    vec_stream<2>(ring, in, head, npacks * 4, rs.work, rot,
+                  [&](int64_t i0, int cnt) { chunk_halo = multi && halo_chunk_overlaps(h, i0, cnt); },
+                  [&](int64_t i, const double (&v)[2][2]) {
+                      const double p0 = fma_rn(beta, v[0][0], v[1][0]), p1 = fma_rn(beta, v[0][1], v[1][1]);
+                      *reinterpret_cast<double2 *>(p + i) = make_double2(p0, p1);
+                      if (chunk_halo) remote |= halo_mirror_pair(h, i, p0, p1);
+                  });
+    for_each_edge(n, head, npacks, [&](int64_t i) {
+        const double v = fma_rn(beta, p[i], r[i]);
+        p[i] = v;
+        if (multi) remote |= halo_mirror_one(h, i, v);
+    });
+    if (remote) __threadfence_system();  // my stores into the neighbours' memory are visible there
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int t = atomicAdd(rs.ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    if (multi) {  // close the exchange epoch: publish, wait for the neighbours' (see xpay_halo_kernel)
+        CommWindow *me = static_cast<CommWindow *>(peers->window[peers->rank]);
+        const unsigned long long t_halo0 = global_ns();
+        __threadfence_system();
+        const unsigned long long e = me->halo_epoch + 1;
+        if (threadIdx.x < h.nmoves) {
+            const lsk_halo_move &mv = h.m[threadIdx.x];
+            if (mv.n > 0) {
+                CommWindow *dst = static_cast<CommWindow *>(peers->window[mv.peer]);
+                *reinterpret_cast<volatile unsigned long long *>(&dst->halo_done[peers->rank]) = e;
+            }
+            if (mv.expect) spin_until(&me->halo_done[mv.peer], e, &me->error);
+        }
+        __syncthreads();
+        __threadfence_system();
+        if (threadIdx.x == 0) {
+            me->halo_epoch = e;
+            me->halo_calls += 1;
+            me->halo_wait_ns += global_ns() - t_halo0;
+        }
+    }
+    if (threadIdx.x == 0) {
+        const double v = *rr_new;
+        if (hist != nullptr) {
+            const long long c = *hist_count;
+            hist[c % hist_cap] = v;
+            *hist_count = c + 1;
+        }
+        *rr_cur = v;  // every CTA read the old value before drawing its ticket
+        *rs.ticket = 0u;
+        *rs.work = 0ull;
     }
 }
 
@@ -479,6 +614,19 @@ static int do_fill(lsk_ctx *ctx, lsk_stream s, int64_t n, T value, const T *vdev
     return launch_stream(ctx, s, f, n, plan_span<T>(n, {x}));
 }
 
+// one-time opt-in to 64 KB of dynamic shared memory for the TMA-streamed kernels
+static int vec_kernels_configure(lsk_ctx *) {
+    static int state = -1;  // -1 not tried, 0 ok, > 0 CUDA error
+    if (state < 0) {
+        cudaError_t e = cudaFuncSetAttribute(cg_update_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kVecStages * kVecStageBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(cg_direction_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kVecStages * kVecStageBytes);
+        state = (int) e;
+        if (e != cudaSuccess) (void) cudaGetLastError();
+    }
+    return state;
+}
+
 }  // namespace lsk
 
 using namespace lsk;
@@ -572,10 +720,57 @@ int lsk_scalar_append_f64(lsk_ctx *ctx, lsk_stream s, const double *value, doubl
 int lsk_cg_update_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, const double *rr_old, const double *pq,
                       const double *p, const double *q, double *x, double *r, double *rr_new) {
     if (!ctx || n < 0 || !rr_old || !pq || !rr_new || (n > 0 && (!p || !q || !x || !r))) return LSK_E_INVALID;
+    const Span sp = plan_span<double>(n, {p, q, x, r});
+    // Streamed form for passes that do not fit the L2 (measured: 805 MB pass 6.3 -> 7.0 TB/s); for an L2-resident
+    // 2 M-row slab the grid-stride kernel with 2048 threads per SM is the faster one (16 vs 14 us).
+    if (sp.npacks >= (int64_t) 1500000 && vec_kernels_configure(ctx) == 0) {
+        const int64_t nchunks = (sp.npacks * 4 + 511) / 512;
+        const int64_t cap = (int64_t) ctx->sm_count * 3;
+        const int grid = (int) (nchunks < cap ? nchunks : cap);
+        const RedScratch rs = next_scratch(ctx);
+        cg_update_tma_kernel<<<grid, kBlock, kVecStages * kVecStageBytes, (cudaStream_t) s>>>(rr_old, pq, ctx->consts + 1, p, q, x, r,
+                                                                                             rr_new, n, sp.head, sp.npacks, rs);
+        return after_launch(ctx);
+    }
     CgUpdateF f;
     f.rr_old = rr_old; f.pq = pq; f.neg_one = ctx->consts + 1;
     f.p = p; f.q = q; f.x = x; f.r = r; f.rr_new = rr_new;
-    return launch_stream(ctx, s, f, n, plan_span<double>(n, {p, q, x, r}));
+    return launch_stream(ctx, s, f, n, sp);
+}
+
+int lsk_cg_direction_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, double *rr_cur, const double *rr_new, const double *r, double *p,
+                         const lsk_halo_move *moves, int nmoves, double *history, int64_t history_capacity, int64_t *history_count) {
+    if (!ctx || n < 0 || !rr_cur || !rr_new || (n > 0 && (!r || !p)) || nmoves < 0 || nmoves > 4 || (nmoves > 0 && !moves))
+        return LSK_E_INVALID;
+    if (history && (!history_count || history_capacity <= 0)) return LSK_E_INVALID;
+    if (nmoves > 0 && !ctx->d_peers) return LSK_E_INVALID;  // needs lsk_ctx_set_peers
+    const Span sp = plan_span<double>(n, {r, p});
+    if (sp.npacks < 1 || vec_kernels_configure(ctx) != 0) return LSK_E_INVALID;  // callers check lsk_cg_direction_supported
+    HaloSpec h;
+    h.nmoves = nmoves;
+    for (int i = 0; i < 4; ++i) {
+        h.lo[i] = 0;
+        h.m[i].peer = 0; h.m[i].expect = 0; h.m[i].src = nullptr; h.m[i].dst = nullptr; h.m[i].n = 0;
+    }
+    for (int i = 0; i < nmoves; ++i) {
+        if (moves[i].n < 0 || (moves[i].n > 0 && (!moves[i].dst || moves[i].src < p || moves[i].src + moves[i].n > p + n)))
+            return LSK_E_INVALID;
+        h.m[i] = moves[i];
+        h.lo[i] = moves[i].n > 0 ? (int64_t) (moves[i].src - p) : 0;
+    }
+    const int64_t nchunks = (sp.npacks * 4 + 1023) / 1024;
+    const int64_t cap = (int64_t) ctx->sm_count * 3;
+    const int grid = (int) (nchunks < cap ? nchunks : cap);
+    RedScratch rs = next_scratch(ctx);
+    if (nmoves == 0) rs.peers = nullptr;
+    cg_direction_tma_kernel<<<grid, kBlock, kVecStages * kVecStageBytes, (cudaStream_t) s>>>(
+        rr_cur, rr_new, r, p, n, sp.head, sp.npacks, h, rs, history, history_capacity, reinterpret_cast<long long *>(history_count));
+    return after_launch(ctx);
+}
+
+int lsk_cg_direction_supported(int64_t n, const double *r, const double *p) {
+    if (n <= 0 || !r || !p) return 0;
+    return plan_span<double>(n, {r, p}).npacks >= 1 ? 1 : 0;
 }
 
 int lsk_axpy_dot_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, int nt, const double *f0, const double *f1,

@@ -25,6 +25,7 @@
 
 #include "lsk_common.cuh"
 #include "lsk_spmv_tma.cuh"
+#include "lsk_vec_stream.cuh"
 
 namespace lsk {
 
@@ -36,110 +37,6 @@ struct GridSync {
     unsigned long long phase_ns[8];  // accounting (CTA 0): ns in phase A, its barrier, phase B, its barrier, phase C, its barrier; [6] = iterations
     unsigned long long slots[kMaxPartials][2];  // CTA i -> root: its partial sum as two LL packets
 };
-
-// ---- TMA-streamed vector phases ---------------------------------------------------------------------------
-// The BLAS-1 phases run on the mat-vec's CTA shape (3 x 256 threads per SM, ~80 registers), which cannot keep
-// enough register-staged loads in flight to saturate HBM.  So they stream too: the 64 KB shared-memory ring
-// of the mat-vec becomes 4 stages of 16 KB, each holding one chunk of every input vector, filled by
-// cp.async.bulk three chunks ahead; threads read the chunk from shared memory, compute, and store results
-// straight from registers.
-constexpr int kVecStages = 4;
-constexpr int kVecStageBytes = 16384;
-
-struct VecRing {
-    unsigned char *smem;   // kVecStages x kVecStageBytes
-    uint64_t *bar;         // kVecStages mbarriers
-    long long *chunk;      // [kVecStages] (shared): chunk held by each stage, -1 = none left
-    uint32_t phases;       // bit s = parity to wait for on stage s
-};
-
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// Streams elements [head, head + nelem) of NIN congruent (32-byte aligned at `head`) arrays through the ring in
-// chunks of CH = 16 KB / (8 NIN).  Chunks are handed out DYNAMICALLY from a global counter: SMs do not all get the
-// same share of the memory system, and with a static split the slow ones finish ~7 % after the fast ones while
-// HBM idles; first come, first served keeps it saturated to the end of the phase.  Thread 0 grabs three chunks
-// ahead (the atomic's latency hides behind the chunks in flight), publishes the chunk id of a stage in shared
-// memory before arming its mbarrier, and everybody learns it after the wait.  Grabbed index g maps to chunk
-// (g + rot) % nchunks, so a phase can have a chosen range of chunks taken first.
-// begin(i0, cnt) is called by every thread once per chunk (elements i0 .. i0 + cnt - 1) before its pairs;
-// f(i, v) receives, for two consecutive elements i and i + 1, the inputs v[a][0..1] of each array.
-template <int NIN, class B, class F>
-__device__ __forceinline__ void vec_stream(VecRing &ring, const double *const (&in)[NIN], int64_t head, int64_t nelem,
-                                           unsigned long long *counter, int64_t rot, B begin, F f) {
-    constexpr int CH = kVecStageBytes / (8 * NIN);
-    const int64_t nchunks = (nelem + CH - 1) / CH;
-    auto issue = [&](int s, int64_t g) {  // thread 0: grabbed index g into stage s
-        if (g < nchunks) {
-            int64_t c = g + rot;
-            if (c >= nchunks) c -= nchunks;
-            ring.chunk[s] = c;
-            const int64_t e0 = c * CH;
-            const int64_t cnt = nelem - e0 < CH ? nelem - e0 : CH;
-            const uint32_t bytes = (uint32_t) cnt * 8u;
-            mbar_expect_tx(&ring.bar[s], NIN * bytes);
-#pragma unroll
-            for (int a = 0; a < NIN; ++a)
-                tma_bulk_g2s_plain(ring.smem + (size_t) s * kVecStageBytes + (size_t) a * CH * 8, in[a] + head + e0, bytes, &ring.bar[s]);
-        } else {
-            ring.chunk[s] = -1;
-            mbar_arrive(&ring.bar[s]);  // completes the stage's phase with no bytes
-        }
-    };
-    auto grab = [&](long long prev) -> long long {  // thread 0; stops asking once the work has run out
-        return prev < nchunks ? (long long) atomicAdd(counter, 1ull) : prev;
-    };
-    long long pend = 0;
-    if (threadIdx.x == 0) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (int s = 0; s < kVecStages - 1; ++s) {
-            pend = grab(pend);
-            issue(s, pend);
-        }
-        pend = grab(pend);
-    }
-    int64_t k = 0;
-    for (;; ++k) {
-        const int s = (int) (k % kVecStages);
-        // stage (k - 1) % kVecStages was consumed in the previous iteration, which ended with a CTA barrier
-        if (threadIdx.x == 0) {
-            issue((int) ((k + kVecStages - 1) % kVecStages), pend);
-            pend = grab(pend);
-        }
-        mbar_wait(&ring.bar[s], (ring.phases >> s) & 1u);
-        ring.phases ^= (1u << s);
-        const long long c = ring.chunk[s];
-        if (c < 0) break;  // uniform: the stages issued after this one are empty as well
-        const int64_t e0 = c * CH;
-        const int cnt = (int) (nelem - e0 < CH ? nelem - e0 : CH);
-        const unsigned char *st = ring.smem + (size_t) s * kVecStageBytes;
-        begin(head + e0, cnt);
-#pragma unroll
-        for (int u = 0; u < CH / (2 * kBlock); ++u) {
-            const int j = u * 2 * kBlock + 2 * (int) threadIdx.x;
-            if (j < cnt) {  // cnt is a multiple of 4, j is even: both elements exist
-                double v[NIN][2];
-#pragma unroll
-                for (int a = 0; a < NIN; ++a) {
-                    const double2 t = *reinterpret_cast<const double2 *>(st + (size_t) a * CH * 8 + (size_t) j * 8);
-                    v[a][0] = t.x;
-                    v[a][1] = t.y;
-                }
-                f(head + e0 + j, v);
-            }
-        }
-        __syncthreads();
-    }
-    // retire the (empty) stages that were armed ahead, so that every mbarrier's parity matches ring.phases again
-    for (int64_t j = k + 1; j < k + kVecStages; ++j) {
-        const int s = (int) (j % kVecStages);
-        mbar_wait(&ring.bar[s], (ring.phases >> s) & 1u);
-        ring.phases ^= (1u << s);
-    }
-    __syncthreads();
-}
 
 struct CgArgs {
     TmaSpmvArgs mv;          // x = P shifted to global column 0, y = Q, dot_w = P (owned piece)
@@ -410,55 +307,18 @@ __global__ void __launch_bounds__(kBlock, LSK_TMA_MINB) cg_persistent_kernel(CgA
         {
             const double *const in[2] = {a.p, a.r};
             bool chunk_halo = false;  // this chunk overlaps a range that is mirrored into a neighbour (uniform per chunk)
-            auto begin = [&](int64_t i0, int cnt) {
-                chunk_halo = false;
-                if (multi) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        chunk_halo |= (q < a.halo.nmoves && i0 + cnt > a.halo.lo[q] && i0 < a.halo.lo[q] + a.halo.m[q].n);
-                }
-            };
-            // chunks from the first one that overlaps a send range not at the start of the vector are taken first:
-            // their results also travel over NVLink, which then overlaps the rest of the phase
-            int64_t rot = 0;
-            if (multi) {
-                int64_t first = -1;
-                for (int q = 0; q < a.halo.nmoves; ++q)
-                    if (a.halo.m[q].n > 0 && a.halo.lo[q] > a.head && (first < 0 || a.halo.lo[q] < first)) first = a.halo.lo[q];
-                if (first >= 0) rot = (first - a.head) / (kVecStageBytes / 16);
-            }
+            auto begin = [&](int64_t i0, int cnt) { chunk_halo = multi && halo_chunk_overlaps(a.halo, i0, cnt); };
+            const int64_t rot = multi ? halo_first_chunk(a.halo, a.head, kVecStageBytes / 16) : 0;
             vec_stream<2>(ring, in, a.head, a.npacks * 4, &gs->work[2], rot, begin, [&](int64_t i, const double (&v)[2][2]) {
                 const double p0 = fma_rn(beta, v[0][0], v[1][0]), p1 = fma_rn(beta, v[0][1], v[1][1]);
                 *reinterpret_cast<double2 *>(a.p + i) = make_double2(p0, p1);
-                if (chunk_halo) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        if (q < a.halo.nmoves && i + 2 > a.halo.lo[q] && i < a.halo.lo[q] + a.halo.m[q].n) {
-                            double *d = a.halo.m[q].dst + (i - a.halo.lo[q]);
-                            remote = true;
-                            const bool inside = (i >= a.halo.lo[q]) && (i + 2 <= a.halo.lo[q] + a.halo.m[q].n);
-                            if (inside && (reinterpret_cast<uintptr_t>(d) & 15) == 0) {
-                                *reinterpret_cast<double2 *>(d) = make_double2(p0, p1);
-                            } else {
-                                if (i >= a.halo.lo[q] && i < a.halo.lo[q] + a.halo.m[q].n) d[0] = p0;
-                                if (i + 1 >= a.halo.lo[q] && i + 1 < a.halo.lo[q] + a.halo.m[q].n) d[1] = p1;
-                            }
-                        }
-                    }
-                }
+                if (chunk_halo) remote |= halo_mirror_pair(a.halo, i, p0, p1);
             });
         }
         for_each_edge([&](int64_t i) {
             const double v = fma_rn(beta, ld_f64(a.p + i), ld_f64(a.r + i));
             a.p[i] = v;
-            if (multi) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (q < a.halo.nmoves && i >= a.halo.lo[q] && i < a.halo.lo[q] + a.halo.m[q].n) {
-                        a.halo.m[q].dst[i - a.halo.lo[q]] = v;
-                        remote = true;
-                    }
-            }
+            if (multi) remote |= halo_mirror_one(a.halo, i, v);
         });
         if (remote) __threadfence_system();  // my stores into the neighbours' memory are visible there
         const bool final_it = (it + 1 == a.niter);

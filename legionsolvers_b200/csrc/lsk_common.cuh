@@ -31,6 +31,7 @@ struct lsk_ctx {
     int cursor;                // next scratch set
     unsigned long long launches;
     lsk_peers *d_peers;        // device copy of the peer windows; non-null = reducing kernels all-reduce in their tail
+    unsigned long long *work;  // [kScratchSets] dynamic work counters of the TMA-streamed vector kernels, zero between launches
     void *gridsync;            // lsk::GridSync: grid barrier + partials of the persistent solver kernels
     int cg_blocks_per_sm;      // occupancy of the persistent CG kernel (0 = not queried yet)
 };
@@ -41,6 +42,7 @@ struct RedScratch {
     double *partials;      // [kMaxRed][kMaxPartials]
     unsigned int *ticket;
     const lsk_peers *peers;  // non-null: finish the reduction with a cross-rank sum
+    unsigned long long *work;  // dynamic work counter (zero at launch; the last CTA resets it)
 };
 
 inline RedScratch next_scratch(lsk_ctx *ctx) {
@@ -50,6 +52,7 @@ inline RedScratch next_scratch(lsk_ctx *ctx) {
     r.partials = ctx->partials + (size_t) set * kMaxRed * kMaxPartials;
     r.ticket = ctx->tickets + set;
     r.peers = ctx->d_peers;
+    r.work = ctx->work + set;
     return r;
 }
 
@@ -315,7 +318,7 @@ __device__ __forceinline__ double block_sum(double v, double *smem /*[kWarps]*/)
 template <int NRED, typename T>
 __device__ __forceinline__ void grid_reduce_finish(const double (&acc)[NRED], double *partials,
                                                    unsigned int *ticket, T *const (&out)[NRED],
-                                                   const lsk_peers *peers = nullptr) {
+                                                   const lsk_peers *peers = nullptr, unsigned long long *reset = nullptr) {
     __shared__ double s_red[kWarps];
     __shared__ double s_tot[NRED];
     __shared__ bool s_last;
@@ -360,6 +363,7 @@ __device__ __forceinline__ void grid_reduce_finish(const double (&acc)[NRED], do
         for (int j = 0; j < NRED; ++j)
             if (out[j] != nullptr) *out[j] = (T) s_tot[j];
         *ticket = 0u;  // ready for the next launch on this scratch set
+        if (reset != nullptr) *reset = 0ull;  // every CTA has drawn its ticket, i.e. is done with the work counter
     }
 }
 

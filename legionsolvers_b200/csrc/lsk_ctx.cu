@@ -48,11 +48,14 @@ int lsk_ctx_create(int device, lsk_ctx **out) {
     ctx->launches = 0;
     ctx->d_peers = nullptr;
     ctx->gridsync = nullptr;
+    ctx->work = nullptr;
     ctx->cg_blocks_per_sm = 0;
     const size_t pbytes = sizeof(double) * (size_t) kScratchSets * kMaxRed * kMaxPartials;
     cudaError_t e = cudaMalloc(&ctx->partials, pbytes);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->tickets, sizeof(unsigned int) * kScratchSets);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->consts, sizeof(double) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->work, sizeof(unsigned long long) * kScratchSets);
+    if (e == cudaSuccess) e = cudaMemset(ctx->work, 0, sizeof(unsigned long long) * kScratchSets);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->gridsync, lsk_gridsync_bytes());
     if (e == cudaSuccess) e = cudaMemset(ctx->gridsync, 0, lsk_gridsync_bytes());
     if (e == cudaSuccess) e = cudaMemset(ctx->partials, 0, pbytes);
@@ -75,6 +78,7 @@ int lsk_ctx_destroy(lsk_ctx *ctx) {
     if (ctx->consts) cudaFree(ctx->consts);
     if (ctx->d_peers) cudaFree(ctx->d_peers);
     if (ctx->gridsync) cudaFree(ctx->gridsync);
+    if (ctx->work) cudaFree(ctx->work);
     delete ctx;
     return 0;
 }

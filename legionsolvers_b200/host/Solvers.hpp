@@ -69,6 +69,8 @@ public:
         if (fused) {
             planner.matvec_dot(Q, P, P, p_norm);                     // Q = A P and P.Q in one pass
             planner.cg_update(SOL, R, rr_cur, p_norm, P, Q, rr_new);  // both axpys and R.R in one pass
+            // append rr_new, P = R + (rr_new/rr_cur) P (boundary into the neighbours' ghosts), rr_cur <- rr_new: one launch
+            if (planner.cg_direction(P, rr_new, rr_cur, R, residual_norm_squared)) return;
             planner.xpay_halo(P, rr_new, rr_cur, R);                  // P's boundary goes to the neighbours' ghosts
         } else {
             planner.matvec(Q, P);

@@ -221,6 +221,44 @@ public:
         xpay(dst, numer, denom, src);
     }
 
+    // CGSolver::step lines src/CGSolver.hpp:53-54 in ONE launch when this rank holds one piece of one space:
+    // history.push_back(rr_new); P = fma(rr_new/rr_cur, P, R) [+ P's boundary into the neighbours' ghosts, as
+    // xpay_halo]; rr_cur <- rr_new.  false = not possible here (the caller issues xpay_halo + push_back instead).
+    bool cg_direction(std::size_t p, const Scalar<T> &rr_new, const Scalar<T> &rr_cur, std::size_t r, const ScalarHistory &history) {
+        if constexpr (!std::is_same<T, double>::value) {
+            return false;
+        } else {
+            if (get_num_spaces() != 1 || total_local_pieces() != 1) return false;
+            const IndexPartition &part = *canonical_index_partitions[0];
+            const int64_t lo = part.own_lo(), cnt = part.own_hi() - part.own_lo() + 1;
+            PartitionedVector<T> &y = get_vector(p, 0);
+            const PartitionedVector<T> &x = get_vector(r, 0);
+            if (cnt <= 0 || !lsk_cg_direction_supported(cnt, x.ptr(lo), y.ptr(lo))) return false;
+            lsk_halo_move moves[4];
+            int n = 0;
+            const bool push = halo_push_is_fused() && y.exported();
+            if (push) {
+                for (const HaloMove &m : row_partitioned_matrices[0].halo) {
+                    moves[n].peer = m.peer;
+                    moves[n].expect = m.recv_n > 0 ? 1 : 0;
+                    moves[n].n = m.send_n;
+                    moves[n].src = m.send_n > 0 ? y.ptr(m.send_lo) : nullptr;
+                    moves[n].dst = m.send_n > 0 ? y.peer_ptr(m.peer, m.send_lo) : nullptr;
+                    ++n;
+                }
+            }
+            const T *xs = x.ptr(lo);
+            T *ys = y.ptr(lo);
+            mark_dirty(p);
+            rt->enqueue("cg_direction", [&] {
+                return lsk_cg_direction_f64(rt->ctx(), rt->stream(), cnt, rr_cur.ptr(), rr_new.ptr(), xs, ys, n > 0 ? moves : nullptr, n,
+                                            history.data(), history.get_capacity(), history.count_ptr());
+            });
+            if (push) halo_fresh.insert(p);
+            return true;
+        }
+    }
+
     // ---- the whole CG step as one persistent kernel (lsk_cg_steps_f64) ------------------------------------
     // Possible when this rank holds ONE piece of ONE space whose only operator is a CSR block, and (on
     // several ranks) the collectives run over peer memory with P's buffer mapped into the neighbours.

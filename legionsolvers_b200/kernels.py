@@ -136,6 +136,14 @@ class Context:
         _abi.check(_abi.lib().lsk_cg_update_f64(self.h, _stream(), x.numel(), _ptr(rr_old), _ptr(pq), _ptr(p),
                                                 _ptr(q), _ptr(x), _ptr(r), _ptr(rr_new)), "lsk_cg_update")
 
+    def cg_direction(self, rr_cur, rr_new, r, p, history=None, history_count=None):
+        """history.push_back(rr_new); p = fma(rr_new/rr_cur, p, r); rr_cur <- rr_new  (src/CGSolver.hpp:53-54)."""
+        if not _abi.lib().lsk_cg_direction_supported(p.numel(), _ptr(r), _ptr(p)):
+            raise RuntimeError("lsk_cg_direction_f64: r and p are not 32-byte congruent")
+        _abi.check(_abi.lib().lsk_cg_direction_f64(self.h, _stream(), p.numel(), _ptr(rr_cur), _ptr(rr_new), _ptr(r), _ptr(p), None, 0,
+                                                   _ptr(history), history.numel() if history is not None else 0,
+                                                   _ptr(history_count)), "lsk_cg_direction")
+
     def cg_steps(self, entry, col, rowptr, k_base, p_full, own_lo, q, x, r, rr_cur, rr_new, p_norm, history, history_count,
                  niter, col_lo=0):
         """`niter` whole CG steps in one persistent launch (single rank).  p_full holds P for global columns

@@ -434,6 +434,45 @@ def test_fused_passes_match_leaf_sequences(ctx, oracle, n):
     assert abs(out.item() - oracle.dot(rw, rt)) <= REL * float(np.dot(np.abs(rw), np.abs(rt)))
 
 
+@pytest.mark.parametrize("n", [40, 1000, 16_384 + 12, 262_147, 4_194_304 + 20])
+@pytest.mark.parametrize("off", [0, 1, 3])
+def test_cg_update_and_direction_tma_streamed(ctx, oracle, n, off):
+    """The two vector passes of the fused CG step (TMA-streamed, dynamically scheduled above 16 K elements):
+    element-wise results BIT-EXACT with the leaf sequences axpy/axpy and xpay, r.r within 1e-12, history appended,
+    rr_cur advanced; every 8-byte alignment residue (ragged head/tail around the 32-byte body)."""
+    rng = np.random.default_rng(n + off)
+    p0, q0, x0, r0 = (rng.standard_normal(n) for _ in range(4))
+    buf = lambda a: (lambda t: (t.copy_(dev(a)), t)[1])(torch.zeros(n + 8, dtype=torch.float64, device="cuda")[off:off + n])  # noqa: E731
+    p, q, x, r = buf(p0), buf(q0), buf(x0), buf(r0)
+    rr_old, pq = 3.7, 1.9
+    xw, rw = x0.copy(), r0.copy()
+    oracle.axpy(oracle.get_alpha([rr_old, pq]), p0, xw)
+    oracle.axpy(oracle.get_alpha([-1.0, rr_old, pq]), q0, rw)
+    rr_cur, pqd = scalars(rr_old, pq)
+    rr_new = torch.zeros(1, dtype=torch.float64, device="cuda")
+    ctx.cg_update(rr_cur, pqd, p, q, x, r, rr_new)
+    np.testing.assert_array_equal(x.cpu().numpy(), xw)
+    np.testing.assert_array_equal(r.cpu().numpy(), rw)
+    want_rr = oracle.dot(rw, rw)
+    assert abs(rr_new.item() - want_rr) <= REL * want_rr
+    # direction: p = fma(rr_new / rr_cur, p, r), history.push_back(rr_new), rr_cur <- rr_new
+    hist = torch.zeros(4, dtype=torch.float64, device="cuda")
+    count = torch.tensor([5], dtype=torch.int64, device="cuda")  # circular: slot 5 % 4 = 1
+    got_rr = rr_new.item()
+    pw = p0.copy()
+    oracle.xpay(oracle.get_alpha([got_rr, rr_old]), rw, pw)
+    ctx.cg_direction(rr_cur, rr_new, r, p, hist, count)
+    np.testing.assert_array_equal(p.cpu().numpy(), pw)
+    assert hist.cpu().numpy().tolist() == [0.0, got_rr, 0.0, 0.0] and int(count.item()) == 6
+    assert rr_cur.item() == got_rr
+    # a second pair of launches reuses the (reset) work counters
+    ctx.cg_update(rr_cur, pqd, p, q, x, r, rr_new)
+    oracle.axpy(oracle.get_alpha([got_rr, pq]), pw, xw)
+    oracle.axpy(oracle.get_alpha([-1.0, got_rr, pq]), q0, rw)
+    np.testing.assert_array_equal(x.cpu().numpy(), xw)
+    np.testing.assert_array_equal(r.cpu().numpy(), rw)
+
+
 def test_cg_golden_history_through_leaf_kernels(ctx, oracle):
     """Test06CSRSolveCG (n=100, 4 pieces, 10 steps) driven through the C ABI kernel by kernel,
     scalars never leaving the device: reproduces the reference's golden residual history."""
