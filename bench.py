@@ -26,7 +26,6 @@ import argparse
 import json
 import os
 import sys
-import threading
 import time
 from pathlib import Path
 
@@ -50,56 +49,77 @@ UNIT = "it/s"
 # clocks during the timed region (pynvml; the recipe's nvidia-smi line, in-process)
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
-    REASONS = {
-        0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
-        0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
-        0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting",
-    }
+    """SM clock, power and clock-event reasons of one GPU while it is under load, sampled by `nvidia-smi -lms` in a
+    SEPARATE process (the profiling guide's recipe).  In-process NVML polling was measured to stall this process's own
+    CUDA launches for milliseconds on some hosts, which desynchronises the ranks of a multi-GPU run."""
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
-    def __init__(self, device_index: int, period_s: float = 0.05):
-        self.samples, self.reasons, self.power = [], set(), []
-        self.max_mhz = None
-        self._stop = threading.Event()
-        self._thread = None
+    def __init__(self, device_index: int, period_ms: int = 25):
+        import shutil
+        import subprocess
+        import tempfile
+
+        self.proc, self.out = None, None
+        exe = shutil.which("nvidia-smi")
+        if exe is None:
+            return
+        # physical index of the device this process uses (CUDA_VISIBLE_DEVICES may remap)
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        ident = str(device_index)
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if device_index < len(ids):
+                ident = ids[device_index]
+        self.out = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            import pynvml
-
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.proc = subprocess.Popen([exe, "-i", ident, f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", str(period_ms)],
+                                         stdout=self.out, stderr=subprocess.DEVNULL)
         except Exception:
-            self.nv = None
-        self.period = period_s
-
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
-                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
-                    self.nv, "nvmlDeviceGetCurrentClocksEventReasons") else self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in self.REASONS.items():
-                    if mask & bit and name != "gpu_idle":
-                        self.reasons.add(name)
-                self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
-            except Exception:
-                pass
-            self._stop.wait(self.period)
+            self.proc = None
 
     def start(self):
-        if self.nv is not None:
-            self._thread = threading.Thread(target=self._run, daemon=True)
-            self._thread.start()
+        pass  # sampling began in the constructor, before the warm-up
 
-    def stop(self):
-        self._stop.set()
-        if self._thread is not None:
-            self._thread.join(timeout=2)
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
-        s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "power_w_max": max(self.power) if self.power else None, "samples": len(s)}
+    def stop(self, t0: float | None = None, t1: float | None = None):
+        """t0, t1: wall-clock bounds (time.time()) of the timed region."""
+        import datetime
+
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.out.flush()
+        self.out.seek(0)
+        rows = []
+        for line in self.out.read().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, int(float(f[1])), int(float(f[2])), float(f[3]), [n for n, v in zip(self.NAMES, f[4:8]) if v.lower().startswith("active")]))
+            except ValueError:
+                continue
+        try:
+            os.unlink(self.out.name)
+        except OSError:
+            pass
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        inside = [r for r in rows if t0 is not None and t1 is not None and t0 <= r[0] <= t1]
+        # the GPU is under the same load from the warm-up on: samples of the timed region if there are any, else
+        # the ones under load around it (power well above idle)
+        loaded = inside or [r for r in rows if r[3] > 250.0] or rows
+        clocks = sorted(r[1] for r in loaded)
+        reasons = sorted({n for r in loaded for n in r[4]})
+        return {"sm_mhz": clocks[len(clocks) // 2], "sm_max_mhz": rows[0][2], "reasons": reasons,
+                "power_w_max": max(r[3] for r in loaded), "samples": len(loaded), "samples_in_timed_region": len(inside),
+                "how": "nvidia-smi -lms in a separate process, from the warm-up to the end of the timed region"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -253,29 +273,38 @@ def run_ours(args):
         rt.end_trace(TRACE)
 
     # ---- warm-up, then EXACTLY K timed steps between barriers, CUDA events on the launching stream ---
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step()
-    # keep warming until the clocks have had ~0.4 s under load (short multi-GPU steps would otherwise be
-    # timed on a GPU still ramping up from idle)
+    rt.fence()
+    # keep warming until the clocks have had ~0.4 s under load (short multi-GPU steps would otherwise be timed on
+    # a GPU still ramping up from idle).  The NUMBER of extra steps is fixed by rank 0 and broadcast: the ranks
+    # must launch the same steps (the collectives are part of them).
     t_w = time.perf_counter()
-    while time.perf_counter() - t_w < 0.4:
+    step()
+    rt.fence()
+    one = max(time.perf_counter() - t_w, 1e-4)
+    extra = torch.tensor([int(min(2000, max(1, 0.4 / one)))], dtype=torch.int64, device="cuda")
+    if dist is not None:
+        dist.broadcast(extra, src=0)
+    for _ in range(int(extra.item())):
         step()
-        rt.fence()
-    barrier()
-    sampler = ClockSampler(local_rank, period_s=0.02)
-    sampler.start()
+    rt.fence()
     launches0 = rt.kernel_launches
     cs0 = rt.comm_stats() if world > 1 else None
     ph0 = rt.cg_phase_stats() if getattr(cg, "persistent", False) else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    wall0 = time.time()
     ev0.record()
     for _ in range(args.steps):
         step()
     ev1.record()
     barrier()
+    wall1 = time.time()
     elapsed_ms = max_over_ranks(ev0.elapsed_time(ev1))
     launches = rt.kernel_launches - launches0
-    clocks = sampler.stop()
+    clocks = sampler.stop(wall0, wall1) if sampler is not None else None
     comm_us = None
     if world > 1:
         cs1 = rt.comm_stats()
