@@ -151,13 +151,15 @@ int lsk_scalar_append_f64(lsk_ctx *ctx, lsk_stream s, const double *value, doubl
  *
  * LSK_SPMV_STREAM adds the rounded products of a row in ascending k, exactly the order of the
  * reference's CPU body (src/CSRMatrixTasks.cpp:73-91): its result is bit-identical to it.
- * The VECTOR/WARP variants reduce a row across lanes (tree order, fma): <= 1e-12 relative.
+ * The LANES/VECTOR/WARP variants reduce a row across lanes (fixed tree order): <= 1e-12 relative.
+ * AUTO: mean row length <= 12 -> STREAM (so the 5- and 7-point stencils stay bit-exact), <= 96 -> LANES, else WARP.
  * ---------------------------------------------------------------------------------------------- */
 enum lsk_spmv_variant {
     LSK_SPMV_AUTO = 0,
     LSK_SPMV_STREAM = 1, /* block streams a contiguous run of non-zeros through shared memory */
     LSK_SPMV_VECTOR = 2, /* 2..16 lanes per row */
-    LSK_SPMV_WARP = 3    /* one warp per row */
+    LSK_SPMV_WARP = 3,   /* one warp per row */
+    LSK_SPMV_LANES = 4   /* the STREAM kernel's TMA-staged tiles with 2, 4 or 8 lanes per row (by mean row length) */
 };
 int lsk_csr_spmv_f64(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const double *entry,
                      const int64_t *col, const lsk_rect *rowptr, int64_t k_base,

@@ -335,7 +335,7 @@ csr_stream_pipe_kernel(int64_t rows, int rpb, int64_t n_row_blocks, const T *__r
 // (conflict-free for odd lengths).  Each thread adds its rounded products in ascending k in a
 // register: bit-identical to the reference CPU body, no product staging, one barrier per tile.
 // ===================================================================================================
-template <int NDOT>
+template <int NDOT, int LPR = 1>
 __global__ void __launch_bounds__(kBlock, LSK_TMA_MINB)
 csr_tma_kernel(TmaSpmvArgs a, double *partials, unsigned int *ticket, double *out_yw, double *out_yy, const lsk_peers *peers) {
     extern __shared__ __align__(128) unsigned char s_dyn[];
@@ -346,7 +346,7 @@ csr_tma_kernel(TmaSpmvArgs a, double *partials, unsigned int *ticket, double *ou
     for (int j = 0; j < (NDOT > 0 ? NDOT : 1); ++j) dacc[j] = 0.0;
     TmaSpmvState st;
     csr_tma_init(st, s_full);
-    csr_tma_run<NDOT, false, false>(a, st, s_dyn, s_full, s_lo, s_hi, dacc, nullptr);
+    csr_tma_run<NDOT, false, false, 0, false, LPR>(a, st, s_dyn, s_full, s_lo, s_hi, dacc, nullptr);
     if constexpr (NDOT > 0) {
         double *out[NDOT];
         out[0] = out_yw;
@@ -456,9 +456,10 @@ coo_segreduce_kernel(int64_t nnz, const T *__restrict__ entry, const long long *
 static int pick_variant(int64_t rows, int64_t nnz) {
     if (rows <= 0) return LSK_SPMV_STREAM;
     const double mean = (double) nnz / (double) rows;
-    // up to a few dozen non-zeros per row one thread adds a row faster than a warp can be scheduled
-    // for it; beyond that the serial adds dominate and a warp per row wins
-    return mean <= 96.0 ? LSK_SPMV_STREAM : LSK_SPMV_WARP;
+    // row-length statistics pick the mapping: up to ~a dozen non-zeros per row a thread owns a row (a 2048-element
+    // tile then feeds all 256 threads); up to ~a hundred, 2-8 lanes share a row of the same TMA-staged tile; beyond
+    // that a warp per row
+    return mean <= 12.0 ? LSK_SPMV_STREAM : mean <= 96.0 ? LSK_SPMV_LANES : LSK_SPMV_WARP;
 }
 
 template <typename T, bool VEC>
@@ -486,26 +487,46 @@ static void launch_pipe_kernel(int ndot, int grid, cudaStream_t st, int64_t rows
         csr_stream_pipe_kernel<T, 2><<<grid, kBlock, 0, st>>>(rows, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers);
 }
 
-static int launch_tma_kernel(int ndot, int grid, cudaStream_t st, int64_t rows, int64_t nnz, int rpb, int64_t nrb,
-                             const double *entry, const long long *col, const lsk_rect *rowptr, int64_t k_base,
-                             const double *x, double *y, const double *dot_w, RedScratch rs, double *o0, double *o1) {
+template <int LPR>
+static int launch_tma_kernel_lpr(int ndot, int grid, cudaStream_t st, const TmaSpmvArgs &a, RedScratch rs, double *o0, double *o1) {
     static bool configured = false;
     if (!configured) {
-        LSK_RETURN_IF_CUDA(cudaFuncSetAttribute(csr_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kTmaSmem));
-        LSK_RETURN_IF_CUDA(cudaFuncSetAttribute(csr_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kTmaSmem));
-        LSK_RETURN_IF_CUDA(cudaFuncSetAttribute(csr_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kTmaSmem));
+        LSK_RETURN_IF_CUDA(cudaFuncSetAttribute(csr_tma_kernel<0, LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kTmaSmem));
+        LSK_RETURN_IF_CUDA(cudaFuncSetAttribute(csr_tma_kernel<1, LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kTmaSmem));
+        LSK_RETURN_IF_CUDA(cudaFuncSetAttribute(csr_tma_kernel<2, LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kTmaSmem));
         configured = true;
     }
+    if (ndot == 0)
+        csr_tma_kernel<0, LPR><<<grid, kBlock, kTmaSmem, st>>>(a, rs.partials, rs.ticket, o0, o1, rs.peers);
+    else if (ndot == 1)
+        csr_tma_kernel<1, LPR><<<grid, kBlock, kTmaSmem, st>>>(a, rs.partials, rs.ticket, o0, o1, rs.peers);
+    else
+        csr_tma_kernel<2, LPR><<<grid, kBlock, kTmaSmem, st>>>(a, rs.partials, rs.ticket, o0, o1, rs.peers);
+    return 0;
+}
+
+// lanes per row 1 (thread per row) .. 8; the row block is sized so that its non-zeros fill about one tile
+static int launch_tma_kernel(lsk_ctx *ctx, int lpr, int ndot, cudaStream_t st, int64_t rows, int64_t nnz, const double *entry,
+                             const long long *col, const lsk_rect *rowptr, int64_t k_base, const double *x, double *y,
+                             const double *dot_w, RedScratch rs, double *o0, double *o1) {
+    const double mean = rows > 0 ? (double) nnz / (double) rows : 1.0;
+    const int unit = 32 / lpr;  // rows per warp
+    int rpb = (int) ((double) kTmaTile / (mean < 1.0 ? 1.0 : mean));
+    rpb = (rpb / unit) * unit;
+    if (rpb < unit) rpb = unit;
+    if (rpb > kBlock / lpr) rpb = kBlock / lpr;
+    const int64_t nrb = rows > 0 ? (rows + rpb - 1) / rpb : 1;
+    const int64_t cap = (int64_t) ctx->sm_count * LSK_TMA_MINB;
+    const int grid = (int) (nrb < cap ? nrb : cap);
     TmaSpmvArgs a;
     a.rows = rows; a.nnz = nnz; a.rpb = rpb; a.n_row_blocks = nrb; a.entry = entry; a.col = col; a.rowptr = rowptr;
     a.k_base = k_base; a.x = x; a.y = y; a.dot_w = dot_w;
-    if (ndot == 0)
-        csr_tma_kernel<0><<<grid, kBlock, kTmaSmem, st>>>(a, rs.partials, rs.ticket, o0, o1, rs.peers);
-    else if (ndot == 1)
-        csr_tma_kernel<1><<<grid, kBlock, kTmaSmem, st>>>(a, rs.partials, rs.ticket, o0, o1, rs.peers);
-    else
-        csr_tma_kernel<2><<<grid, kBlock, kTmaSmem, st>>>(a, rs.partials, rs.ticket, o0, o1, rs.peers);
-    return 0;
+    switch (lpr) {
+    case 1: return launch_tma_kernel_lpr<1>(ndot, grid, st, a, rs, o0, o1);
+    case 2: return launch_tma_kernel_lpr<2>(ndot, grid, st, a, rs, o0, o1);
+    case 4: return launch_tma_kernel_lpr<4>(ndot, grid, st, a, rs, o0, o1);
+    default: return launch_tma_kernel_lpr<8>(ndot, grid, st, a, rs, o0, o1);
+    }
 }
 
 template <typename T, int V>
@@ -528,7 +549,7 @@ static int csr_spmv(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const
     if (rows > 0 && (!rowptr || !y || !x_shifted)) return LSK_E_INVALID;
     if (nnz > 0 && (!entry || !col)) return LSK_E_INVALID;
     if ((dot_w == nullptr) != (dot_out == nullptr)) return LSK_E_INVALID;
-    if (variant < LSK_SPMV_AUTO || variant > LSK_SPMV_WARP) return LSK_E_INVALID;
+    if (variant < LSK_SPMV_AUTO || variant > LSK_SPMV_LANES) return LSK_E_INVALID;
     // the fused reductions share one kernel shape: {} | {y.w} | {y.w, y.y}; y.y alone rides on a
     // y.w slot pointed at y itself
     int ndot = 0;
@@ -545,6 +566,23 @@ static int csr_spmv(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const
     RedScratch rs = {nullptr, nullptr, nullptr};
     if (ndot > 0) rs = next_scratch(ctx);
 
+    // the TMA kernels need fp64 and col / entry 16-byte aligned at the same elements
+    const bool tma_ok = std::is_same<T, double>::value && reinterpret_cast<uintptr_t>(entry) % 8 == 0 &&
+                        reinterpret_cast<uintptr_t>(col) % 8 == 0 &&
+                        (((reinterpret_cast<uintptr_t>(entry) >> 3) & 1) == ((reinterpret_cast<uintptr_t>(col) >> 3) & 1));
+    if (variant == LSK_SPMV_LANES) {
+        if (tma_ok) {
+            const double mean = rows > 0 ? (double) nnz / (double) rows : 1.0;
+            const int lpr = mean <= 16.0 ? 2 : mean <= 40.0 ? 4 : 8;
+            const int rc = launch_tma_kernel(ctx, lpr, ndot, st, rows, nnz, reinterpret_cast<const double *>(entry), colp, rowptr, k_base,
+                                             reinterpret_cast<const double *>(x_shifted), reinterpret_cast<double *>(y),
+                                             reinterpret_cast<const double *>(w), rs, reinterpret_cast<double *>(o0),
+                                             reinterpret_cast<double *>(o1));
+            if (rc != 0) return rc;
+            return after_launch(ctx);
+        }
+        variant = LSK_SPMV_VECTOR;  // same idea without the TMA staging (fp32, odd alignments)
+    }
     if (variant == LSK_SPMV_STREAM) {
         const double mean = rows > 0 ? (double) nnz / (double) rows : 1.0;
         int rpb = (int) ((double) kTile / (mean < 1.0 ? 1.0 : mean));
@@ -563,21 +601,11 @@ static int csr_spmv(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const
                          (reinterpret_cast<uintptr_t>(col) % 8 == 0);
         static const char *impl_env = getenv("LSK_SPMV_IMPL");  // developer A/B switch: tma | pipe | regs
         const int impl = !impl_env ? 0 : (impl_env[0] == 'p' ? 1 : impl_env[0] == 'r' ? 2 : 0);
-        // the TMA kernel needs col and entry 16-byte aligned at the same elements
-        const bool par = (((reinterpret_cast<uintptr_t>(entry) >> 3) & 1) == ((reinterpret_cast<uintptr_t>(col) >> 3) & 1));
-        if (std::is_same<T, double>::value && par && impl == 0 && reinterpret_cast<uintptr_t>(entry) % 8 == 0 &&
-            reinterpret_cast<uintptr_t>(col) % 8 == 0) {
-            int trpb = (int) ((double) kTmaTile / (mean < 1.0 ? 1.0 : mean));
-            trpb = (trpb / 32) * 32;
-            if (trpb < 32) trpb = 32;
-            if (trpb > kBlock) trpb = kBlock;
-            const int64_t tnrb = rows > 0 ? (rows + trpb - 1) / trpb : 1;
-            const int64_t tcap = (int64_t) ctx->sm_count * LSK_TMA_MINB;
-            const int tgrid = (int) (tnrb < tcap ? tnrb : tcap);
-            const int rc = launch_tma_kernel(ndot, tgrid, st, rows, nnz, trpb, tnrb, reinterpret_cast<const double *>(entry),
-                                             colp, rowptr, k_base, reinterpret_cast<const double *>(x_shifted),
-                                             reinterpret_cast<double *>(y), reinterpret_cast<const double *>(w), rs,
-                                             reinterpret_cast<double *>(o0), reinterpret_cast<double *>(o1));
+        if (tma_ok && impl == 0) {
+            const int rc = launch_tma_kernel(ctx, 1, ndot, st, rows, nnz, reinterpret_cast<const double *>(entry), colp, rowptr, k_base,
+                                             reinterpret_cast<const double *>(x_shifted), reinterpret_cast<double *>(y),
+                                             reinterpret_cast<const double *>(w), rs, reinterpret_cast<double *>(o0),
+                                             reinterpret_cast<double *>(o1));
             if (rc != 0) return rc;
         } else if (vec && impl != 2)
             launch_pipe_kernel<T>(ndot, grid, st, rows, rpb, nrb, entry, colp, rowptr, k_base, x_shifted, y, w, rs, o0, o1);

@@ -188,7 +188,11 @@ struct TmaDynamic {
     long long *s_rbq;             // shared, 2 entries
     long long rot;
 };
-template <int NDOT, bool COHERENT, bool GATED, int PART = 0, bool DYN = false>
+//   LPR       lanes per row (1, 2, 4, 8).  1: a thread owns a row and adds its products in ascending k (bit-identical to
+//             the reference CPU body).  > 1, for rows of a few dozen non-zeros where one thread per row would leave
+//             most lanes of a tile idle: LPR adjacent lanes stride one row and their partial sums are combined with
+//             shuffles (fixed tree order: deterministic, <= 1e-12 from the sequential sum).
+template <int NDOT, bool COHERENT, bool GATED, int PART = 0, bool DYN = false, int LPR = 1>
 __device__ __forceinline__ void csr_tma_run(const TmaSpmvArgs &a, TmaSpmvState &st, unsigned char *s_dyn, uint64_t *s_full,
                                             long long (*s_lo)[kWarps], long long (*s_hi)[kWarps],
                                             double (&dacc)[NDOT > 0 ? NDOT : 1], const GhostGate *gate,
@@ -197,6 +201,12 @@ __device__ __forceinline__ void csr_tma_run(const TmaSpmvArgs &a, TmaSpmvState &
     long long (*s_col)[kTmaTile] = reinterpret_cast<long long (*)[kTmaTile]>(s_dyn);
     double (*s_ent)[kTmaTile] = reinterpret_cast<double (*)[kTmaTile]>(s_dyn + (size_t) S * kTmaTile * sizeof(long long));
     const int tid = threadIdx.x;
+    // row (within the row block) and sub-lane of this thread.  With LPR lanes per row a warp covers RPW = 32 / LPR rows
+    // and the lanes of one row sit RPW apart: lanes 0 .. RPW-1 read element s of RPW CONSECUTIVE rows -- the same stencil
+    // leg, one or two cache lines -- exactly like the thread-per-row mapping, instead of LPR scattered runs.
+    constexpr int RPW = 32 / LPR;
+    const int trow = (tid >> 5) * RPW + (tid & 31) % RPW;
+    const int tsub = (tid & 31) / RPW;
     const int64_t G = gridDim.x;
     const int64_t rows = a.rows, n_row_blocks = a.n_row_blocks;
     const int rpb = a.rpb;
@@ -218,8 +228,8 @@ __device__ __forceinline__ void csr_tma_run(const TmaSpmvArgs &a, TmaSpmvState &
         lo = LLONG_MAX;
         hi1 = LLONG_MIN;
         if (rb < n_row_blocks) {
-            const int64_t r = rb * rpb + tid;
-            if (tid < rpb && r < rows) {
+            const int64_t r = rb * rpb + trow;
+            if (trow < rpb && r < rows) {
 #ifdef LSK_EXP_RECT_LDG
                 const longlong2 rc = __ldg(reinterpret_cast<const longlong2 *>(rowptr + r));
 #else
@@ -374,8 +384,8 @@ __device__ __forceinline__ void csr_tma_run(const TmaSpmvArgs &a, TmaSpmvState &
         // the fused dot's w[r] is requested now, so that its latency hides behind the gathers below
         double wv = 0.0;
         if constexpr (NDOT >= 1) {
-            const int64_t r = rb * rpb + tid;
-            if (last_tile && tid < rpb && r < rows) wv = COHERENT ? ld_f64(a.dot_w + r) : __ldg(a.dot_w + r);
+            const int64_t r = rb * rpb + trow;
+            if (last_tile && tsub == 0 && trow < rpb && r < rows) wv = COHERENT ? ld_f64(a.dot_w + r) : __ldg(a.dot_w + r);
         }
         mbar_wait(&s_full[stage], (phases >> stage) & 1u);
         phases ^= (1u << stage);
@@ -386,7 +396,21 @@ __device__ __forceinline__ void csr_tma_run(const TmaSpmvArgs &a, TmaSpmvState &
             const double *se = s_ent[stage];
             // up to kChunk gathers in flight per thread; the adds stay in ascending k
             constexpr int kChunk = 8;
-            long long j = ka;
+            long long j = ka < kb ? ka : kb;  // (rows without elements in this tile carry sentinel bounds)
+            if constexpr (LPR > 1) {
+                // LPR lanes stride the row: lane `sub` takes elements ka + sub, ka + sub + LPR, ...
+                for (j += tsub; j < kb; j += (long long) kChunk * LPR) {
+                    const int o = (int) (j - t0);
+                    double xv[kChunk];
+#pragma unroll
+                    for (int e = 0; e < kChunk; ++e)
+                        xv[e] = (j + e * LPR < kb) ? (COHERENT ? ld_f64(x + sc[o + e * LPR]) : __ldg(x + sc[o + e * LPR])) : 0.0;
+#pragma unroll
+                    for (int e = 0; e < kChunk; ++e)
+                        if (j + e * LPR < kb) acc = add_rn(acc, mul_rn(se[o + e * LPR], xv[e]));
+                }
+                j = kb;  // nothing left for the one-lane loops below
+            }
             for (; j + kChunk <= kb; j += kChunk) {  // full chunks: no predication
                 const int o = (int) (j - t0);
                 double xv[kChunk];
@@ -408,8 +432,12 @@ __device__ __forceinline__ void csr_tma_run(const TmaSpmvArgs &a, TmaSpmvState &
             }
         }
         if (last_tile) {
-            const int64_t r = rb * rpb + tid;
-            if (tid < rpb && r < rows) {
+            if constexpr (LPR > 1) {
+#pragma unroll
+                for (int o = 16; o >= RPW; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            }
+            const int64_t r = rb * rpb + trow;
+            if (tsub == 0 && trow < rpb && r < rows) {
                 a.y[r] = acc;
                 if constexpr (NDOT >= 1) dacc[0] = fma(acc, wv, dacc[0]);
                 if constexpr (NDOT >= 2) dacc[NDOT - 1] = fma(acc, acc, dacc[NDOT - 1]);

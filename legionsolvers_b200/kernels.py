@@ -12,7 +12,7 @@ import torch
 
 from . import _abi
 
-SPMV_AUTO, SPMV_STREAM, SPMV_VECTOR, SPMV_WARP = 0, 1, 2, 3
+SPMV_AUTO, SPMV_STREAM, SPMV_VECTOR, SPMV_WARP, SPMV_LANES = 0, 1, 2, 3, 4
 OP_NEG, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_SQRT, OP_RSQRT, OP_DUMMY, OP_COPY = range(9)
 
 

@@ -215,6 +215,8 @@ def test_cg_golden_history(rt, oracle, fmt, fused, traced):
 # ---- planner mat-vec: bit-exact --------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dim_flag,shape,pieces", [(2, (64, 64), 4), (3, (24, 24, 24), 8), (4, (16, 16, 16), 4), (3, (20, 20, 20), 1)])
 def test_planner_matvec_bit_exact(rt, oracle, dim_flag, shape, pieces):
+    """Bit-exact where the planner's mat-vec resolves to the thread-per-row kernel (<= 12 non-zeros per row: the 5- and
+    7-point stencils); within 1e-12 of |A||x| for the 27-point stencil (2-8 lanes per row, tree order)."""
     off, val = oracle.benchmark_stencil(dim_flag)
     m = oracle.stencil_csr(shape, off, val)
     rng = np.random.default_rng(11)
@@ -222,10 +224,20 @@ def test_planner_matvec_bit_exact(rt, oracle, dim_flag, shape, pieces):
     pl, opl, _, _ = build_system(rt, oracle, m, pieces, rhs=[x])
     pl.allocate_workspace(2); opl.allocate_workspace(2)
     pl.matvec(2, 1); opl.matvec(2, 1)
-    np.testing.assert_array_equal(pl.vector_to_numpy(2, 0, m.n_rows), opl.vector(2))
-    yw, yy = pl.matvec_dot(3, 1, 1, want_yy=True)
-    np.testing.assert_array_equal(pl.vector_to_numpy(3, 0, m.n_rows), opl.vector(2))
     y = opl.vector(2)
+    exact = m.nnz <= 12 * m.n_rows
+    absax = np.zeros(m.n_rows)
+    oracle.csr_matvec(oracle.Matrix(m.n_rows, m.n_cols, np.abs(m.entry), m.col, rowptr=m.rowptr), np.abs(x), absax)
+
+    def check(got):
+        if exact:
+            np.testing.assert_array_equal(got, y)
+        else:
+            assert np.all(np.abs(got - y) <= 1e-12 * np.maximum(absax, 1e-300))
+
+    check(pl.vector_to_numpy(2, 0, m.n_rows))
+    yw, yy = pl.matvec_dot(3, 1, 1, want_yy=True)
+    check(pl.vector_to_numpy(3, 0, m.n_rows))
     assert abs(yw - float(y @ x)) <= 1e-12 * float(np.abs(y) @ np.abs(x))
     assert abs(yy - float(y @ y)) <= 1e-12 * float(y @ y)
     # COO block through the same planner: accumulate semantics on a zero-filled destination

@@ -210,11 +210,14 @@ def test_csr_spmv_whole_matrix(ctx, oracle, dim_flag, shape):
     entry, col, rowptr, xd = dev(m.entry), dev(m.col), K.rect_tensor(m.rowptr), dev(x)
     absax = np.zeros(m.n_rows)
     oracle.csr_matvec(oracle.Matrix(m.n_rows, m.n_cols, np.abs(m.entry), m.col, rowptr=m.rowptr), np.abs(x), absax)
-    for variant in (K.SPMV_AUTO, K.SPMV_STREAM, K.SPMV_VECTOR, K.SPMV_WARP):
+    # AUTO resolves to the thread-per-row STREAM kernel up to 12 non-zeros per row on average (5- / 7-point stencils,
+    # 1-D Laplacian) and to LANES (2-8 lanes per row, tree order) for the 27-point stencil
+    exact = (K.SPMV_STREAM,) + ((K.SPMV_AUTO,) if m.nnz <= 12 * m.n_rows else ())
+    for variant in (K.SPMV_AUTO, K.SPMV_STREAM, K.SPMV_LANES, K.SPMV_VECTOR, K.SPMV_WARP):
         y = torch.full((m.n_rows,), 7.0, dtype=torch.float64, device="cuda")  # beta = 0: overwritten
         ctx.csr_spmv(m.n_rows, m.nnz, entry, col, rowptr, 0, xd, 0, y, variant=variant)
         got = y.cpu().numpy()
-        if variant in (K.SPMV_AUTO, K.SPMV_STREAM):
+        if variant in exact:
             np.testing.assert_array_equal(got, want)  # same order, same rounding as the CPU body
         else:
             assert np.all(np.abs(got - want) <= REL * np.maximum(absax, 1e-300))
@@ -239,7 +242,7 @@ def test_csr_spmv_pieces_with_fused_dots(ctx, oracle, pieces, dim_flag, shape):
     oracle.csr_matvec(m, x, want)
     entry, col, rowptr, wd = dev(m.entry), dev(m.col), K.rect_tensor(m.rowptr), dev(w)
     y = torch.zeros(n, dtype=torch.float64, device="cuda")
-    for variant in (K.SPMV_STREAM, K.SPMV_VECTOR):
+    for variant in (K.SPMV_STREAM, K.SPMV_LANES, K.SPMV_VECTOR):
         y.zero_()
         for c in range(pieces):
             r_lo, r_hi = pl.piece_bounds(0, c)
@@ -293,7 +296,7 @@ def test_csr_spmv_ragged_rows_and_empty_rows(ctx, oracle):
         e_buf = torch.zeros(nnz + 8, dtype=torch.float64, device="cuda")
         c_buf = torch.zeros(nnz + 8, dtype=torch.int64, device="cuda")
         e_buf[pad:pad + nnz] = dev(entry); c_buf[pad:pad + nnz] = dev(col)
-        for variant in (K.SPMV_STREAM, K.SPMV_VECTOR, K.SPMV_WARP):
+        for variant in (K.SPMV_STREAM, K.SPMV_LANES, K.SPMV_VECTOR, K.SPMV_WARP):
             y = torch.full((n_rows,), -3.0, dtype=torch.float64, device="cuda")
             ctx.csr_spmv(n_rows, nnz, e_buf[pad:pad + nnz], c_buf[pad:pad + nnz], K.rect_tensor(rowptr), 0,
                          dev(x), 0, y, variant=variant)
