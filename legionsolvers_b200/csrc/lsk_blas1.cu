@@ -207,8 +207,10 @@ cg_update_tma_kernel(const double *rr_old, const double *pq, const double *neg_o
                      double *r, double *rr_new, int64_t n, int64_t head, int64_t npacks, RedScratch rs) {
     extern __shared__ __align__(128) unsigned char s_dyn[];
     __shared__ __align__(8) VecKernelShared sh;
+    pdl_launch_dependents();
     VecRing ring;
     vec_ring_init(ring, s_dyn, sh);
+    pdl_wait();  // everything below reads what the mat-vec before this kernel produced (q, p.q)
     const double a1 = div_rn(*rr_old, *pq);
     const double a2 = div_rn(mul_rn(*neg_one, *rr_old), *pq);
     double racc = 0.0;
@@ -241,8 +243,10 @@ cg_direction_tma_kernel(double *rr_cur, const double *rr_new, const double *r, d
     extern __shared__ __align__(128) unsigned char s_dyn[];
     __shared__ __align__(8) VecKernelShared sh;
     __shared__ bool s_last;
+    pdl_launch_dependents();
     VecRing ring;
     vec_ring_init(ring, s_dyn, sh);
+    pdl_wait();  // rr_new and r come from the update kernel before this one
     const lsk_peers *peers = rs.peers;
     const bool multi = (peers != nullptr && h.nmoves > 0);
     const double beta = div_rn(*rr_new, *rr_cur);  // xpay(P, rr_new, rr_cur, R): alpha = f0 / f1
@@ -728,8 +732,8 @@ int lsk_cg_update_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, const double *rr_ol
         const int64_t cap = (int64_t) ctx->sm_count * 3;
         const int grid = (int) (nchunks < cap ? nchunks : cap);
         const RedScratch rs = next_scratch(ctx);
-        cg_update_tma_kernel<<<grid, kBlock, kVecStages * kVecStageBytes, (cudaStream_t) s>>>(rr_old, pq, ctx->consts + 1, p, q, x, r,
-                                                                                             rr_new, n, sp.head, sp.npacks, rs);
+        LSK_RETURN_IF_CUDA(launch_pdl(cg_update_tma_kernel, grid, kBlock, (size_t) kVecStages * kVecStageBytes, (cudaStream_t) s, rr_old, pq,
+                                      (const double *) (ctx->consts + 1), p, q, x, r, rr_new, n, sp.head, sp.npacks, rs));
         return after_launch(ctx);
     }
     CgUpdateF f;
@@ -763,8 +767,9 @@ int lsk_cg_direction_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, double *rr_cur, 
     const int grid = (int) (nchunks < cap ? nchunks : cap);
     RedScratch rs = next_scratch(ctx);
     if (nmoves == 0) rs.peers = nullptr;
-    cg_direction_tma_kernel<<<grid, kBlock, kVecStages * kVecStageBytes, (cudaStream_t) s>>>(
-        rr_cur, rr_new, r, p, n, sp.head, sp.npacks, h, rs, history, history_capacity, reinterpret_cast<long long *>(history_count));
+    LSK_RETURN_IF_CUDA(launch_pdl(cg_direction_tma_kernel, grid, kBlock, (size_t) kVecStages * kVecStageBytes, (cudaStream_t) s, rr_cur, rr_new,
+                                  r, p, n, sp.head, sp.npacks, h, rs, history, (long long) history_capacity,
+                                  reinterpret_cast<long long *>(history_count)));
     return after_launch(ctx);
 }
 

@@ -7,6 +7,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/lsk.h"
 
@@ -368,6 +369,38 @@ __device__ __forceinline__ void grid_reduce_finish(const double (&acc)[NRED], do
 }
 
 #endif  // __CUDACC__
+
+// ---- programmatic dependent launch (PDL) -- OPT-IN (LSK_PDL=1), measured harmful for the full CG chain ----------
+// The three kernels of a CG iteration depend on each other, so every boundary costs the launch latency plus the ramp of
+// the next kernel's pipeline.  With PDL the next kernel is scheduled as soon as this one's CTAs have all started
+// (pdl_launch_dependents at the top), runs its prologue on SMs as they drain -- barrier set-up, and for the mat-vec the
+// rowptr loads and the TMA copy of its first matrix tile, which do not depend on the predecessor -- and blocks in
+// pdl_wait until the predecessor has completed and its writes are visible.  Both are no-ops for a kernel launched
+// without the attribute / followed by one without it.
+// Measured on B200 (256^3, same box, alternating runs): back-to-back mat-vecs gain 1 % (442 -> 439 us) and the CG
+// iteration whose x/r update is the grid-stride kernel gains 1 %, but the chain mat-vec -> cg_update_tma ->
+// cg_direction_tma with all three edges programmatic drops from 1618 to 1180 it/s (power 630 -> 520 W: the GPU idles
+// ~65 us per boundary).  Not understood yet, so the attribute is only set when LSK_PDL=1.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned) grid);
+    cfg.blockDim = dim3((unsigned) block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    static const bool on = [] { const char *e = getenv("LSK_PDL"); return e && e[0] == '1'; }();
+    cfg.numAttrs = on ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
 
 // ---- host-side launch bookkeeping --------------------------------------------------------------------
 #define LSK_RETURN_IF_CUDA(expr)                  \

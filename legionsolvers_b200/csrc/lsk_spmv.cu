@@ -344,9 +344,15 @@ csr_tma_kernel(TmaSpmvArgs a, double *partials, unsigned int *ticket, double *ou
     double dacc[NDOT > 0 ? NDOT : 1];
 #pragma unroll
     for (int j = 0; j < (NDOT > 0 ? NDOT : 1); ++j) dacc[j] = 0.0;
+    pdl_launch_dependents();
     TmaSpmvState st;
     csr_tma_init(st, s_full);
-    csr_tma_run<NDOT, false, false, 0, false, LPR>(a, st, s_dyn, s_full, s_lo, s_hi, dacc, nullptr);
+    // prologue (rowptr rects of the first row blocks, TMA copy of the first matrix tile) does not depend on the kernel
+    // before this one; x, the fused dot's w and y do
+    TmaCursor cur;
+    csr_tma_run<NDOT, false, false, 1, false, LPR>(a, st, s_dyn, s_full, s_lo, s_hi, dacc, nullptr, &cur);
+    pdl_wait();
+    csr_tma_run<NDOT, false, false, 2, false, LPR>(a, st, s_dyn, s_full, s_lo, s_hi, dacc, nullptr, &cur);
     if constexpr (NDOT > 0) {
         double *out[NDOT];
         out[0] = out_yw;
@@ -496,13 +502,14 @@ static int launch_tma_kernel_lpr(int ndot, int grid, cudaStream_t st, const TmaS
         LSK_RETURN_IF_CUDA(cudaFuncSetAttribute(csr_tma_kernel<2, LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kTmaSmem));
         configured = true;
     }
+    cudaError_t e;
     if (ndot == 0)
-        csr_tma_kernel<0, LPR><<<grid, kBlock, kTmaSmem, st>>>(a, rs.partials, rs.ticket, o0, o1, rs.peers);
+        e = launch_pdl(csr_tma_kernel<0, LPR>, grid, kBlock, kTmaSmem, st, a, rs.partials, rs.ticket, o0, o1, rs.peers);
     else if (ndot == 1)
-        csr_tma_kernel<1, LPR><<<grid, kBlock, kTmaSmem, st>>>(a, rs.partials, rs.ticket, o0, o1, rs.peers);
+        e = launch_pdl(csr_tma_kernel<1, LPR>, grid, kBlock, kTmaSmem, st, a, rs.partials, rs.ticket, o0, o1, rs.peers);
     else
-        csr_tma_kernel<2, LPR><<<grid, kBlock, kTmaSmem, st>>>(a, rs.partials, rs.ticket, o0, o1, rs.peers);
-    return 0;
+        e = launch_pdl(csr_tma_kernel<2, LPR>, grid, kBlock, kTmaSmem, st, a, rs.partials, rs.ticket, o0, o1, rs.peers);
+    return (int) e;
 }
 
 // lanes per row 1 (thread per row) .. 8; the row block is sized so that its non-zeros fill about one tile
