@@ -6,7 +6,10 @@
 // alpha folded on the device from up to four scalar slots, reductions finished on the device in a
 // fixed order.  Element-wise arithmetic is exactly the reference CPU body's (std::fma where it uses
 // std::fma, a rounded multiply for scal), so vector results are bit-identical to the oracle.
+#include <stdlib.h>
+
 #include <initializer_list>
+#include <type_traits>
 
 #include "lsk_common.cuh"
 #include "lsk_vec_stream.cuh"
@@ -68,9 +71,48 @@ static Span plan_span(int64_t n, std::initializer_list<const void *> ptrs) {
     return s;
 }
 
+constexpr int64_t kTmaStreamMinPacksDefault = 1500000;  // 6 M elements: passes that do not fit the L2
+static int64_t tma_stream_min_packs() {  // LSK_TMA_STREAM_MIN_PACKS: developer A/B knob
+    static const int64_t v = [] {
+        const char *e = getenv("LSK_TMA_STREAM_MIN_PACKS");
+        return e ? (int64_t) atoll(e) : kTmaStreamMinPacksDefault;
+    }();
+    return v;
+}
+#define kTmaStreamMinPacks tma_stream_min_packs()
+
+template <typename F>
+__global__ void __launch_bounds__(kBlock, 3) stream_tma_kernel(F f, int64_t n, int64_t head, int64_t npacks, RedScratch rs);
+
+template <typename F, typename = void>
+struct HasTmaForm : std::false_type {};
+template <typename F>
+struct HasTmaForm<F, std::enable_if_t<std::is_same<typename F::T, double>::value && (F::NIN >= 1)>> : std::true_type {};
+
+template <typename F>
+static int tma_stream_configure() {
+    static int state = -1;
+    if (state < 0) {
+        const cudaError_t e = cudaFuncSetAttribute(stream_tma_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVecStages * kVecStageBytes);
+        state = (int) e;
+        if (e != cudaSuccess) (void) cudaGetLastError();
+    }
+    return state;
+}
+
 template <typename F>
 static int launch_stream(lsk_ctx *ctx, lsk_stream s, F f, int64_t n, Span sp) {
     if (n == 0 && F::NRED == 0) return 0;
+    if constexpr (HasTmaForm<F>::value) {
+        if (sp.npacks >= kTmaStreamMinPacks && tma_stream_configure<F>() == 0) {
+            const int64_t nchunks = (sp.npacks * 4 + VecChunk<F::NIN>::value - 1) / VecChunk<F::NIN>::value;
+            const int64_t cap = (int64_t) ctx->sm_count * 3;
+            const int grid = (int) (nchunks < cap ? nchunks : cap);
+            const RedScratch rs = next_scratch(ctx);
+            stream_tma_kernel<F><<<grid, kBlock, kVecStages * kVecStageBytes, (cudaStream_t) s>>>(f, n, sp.head, sp.npacks, rs);
+            return after_launch(ctx);
+        }
+    }
     const int64_t items = sp.npacks > 0 ? sp.npacks : n;
     const int grid = stream_grid(ctx, items > 0 ? items : 1, 8);
     RedScratch rs = {nullptr, nullptr, nullptr, nullptr};
@@ -308,6 +350,46 @@ cg_direction_tma_kernel(double *rr_cur, const double *rr_new, const double *r, d
     }
 }
 
+// The same traversal for any fp64 functor that names its input arrays (NIN <= 4) and provides pair(i, v, acc):
+// scal / axpy / xpay / dot / dot2 / axpy_dot / bicg_p_update above 6 M elements (below, the vectors of the benchmark
+// slabs are L2-resident and the grid-stride kernel with 2048 threads per SM is faster).
+template <typename F>
+__global__ void __launch_bounds__(kBlock, 3)
+stream_tma_kernel(F f, int64_t n, int64_t head, int64_t npacks, RedScratch rs) {
+    constexpr int NRED = F::NRED;
+    constexpr int NIN = F::NIN;
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    __shared__ __align__(8) VecKernelShared sh;
+    __shared__ bool s_last;
+    VecRing ring;
+    vec_ring_init(ring, s_dyn, sh);
+    f.init();
+    double acc[NRED > 0 ? NRED : 1];
+#pragma unroll
+    for (int j = 0; j < (NRED > 0 ? NRED : 1); ++j) acc[j] = 0.0;
+    const double *in[NIN];
+    f.inputs(in);
+    const double *const (&cin)[NIN] = in;
+    vec_stream<NIN>(ring, cin, head, npacks * 4, rs.work, 0, [](int64_t, int) {}, [&](int64_t i, const double (&v)[NIN][2]) { f.pair(i, v, acc); });
+    for_each_edge(n, head, npacks, [&](int64_t i) { f.scalar(i, acc); });
+    if constexpr (NRED > 0) {
+        double *out[NRED];
+        f.outs(out);
+        grid_reduce_finish<NRED, double>(acc, rs.partials, rs.ticket, out, rs.peers, rs.work);
+    } else {  // the last CTA to finish re-arms the work counter
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            s_last = (atomicAdd(rs.ticket, 1u) == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (s_last && threadIdx.x == 0) {
+            *rs.ticket = 0u;
+            *rs.work = 0ull;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Functors
 // ---------------------------------------------------------------------------------------------------
@@ -318,6 +400,11 @@ struct ScalF {  // ScalTask: x = alpha * x  (src/LinearAlgebraTasks.cpp:41)
     Alpha<T> al; T *x; T a;
     __device__ void init() { a = fold_alpha(al); }
     __device__ void scalar(int64_t i, double *) { x[i] = mul_rn(a, x[i]); }
+    static constexpr int NIN = 1;
+    __device__ void inputs(const double **in) { in[0] = reinterpret_cast<const double *>(x); }
+    __device__ void pair(int64_t i, const double (&v)[1][2], double *) {
+        *reinterpret_cast<double2 *>(x + i) = make_double2(mul_rn((double) a, v[0][0]), mul_rn((double) a, v[0][1]));
+    }
     __device__ void pack(int64_t i, double *) {
         Pack32 px = ld256(x + i);
 #pragma unroll
@@ -333,6 +420,11 @@ struct AxpyF {  // AxpyTask: y = fma(alpha, x, y)  (src/LinearAlgebraTasks.cpp:8
     Alpha<T> al; const T *x; T *y; T a;
     __device__ void init() { a = fold_alpha(al); }
     __device__ void scalar(int64_t i, double *) { y[i] = fma_rn(a, x[i], y[i]); }
+    static constexpr int NIN = 2;
+    __device__ void inputs(const double **in) { in[0] = reinterpret_cast<const double *>(x); in[1] = reinterpret_cast<const double *>(y); }
+    __device__ void pair(int64_t i, const double (&v)[2][2], double *) {
+        *reinterpret_cast<double2 *>(y + i) = make_double2(fma_rn((double) a, v[0][0], v[1][0]), fma_rn((double) a, v[0][1], v[1][1]));
+    }
     __device__ void pack(int64_t i, double *) {
         const Pack32 px = ld256(x + i);
         Pack32 py = ld256(y + i);
@@ -350,6 +442,11 @@ struct XpayF {  // XpayTask: y = fma(alpha, y, x)  (src/LinearAlgebraTasks.cpp:1
     Alpha<T> al; const T *x; T *y; T a;
     __device__ void init() { a = fold_alpha(al); }
     __device__ void scalar(int64_t i, double *) { y[i] = fma_rn(a, y[i], x[i]); }
+    static constexpr int NIN = 2;
+    __device__ void inputs(const double **in) { in[0] = reinterpret_cast<const double *>(x); in[1] = reinterpret_cast<const double *>(y); }
+    __device__ void pair(int64_t i, const double (&v)[2][2], double *) {
+        *reinterpret_cast<double2 *>(y + i) = make_double2(fma_rn((double) a, v[1][0], v[0][0]), fma_rn((double) a, v[1][1], v[0][1]));
+    }
     __device__ void pack(int64_t i, double *) {
         const Pack32 px = ld256(x + i);
         Pack32 py = ld256(y + i);
@@ -383,6 +480,12 @@ struct DotF {  // DotTask: sum v*w
     __device__ void init() {}
     __device__ void outs(T **o) { o[0] = out; }
     __device__ void scalar(int64_t i, double *acc) { acc[0] = fma((double) v[i], (double) w[i], acc[0]); }
+    static constexpr int NIN = 2;
+    __device__ void inputs(const double **in) { in[0] = reinterpret_cast<const double *>(v); in[1] = reinterpret_cast<const double *>(w); }
+    __device__ void pair(int64_t, const double (&u)[2][2], double *acc) {
+        acc[0] = fma(u[0][0], u[1][0], acc[0]);
+        acc[0] = fma(u[0][1], u[1][1], acc[0]);
+    }
     __device__ void pack(int64_t i, double *acc) {
         const Pack32 pv = ld256(v + i);
         const Pack32 pw = ld256(w + i);
@@ -402,6 +505,15 @@ struct Dot2F {  // r.u and u.u in one pass (src/BiCGStabSolver.hpp:75-76)
         const double b = w[i];
         acc[0] = fma(v[i], b, acc[0]);
         acc[1] = fma(b, b, acc[1]);
+    }
+    static constexpr int NIN = 2;
+    __device__ void inputs(const double **in) { in[0] = v; in[1] = w; }
+    __device__ void pair(int64_t, const double (&u)[2][2], double *acc) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            acc[0] = fma(u[0][e], u[1][e], acc[0]);
+            acc[1] = fma(u[1][e], u[1][e], acc[1]);
+        }
     }
     __device__ void pack(int64_t i, double *acc) {
         const Pack32 pv = ld256(v + i);
@@ -460,6 +572,15 @@ struct AxpyDotF {  // y = fma(alpha, x, y); out = sum y*w  (w may alias y)
         y[i] = yn;
         acc[0] = fma(yn, wv, acc[0]);
     }
+    static constexpr int NIN = 3;
+    __device__ void inputs(const double **in) { in[0] = x; in[1] = y; in[2] = w; }
+    __device__ void pair(int64_t i, const double (&v)[3][2], double *acc) {
+        const bool alias = (w == y);  // then the streamed copy of w is the OLD y: use the new one
+        const double y0 = fma_rn(a, v[0][0], v[1][0]), y1 = fma_rn(a, v[0][1], v[1][1]);
+        *reinterpret_cast<double2 *>(y + i) = make_double2(y0, y1);
+        acc[0] = fma(y0, alias ? y0 : v[2][0], acc[0]);
+        acc[0] = fma(y1, alias ? y1 : v[2][1], acc[0]);
+    }
     __device__ void pack(int64_t i, double *acc) {
         const Pack32 px = ld256(x + i);
         Pack32 py = ld256(y + i);
@@ -488,6 +609,12 @@ struct BicgPUpdateF {  // src/BiCGStabSolver.hpp:64-69
     __device__ void scalar(int64_t i, double *) {
         const double t = fma_rn(nomega, v[i], p[i]);   // axpy(P, -omega, V)
         p[i] = fma_rn(beta, t, r[i]);                  // xpay(P, beta, R)
+    }
+    static constexpr int NIN = 3;
+    __device__ void inputs(const double **in) { in[0] = v; in[1] = r; in[2] = p; }
+    __device__ void pair(int64_t i, const double (&u)[3][2], double *) {
+        const double t0 = fma_rn(nomega, u[0][0], u[2][0]), t1 = fma_rn(nomega, u[0][1], u[2][1]);
+        *reinterpret_cast<double2 *>(p + i) = make_double2(fma_rn(beta, t0, u[1][0]), fma_rn(beta, t1, u[1][1]));
     }
     __device__ void pack(int64_t i, double *) {
         const Pack32 pv = ld256(v + i);
@@ -727,7 +854,7 @@ int lsk_cg_update_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, const double *rr_ol
     const Span sp = plan_span<double>(n, {p, q, x, r});
     // Streamed form for passes that do not fit the L2 (measured: 805 MB pass 6.3 -> 7.0 TB/s); for an L2-resident
     // 2 M-row slab the grid-stride kernel with 2048 threads per SM is the faster one (16 vs 14 us).
-    if (sp.npacks >= (int64_t) 1500000 && vec_kernels_configure(ctx) == 0) {
+    if (sp.npacks >= kTmaStreamMinPacks && vec_kernels_configure(ctx) == 0) {
         const int64_t nchunks = (sp.npacks * 4 + 511) / 512;
         const int64_t cap = (int64_t) ctx->sm_count * 3;
         const int grid = (int) (nchunks < cap ? nchunks : cap);

@@ -41,10 +41,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 // (g + rot) % nchunks, so a phase can have a chosen range of chunks taken first.
 // begin(i0, cnt) is called by every thread once per chunk (elements i0 .. i0 + cnt - 1) before its pairs;
 // f(i, v) receives, for two consecutive elements i and i + 1, the inputs v[a][0..1] of each array.
+// elements per chunk: a multiple of 512 (two per thread and pass) that fits NIN arrays into one 16 KB stage
+template <int NIN>
+struct VecChunk {
+    static constexpr int value = NIN == 1 ? 2048 : NIN == 2 ? 1024 : 512;
+    static_assert(NIN >= 1 && NIN <= 4, "a stage holds one chunk of up to four arrays");
+};
+
 template <int NIN, class B, class F>
 __device__ __forceinline__ void vec_stream(VecRing &ring, const double *const (&in)[NIN], int64_t head, int64_t nelem,
                                            unsigned long long *counter, int64_t rot, B begin, F f) {
-    constexpr int CH = kVecStageBytes / (8 * NIN);
+    constexpr int CH = VecChunk<NIN>::value;
     const int64_t nchunks = (nelem + CH - 1) / CH;
     auto issue = [&](int s, int64_t g) {  // thread 0: grabbed index g into stage s
         if (g < nchunks) {

@@ -609,3 +609,54 @@ def test_cg_steps_misaligned_vectors_and_odd_k(ctx, oracle):
     assert np.max(np.abs(st["hist"].cpu().numpy() - want) / want) <= 1e-10
     xo = opl.vector(0)
     assert np.max(np.abs(st["x"].cpu().numpy() - xo)) <= 1e-10 * np.max(np.abs(xo))
+
+
+@pytest.mark.parametrize("off", [0, 1, 2, 3])
+def test_blas1_tma_streamed_large(ctx, oracle, off):
+    """Above 6 M elements scal / axpy / xpay / dot / dot2 / axpy_dot / bicg_p_update take the TMA-streamed, dynamically
+    scheduled form: same element-wise arithmetic (bit-exact), dots within 1e-12; ragged edges at every alignment."""
+    n = 6_291_456 + 23
+    rng = np.random.default_rng(100 + off)
+    x0, y0, w0 = rng.standard_normal(n), rng.standard_normal(n), rng.standard_normal(n)
+    mk = lambda a: (lambda t: (t.copy_(dev(a)), t)[1])(torch.zeros(n + 8, dtype=torch.float64, device="cuda")[off:off + n])  # noqa: E731
+    f = [0.37, -1.9, 0.61]
+    alpha = oracle.get_alpha(f)
+    terms = scalars(*f)
+    out = torch.zeros(1, dtype=torch.float64, device="cuda")
+    # scal
+    xd = mk(x0); xw = x0.copy()
+    oracle.scal(alpha, xw); ctx.scal(terms, xd)
+    np.testing.assert_array_equal(xd.cpu().numpy(), xw)
+    # axpy, xpay
+    xd, yd = mk(x0), mk(y0); yw = y0.copy()
+    oracle.axpy(alpha, x0, yw); ctx.axpy(terms, xd, yd)
+    np.testing.assert_array_equal(yd.cpu().numpy(), yw)
+    oracle.xpay(alpha, x0, yw); ctx.xpay(terms, xd, yd)
+    np.testing.assert_array_equal(yd.cpu().numpy(), yw)
+    # dot, dot2
+    wd = mk(w0)
+    ctx.dot(xd, wd, out)
+    assert abs(out.item() - oracle.dot(x0, w0)) <= REL * float(np.dot(np.abs(x0), np.abs(w0)))
+    o2 = torch.zeros(1, dtype=torch.float64, device="cuda")
+    ctx.dot2(xd, wd, out, o2)
+    assert abs(out.item() - oracle.dot(x0, w0)) <= REL * float(np.dot(np.abs(x0), np.abs(w0)))
+    assert abs(o2.item() - oracle.dot(w0, w0)) <= REL * oracle.dot(w0, w0)
+    # axpy_dot, separate w and aliased w = y
+    yd = mk(y0); yw = y0.copy()
+    oracle.axpy(alpha, x0, yw); ctx.axpy_dot(terms, xd, yd, wd, out)
+    np.testing.assert_array_equal(yd.cpu().numpy(), yw)
+    assert abs(out.item() - oracle.dot(yw, w0)) <= REL * float(np.dot(np.abs(yw), np.abs(w0)))
+    yd = mk(y0)
+    ctx.axpy_dot(terms, xd, yd, yd, out)
+    assert abs(out.item() - oracle.dot(yw, yw)) <= REL * oracle.dot(yw, yw)
+    # bicg_p_update: P += (-omega) V ; P = beta P + R
+    rho_new, rho_old, al, om = 1.3, 0.9, 0.41, 0.77
+    beta = oracle.scalar("mul", oracle.scalar("div", rho_new, rho_old), oracle.scalar("div", al, om))
+    pw = y0.copy()
+    oracle.axpy(-om, x0, pw); oracle.xpay(beta, w0, pw)
+    pd = mk(y0)
+    ctx.bicg_p_update(*scalars(rho_new, rho_old, al, om), xd, wd, pd)
+    np.testing.assert_array_equal(pd.cpu().numpy(), pw)
+    # and once more: the work counters were re-armed by the last CTA of every launch
+    ctx.dot(xd, wd, out)
+    assert abs(out.item() - oracle.dot(x0, w0)) <= REL * float(np.dot(np.abs(x0), np.abs(w0)))
