@@ -15,7 +15,9 @@ iterations after warm-up traces.  `value` is the whole-job rate with everything 
 memory, a fresh solve of `iters_per_step` iterations, D2H of the solution and the residual history).
 
 At N > 1 (launched under torchrun) the FIXED 256^3 problem is row-partitioned over the N GPUs --
-strong scaling -- with the ghost-x halo exchange and the dot-product all-reduces on NCCL.
+strong scaling -- with the ghost-x halo exchange and the dot-product all-reduces over NVLink peer memory
+(fused into the kernels that produce the data; LSK_COMM=nccl keeps them on NCCL).  `--persistent` runs the
+whole CG step as one persistent kernel per trace instead of three leaf kernels per iteration.
 
 `--impl reference` times the reference's CPU task variants (the oracle restatement; the reference
 itself needs Legion and cannot be built here) on the host cores, on a bounded sample.

@@ -79,7 +79,6 @@ static int64_t tma_stream_min_packs() {  // LSK_TMA_STREAM_MIN_PACKS: developer 
     }();
     return v;
 }
-#define kTmaStreamMinPacks tma_stream_min_packs()
 
 template <typename F>
 __global__ void __launch_bounds__(kBlock, 3) stream_tma_kernel(F f, int64_t n, int64_t head, int64_t npacks, RedScratch rs);
@@ -104,7 +103,7 @@ template <typename F>
 static int launch_stream(lsk_ctx *ctx, lsk_stream s, F f, int64_t n, Span sp) {
     if (n == 0 && F::NRED == 0) return 0;
     if constexpr (HasTmaForm<F>::value) {
-        if (sp.npacks >= kTmaStreamMinPacks && tma_stream_configure<F>() == 0) {
+        if (sp.npacks >= tma_stream_min_packs() && tma_stream_configure<F>() == 0) {
             const int64_t nchunks = (sp.npacks * 4 + VecChunk<F::NIN>::value - 1) / VecChunk<F::NIN>::value;
             const int64_t cap = (int64_t) ctx->sm_count * 3;
             const int grid = (int) (nchunks < cap ? nchunks : cap);
@@ -854,7 +853,7 @@ int lsk_cg_update_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, const double *rr_ol
     const Span sp = plan_span<double>(n, {p, q, x, r});
     // Streamed form for passes that do not fit the L2 (measured: 805 MB pass 6.3 -> 7.0 TB/s); for an L2-resident
     // 2 M-row slab the grid-stride kernel with 2048 threads per SM is the faster one (16 vs 14 us).
-    if (sp.npacks >= kTmaStreamMinPacks && vec_kernels_configure(ctx) == 0) {
+    if (sp.npacks >= tma_stream_min_packs() && vec_kernels_configure(ctx) == 0) {
         const int64_t nchunks = (sp.npacks * 4 + 511) / 512;
         const int64_t cap = (int64_t) ctx->sm_count * 3;
         const int grid = (int) (nchunks < cap ? nchunks : cap);

@@ -258,12 +258,6 @@ __global__ void __launch_bounds__(kBlock, LSK_TMA_MINB) cg_persistent_kernel(CgA
         // ---- phase A: q = A p, partial p.q -------------------------------------------------------------
         if (threadIdx.x == 0) gate.want = halo_base + (unsigned long long) it;  // published by the mat-vec's first CTA barrier
         // (its prologue -- first rects, first matrix tile in flight -- ran before the previous grid barrier)
-#ifdef LSK_EXP_NO_PREFETCH
-        if (it > 0) {
-            if (multi) matvec_phase<true, 1>(a.mv, st, s_dyn, &s_mv, &gate, cur, &gs->work[0]);
-            else matvec_phase<false, 1>(a.mv, st, s_dyn, &s_mv, nullptr, cur, &gs->work[0]);
-        }
-#endif
         const double pq_part = multi ? matvec_phase<true, 2>(a.mv, st, s_dyn, &s_mv, &gate, cur, &gs->work[0])
                                      : matvec_phase<false, 2>(a.mv, st, s_dyn, &s_mv, nullptr, cur, &gs->work[0]);
         lap(0);
@@ -323,11 +317,7 @@ __global__ void __launch_bounds__(kBlock, LSK_TMA_MINB) cg_persistent_kernel(CgA
         if (remote) __threadfence_system();  // my stores into the neighbours' memory are visible there
         const bool final_it = (it + 1 == a.niter);
         // the ring is free again: start the next mat-vec's first matrix tile now, so that it lands during the barrier
-#ifdef LSK_EXP_NO_PREFETCH
-        if (false) {
-#else
         if (!final_it) {
-#endif
             if (multi) matvec_phase<true, 1>(a.mv, st, s_dyn, &s_mv, &gate, cur, &gs->work[0]);
             else matvec_phase<false, 1>(a.mv, st, s_dyn, &s_mv, nullptr, cur, &gs->work[0]);
         }

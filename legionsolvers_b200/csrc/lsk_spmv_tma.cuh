@@ -102,13 +102,9 @@ __device__ __forceinline__ longlong2 ld_rect_stream(const lsk_rect *p) {
 // weak, L1-cacheable load on the COHERENT path (never LDG.CONSTANT): for vectors that the same kernel
 // also writes in another phase, made visible by a grid barrier (fence + L1 invalidation)
 __device__ __forceinline__ double ld_f64(const double *p) {
-#ifdef LSK_EXP_NC_GATHER
-    return __ldg(p);
-#else
     double v;
     asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
-#endif
 }
 // L2 load (bypasses L1): ghost values stored by a peer GPU while this kernel runs
 __device__ __forceinline__ double ld_f64_cg(const double *p) {
@@ -230,11 +226,7 @@ __device__ __forceinline__ void csr_tma_run(const TmaSpmvArgs &a, TmaSpmvState &
         if (rb < n_row_blocks) {
             const int64_t r = rb * rpb + trow;
             if (trow < rpb && r < rows) {
-#ifdef LSK_EXP_RECT_LDG
-                const longlong2 rc = __ldg(reinterpret_cast<const longlong2 *>(rowptr + r));
-#else
                 const longlong2 rc = ld_rect_stream(rowptr + r);
-#endif
                 if (rc.y >= rc.x) {
                     lo = rc.x - k_base;
                     hi1 = rc.y + 1 - k_base;

@@ -49,3 +49,42 @@ def test_null_context_is_rejected_not_crashing():
     assert L.lsk_csr_spmv_f64(None, None, 1, 1, None, None, None, 0, None, None, None, None, None, 0) == -1
     assert L.lsk_csr_spmv_pick(100, 700) == 1   # 7 nnz/row -> stream variant
     assert L.lsk_csr_spmv_pick(100, 100000) == 3  # long rows -> warp per row
+
+
+def test_spmv_variant_choice_by_row_length_statistics():
+    """AUTO: a thread per row up to 12 non-zeros per row, 2-8 lanes per row up to 96, a warp per row beyond."""
+    L = _abi.lib()
+    assert L.lsk_csr_spmv_pick(1 << 20, 5 << 20) == 1    # 2-D 5-point   -> STREAM (bit-exact)
+    assert L.lsk_csr_spmv_pick(1 << 20, 7 << 20) == 1    # 3-D 7-point   -> STREAM
+    assert L.lsk_csr_spmv_pick(1 << 20, 27 << 20) == 4   # 3-D 27-point  -> LANES
+    assert L.lsk_csr_spmv_pick(1 << 20, 96 << 20) == 4
+    assert L.lsk_csr_spmv_pick(1 << 20, 200 << 20) == 3  # long rows     -> WARP
+    assert L.lsk_csr_spmv_pick(0, 0) == 1
+
+
+def test_host_only_entry_points_of_the_cg_step():
+    """Eligibility checks and row-block arithmetic of the persistent / fused CG kernels run on the host: no GPU needed."""
+    L = _abi.lib()
+    # row blocks: one block's non-zeros fill about one 2048-element tile, at most 256 rows (one thread each)
+    assert L.lsk_cg_row_blocks(0, 0) == 0
+    assert L.lsk_cg_row_blocks(1 << 20, 7 << 20) == (1 << 20) // 256    # 7 nnz / row -> 256 rows per block
+    assert L.lsk_cg_row_blocks(1 << 20, 27 << 20) == (1 << 20) // 64    # 27 nnz / row -> 64 rows per block
+    pb = _abi.CgProblem()
+    assert L.lsk_cg_steps_supported(C.byref(pb)) == 0                   # empty problem
+    pb.rows, pb.nnz = 100, 298
+    pb.entry, pb.col, pb.rowptr = 0x1000, 0x2000, 0x3000
+    assert L.lsk_cg_steps_supported(C.byref(pb)) == 1
+    pb.col = 0x2008                                                    # col / entry not 16-byte aligned at the same elements
+    assert L.lsk_cg_steps_supported(C.byref(pb)) == 0
+    pb.col, pb.nmoves = 0x2000, 5                                      # more neighbours than the kernel mirrors to
+    assert L.lsk_cg_steps_supported(C.byref(pb)) == 0
+    # the fused direction kernel streams r and p with TMA: they must be 32-byte congruent and hold one aligned pack
+    assert L.lsk_cg_direction_supported(1000, 0x10000, 0x20000) == 1
+    assert L.lsk_cg_direction_supported(1000, 0x10008, 0x20008) == 1
+    assert L.lsk_cg_direction_supported(1000, 0x10008, 0x20010) == 0
+    assert L.lsk_cg_direction_supported(3, 0x10008, 0x20008) == 0
+    assert L.lsk_cg_direction_supported(0, 0x10000, 0x20000) == 0
+    # calls that would touch the device are refused without a context
+    assert L.lsk_cg_steps_f64(None, None, C.byref(pb), 1) == -1
+    assert L.lsk_cg_direction_f64(None, None, 8, None, None, None, None, None, 0, None, 0, None) == -1
+    assert L.lsk_gridsync_bytes() > 4096 * 16
