@@ -395,32 +395,61 @@ def run_ours(args):
         return 0
 
     # ---- end to end through the host-buffer API ------------------------------------------------------
+    # Every step is a FRESH solve of `ipt` iterations: its right-hand side comes from pinned host memory, its solution
+    # and residual history go back to the host.  The copies run on a second stream and are double-buffered against the
+    # iterations -- the H2D of step k+1's right-hand side starts as soon as step k's reset has consumed the previous one,
+    # the D2H of step k's solution (staged device-to-device) overlaps step k+1 -- the way a production caller would
+    # drive independent solves.  All copies of all steps lie inside the timed region.
     b_host = torch.ones(n, dtype=torch.float64).pin_memory()
     x_host = torch.zeros(n, dtype=torch.float64).pin_memory()
-    b_np, x_np = b_host.numpy(), x_host.numpy()
-    e2e_steps = max(2, min(args.steps, 5))
+    x_stage = torch.zeros(n_local, dtype=torch.float64, device="cuda")
+    e2e_steps = max(2, min(args.steps, 10))
     TRACE_E2E = 52
+    copy_stream = torch.cuda.Stream()
+    cs = copy_stream.cuda_stream
+    b_glob, x_stage_glob = b_host.data_ptr(), x_stage.data_ptr() - 8 * own_lo
+    x_host_own = x_host[own_lo:own_lo + n_local]
 
-    def e2e_step():
-        pl.vector_from_numpy(1, 0, b_np)          # H2D: this step's right-hand side (owned rows)
-        pl.zero_fill(0)
-        cg.reset()
-        rt.begin_trace(TRACE_E2E)
-        for _ in range(ipt):
-            cg.step()
-        rt.end_trace(TRACE_E2E)
-        S._check(_abi.lib().lsk_planner_vector_to_host(pl.h, 0, 0, x_np.ctypes.data), "vector_to_host")  # D2H: solution
-        return cg.residual_norm_squared               # D2H: residual history (synchronises)
+    def e2e_run(nsteps):
+        ev_h2d, ev_reset, ev_solved, ev_d2h = (torch.cuda.Event() for _ in range(4))
+        copy_stream.wait_stream(tstream)
+        pl.vector_from_async(1, 0, b_glob, cs)       # H2D: right-hand side of the first step
+        ev_h2d.record(copy_stream)
+        ev_d2h.record(copy_stream)
+        hist = None
+        for k in range(nsteps):
+            tstream.wait_event(ev_h2d)                # this step's right-hand side has landed
+            pl.zero_fill(0)
+            cg.reset()                                # P <- RHS, R <- RHS, rr0: the last readers of RHS
+            ev_reset.record(tstream)
+            if k + 1 < nsteps:                        # H2D of the NEXT step's right-hand side, under this step's iterations
+                copy_stream.wait_event(ev_reset)
+                pl.vector_from_async(1, 0, b_glob, cs)
+                ev_h2d.record(copy_stream)
+            rt.begin_trace(TRACE_E2E)
+            for _ in range(ipt):
+                cg.step()
+            rt.end_trace(TRACE_E2E)
+            tstream.wait_event(ev_d2h)                # the staging buffer's previous content is on the host
+            pl.vector_to_async(0, 0, x_stage_glob, stream)   # solution -> staging buffer (device to device)
+            ev_solved.record(tstream)
+            copy_stream.wait_event(ev_solved)
+            with torch.cuda.stream(copy_stream):      # D2H: this step's solution, under the next step's iterations
+                x_host_own.copy_(x_stage, non_blocking=True)
+            ev_d2h.record(copy_stream)
+            hist = cg.residual_norm_squared           # D2H: this step's residual history (waits for its iterations)
+        copy_stream.synchronize()
+        return hist
 
-    e2e_step()
+    e2e_run(2)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        hist = e2e_step()
+    hist = e2e_run(e2e_steps)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = e2e_steps * ipt / e2e_s
     rr_final = float(hist[-1])
+    x_check = float(x_host_own.abs().max())  # the solution really arrived
 
     # ---- CPU baseline on the box's host cores (rank 0, N = 1 only), bounded sample ---------------------
     cpu_baseline = None
@@ -459,7 +488,9 @@ def run_ours(args):
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n_local,
                     "d2h_bytes_per_step": 8 * n_local + 8 * (ipt + 1), "steps": e2e_steps,
-                    "what": "per step: H2D rhs (pinned) -> reset -> iters_per_step CG iterations -> D2H solution + residual history"},
+                    "what": ("per step: H2D rhs (pinned) -> reset -> iters_per_step CG iterations -> D2H solution + residual history; "
+                             "copies on a second stream, double-buffered against the iterations of the neighbouring steps"),
+                    "solution_abs_max": x_check},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

@@ -105,6 +105,12 @@ int lsk_planner_matvec(lsk_planner *pl, int dst, int src);
 int lsk_planner_matvec_dot(lsk_planner *pl, int dst, int src, int w, double *out_yw, double *out_yy);
 int lsk_planner_vector_to_host(lsk_planner *pl, int vec, int space, double *global);
 int lsk_planner_vector_from_host(lsk_planner *pl, int vec, int space, const double *global);
+/* Asynchronous copies of the OWNED rows, `global + own_lo` <-> the vector, with cudaMemcpyAsync(cudaMemcpyDefault) on
+ * `stream` (a cudaStream_t; NULL = the runtime's stream) and no synchronisation: `global` may be pinned host memory or
+ * device memory.  On a stream other than the runtime's the caller orders the copy against the solver's work with
+ * events -- this is how the I/O of one solve overlaps the iterations of the next (bench.py's end-to-end loop). */
+int lsk_planner_vector_to_async(lsk_planner *pl, int vec, int space, double *global, void *stream);
+int lsk_planner_vector_from_async(lsk_planner *pl, int vec, int space, const double *global, void *stream);
 
 /* ---- solvers (src/CGSolver.hpp, src/BiCGStabSolver.hpp, src/GMRESSolver.hpp) -------------------------------------- */
 enum lsk_solver_kind { LSK_SOLVER_CG = 1, LSK_SOLVER_BICGSTAB = 2, LSK_SOLVER_GMRES = 3 }; /* BenchmarkStencil -solver */

@@ -104,6 +104,8 @@ def declare(L) -> None:
     L.lsk_planner_matvec_dot.argtypes = [vp, ci, ci, ci, C.POINTER(dbl), C.POINTER(dbl)]
     L.lsk_planner_vector_to_host.argtypes = [vp, ci, ci, vp]
     L.lsk_planner_vector_from_host.argtypes = [vp, ci, ci, vp]
+    L.lsk_planner_vector_to_async.argtypes = [vp, ci, ci, vp, vp]
+    L.lsk_planner_vector_from_async.argtypes = [vp, ci, ci, vp, vp]
 
     L.lsk_solver_create.argtypes = [vp, ci, ci, ci, C.POINTER(vp)]
     L.lsk_solver_destroy.argtypes = [vp]

@@ -297,6 +297,24 @@ public:
                                        rt->stream()), "vector D2H");
     }
 
+    // Asynchronous forms on a stream of the caller's choice (null = the runtime's stream), for overlapping the I/O of
+    // one solve with the iterations of another: `global_array` may be pinned host memory or device memory
+    // (cudaMemcpyDefault).  On a foreign stream the caller orders the copy against the solver's work with events.
+    void copy_from_async(const T *global_array, cudaStream_t s) {
+        Runtime *rt = st->rt;
+        const IndexPartition &p = *st->part;
+        if (!p.owns_any()) return;
+        rt->check_cuda(cudaMemcpyAsync(ptr(p.own_lo()), global_array + p.own_lo(), sizeof(T) * (size_t) (p.own_hi() - p.own_lo() + 1),
+                                       cudaMemcpyDefault, s ? s : rt->stream()), "vector copy-in (async)");
+    }
+    void copy_to_async(T *global_array, cudaStream_t s) const {
+        Runtime *rt = st->rt;
+        const IndexPartition &p = *st->part;
+        if (!p.owns_any()) return;
+        rt->check_cuda(cudaMemcpyAsync(global_array + p.own_lo(), ptr(p.own_lo()), sizeof(T) * (size_t) (p.own_hi() - p.own_lo() + 1),
+                                       cudaMemcpyDefault, s ? s : rt->stream()), "vector copy-out (async)");
+    }
+
     void require_same(const PartitionedVector &x) const {
         if (st->part != x.st->part && !st->part->same_as(*x.st->part))
             st->rt->fail(LSK_E_INVALID, "vectors live on different partitions");

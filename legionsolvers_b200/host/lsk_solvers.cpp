@@ -378,6 +378,14 @@ int lsk_planner_vector_from_host(lsk_planner *pl, int vec, int space, const doub
         pl->rt->fence();
     });
 }
+int lsk_planner_vector_to_async(lsk_planner *pl, int vec, int space, double *global, void *stream) {
+    REQUIRE(pl && global && vec >= 0 && space >= 0);
+    return guard([&] { pl->pl->get_vector((size_t) vec, (size_t) space).copy_to_async(global, static_cast<cudaStream_t>(stream)); });
+}
+int lsk_planner_vector_from_async(lsk_planner *pl, int vec, int space, const double *global, void *stream) {
+    REQUIRE(pl && global && vec >= 0 && space >= 0);
+    return guard([&] { pl->pl->get_vector((size_t) vec, (size_t) space).copy_from_async(global, static_cast<cudaStream_t>(stream)); });
+}
 
 // ---- solvers -----------------------------------------------------------------------------------------------------
 int lsk_solver_create(lsk_planner *pl, int kind, int restart, int fused, lsk_solver **out) {

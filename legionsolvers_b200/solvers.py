@@ -327,6 +327,14 @@ class SquarePlanner:
     def vector_from_numpy(self, vec, space, a: np.ndarray):
         _check(_abi.lib().lsk_planner_vector_from_host(self.h, vec, space, _np_ptr(a, np.float64)), "vector_from_host")
 
+    def vector_to_async(self, vec, space, global_ptr: int, stream: int | None = None):
+        """Owned rows -> `global_ptr + 8 * own_lo` (pinned host or device memory), asynchronously on `stream`
+        (a cudaStream_t handle; None = the runtime's stream).  No synchronisation: order foreign streams with events."""
+        _check(_abi.lib().lsk_planner_vector_to_async(self.h, vec, space, global_ptr, stream), "vector_to_async")
+
+    def vector_from_async(self, vec, space, global_ptr: int, stream: int | None = None):
+        _check(_abi.lib().lsk_planner_vector_from_async(self.h, vec, space, global_ptr, stream), "vector_from_async")
+
     def destroy(self):
         if getattr(self, "h", None):
             _abi.lib().lsk_planner_destroy(self.h)
