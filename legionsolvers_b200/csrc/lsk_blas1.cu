@@ -89,21 +89,18 @@ template <typename F>
 struct HasTmaForm<F, std::enable_if_t<std::is_same<typename F::T, double>::value && (F::NIN >= 1)>> : std::true_type {};
 
 template <typename F>
-static int tma_stream_configure() {
-    static int state = -1;
-    if (state < 0) {
-        const cudaError_t e = cudaFuncSetAttribute(stream_tma_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVecStages * kVecStageBytes);
-        state = (int) e;
-        if (e != cudaSuccess) (void) cudaGetLastError();
-    }
-    return state;
+static int tma_stream_configure(lsk_ctx *ctx) {
+    static const int family = configure_family_index();
+    return configure_once(ctx, family, [] {
+        return cudaFuncSetAttribute(stream_tma_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVecStages * kVecStageBytes);
+    });
 }
 
 template <typename F>
 static int launch_stream(lsk_ctx *ctx, lsk_stream s, F f, int64_t n, Span sp) {
     if (n == 0 && F::NRED == 0) return 0;
     if constexpr (HasTmaForm<F>::value) {
-        if (sp.npacks >= tma_stream_min_packs() && tma_stream_configure<F>() == 0) {
+        if (sp.npacks >= tma_stream_min_packs() && tma_stream_configure<F>(ctx) == 0) {
             const int64_t nchunks = (sp.npacks * 4 + VecChunk<F::NIN>::value - 1) / VecChunk<F::NIN>::value;
             const int64_t cap = (int64_t) ctx->sm_count * 3;
             const int grid = (int) (nchunks < cap ? nchunks : cap);
@@ -744,17 +741,15 @@ static int do_fill(lsk_ctx *ctx, lsk_stream s, int64_t n, T value, const T *vdev
     return launch_stream(ctx, s, f, n, plan_span<T>(n, {x}));
 }
 
-// one-time opt-in to 64 KB of dynamic shared memory for the TMA-streamed kernels
-static int vec_kernels_configure(lsk_ctx *) {
-    static int state = -1;  // -1 not tried, 0 ok, > 0 CUDA error
-    if (state < 0) {
+// opt-in to 64 KB of dynamic shared memory for the two CG vector kernels (once per context, i.e. per device)
+static int vec_kernels_configure(lsk_ctx *ctx) {
+    static const int family = configure_family_index();
+    return configure_once(ctx, family, [] {
         cudaError_t e = cudaFuncSetAttribute(cg_update_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kVecStages * kVecStageBytes);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(cg_direction_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kVecStages * kVecStageBytes);
-        state = (int) e;
-        if (e != cudaSuccess) (void) cudaGetLastError();
-    }
-    return state;
+        return e;
+    });
 }
 
 }  // namespace lsk

@@ -33,6 +33,8 @@ struct lsk_ctx {
     unsigned long long launches;
     lsk_peers *d_peers;        // device copy of the peer windows; non-null = reducing kernels all-reduce in their tail
     unsigned long long *work;  // [kScratchSets] dynamic work counters of the TMA-streamed vector kernels, zero between launches
+    unsigned long long configured;  // one bit per kernel family whose dynamic shared-memory opt-in was done on THIS device
+                                    // (function attributes are per device: a process may hold contexts on several GPUs)
     void *gridsync;            // lsk::GridSync: grid barrier + partials of the persistent solver kernels
     int cg_blocks_per_sm;      // occupancy of the persistent CG kernel (0 = not queried yet)
 };
@@ -408,6 +410,30 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, siz
         cudaError_t e_ = (expr);                  \
         if (e_ != cudaSuccess) return (int) e_;   \
     } while (0)
+
+// Per-context, per-kernel-family opt-in to more than 48 KB of dynamic shared memory.  `family` indices are handed out
+// process-wide on first use (configure_family_index); the "done" bit lives in the context, i.e. per device.
+inline int configure_family_index() {
+    static int next = 0;
+    return next++;
+}
+template <class Setup>
+inline int configure_once(lsk_ctx *ctx, int family, Setup setup) {
+    if (family < 0 || family >= 64) return (int) cudaErrorInvalidValue;
+    const unsigned long long bit = 1ull << family;
+    if (ctx->configured & bit) return 0;
+    int current = -1;
+    (void) cudaGetDevice(&current);
+    if (current != ctx->device) (void) cudaSetDevice(ctx->device);  // function attributes apply to the current device
+    const cudaError_t e = setup();
+    if (current >= 0 && current != ctx->device) (void) cudaSetDevice(current);
+    if (e != cudaSuccess) {
+        (void) cudaGetLastError();
+        return (int) e;
+    }
+    ctx->configured |= bit;
+    return 0;
+}
 
 inline int after_launch(lsk_ctx *ctx) {
     ctx->launches += 1;

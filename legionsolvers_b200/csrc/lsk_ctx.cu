@@ -49,6 +49,7 @@ int lsk_ctx_create(int device, lsk_ctx **out) {
     ctx->d_peers = nullptr;
     ctx->gridsync = nullptr;
     ctx->work = nullptr;
+    ctx->configured = 0;
     ctx->cg_blocks_per_sm = 0;
     const size_t pbytes = sizeof(double) * (size_t) kScratchSets * kMaxRed * kMaxPartials;
     cudaError_t e = cudaMalloc(&ctx->partials, pbytes);

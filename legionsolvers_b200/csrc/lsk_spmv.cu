@@ -494,14 +494,16 @@ static void launch_pipe_kernel(int ndot, int grid, cudaStream_t st, int64_t rows
 }
 
 template <int LPR>
-static int launch_tma_kernel_lpr(int ndot, int grid, cudaStream_t st, const TmaSpmvArgs &a, RedScratch rs, double *o0, double *o1) {
-    static bool configured = false;
-    if (!configured) {
-        LSK_RETURN_IF_CUDA(cudaFuncSetAttribute(csr_tma_kernel<0, LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kTmaSmem));
-        LSK_RETURN_IF_CUDA(cudaFuncSetAttribute(csr_tma_kernel<1, LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kTmaSmem));
-        LSK_RETURN_IF_CUDA(cudaFuncSetAttribute(csr_tma_kernel<2, LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kTmaSmem));
-        configured = true;
-    }
+static int launch_tma_kernel_lpr(lsk_ctx *ctx, int ndot, int grid, cudaStream_t st, const TmaSpmvArgs &a, RedScratch rs, double *o0,
+                                 double *o1) {
+    static const int family = configure_family_index();
+    const int rc = configure_once(ctx, family, [] {
+        cudaError_t e = cudaFuncSetAttribute(csr_tma_kernel<0, LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kTmaSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(csr_tma_kernel<1, LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kTmaSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(csr_tma_kernel<2, LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kTmaSmem);
+        return e;
+    });
+    if (rc != 0) return rc;
     cudaError_t e;
     if (ndot == 0)
         e = launch_pdl(csr_tma_kernel<0, LPR>, grid, kBlock, kTmaSmem, st, a, rs.partials, rs.ticket, o0, o1, rs.peers);
@@ -529,10 +531,10 @@ static int launch_tma_kernel(lsk_ctx *ctx, int lpr, int ndot, cudaStream_t st, i
     a.rows = rows; a.nnz = nnz; a.rpb = rpb; a.n_row_blocks = nrb; a.entry = entry; a.col = col; a.rowptr = rowptr;
     a.k_base = k_base; a.x = x; a.y = y; a.dot_w = dot_w;
     switch (lpr) {
-    case 1: return launch_tma_kernel_lpr<1>(ndot, grid, st, a, rs, o0, o1);
-    case 2: return launch_tma_kernel_lpr<2>(ndot, grid, st, a, rs, o0, o1);
-    case 4: return launch_tma_kernel_lpr<4>(ndot, grid, st, a, rs, o0, o1);
-    default: return launch_tma_kernel_lpr<8>(ndot, grid, st, a, rs, o0, o1);
+    case 1: return launch_tma_kernel_lpr<1>(ctx, ndot, grid, st, a, rs, o0, o1);
+    case 2: return launch_tma_kernel_lpr<2>(ctx, ndot, grid, st, a, rs, o0, o1);
+    case 4: return launch_tma_kernel_lpr<4>(ctx, ndot, grid, st, a, rs, o0, o1);
+    default: return launch_tma_kernel_lpr<8>(ctx, ndot, grid, st, a, rs, o0, o1);
     }
 }
 
