@@ -1,5 +1,5 @@
 /*
- * lsk_solvers.h -- C ABI of the C++ host layer (legionsolvers_b200/host/*.hpp): the planner-level
+ * lsk_solvers.h -- C ABI of the C++ host layer (legionsolvers_b200/host/ headers): the planner-level
  * API of the reference (PartitionedVector, CSRMatrix / COOMatrix, SquarePlanner, CGSolver,
  * BiCGStabSolver, GMRESSolver) as opaque handles, for callers that are not C++ (the Python tests
  * and bench.py drive everything through this file and lsk.h).
