@@ -357,7 +357,8 @@ int lsk_cg_direction_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, double *rr_cur, 
  * on one CSR piece per GPU, with grid barriers between the phases instead of kernel boundaries.  With
  * lsk_ctx_set_peers in effect the two dot products are summed across ranks inside the grid barrier
  * and the boundary of p is stored into the neighbours' ghost regions (`moves`, as for
- * lsk_xpay_halo_f64); consumers wait per ghost access, so no rank ever waits at a halo barrier.
+ * lsk_xpay_halo_f64); a CTA waits for the neighbours' epoch only before it consumes a row block that references
+ * ghost columns, so no rank ever waits at a halo barrier.
  * Element-wise arithmetic is identical to the leaf-task sequence.  Preconditions: the ghosts of p are
  * current at entry (they are again at exit); entry/col 16-byte aligned at the same elements.
  * ---------------------------------------------------------------------------------------------- */
@@ -377,7 +378,7 @@ typedef struct {
     const lsk_halo_move *moves;   /* boundary sub-ranges of P's owned piece to push; NULL / 0 on one rank */
     int nmoves;                   /* <= 4 */
     const uint8_t *ghost_blocks;  /* optional (several ranks): lsk_cg_row_blocks() flags from lsk_cg_ghost_blocks; only
-                                     flagged row blocks pay the per-gather ghost test.  NULL = test everywhere */
+                                     flagged row blocks wait for the neighbours' halo epoch before they are consumed.  NULL = every block does */
 } lsk_cg_problem;
 /* number of row blocks the kernel cuts `rows` into, and the flags "row block references a column outside the
  * owned rows [own_lo, own_lo + rows)" (one byte per row block, computed once per matrix piece) */

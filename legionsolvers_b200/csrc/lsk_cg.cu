@@ -6,15 +6,17 @@
 // co-resident wave of CTAs alive for `niter` complete iterations:
 //
 //   phase A   q = A p          (the TMA-staged thread-per-row mat-vec of lsk_spmv_tma.cuh) + p.q partial
-//   sync 1    grid barrier; its LAST ARRIVER folds the partials (fixed order) and, on several GPUs,
-//             exchanges the rank sums over NVLink peer memory (LL packets), then releases the grid
+//   sync 1    grid barrier (gather-broadcast through CTA 0 with LL packets); CTA 0 sums the partials in a
+//             fixed order and, on several GPUs, exchanges the rank sums over NVLink peer memory, then
+//             releases the grid
 //   phase B   x = fma(rr/pq, p, x);  r = fma((-1*rr)/pq, q, r);  r.r partial      (:50-52)
 //   sync 2    same as sync 1 for r.r
 //   phase C   p = fma(rr_new/rr, p, r)                                             (:54)
 //             boundary elements are also stored into the neighbours' ghost regions
-//   sync 3    grid barrier; the last arriver publishes "my halo of this iteration has landed" to the
-//             neighbours.  Nobody waits here: in the next phase A only the threads that actually gather
-//             a ghost column wait for the neighbour's flag (and then read through L2).
+//   sync 3    grid barrier; CTA 0 publishes "my halo of this iteration has landed" to the neighbours.
+//             Nobody waits here: in the next phase A a CTA waits for the neighbours' flag only before it
+//             consumes a row block that references ghost columns (lsk_spmv_tma.cuh, GhostGate) -- and those
+//             blocks are walked mid-phase, when the halo has long arrived.
 //
 // Element-wise arithmetic is the reference's (same fma / rounded multiply per element as the
 // 3-kernel fused path and the oracle); scalars never leave the device; the residual history is

@@ -106,13 +106,6 @@ __device__ __forceinline__ double ld_f64(const double *p) {
     asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
 }
-// L2 load (bypasses L1): ghost values stored by a peer GPU while this kernel runs
-__device__ __forceinline__ double ld_f64_cg(const double *p) {
-    double v;
-    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
-}
-
 struct TmaSpmvArgs {
     int64_t rows, nnz;
     int rpb;                 // rows per row block (<= kBlock, one thread per row)

@@ -300,7 +300,7 @@ public:
             if (!lsk_cg_steps_supported(pb)) return false;
             if (nm > 0) {
                 // which row blocks reference ghost columns: computed once (outside any trace), so that only
-                // those pay the per-gather ghost test inside the kernel
+                // those wait for the neighbours' halo epoch inside the kernel
                 if (cg_ghost_blocks.count == 0 && !rt->capturing() && !rt->replaying()) {
                     cg_ghost_blocks = DeviceBuffer<uint8_t>(rt, (size_t) lsk_cg_row_blocks(pb->rows, pb->nnz));
                     uint8_t *flags = cg_ghost_blocks.ptr;
