@@ -145,3 +145,36 @@ def test_gloo_world2_halo_plan_and_cg():
     # 3-D 7-point, row-major: the halo is exactly one ny*nz plane each way
     assert s0_n == s1_n == 6 * 5
     assert g0 == (0, 4 * 30 + 30 - 1) and g1 == (4 * 30 - 30, 8 * 30 - 1)
+
+
+def test_gloo_world4_halo_plan_and_cg():
+    """Four ranks over gloo: the two middle ranks trade a plane with BOTH neighbours and nothing with the others;
+    distributed CG on the planned halo equals the single-process oracle on every rank."""
+    import torch.multiprocessing as mp
+
+    world = 4
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, 29541, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    plane = 6 * 5
+    plans = {}
+    for rank, err, xerr, moves, ghost in out:
+        assert err <= 1e-12 and xerr <= 1e-12, (rank, err, xerr)
+        plans[rank] = {peer: (s_lo, s_n, r_lo, r_n) for peer, s_lo, s_n, r_lo, r_n in moves}
+        # ghost interval = owned rows (2 planes) plus one plane on each interior side
+        lo, hi = rank * 2 * plane, (rank + 1) * 2 * plane - 1
+        assert ghost == (max(0, lo - plane), min(world * 2 * plane - 1, hi + plane))
+    for a in range(world):
+        for b in range(world):
+            if a == b:
+                continue
+            s_lo, s_n, _, _ = plans[a][b]
+            _, _, r_lo, r_n = plans[b][a]
+            assert (s_lo, s_n) == (r_lo, r_n) or (s_n == 0 and r_n == 0)   # what a sends to b is what b receives from a
+            assert s_n == (plane if abs(a - b) == 1 else 0)                  # one plane to each neighbour, nothing further
