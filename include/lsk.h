@@ -344,11 +344,34 @@ int lsk_xpay_halo_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, int n_terms, const 
  * then *rr_cur = *rr_new for the next step.  `history` may be NULL (no append); otherwise circular like
  * lsk_scalar_append_f64.  With `moves` (nmoves <= 4; needs lsk_ctx_set_peers) the boundary of p is also stored into
  * the neighbours' ghost regions and the exchange epoch is closed, exactly as lsk_xpay_halo_f64 does.
- * TMA-streamed: r and p must be 32-byte congruent (lsk_cg_direction_supported). */
+ * TMA-streamed: r and p must be 32-byte congruent (lsk_cg_direction_supported).
+ * halo_open != 0: the kernel publishes its halo but does NOT wait for the neighbours' -- the exchange stays open and its
+ * consumer waits instead: lsk_csr_spmv_gated_f64 per row block (the halo wait leaves the critical path), or
+ * lsk_halo_wait_f64 for any other reader of the ghosts. */
 int lsk_cg_direction_supported(int64_t n, const double *r, const double *p);
 int lsk_cg_direction_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, double *rr_cur, const double *rr_new, const double *r,
-                         double *p, const lsk_halo_move *moves, int nmoves, double *history,
+                         double *p, const lsk_halo_move *moves, int nmoves, int halo_open, double *history,
                          int64_t history_capacity, int64_t *history_count);
+/* Closes an open exchange: when the kernel completes, the data of every peer with moves[i].expect != 0 has landed. */
+int lsk_halo_wait_f64(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, const lsk_halo_move *moves, int nmoves);
+
+/* CSRMatvecTask on several GPUs with the halo wait INSIDE the mat-vec (needs lsk_ctx_set_peers): identical to
+ * lsk_csr_spmv_f64, except that ghost columns of x (outside the rows this rank owns) may still be in flight from the
+ * neighbours when the kernel starts.  `ghost_blocks` (lsk_csr_spmv_row_blocks() bytes, from lsk_csr_ghost_blocks; NULL =
+ * every row block) marks the row blocks that reference a ghost column; before the kernel feeds the first such block to a
+ * CTA it waits until every peer with moves[i].expect != 0 has published the pair's current exchange (the one an
+ * open lsk_cg_direction_f64 / lsk_xpay_halo_f64 of this rank counted last), then fences.  Marked blocks are walked
+ * last-ish (each CTA starts in the middle of its list), so on a banded matrix nobody waits.  Only moves[i].peer and
+ * moves[i].expect are read.  STREAM / LANES variants only (lsk_csr_spmv_gated_supported). */
+int lsk_csr_spmv_gated_supported(int64_t rows, int64_t nnz, const double *entry, const int64_t *col, const lsk_rect *rowptr,
+                                 int variant);
+int64_t lsk_csr_spmv_row_blocks(int64_t rows, int64_t nnz, int variant);
+int lsk_csr_ghost_blocks(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const int64_t *col, const lsk_rect *rowptr,
+                         int64_t k_base, int64_t own_lo, int64_t own_n, int variant, uint8_t *flags);
+int lsk_csr_spmv_gated_f64(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const double *entry, const int64_t *col,
+                           const lsk_rect *rowptr, int64_t k_base, const double *x_shifted, double *y, const double *dot_w,
+                           double *dot_out, double *dot_yy_out, int variant, const uint8_t *ghost_blocks,
+                           const lsk_halo_move *moves, int nmoves);
 
 /* ------------------------------------------------------------------------------------------------
  * The whole CG step as one persistent kernel -- CGSolver::step (src/CGSolver.hpp:46-55) `niter` times:

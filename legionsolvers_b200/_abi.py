@@ -104,7 +104,13 @@ def _declare(L: C.CDLL) -> None:
     L.lsk_bicg_p_update_f64.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp]
     L.lsk_bicg_tail_f64.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.lsk_cg_direction_supported.argtypes = [i64, vp, vp]
-    L.lsk_cg_direction_f64.argtypes = [vp, vp, i64, vp, vp, vp, vp, C.POINTER(HaloMove), ci, vp, i64, vp]
+    L.lsk_cg_direction_f64.argtypes = [vp, vp, i64, vp, vp, vp, vp, C.POINTER(HaloMove), ci, ci, vp, i64, vp]
+    L.lsk_halo_wait_f64.argtypes = [vp, vp, vp, C.POINTER(HaloMove), ci]
+    L.lsk_csr_spmv_gated_supported.argtypes = [i64, i64, vp, vp, vp, ci]
+    L.lsk_csr_spmv_row_blocks.argtypes = [i64, i64, ci]
+    L.lsk_csr_spmv_row_blocks.restype = i64
+    L.lsk_csr_ghost_blocks.argtypes = [vp, vp, i64, i64, vp, vp, i64, i64, i64, ci, vp]
+    L.lsk_csr_spmv_gated_f64.argtypes = [vp, vp, i64, i64, vp, vp, vp, i64, vp, vp, vp, vp, vp, ci, vp, C.POINTER(HaloMove), ci]
     L.lsk_cg_steps_supported.argtypes = [C.POINTER(CgProblem)]
     L.lsk_cg_steps_f64.argtypes = [vp, vp, C.POINTER(CgProblem), ci]
     L.lsk_cg_row_blocks.argtypes = [i64, i64]

@@ -175,7 +175,7 @@ xpay_halo_kernel(Alpha<double> al, const double *__restrict__ x, double *__restr
         y[i] = v;
         mirror(i, v);
     }
-    // ---- epilogue: last CTA closes the exchange epoch
+    // ---- epilogue: last CTA closes the exchange
     CommWindow *me = static_cast<CommWindow *>(peers->window[peers->rank]);
     __shared__ bool s_last;
     if (remote) __threadfence_system();  // my stores into the neighbours' memory are visible there
@@ -187,25 +187,8 @@ xpay_halo_kernel(Alpha<double> al, const double *__restrict__ x, double *__restr
     }
     __syncthreads();
     if (!s_last) return;
-    const unsigned long long t_halo0 = global_ns();
-    __threadfence_system();
-    const unsigned long long e = me->halo_epoch + 1;
-    if (threadIdx.x < h.nmoves) {
-        const lsk_halo_move &mv = h.m[threadIdx.x];
-        if (mv.n > 0) {
-            CommWindow *dst = static_cast<CommWindow *>(peers->window[mv.peer]);
-            *reinterpret_cast<volatile unsigned long long *>(&dst->halo_done[peers->rank]) = e;
-        }
-        if (mv.expect) spin_until(&me->halo_done[mv.peer], e, &me->error);
-    }
-    __syncthreads();
-    __threadfence_system();
-    if (threadIdx.x == 0) {
-        me->halo_epoch = e;
-        me->halo_ticket = 0u;
-        me->halo_calls += 1;
-        me->halo_wait_ns += global_ns() - t_halo0;
-    }
+    halo_publish(peers, h.m, h.nmoves, h.open == 0);
+    if (threadIdx.x == 0) me->halo_ticket = 0u;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -312,27 +295,7 @@ cg_direction_tma_kernel(double *rr_cur, const double *rr_new, const double *r, d
     }
     __syncthreads();
     if (!s_last) return;
-    if (multi) {  // close the exchange epoch: publish, wait for the neighbours' (see xpay_halo_kernel)
-        CommWindow *me = static_cast<CommWindow *>(peers->window[peers->rank]);
-        const unsigned long long t_halo0 = global_ns();
-        __threadfence_system();
-        const unsigned long long e = me->halo_epoch + 1;
-        if (threadIdx.x < h.nmoves) {
-            const lsk_halo_move &mv = h.m[threadIdx.x];
-            if (mv.n > 0) {
-                CommWindow *dst = static_cast<CommWindow *>(peers->window[mv.peer]);
-                *reinterpret_cast<volatile unsigned long long *>(&dst->halo_done[peers->rank]) = e;
-            }
-            if (mv.expect) spin_until(&me->halo_done[mv.peer], e, &me->error);
-        }
-        __syncthreads();
-        __threadfence_system();
-        if (threadIdx.x == 0) {
-            me->halo_epoch = e;
-            me->halo_calls += 1;
-            me->halo_wait_ns += global_ns() - t_halo0;
-        }
-    }
+    if (multi) halo_publish(peers, h.m, h.nmoves, h.open == 0);  // publish; wait for the neighbours' unless the exchange stays open
     if (threadIdx.x == 0) {
         const double v = *rr_new;
         if (hist != nullptr) {
@@ -779,8 +742,11 @@ int lsk_xpay_halo_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, int nt, const doubl
     if (!ctx->d_peers) return LSK_E_INVALID;  // needs lsk_ctx_set_peers
     HaloSpec h;
     h.nmoves = nmoves;
+    h.open = 0;
     for (int i = 0; i < nmoves; ++i) {
         h.m[i] = moves[i];
+        for (int j = 0; j < i; ++j)
+            if (moves[j].peer == moves[i].peer) return LSK_E_INVALID;  // exchanges are numbered per pair: one move per peer
         if (moves[i].n < 0 || (moves[i].n > 0 && (!moves[i].dst || moves[i].src < y || moves[i].src + moves[i].n > y + n)))
             return LSK_E_INVALID;
         h.lo[i] = moves[i].n > 0 ? (int64_t) (moves[i].src - y) : 0;
@@ -864,7 +830,8 @@ int lsk_cg_update_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, const double *rr_ol
 }
 
 int lsk_cg_direction_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, double *rr_cur, const double *rr_new, const double *r, double *p,
-                         const lsk_halo_move *moves, int nmoves, double *history, int64_t history_capacity, int64_t *history_count) {
+                         const lsk_halo_move *moves, int nmoves, int halo_open, double *history, int64_t history_capacity,
+                         int64_t *history_count) {
     if (!ctx || n < 0 || !rr_cur || !rr_new || (n > 0 && (!r || !p)) || nmoves < 0 || nmoves > 4 || (nmoves > 0 && !moves))
         return LSK_E_INVALID;
     if (history && (!history_count || history_capacity <= 0)) return LSK_E_INVALID;
@@ -873,6 +840,7 @@ int lsk_cg_direction_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, double *rr_cur, 
     if (sp.npacks < 1 || vec_kernels_configure(ctx) != 0) return LSK_E_INVALID;  // callers check lsk_cg_direction_supported
     HaloSpec h;
     h.nmoves = nmoves;
+    h.open = halo_open ? 1 : 0;
     for (int i = 0; i < 4; ++i) {
         h.lo[i] = 0;
         h.m[i].peer = 0; h.m[i].expect = 0; h.m[i].src = nullptr; h.m[i].dst = nullptr; h.m[i].n = 0;
@@ -880,6 +848,8 @@ int lsk_cg_direction_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, double *rr_cur, 
     for (int i = 0; i < nmoves; ++i) {
         if (moves[i].n < 0 || (moves[i].n > 0 && (!moves[i].dst || moves[i].src < p || moves[i].src + moves[i].n > p + n)))
             return LSK_E_INVALID;
+        for (int j = 0; j < i; ++j)
+            if (moves[j].peer == moves[i].peer) return LSK_E_INVALID;
         h.m[i] = moves[i];
         h.lo[i] = moves[i].n > 0 ? (int64_t) (moves[i].src - p) : 0;
     }

@@ -20,9 +20,10 @@
 //
 // Element-wise arithmetic is the reference's (same fma / rounded multiply per element as the
 // 3-kernel fused path and the oracle); scalars never leave the device; the residual history is
-// appended by the kernel.  Matrix tiles come through the async proxy (TMA) and are read-only; the
-// vectors are re-read on the coherent path after each grid barrier (fence + bar.sync, the
-// cooperative-groups grid.sync protocol).
+// appended by the kernel.  Matrix tiles come through the async proxy (TMA) and are read-only.  The
+// vectors are written with generic-proxy stores and re-read -- by the mat-vec's gathers on the coherent
+// path, by the vector phases through cp.async.bulk (async proxy) -- after a grid barrier: every thread
+// issues fence.proxy.async before it arrives, thread 0 fences at gpu scope around the barrier's packets.
 #include <stdlib.h>
 
 #include "lsk_common.cuh"
@@ -116,6 +117,9 @@ __device__ __forceinline__ double grid_sync(GridSync *gs, unsigned int &gen, con
     double b = 0.0;
     if constexpr (REDUCE) b = block_sum(v, s_red);  // valid in warp 0
     if (threadIdx.x == 0) s_err = 0;
+    // q, x, r, p are written with ordinary (generic-proxy) stores and re-read in the next phase by cp.async.bulk
+    // (async proxy), possibly from another CTA: order them across the proxies before this thread arrives
+    asm volatile("fence.proxy.async;" ::: "memory");
     __syncthreads();  // every thread's writes of the phase are ordered before thread 0's fence below
     if (blockIdx.x != 0) {
         if (threadIdx.x == 0) {
@@ -212,7 +216,8 @@ __global__ void __launch_bounds__(kBlock, LSK_TMA_MINB) cg_persistent_kernel(CgA
     const lsk_peers *peers = a.peers;
     const bool multi = (peers != nullptr && peers->nranks > 1);
     CommWindow *me = multi ? static_cast<CommWindow *>(peers->window[peers->rank]) : nullptr;
-    const unsigned long long halo_base = multi ? *reinterpret_cast<volatile unsigned long long *>(&me->halo_epoch) : 0ull;
+    // exchanges are numbered per pair of ranks (CommWindow::halo_sent); s_hbase[q] = the pair counter of move q at entry
+    __shared__ unsigned long long s_hbase[4];
     // state that only one thread (or only the rare ghost path) needs lives in shared memory, not in registers:
     // the mat-vec phase runs at the register limit of 3 CTAs per SM
     __shared__ GhostGate gate;
@@ -222,11 +227,15 @@ __global__ void __launch_bounds__(kBlock, LSK_TMA_MINB) cg_persistent_kernel(CgA
     if (threadIdx.x == 0) {
         gate.blocks = a.ghost_blocks;
         gate.nflags = 0;
-        gate.want = halo_base;
         gate.error = &gs->error;
         if (multi) {
-            for (int q = 0; q < a.halo.nmoves; ++q)
-                if (a.halo.m[q].expect) gate.flag[gate.nflags++] = &me->halo_done[a.halo.m[q].peer];
+            for (int q = 0; q < a.halo.nmoves; ++q) {
+                s_hbase[q] = *reinterpret_cast<volatile unsigned long long *>(&me->halo_sent[a.halo.m[q].peer]);
+                if (a.halo.m[q].expect) {
+                    gate.want[gate.nflags] = s_hbase[q];
+                    gate.flag[gate.nflags++] = &me->halo_done[a.halo.m[q].peer];
+                }
+            }
         }
         s_hcount = scribe ? *reinterpret_cast<volatile long long *>(a.hist_count) : 0;
         s_tmark = global_ns();
@@ -258,7 +267,11 @@ __global__ void __launch_bounds__(kBlock, LSK_TMA_MINB) cg_persistent_kernel(CgA
     else matvec_phase<false, 1>(a.mv, st, s_dyn, &s_mv, nullptr, cur, &gs->work[0]);
     for (int it = 0; it < a.niter; ++it) {
         // ---- phase A: q = A p, partial p.q -------------------------------------------------------------
-        if (threadIdx.x == 0) gate.want = halo_base + (unsigned long long) it;  // published by the mat-vec's first CTA barrier
+        if (threadIdx.x == 0 && multi) {  // published by the mat-vec's first CTA barrier
+            int f = 0;
+            for (int q = 0; q < a.halo.nmoves; ++q)
+                if (a.halo.m[q].expect) gate.want[f++] = s_hbase[q] + (unsigned long long) it;
+        }
         // (its prologue -- first rects, first matrix tile in flight -- ran before the previous grid barrier)
         const double pq_part = multi ? matvec_phase<true, 2>(a.mv, st, s_dyn, &s_mv, &gate, cur, &gs->work[0])
                                      : matvec_phase<false, 2>(a.mv, st, s_dyn, &s_mv, nullptr, cur, &gs->work[0]);
@@ -323,7 +336,6 @@ __global__ void __launch_bounds__(kBlock, LSK_TMA_MINB) cg_persistent_kernel(CgA
             if (multi) matvec_phase<true, 1>(a.mv, st, s_dyn, &s_mv, &gate, cur, &gs->work[0]);
             else matvec_phase<false, 1>(a.mv, st, s_dyn, &s_mv, nullptr, cur, &gs->work[0]);
         }
-        const unsigned long long e_now = halo_base + (unsigned long long) it + 1ull;
         lap(4);
         grid_sync<false>(gs, gen, peers, 0.0, err, [&] {
             if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long *>(&gs->work[2]) = 0ull;  // everybody is done with phase C
@@ -333,18 +345,19 @@ __global__ void __launch_bounds__(kBlock, LSK_TMA_MINB) cg_persistent_kernel(CgA
             __threadfence_system();
             if (threadIdx.x < a.halo.nmoves) {
                 const lsk_halo_move &mv = a.halo.m[threadIdx.x];
+                const unsigned long long e_now = s_hbase[threadIdx.x] + (unsigned long long) it + 1ull;
                 if (mv.n > 0) {
                     CommWindow *dst = static_cast<CommWindow *>(peers->window[mv.peer]);
                     *reinterpret_cast<volatile unsigned long long *>(&dst->halo_done[peers->rank]) = e_now;
                 }
                 // leaving the kernel: the ghosts must be current for whatever runs next on this stream
                 if (final_it && mv.expect) spin_until(&me->halo_done[mv.peer], e_now, &gs->error);
+                if (final_it) me->halo_sent[mv.peer] = e_now;
             }
             __syncthreads();
             if (final_it) {
                 __threadfence_system();
                 if (threadIdx.x == 0) {
-                    me->halo_epoch = e_now;
                     me->halo_calls += (unsigned long long) a.niter;
                     me->halo_wait_ns += global_ns() - t0;
                 }
@@ -370,9 +383,9 @@ __global__ void __launch_bounds__(kBlock, LSK_TMA_MINB) cg_persistent_kernel(CgA
         }
         if (multi && gs->error) me->error = 1;
     }
-    if (err && multi && done < a.niter && blockIdx.x == 0 && threadIdx.x == 0) {
+    if (err && multi && done < a.niter && blockIdx.x == 0 && threadIdx.x < a.halo.nmoves) {
         // a wait gave up: keep the epoch arithmetic of later launches consistent anyway
-        me->halo_epoch = halo_base + (unsigned long long) a.niter;
+        me->halo_sent[a.halo.m[threadIdx.x].peer] = s_hbase[threadIdx.x] + (unsigned long long) a.niter;
     }
 }
 

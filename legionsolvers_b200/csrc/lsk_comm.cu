@@ -28,15 +28,19 @@ struct HaloArgs {
 __global__ void __launch_bounds__(kBlock) halo_exchange_kernel(lsk_peers peers, HaloArgs a) {
     CommWindow *me = static_cast<CommWindow *>(peers.window[peers.rank]);
     __shared__ bool s_last;
-    const unsigned long long e = me->halo_epoch + 1;  // written only by the last CTA, after everyone read it
+    // exchange number of each pair (me, peer): the pair counters are written only by the last CTA, after everyone read them
     // 1. tell every peer I receive from that my ghost region may be overwritten (all my earlier kernels
     //    on this stream -- the readers of the previous ghost values -- have completed)
     if (blockIdx.x == 0 && threadIdx.x < a.nmoves && a.m[threadIdx.x].expect) {
-        CommWindow *dst = static_cast<CommWindow *>(peers.window[a.m[threadIdx.x].peer]);
-        *reinterpret_cast<volatile unsigned long long *>(&dst->halo_ready[peers.rank]) = e;
+        const int p = a.m[threadIdx.x].peer;
+        CommWindow *dst = static_cast<CommWindow *>(peers.window[p]);
+        *reinterpret_cast<volatile unsigned long long *>(&dst->halo_ready[peers.rank]) = me->halo_sent[p] + 1;
     }
     // 2. wait until every peer I send to is ready
-    if (threadIdx.x < a.nmoves && a.m[threadIdx.x].n > 0) spin_until(&me->halo_ready[a.m[threadIdx.x].peer], e, &me->error);
+    if (threadIdx.x < a.nmoves && a.m[threadIdx.x].n > 0) {
+        const int p = a.m[threadIdx.x].peer;
+        spin_until(&me->halo_ready[p], me->halo_sent[p] + 1, &me->error);
+    }
     __syncthreads();
     // 3. store my boundary values straight into the peers' ghost regions
     for (int i = 0; i < a.nmoves; ++i) {
@@ -54,7 +58,7 @@ __global__ void __launch_bounds__(kBlock) halo_exchange_kernel(lsk_peers peers, 
             for (int64_t k = tid; k < n; k += stride) dst[k] = src[k];
         }
     }
-    // 4. the last CTA to finish publishes "done" to the peers, waits for theirs, and closes the epoch
+    // 4. the last CTA to finish publishes "done" to the peers, waits for theirs, and advances the pair counters
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -63,24 +67,20 @@ __global__ void __launch_bounds__(kBlock) halo_exchange_kernel(lsk_peers peers, 
     }
     __syncthreads();
     if (!s_last) return;
-    const unsigned long long t_halo0 = global_ns();
-    __threadfence_system();
-    if (threadIdx.x < a.nmoves) {
-        const lsk_halo_move &mv = a.m[threadIdx.x];
-        if (mv.n > 0) {
-            CommWindow *dst = static_cast<CommWindow *>(peers.window[mv.peer]);
-            *reinterpret_cast<volatile unsigned long long *>(&dst->halo_done[peers.rank]) = e;
-        }
-        if (mv.expect) spin_until(&me->halo_done[mv.peer], e, &me->error);
+    halo_publish(&peers, a.m, a.nmoves, true);
+    if (threadIdx.x == 0) me->halo_ticket = 0u;
+}
+
+// Closes an OPEN exchange (halo_publish without wait) for consumers that cannot wait per row block: one thread per
+// peer this rank receives from blocks until that peer's data of the pair's latest exchange has landed.
+__global__ void __launch_bounds__(32) halo_wait_kernel(lsk_peers peers, HaloArgs a) {
+    CommWindow *me = static_cast<CommWindow *>(peers.window[peers.rank]);
+    if (threadIdx.x < a.nmoves && a.m[threadIdx.x].expect) {
+        const int p = a.m[threadIdx.x].peer;
+        spin_until(&me->halo_done[p], me->halo_sent[p], &me->error);
     }
-    __syncthreads();
+    __syncwarp();
     __threadfence_system();
-    if (threadIdx.x == 0) {
-        me->halo_epoch = e;
-        me->halo_ticket = 0u;
-        me->halo_calls += 1;
-        me->halo_wait_ns += global_ns() - t_halo0;
-    }
 }
 
 }  // namespace lsk
@@ -115,6 +115,8 @@ int lsk_halo_exchange_f64(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, co
         a.m[i] = moves[i];
         if (moves[i].peer < 0 || moves[i].peer >= peers->nranks || moves[i].n < 0) return LSK_E_INVALID;
         if (moves[i].n > 0 && (!moves[i].src || !moves[i].dst)) return LSK_E_INVALID;
+        for (int j = 0; j < i; ++j)
+            if (moves[j].peer == moves[i].peer) return LSK_E_INVALID;  // exchanges are numbered per pair: one move per peer
         total += moves[i].n;
     }
     // enough CTAs to keep NVLink busy for a few hundred KB, few enough that the epilogue stays cheap
@@ -122,6 +124,19 @@ int lsk_halo_exchange_f64(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, co
     if (grid < 1) grid = 1;
     if (grid > 32) grid = 32;
     halo_exchange_kernel<<<grid, kBlock, 0, (cudaStream_t) s>>>(*peers, a);
+    return after_launch(ctx);
+}
+
+int lsk_halo_wait_f64(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, const lsk_halo_move *moves, int nmoves) {
+    if (!ctx || !peers_ok(peers) || nmoves < 0 || nmoves > 32 || (nmoves > 0 && !moves)) return LSK_E_INVALID;
+    if (nmoves == 0) return 0;
+    HaloArgs a;
+    a.nmoves = nmoves;
+    for (int i = 0; i < nmoves; ++i) {
+        if (moves[i].peer < 0 || moves[i].peer >= peers->nranks) return LSK_E_INVALID;
+        a.m[i] = moves[i];
+    }
+    halo_wait_kernel<<<1, 32, 0, (cudaStream_t) s>>>(*peers, a);
     return after_launch(ctx);
 }
 

@@ -32,6 +32,7 @@ struct lsk_ctx {
     int cursor;                // next scratch set
     unsigned long long launches;
     lsk_peers *d_peers;        // device copy of the peer windows; non-null = reducing kernels all-reduce in their tail
+    lsk_peers h_peers;         // host copy (valid while d_peers is non-null): window addresses for the gated mat-vec
     unsigned long long *work;  // [kScratchSets] dynamic work counters of the TMA-streamed vector kernels, zero between launches
     unsigned long long configured;  // one bit per kernel family whose dynamic shared-memory opt-in was done on THIS device
                                     // (function attributes are per device: a process may hold contexts on several GPUs)
@@ -189,11 +190,14 @@ struct CommWindow {
     // written by PEERS (remote stores over NVLink)
     unsigned long long ar_pkt[2][LSK_MAX_RANKS][kMaxRed][2];  // all-reduce packets {32 data bits | epoch << 32},
                                                                // by epoch parity, source rank, value, half
-    unsigned long long halo_ready[LSK_MAX_RANKS];      // peer r may overwrite... is ready to RECEIVE this epoch
-    unsigned long long halo_done[LSK_MAX_RANKS];       // peer r's data of this epoch has landed here
+    unsigned long long halo_ready[LSK_MAX_RANKS];      // peer r is ready to RECEIVE exchange #e of the pair (me, r)
+    unsigned long long halo_done[LSK_MAX_RANKS];       // peer r's data of exchange #e of the pair (me, r) has landed here
     // local state
     unsigned long long ar_epoch;
-    unsigned long long halo_epoch;
+    // Exchanges are counted PER PAIR of ranks: halo_sent[r] = exchanges this rank has started with peer r.  Two ranks
+    // trade data in an exchange iff either sends to the other, so both advance their pair counter together even when
+    // other pairs of the job skip that exchange (different halos per block, ranks without neighbours).
+    unsigned long long halo_sent[LSK_MAX_RANKS];
     unsigned int halo_ticket;
     int error;
     // accounting (cheap, always on): time spent inside the collectives by the thread that closes them
@@ -246,6 +250,7 @@ __device__ __forceinline__ void allreduce_warp(const lsk_peers &peers, double *v
     const int par = (int) (e & 1);
     const unsigned long long t0 = (r == 0) ? global_ns() : 0ull;
     double got[kMaxRed];
+    bool timed_out = false;
     if (r < peers.nranks) {
         CommWindow *dst = static_cast<CommWindow *>(peers.window[r]);
         for (int j = 0; j < count; ++j) {
@@ -264,10 +269,13 @@ __device__ __forceinline__ void allreduce_warp(const lsk_peers &peers, double *v
                 b = pk[1];
                 if (spin_expired(polls, t_start)) {
                     me->error = 1;
+                    timed_out = true;
                     break;
                 }
             } while ((a >> 32) != (tag >> 32) || (b >> 32) != (tag >> 32));
-            got[j] = __longlong_as_double((long long) ((a & 0xffffffffull) | (b << 32)));
+            // a sum assembled from a packet that never arrived must not look like a number
+            got[j] = timed_out ? __longlong_as_double(0x7ff8000000000000ll)
+                               : __longlong_as_double((long long) ((a & 0xffffffffull) | (b << 32)));
         }
     }
     // rank-order sum: lane 0 collects lane q's value
@@ -287,9 +295,37 @@ __device__ __forceinline__ void allreduce_warp(const lsk_peers &peers, double *v
 // boundary sub-ranges of a vector y that are mirrored into the neighbours' ghost regions (xpay_halo, CG kernel)
 struct HaloSpec {
     int nmoves;
+    int open;       // non-zero: publish only, the consumer of the ghosts waits (see halo_publish)
     lsk_halo_move m[4];
     int64_t lo[4];  // send range start as an element index into y
 };
+
+// Executed by ALL threads of the last CTA of a kernel that stored halo data into its neighbours (after its own
+// system-scope fence and the ticket that made it the last): publish "exchange #e of our pair has landed" to every
+// peer this rank sent to, advance the pair counters, and -- when `wait` -- block until the peers' data of the same
+// exchange has landed here.  Without `wait` the exchange stays OPEN: its consumer must wait for
+// halo_done[peer] >= halo_sent[peer] itself (the gated mat-vec does, per row block; lsk_halo_wait_f64 otherwise).
+__device__ __forceinline__ void halo_publish(const lsk_peers *peers, const lsk_halo_move *m, int nmoves, bool wait) {
+    CommWindow *me = static_cast<CommWindow *>(peers->window[peers->rank]);
+    const unsigned long long t0 = global_ns();
+    __threadfence_system();
+    if ((int) threadIdx.x < nmoves) {
+        const lsk_halo_move &mv = m[threadIdx.x];
+        const unsigned long long e = me->halo_sent[mv.peer] + 1;
+        if (mv.n > 0) {
+            CommWindow *dst = static_cast<CommWindow *>(peers->window[mv.peer]);
+            *reinterpret_cast<volatile unsigned long long *>(&dst->halo_done[peers->rank]) = e;
+        }
+        if (wait && mv.expect) spin_until(&me->halo_done[mv.peer], e, &me->error);
+        me->halo_sent[mv.peer] = e;
+    }
+    __syncthreads();
+    __threadfence_system();
+    if (threadIdx.x == 0) {
+        me->halo_calls += 1;
+        me->halo_wait_ns += global_ns() - t0;
+    }
+}
 
 // ---- deterministic reductions ----------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {
@@ -298,8 +334,12 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// All threads of the CTA call this; the result is valid in thread 0.
-__device__ __forceinline__ double block_sum(double v, double *smem /*[kWarps]*/) {
+// All threads of the CTA call this; the result is valid in thread 0.  NT = threads per CTA (a multiple of 32).
+// The warp totals are combined by the same xor tree for every NT (steps that only meet zeros change nothing), so a
+// kernel with extra non-contributing warps produces the bits of the 256-thread form.
+template <int NT = kBlock>
+__device__ __forceinline__ double block_sum(double v, double *smem /*[NT / 32]*/) {
+    constexpr int NW = NT / 32;
     v = warp_sum(v);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __syncthreads();  // smem may still be in use by a previous call
@@ -307,9 +347,9 @@ __device__ __forceinline__ double block_sum(double v, double *smem /*[kWarps]*/)
     __syncthreads();
     double r = 0.0;
     if (warp == 0) {
-        r = lane < kWarps ? smem[lane] : 0.0;
+        r = lane < NW ? smem[lane] : 0.0;
 #pragma unroll
-        for (int o = kWarps / 2; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+        for (int o = (NW > 16 ? 16 : NW > 8 ? 8 : NW > 4 ? 4 : NW > 2 ? 2 : 1); o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
     }
     return r;
 }
@@ -318,16 +358,16 @@ __device__ __forceinline__ double block_sum(double v, double *smem /*[kWarps]*/)
 // CTA that draws the last ticket folds them (thread-strided, then block_sum) and writes the result.
 // No second launch, no atomics on the values, bitwise reproducible for a given grid size.
 // Accumulation is fp64 for both entry types; the result is narrowed on the final store.
-template <int NRED, typename T>
+template <int NRED, typename T, int NT = kBlock>
 __device__ __forceinline__ void grid_reduce_finish(const double (&acc)[NRED], double *partials,
                                                    unsigned int *ticket, T *const (&out)[NRED],
                                                    const lsk_peers *peers = nullptr, unsigned long long *reset = nullptr) {
-    __shared__ double s_red[kWarps];
+    __shared__ double s_red[NT / 32];
     __shared__ double s_tot[NRED];
     __shared__ bool s_last;
 #pragma unroll
     for (int j = 0; j < NRED; ++j) {
-        const double b = block_sum(acc[j], s_red);
+        const double b = block_sum<NT>(acc[j], s_red);
         if (threadIdx.x == 0) partials[(size_t) j * kMaxPartials + blockIdx.x] = b;
     }
     if (threadIdx.x == 0) {
@@ -342,8 +382,10 @@ __device__ __forceinline__ void grid_reduce_finish(const double (&acc)[NRED], do
     for (int j = 0; j < NRED; ++j) {
         double v = 0.0;
         const volatile double *pj = partials + (size_t) j * kMaxPartials;
-        for (unsigned int i = threadIdx.x; i < gridDim.x; i += kBlock) v += pj[i];
-        v = block_sum(v, s_red);
+        // the fold is done by the first kBlock threads in the 256-thread pattern whatever NT is (same bits)
+        if (threadIdx.x < kBlock)
+            for (unsigned int i = threadIdx.x; i < gridDim.x; i += kBlock) v += pj[i];
+        v = block_sum<NT>(v, s_red);
         if (threadIdx.x == 0) s_tot[j] = v;
     }
     __syncthreads();

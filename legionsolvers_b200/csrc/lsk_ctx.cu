@@ -98,6 +98,7 @@ int lsk_ctx_set_peers(lsk_ctx *ctx, const lsk_peers *peers) {
     if (peers->nranks < 1 || peers->nranks > LSK_MAX_RANKS || peers->rank < 0 || peers->rank >= peers->nranks) return LSK_E_INVALID;
     if (!ctx->d_peers) LSK_RETURN_IF_CUDA(cudaMalloc(&ctx->d_peers, sizeof(lsk_peers)));
     LSK_RETURN_IF_CUDA(cudaMemcpy(ctx->d_peers, peers, sizeof(lsk_peers), cudaMemcpyHostToDevice));
+    ctx->h_peers = *peers;
     return 0;
 }
 

@@ -16,6 +16,7 @@
 
 #include "lsk_common.cuh"
 #include "lsk_spmv_tma.cuh"
+#include "lsk_spmv_ws.cuh"
 
 namespace lsk {
 
@@ -154,7 +155,7 @@ csr_stream_kernel(int64_t rows, int rpb, int64_t n_row_blocks, const T *__restri
         }
         if (have) {
             y[r0 + tid] = acc;
-            if constexpr (NDOT >= 1) dacc[0] = fma((double) acc, (double) __ldg(dot_w + r0 + tid), dacc[0]);
+            if constexpr (NDOT >= 1) dacc[0] = fma((double) acc, dot_w != y ? (double) __ldg(dot_w + r0 + tid) : (double) acc, dacc[0]);
             if constexpr (NDOT >= 2) dacc[NDOT - 1] = fma((double) acc, (double) acc, dacc[NDOT - 1]);
         }
     }
@@ -297,7 +298,7 @@ csr_stream_pipe_kernel(int64_t rows, int rpb, int64_t n_row_blocks, const T *__r
             const int64_t r = rb * rpb + tid;
             if (tid < rpb && r < rows) {
                 y[r] = acc;
-                if constexpr (NDOT >= 1) dacc[0] = fma((double) acc, (double) __ldg(dot_w + r), dacc[0]);
+                if constexpr (NDOT >= 1) dacc[0] = fma((double) acc, dot_w != y ? (double) __ldg(dot_w + r) : (double) acc, dacc[0]);
                 if constexpr (NDOT >= 2) dacc[NDOT - 1] = fma((double) acc, (double) acc, dacc[NDOT - 1]);
             }
             acc = (T) 0;
@@ -392,7 +393,7 @@ csr_vector_kernel(int64_t rows, const T *__restrict__ entry, const long long *__
         for (int o = V / 2; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o, V);
         if (active && sub == 0) {
             y[row] = sum;
-            if constexpr (NDOT >= 1) dacc[0] = fma((double) sum, (double) __ldg(dot_w + row), dacc[0]);
+            if constexpr (NDOT >= 1) dacc[0] = fma((double) sum, dot_w != y ? (double) __ldg(dot_w + row) : (double) sum, dacc[0]);
             if constexpr (NDOT >= 2) dacc[NDOT - 1] = fma((double) sum, (double) sum, dacc[NDOT - 1]);
         }
     }
@@ -538,6 +539,73 @@ static int launch_tma_kernel(lsk_ctx *ctx, int lpr, int ndot, cudaStream_t st, i
     }
 }
 
+// ---- the warp-specialised kernel (lsk_spmv_ws.cuh): lanes per row 1 .. 8, optional ghost gate ------------------------
+template <int LPR, bool GATED>
+static int launch_ws_kernel_cfg(lsk_ctx *ctx, int ndot, int grid, cudaStream_t st, const TmaSpmvArgs &a, const WsGate &g, RedScratch rs,
+                                double *o0, double *o1) {
+    static const int family = configure_family_index();
+    const int rc = configure_once(ctx, family, [] {
+        cudaError_t e = cudaFuncSetAttribute(csr_ws_kernel<0, LPR, GATED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kWsSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(csr_ws_kernel<1, LPR, GATED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kWsSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(csr_ws_kernel<2, LPR, GATED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kWsSmem);
+        return e;
+    });
+    if (rc != 0) return rc;
+    cudaError_t e;
+    if (ndot == 0) e = launch_pdl(csr_ws_kernel<0, LPR, GATED>, grid, kWsThreads, kWsSmem, st, a, g, rs, o0, o1);
+    else if (ndot == 1) e = launch_pdl(csr_ws_kernel<1, LPR, GATED>, grid, kWsThreads, kWsSmem, st, a, g, rs, o0, o1);
+    else e = launch_pdl(csr_ws_kernel<2, LPR, GATED>, grid, kWsThreads, kWsSmem, st, a, g, rs, o0, o1);
+    return (int) e;
+}
+
+template <int LPR>
+static int launch_ws_kernel_lpr(lsk_ctx *ctx, int ndot, int grid, cudaStream_t st, const TmaSpmvArgs &a, const WsGate *g, RedScratch rs,
+                                double *o0, double *o1) {
+    WsGate none = {};
+    if (g != nullptr) return launch_ws_kernel_cfg<LPR, true>(ctx, ndot, grid, st, a, *g, rs, o0, o1);
+    return launch_ws_kernel_cfg<LPR, false>(ctx, ndot, grid, st, a, none, rs, o0, o1);
+}
+
+static int ws_lanes_per_row(int64_t rows, int64_t nnz, int variant) {
+    if (variant != LSK_SPMV_LANES) return 1;
+    const double mean = rows > 0 ? (double) nnz / (double) rows : 1.0;
+    return mean <= 16.0 ? 2 : mean <= 40.0 ? 4 : 8;
+}
+
+static int launch_ws_kernel(lsk_ctx *ctx, int lpr, int ndot, cudaStream_t st, int64_t rows, int64_t nnz, const double *entry,
+                            const long long *col, const lsk_rect *rowptr, int64_t k_base, const double *x, double *y,
+                            const double *dot_w, const WsGate *gate, double *o0, double *o1) {
+    const int rpb = ws_rows_per_block(rows, nnz, lpr);
+    const int64_t nrb = rows > 0 ? (rows + rpb - 1) / rpb : 0;  // no rows: one CTA that only finishes the fused dots (0)
+    static const char *cta_env = getenv("LSK_WS_CTAS");  // developer knob: CTAs per SM
+    const int64_t cap = (int64_t) ctx->sm_count * (cta_env ? atoi(cta_env) : LSK_WS_MINB);
+    const int grid = (int) (nrb < 1 ? 1 : nrb < cap ? nrb : cap);
+    TmaSpmvArgs a;
+    a.rows = rows; a.nnz = nnz; a.rpb = rpb; a.n_row_blocks = nrb; a.entry = entry; a.col = col; a.rowptr = rowptr;
+    a.k_base = k_base; a.x = x; a.y = y; a.dot_w = dot_w;
+    RedScratch rs = {nullptr, nullptr, nullptr, nullptr};
+    if (ndot > 0) rs = next_scratch(ctx);
+    switch (lpr) {
+    case 1: return launch_ws_kernel_lpr<1>(ctx, ndot, grid, st, a, gate, rs, o0, o1);
+    case 2: return launch_ws_kernel_lpr<2>(ctx, ndot, grid, st, a, gate, rs, o0, o1);
+    case 4: return launch_ws_kernel_lpr<4>(ctx, ndot, grid, st, a, gate, rs, o0, o1);
+    default: return launch_ws_kernel_lpr<8>(ctx, ndot, grid, st, a, gate, rs, o0, o1);
+    }
+}
+
+// one thread per row: flags[row / rpb] = 1 if the row references a column outside [own_lo, own_lo + own_n)
+__global__ void __launch_bounds__(kBlock) csr_ghost_blocks_kernel(int64_t rows, int rpb, const lsk_rect *__restrict__ rowptr,
+                                                                  int64_t k_base, const long long *__restrict__ col, long long own_lo,
+                                                                  unsigned long long own_n, unsigned char *flags) {
+    for (int64_t r = (int64_t) blockIdx.x * kBlock + threadIdx.x; r < rows; r += (int64_t) gridDim.x * kBlock) {
+        const longlong2 rc = __ldg(reinterpret_cast<const longlong2 *>(rowptr + r));
+        bool ghost = false;
+        for (long long k = rc.x - k_base; k <= rc.y - k_base; ++k)
+            ghost |= ((unsigned long long) (__ldg(col + k) - own_lo) >= own_n);
+        if (ghost) flags[r / rpb] = 1;
+    }
+}
+
 template <typename T, int V>
 static void launch_vector_kernel(int ndot, int grid, cudaStream_t st, int64_t rows, const T *entry,
                                  const long long *col, const lsk_rect *rowptr, int64_t k_base, const T *x,
@@ -553,14 +621,14 @@ static void launch_vector_kernel(int ndot, int grid, cudaStream_t st, int64_t ro
 template <typename T>
 static int csr_spmv(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const T *entry,
                     const int64_t *col, const lsk_rect *rowptr, int64_t k_base, const T *x_shifted, T *y,
-                    const T *dot_w, T *dot_out, T *dot_yy_out, int variant) {
+                    const T *dot_w, T *dot_out, T *dot_yy_out, int variant, const WsGate *gate = nullptr) {
     if (!ctx || rows < 0 || nnz < 0) return LSK_E_INVALID;
     if (rows > 0 && (!rowptr || !y || !x_shifted)) return LSK_E_INVALID;
     if (nnz > 0 && (!entry || !col)) return LSK_E_INVALID;
     if ((dot_w == nullptr) != (dot_out == nullptr)) return LSK_E_INVALID;
     if (variant < LSK_SPMV_AUTO || variant > LSK_SPMV_LANES) return LSK_E_INVALID;
     // the fused reductions share one kernel shape: {} | {y.w} | {y.w, y.y}; y.y alone rides on a
-    // y.w slot pointed at y itself
+    // y.w slot pointed at y itself (the kernels then use the row's own result for w)
     int ndot = 0;
     const T *w = dot_w;
     T *o0 = dot_out, *o1 = dot_yy_out;
@@ -572,15 +640,28 @@ static int csr_spmv(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const
     if (variant == LSK_SPMV_AUTO) variant = pick_variant(rows, nnz);
     const cudaStream_t st = (cudaStream_t) s;
     const long long *colp = reinterpret_cast<const long long *>(col);
-    RedScratch rs = {nullptr, nullptr, nullptr};
-    if (ndot > 0) rs = next_scratch(ctx);
 
     // the TMA kernels need fp64 and col / entry 16-byte aligned at the same elements
     const bool tma_ok = std::is_same<T, double>::value && reinterpret_cast<uintptr_t>(entry) % 8 == 0 &&
                         reinterpret_cast<uintptr_t>(col) % 8 == 0 &&
                         (((reinterpret_cast<uintptr_t>(entry) >> 3) & 1) == ((reinterpret_cast<uintptr_t>(col) >> 3) & 1));
+    static const char *impl_env = getenv("LSK_SPMV_IMPL");  // developer A/B switch: ws (default) | tma | pipe | regs
+    const int impl = !impl_env ? 0 : (impl_env[0] == 't' ? 3 : impl_env[0] == 'p' ? 1 : impl_env[0] == 'r' ? 2 : 0);
+    // ... and the warp-specialised one copies the rects with TMA as well: rowptr 16-byte aligned
+    const bool ws_ok = tma_ok && reinterpret_cast<uintptr_t>(rowptr) % 16 == 0 && (variant == LSK_SPMV_STREAM || variant == LSK_SPMV_LANES);
+    if (gate != nullptr && !ws_ok) return LSK_E_INVALID;  // callers check lsk_csr_spmv_gated_supported
+    if (ws_ok && (impl == 0 || gate != nullptr)) {
+        // the warp-specialised TMA pipeline: thread per row (bit-exact) or 2-8 lanes per row
+        const int rc = launch_ws_kernel(ctx, ws_lanes_per_row(rows, nnz, variant), ndot, st, rows, nnz, reinterpret_cast<const double *>(entry),
+                                        colp, rowptr, k_base, reinterpret_cast<const double *>(x_shifted), reinterpret_cast<double *>(y),
+                                        reinterpret_cast<const double *>(w), gate, reinterpret_cast<double *>(o0), reinterpret_cast<double *>(o1));
+        if (rc != 0) return rc;
+        return after_launch(ctx);
+    }
+    RedScratch rs = {nullptr, nullptr, nullptr, nullptr};
+    if (ndot > 0) rs = next_scratch(ctx);
     if (variant == LSK_SPMV_LANES) {
-        if (tma_ok) {
+        if (tma_ok) {  // round-1 kernel (LSK_SPMV_IMPL=tma)
             const double mean = rows > 0 ? (double) nnz / (double) rows : 1.0;
             const int lpr = mean <= 16.0 ? 2 : mean <= 40.0 ? 4 : 8;
             const int rc = launch_tma_kernel(ctx, lpr, ndot, st, rows, nnz, reinterpret_cast<const double *>(entry), colp, rowptr, k_base,
@@ -608,9 +689,7 @@ static int csr_spmv(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const
                           ((reinterpret_cast<uintptr_t>(col) >> 3) & 3)) &&
                          (reinterpret_cast<uintptr_t>(entry) % sizeof(T) == 0) &&
                          (reinterpret_cast<uintptr_t>(col) % 8 == 0);
-        static const char *impl_env = getenv("LSK_SPMV_IMPL");  // developer A/B switch: tma | pipe | regs
-        const int impl = !impl_env ? 0 : (impl_env[0] == 'p' ? 1 : impl_env[0] == 'r' ? 2 : 0);
-        if (tma_ok && impl == 0) {
+        if (tma_ok && impl == 3) {
             const int rc = launch_tma_kernel(ctx, 1, ndot, st, rows, nnz, reinterpret_cast<const double *>(entry), colp, rowptr, k_base,
                                              reinterpret_cast<const double *>(x_shifted), reinterpret_cast<double *>(y),
                                              reinterpret_cast<const double *>(w), rs, reinterpret_cast<double *>(o0),
@@ -669,6 +748,58 @@ int lsk_csr_spmv_f64(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, cons
     return csr_spmv<double>(ctx, s, rows, nnz, entry, col, rowptr, k_base, x_shifted, y, dot_w, dot_out,
                             dot_yy_out, variant);
 }
+// ---- gated form (several GPUs): ghost columns guarded per row block --------------------------------------------------
+static int gated_variant(int64_t rows, int64_t nnz, int variant) {
+    if (variant == LSK_SPMV_AUTO) variant = pick_variant(rows, nnz);
+    return variant;
+}
+int lsk_csr_spmv_gated_supported(int64_t rows, int64_t nnz, const double *entry, const int64_t *col, const lsk_rect *rowptr, int variant) {
+    if (rows <= 0 || nnz <= 0 || !entry || !col || !rowptr) return 0;
+    if (reinterpret_cast<uintptr_t>(rowptr) % 16 != 0) return 0;
+    const uintptr_t e = reinterpret_cast<uintptr_t>(entry), c = reinterpret_cast<uintptr_t>(col);
+    if (e % 8 != 0 || c % 8 != 0 || ((e >> 3) & 1) != ((c >> 3) & 1)) return 0;
+    variant = gated_variant(rows, nnz, variant);
+    return (variant == LSK_SPMV_STREAM || variant == LSK_SPMV_LANES) ? 1 : 0;
+}
+int64_t lsk_csr_spmv_row_blocks(int64_t rows, int64_t nnz, int variant) {
+    if (rows <= 0) return 0;
+    variant = gated_variant(rows, nnz, variant);
+    const int rpb = ws_rows_per_block(rows, nnz, ws_lanes_per_row(rows, nnz, variant));
+    return (rows + rpb - 1) / rpb;
+}
+int lsk_csr_ghost_blocks(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const int64_t *col, const lsk_rect *rowptr,
+                         int64_t k_base, int64_t own_lo, int64_t own_n, int variant, uint8_t *flags) {
+    if (!ctx || !flags || rows <= 0 || !rowptr || !col || own_n < 0) return LSK_E_INVALID;
+    variant = gated_variant(rows, nnz, variant);
+    const int rpb = ws_rows_per_block(rows, nnz, ws_lanes_per_row(rows, nnz, variant));
+    const int64_t nrb = (rows + rpb - 1) / rpb;
+    LSK_RETURN_IF_CUDA(cudaMemsetAsync(flags, 0, (size_t) nrb, (cudaStream_t) s));
+    const int grid = stream_grid(ctx, rows, 8);
+    csr_ghost_blocks_kernel<<<grid, kBlock, 0, (cudaStream_t) s>>>(rows, rpb, rowptr, k_base, reinterpret_cast<const long long *>(col),
+                                                                  own_lo, (unsigned long long) own_n, flags);
+    return after_launch(ctx);
+}
+int lsk_csr_spmv_gated_f64(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const double *entry, const int64_t *col,
+                           const lsk_rect *rowptr, int64_t k_base, const double *x_shifted, double *y, const double *dot_w,
+                           double *dot_out, double *dot_yy_out, int variant, const uint8_t *ghost_blocks, const lsk_halo_move *moves,
+                           int nmoves) {
+    if (!ctx || nmoves < 0 || nmoves > 4 || (nmoves > 0 && !moves)) return LSK_E_INVALID;
+    if (!ctx->d_peers) return LSK_E_INVALID;  // needs lsk_ctx_set_peers
+    if (!lsk_csr_spmv_gated_supported(rows, nnz, entry, col, rowptr, variant)) return LSK_E_INVALID;
+    CommWindow *me = static_cast<CommWindow *>(ctx->h_peers.window[ctx->h_peers.rank]);
+    WsGate g = {};
+    g.blocks = ghost_blocks;
+    g.error = &me->error;
+    for (int i = 0; i < nmoves; ++i) {
+        if (moves[i].peer < 0 || moves[i].peer >= ctx->h_peers.nranks) return LSK_E_INVALID;
+        if (!moves[i].expect) continue;
+        g.flag[g.nflags] = &me->halo_done[moves[i].peer];
+        g.want[g.nflags] = &me->halo_sent[moves[i].peer];
+        ++g.nflags;
+    }
+    return csr_spmv<double>(ctx, s, rows, nnz, entry, col, rowptr, k_base, x_shifted, y, dot_w, dot_out, dot_yy_out, variant, &g);
+}
+
 int lsk_csr_spmv_f32(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const float *entry,
                      const int64_t *col, const lsk_rect *rowptr, int64_t k_base, const float *x_shifted,
                      float *y, const float *dot_w, float *dot_out, float *dot_yy_out, int variant) {

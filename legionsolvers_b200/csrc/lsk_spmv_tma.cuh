@@ -59,18 +59,26 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+// try_wait sleeps in hardware between polls.  A wait that has not completed after kSpinLimitNs can only be a protocol
+// bug or a lost copy: trap (the launch fails loudly) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
+    const uint32_t addr = smem_u32(bar);
+    unsigned int polls = 0;
+    unsigned long long t_start = 0;
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (spin_expired(polls, t_start)) __trap();
+    }
 }
 __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar,
                                              uint64_t policy) {
@@ -127,13 +135,13 @@ struct TmaSpmvArgs {
 struct GhostGate {
     const unsigned char *blocks;
     int nflags;
-    const volatile unsigned long long *flag[4];
-    unsigned long long want;
+    const volatile unsigned long long *flag[4];   // halo_done[peer] in this rank's window
+    unsigned long long want[4];                   // the pair's exchange number (per peer, see CommWindow::halo_sent)
     int *error;
 };
 
 static __device__ __noinline__ void ghost_gate_wait(const GhostGate &g) {
-    for (int q = 0; q < g.nflags; ++q) spin_until(g.flag[q], g.want, g.error);
+    for (int q = 0; q < g.nflags; ++q) spin_until(g.flag[q], g.want[q], g.error);
     __threadfence_system();
 }
 
@@ -370,7 +378,7 @@ __device__ __forceinline__ void csr_tma_run(const TmaSpmvArgs &a, TmaSpmvState &
         double wv = 0.0;
         if constexpr (NDOT >= 1) {
             const int64_t r = rb * rpb + trow;
-            if (last_tile && tsub == 0 && trow < rpb && r < rows) wv = COHERENT ? ld_f64(a.dot_w + r) : __ldg(a.dot_w + r);
+            if (last_tile && tsub == 0 && trow < rpb && r < rows && a.dot_w != a.y) wv = COHERENT ? ld_f64(a.dot_w + r) : __ldg(a.dot_w + r);
         }
         mbar_wait(&s_full[stage], (phases >> stage) & 1u);
         phases ^= (1u << stage);
@@ -424,7 +432,7 @@ __device__ __forceinline__ void csr_tma_run(const TmaSpmvArgs &a, TmaSpmvState &
             const int64_t r = rb * rpb + trow;
             if (tsub == 0 && trow < rpb && r < rows) {
                 a.y[r] = acc;
-                if constexpr (NDOT >= 1) dacc[0] = fma(acc, wv, dacc[0]);
+                if constexpr (NDOT >= 1) dacc[0] = fma(acc, a.dot_w != a.y ? wv : acc, dacc[0]);  // w == y: the y.y-only form
                 if constexpr (NDOT >= 2) dacc[NDOT - 1] = fma(acc, acc, dacc[NDOT - 1]);
             }
             acc = 0.0;

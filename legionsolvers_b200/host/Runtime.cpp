@@ -147,6 +147,10 @@ void Runtime::halo_exchange_p2p(const lsk_halo_move *moves, int nmoves) {
     enqueue("halo exchange", [&] { return lsk_halo_exchange_f64(ctx_, stream_, &peers_, moves, nmoves); });
 }
 
+void Runtime::halo_wait_p2p(const lsk_halo_move *moves, int nmoves) {
+    enqueue("halo wait", [&] { return lsk_halo_wait_f64(ctx_, stream_, &peers_, moves, nmoves); });
+}
+
 void Runtime::set_fused_collectives(bool on) {
     if (on && !p2p_) return;
     if (on == fused_) return;

@@ -30,6 +30,9 @@ class SquarePlanner {
         IntervalPartition kernel_partition, ghost_partition;
         std::vector<HaloMove> halo;  // what to trade with each peer before a mat-vec
         std::vector<Scalar<T>> part_yw, part_yy;  // per-colour partial slots of the fused dots
+        // gated mat-vec (one local piece, CSR): which row blocks reference ghost columns; -1 = not looked at yet, 0 = unavailable
+        int64_t gate_nrb = -1;
+        DeviceBuffer<uint8_t> gate_blocks;
     };
 
     Runtime *rt;
@@ -42,7 +45,58 @@ class SquarePlanner {
     uint64_t halo_bytes_per_matvec = 0;
     DeviceBuffer<uint8_t> cg_ghost_blocks;  // lsk_cg_ghost_blocks flags of the (single) CSR block, see cg_problem
     std::set<std::size_t> halo_fresh;  // vector ids whose ghost values are current on every rank
-    void mark_dirty(std::size_t vec_idx) { halo_fresh.erase(vec_idx); }
+    // vector ids whose boundary has been pushed into the neighbours but whose own ghosts have not been awaited yet (an OPEN
+    // exchange, lsk_cg_direction_f64 halo_open): the next mat-vec of that vector waits per row block, any other reader of the
+    // ghosts closes the exchange first (close_halo)
+    std::set<std::size_t> halo_open;
+    void mark_dirty(std::size_t vec_idx) {
+        halo_fresh.erase(vec_idx);
+        halo_open.erase(vec_idx);
+    }
+
+    int fill_moves(const Block &b, const PartitionedVector<T> &v, lsk_halo_move *moves) const {
+        int n = 0;
+        for (const HaloMove &m : b.halo) {
+            moves[n].peer = m.peer;
+            moves[n].expect = m.recv_n > 0 ? 1 : 0;
+            moves[n].n = m.send_n;
+            moves[n].src = m.send_n > 0 ? reinterpret_cast<const double *>(v.ptr(m.send_lo)) : nullptr;
+            moves[n].dst = m.send_n > 0 ? reinterpret_cast<double *>(v.peer_ptr(m.peer, m.send_lo)) : nullptr;
+            ++n;
+        }
+        return n;
+    }
+
+    // the gated mat-vec is available for block b: one CSR piece per rank, flags computed (once, outside any trace)
+    bool gate_ready(Block &b) {
+        if (!halo_push_is_fused() || total_local_pieces() != 1) return false;
+        static const bool off = [] { const char *e = getenv("LSK_HALO_OPEN"); return e && e[0] == '0'; }();  // developer A/B switch
+        if (off) return false;
+        if (b.gate_nrb < 0) {
+            if (rt->capturing() || rt->replaying()) return false;
+            const IndexPartition &range = *canonical_index_partitions[b.range_index];
+            const int c = range.first_color;
+            b.gate_nrb = b.matrix->gate_row_blocks(c, range.lo[(size_t) c], range.piece_size(c), b.kernel_partition);
+            if (b.gate_nrb > 0) {
+                b.gate_blocks = DeviceBuffer<uint8_t>(rt, (size_t) b.gate_nrb);
+                b.matrix->gate_flags(c, range.lo[(size_t) c], range.piece_size(c), b.kernel_partition, b.gate_blocks.ptr);
+            }
+        }
+        return b.gate_nrb > 0;
+    }
+
+    // close an open exchange of vector `vec_idx` for readers that cannot wait per row block
+    void close_halo(std::size_t vec_idx) {
+        if (!halo_open.count(vec_idx)) return;
+        if constexpr (std::is_same<T, double>::value) {
+            const Block &b = row_partitioned_matrices[0];
+            lsk_halo_move moves[LSK_MAX_HALO_MOVES];
+            const int n = fill_moves(b, get_vector(vec_idx, b.domain_index), moves);
+            rt->halo_wait_p2p(moves, n);
+        }
+        halo_open.erase(vec_idx);
+        halo_fresh.insert(vec_idx);
+    }
 
     void register_space(size_t idx, const PartitionedVector<T> &v) {
         if (canonical_index_partitions.size() > idx) {
@@ -109,15 +163,7 @@ class SquarePlanner {
             if (rt->p2p() && v.exported() && b.halo.size() <= LSK_MAX_HALO_MOVES) {
                 // one kernel: ready-handshake, P2P stores into the peers' ghost regions, epoch flags
                 lsk_halo_move moves[LSK_MAX_HALO_MOVES];
-                int n = 0;
-                for (const HaloMove &m : b.halo) {
-                    moves[n].peer = m.peer;
-                    moves[n].expect = m.recv_n > 0 ? 1 : 0;
-                    moves[n].n = m.send_n;
-                    moves[n].src = m.send_n > 0 ? v.ptr(m.send_lo) : nullptr;
-                    moves[n].dst = m.send_n > 0 ? v.peer_ptr(m.peer, m.send_lo) : nullptr;
-                    ++n;
-                }
+                const int n = fill_moves(b, v, moves);
                 rt->halo_exchange_p2p(moves, n);
                 return;
             }
@@ -180,6 +226,7 @@ public:
         std::set<size_t> done;
         for (const Block &b : row_partitioned_matrices)
             if (done.insert(b.domain_index).second) exchange_halo(b, get_vector(vec_idx, b.domain_index));
+        halo_open.erase(vec_idx);  // a full exchange supersedes an open one (pair counters only move forward)
         halo_fresh.insert(vec_idx);
     }
 
@@ -199,18 +246,11 @@ public:
                 const PartitionedVector<T> &x = get_vector(src, 0);
                 const IndexPartition &p = *canonical_index_partitions[0];
                 lsk_halo_move moves[4];
-                int n = 0;
-                for (const HaloMove &m : blk->halo) {
-                    moves[n].peer = m.peer;
-                    moves[n].expect = m.recv_n > 0 ? 1 : 0;
-                    moves[n].n = m.send_n;
-                    moves[n].src = m.send_n > 0 ? y.ptr(m.send_lo) : nullptr;
-                    moves[n].dst = m.send_n > 0 ? y.peer_ptr(m.peer, m.send_lo) : nullptr;
-                    ++n;
-                }
+                const int n = fill_moves(*blk, y, moves);
                 const int64_t lo = p.own_lo(), cnt = p.own_hi() - p.own_lo() + 1;
                 const T *xs = x.ptr(lo);
                 T *ys = y.ptr(lo);
+                mark_dirty(dst);
                 rt->enqueue("xpay_halo", [&] {
                     return lsk_xpay_halo_f64(rt->ctx(), rt->stream(), cnt, 2, numer.ptr(), denom.ptr(), nullptr, nullptr, xs, ys, moves, n);
                 });
@@ -237,24 +277,19 @@ public:
             lsk_halo_move moves[4];
             int n = 0;
             const bool push = halo_push_is_fused() && y.exported();
-            if (push) {
-                for (const HaloMove &m : row_partitioned_matrices[0].halo) {
-                    moves[n].peer = m.peer;
-                    moves[n].expect = m.recv_n > 0 ? 1 : 0;
-                    moves[n].n = m.send_n;
-                    moves[n].src = m.send_n > 0 ? y.ptr(m.send_lo) : nullptr;
-                    moves[n].dst = m.send_n > 0 ? y.peer_ptr(m.peer, m.send_lo) : nullptr;
-                    ++n;
-                }
-            }
+            if (push) n = fill_moves(row_partitioned_matrices[0], y, moves);
+            // leave the exchange open when the next mat-vec can wait for the neighbours per row block: the halo
+            // wait then sits behind ~all of that mat-vec instead of at the end of this kernel
+            const bool open = push && n > 0 && gate_ready(row_partitioned_matrices[0]);
             const T *xs = x.ptr(lo);
             T *ys = y.ptr(lo);
             mark_dirty(p);
             rt->enqueue("cg_direction", [&] {
                 return lsk_cg_direction_f64(rt->ctx(), rt->stream(), cnt, rr_cur.ptr(), rr_new.ptr(), xs, ys, n > 0 ? moves : nullptr, n,
-                                            history.data(), history.get_capacity(), history.count_ptr());
+                                            open ? 1 : 0, history.data(), history.get_capacity(), history.count_ptr());
             });
-            if (push) halo_fresh.insert(p);
+            if (open) halo_open.insert(p);
+            else if (push) halo_fresh.insert(p);
             return true;
         }
     }
@@ -285,15 +320,7 @@ public:
             pb->q = get_vector(q, 0).ptr(lo);
             pb->x = get_vector(sol, 0).ptr(lo);
             pb->r = get_vector(r, 0).ptr(lo);
-            int nm = 0;
-            for (const HaloMove &m : blk.halo) {
-                moves[nm].peer = m.peer;
-                moves[nm].expect = m.recv_n > 0 ? 1 : 0;
-                moves[nm].n = m.send_n;
-                moves[nm].src = m.send_n > 0 ? vp.ptr(m.send_lo) : nullptr;
-                moves[nm].dst = m.send_n > 0 ? vp.peer_ptr(m.peer, m.send_lo) : nullptr;
-                ++nm;
-            }
+            const int nm = fill_moves(blk, vp, moves);
             pb->moves = nm > 0 ? moves : nullptr;
             pb->nmoves = nm;
             pb->ghost_blocks = nullptr;
@@ -324,6 +351,7 @@ public:
             pb.history = history.data();
             pb.history_capacity = history.get_capacity();
             pb.history_count = history.count_ptr();
+            close_halo(p);
             mark_dirty(sol);
             mark_dirty(r);
             mark_dirty(q);
@@ -537,6 +565,26 @@ private:
     void matvec_impl(std::size_t dst_idx, std::size_t src_idx, const Scalar<T> *yw, const Scalar<T> *yy, std::size_t w_idx) {
         const size_t S = get_num_spaces();
         mark_dirty(dst_idx);
+        // Ghosts of src pushed by the kernel that produced it (fresh, or an exchange still OPEN): the (single) CSR block
+        // runs the gated kernel, which waits for the neighbours per row block.  It is used for fresh ghosts as well --
+        // the gate is then already satisfied -- so that a step launches the same kernels whether its source's exchange
+        // has been closed or not (a recorded trace is replayed from either state).
+        lsk_halo_move gate_moves[4];
+        MatvecGate gate;
+        bool gated = false;
+        if (halo_open.count(src_idx) || halo_fresh.count(src_idx)) {
+            Block &b0 = row_partitioned_matrices[0];
+            if (row_partitioned_matrices.size() == 1 && !b0.halo.empty() && b0.halo.size() <= 4 && gate_ready(b0)) {
+                gate.blocks = b0.gate_blocks.ptr;
+                gate.nmoves = fill_moves(b0, get_vector(src_idx, b0.domain_index), gate_moves);
+                gate.moves = gate_moves;
+                gated = true;
+                halo_open.erase(src_idx);
+                halo_fresh.insert(src_idx);  // once that kernel has completed
+            } else {
+                close_halo(src_idx);
+            }
+        }
         const bool src_fresh = halo_fresh.count(src_idx) != 0;
         std::vector<bool> overwritten(S, false);
         for (const Block &b : row_partitioned_matrices)
@@ -564,9 +612,9 @@ private:
                         parts_yy.push_back(fz.yy[(size_t) c]);
                     }
                 }
-                b.matrix->matvec(get_vector(dst_idx, b.range_index), src, b.kernel_partition, b.ghost_partition, &fz);
+                b.matrix->matvec(get_vector(dst_idx, b.range_index), src, b.kernel_partition, b.ghost_partition, &fz, gated ? &gate : nullptr);
             } else {
-                b.matrix->matvec(get_vector(dst_idx, b.range_index), src, b.kernel_partition, b.ghost_partition, nullptr);
+                b.matrix->matvec(get_vector(dst_idx, b.range_index), src, b.kernel_partition, b.ghost_partition, nullptr, gated ? &gate : nullptr);
             }
         };
         // overwriting (CSR) blocks first, accumulating (COO) blocks after

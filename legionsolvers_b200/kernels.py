@@ -140,7 +140,7 @@ class Context:
         """history.push_back(rr_new); p = fma(rr_new/rr_cur, p, r); rr_cur <- rr_new  (src/CGSolver.hpp:53-54)."""
         if not _abi.lib().lsk_cg_direction_supported(p.numel(), _ptr(r), _ptr(p)):
             raise RuntimeError("lsk_cg_direction_f64: r and p are not 32-byte congruent")
-        _abi.check(_abi.lib().lsk_cg_direction_f64(self.h, _stream(), p.numel(), _ptr(rr_cur), _ptr(rr_new), _ptr(r), _ptr(p), None, 0,
+        _abi.check(_abi.lib().lsk_cg_direction_f64(self.h, _stream(), p.numel(), _ptr(rr_cur), _ptr(rr_new), _ptr(r), _ptr(p), None, 0, 0,
                                                    _ptr(history), history.numel() if history is not None else 0,
                                                    _ptr(history_count)), "lsk_cg_direction")
 

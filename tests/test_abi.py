@@ -86,5 +86,15 @@ def test_host_only_entry_points_of_the_cg_step():
     assert L.lsk_cg_direction_supported(0, 0x10000, 0x20000) == 0
     # calls that would touch the device are refused without a context
     assert L.lsk_cg_steps_f64(None, None, C.byref(pb), 1) == -1
-    assert L.lsk_cg_direction_f64(None, None, 8, None, None, None, None, None, 0, None, 0, None) == -1
+    assert L.lsk_cg_direction_f64(None, None, 8, None, None, None, None, None, 0, 0, None, 0, None) == -1
     assert L.lsk_gridsync_bytes() > 4096 * 16
+    # the gated mat-vec: same row-block arithmetic as the kernel, eligibility by alignment and variant
+    assert L.lsk_csr_spmv_row_blocks(1 << 20, 7 << 20, 0) == (1 << 20) // 256
+    assert L.lsk_csr_spmv_row_blocks(1 << 20, 27 << 20, 0) == (1 << 20) // 64   # 4 lanes per row: 64 rows per block
+    assert L.lsk_csr_spmv_row_blocks(0, 0, 0) == 0
+    assert L.lsk_csr_spmv_gated_supported(100, 700, 0x1000, 0x2000, 0x3000, 0) == 1
+    assert L.lsk_csr_spmv_gated_supported(100, 700, 0x1008, 0x2000, 0x3000, 0) == 0    # col / entry not aligned together
+    assert L.lsk_csr_spmv_gated_supported(100, 700, 0x1000, 0x2000, 0x3008, 0) == 0    # rects are copied with TMA: 16-byte aligned
+    assert L.lsk_csr_spmv_gated_supported(100, 100000, 0x1000, 0x2000, 0x3000, 0) == 0  # warp-per-row variant has no gate
+    assert L.lsk_csr_spmv_gated_f64(None, None, 1, 1, None, None, None, 0, None, None, None, None, None, 0, None, None, 0) == -1
+    assert L.lsk_halo_wait_f64(None, None, None, None, 0) == -1

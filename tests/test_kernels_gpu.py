@@ -257,8 +257,9 @@ def test_csr_spmv_pieces_with_fused_dots(ctx, oracle, pieces, dim_flag, shape):
             yp = want[r_lo:r_hi + 1]
             assert abs(d1.item() - float(np.dot(yp, w[r_lo:r_hi + 1]))) <= 1e-11 * float(np.dot(np.abs(yp), np.abs(w[r_lo:r_hi + 1])) + 1e-300)
             assert abs(d2.item() - float(np.dot(yp, yp))) <= 1e-11 * float(np.dot(yp, yp) + 1e-300)
-            # y.y alone
+            # y.y alone (y poisoned first: the kernel must use the row's NEW result, not what y held before)
             d3 = torch.zeros_like(d1)
+            y[r_lo:r_hi + 1] = 123.0
             ctx.csr_spmv(rows, nnz, entry[k_lo:k_hi + 1], col[k_lo:k_hi + 1], rowptr[r_lo:r_hi + 1], k_lo,
                          ghost, g_lo, y[r_lo:r_hi + 1], dot_yy_out=d3, variant=variant)
             assert d3.item() == d2.item()
@@ -313,6 +314,50 @@ def test_csr_spmv_ragged_rows_and_empty_rows(ctx, oracle):
     ctx.csr_spmv(n_rows, nnz, e_buf[1:1 + nnz], c_buf[2:2 + nnz], K.rect_tensor(rowptr), 0, dev(x), 0, y,
                  variant=K.SPMV_STREAM)
     np.testing.assert_array_equal(y.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("order", ["reversed", "shuffled", "block_shuffled"])
+def test_csr_spmv_rows_stored_out_of_order(ctx, oracle, order):
+    """The reference's rowptr is a field of arbitrary Rect<1> (src/CSRMatrix.hpp:24-26): nothing forces row r + 1 to be
+    stored after row r.  The warp-specialised kernel guesses a row block's run of non-zeros from its end rows and
+    must still produce the reference result -- bit for bit -- when rows are stored in any order."""
+    from legionsolvers_b200 import kernels as K
+
+    rng = np.random.default_rng(7)
+    n_rows, n_cols = 3000, 3000
+    lens = rng.integers(0, 15, n_rows)
+    lens[[17, 1500]] = [900, 2600]  # a few long rows as well (multi-tile)
+    perm = {"reversed": np.arange(n_rows)[::-1], "shuffled": rng.permutation(n_rows),
+            "block_shuffled": np.concatenate([b for b in rng.permutation(np.array_split(np.arange(n_rows), 40))])}[order]
+    starts = np.zeros(n_rows, dtype=np.int64)
+    pos = 0
+    for r in perm:  # storage order
+        starts[r] = pos
+        pos += lens[r]
+    nnz = int(pos)
+    col = np.zeros(nnz, dtype=np.int64)
+    entry = rng.standard_normal(nnz)
+    for r in range(n_rows):
+        col[starts[r]:starts[r] + lens[r]] = np.sort(rng.choice(n_cols, size=lens[r], replace=False))
+    rowptr = np.empty(n_rows, dtype=oracle.RECT_DTYPE)
+    rowptr["lo"], rowptr["hi"] = starts, starts + lens - 1
+    x = rng.standard_normal(n_cols)
+    want = np.zeros(n_rows)
+    for r in range(n_rows):
+        for k in range(rowptr["lo"][r], rowptr["hi"][r] + 1):
+            want[r] += entry[k] * x[col[k]]
+    absrow = np.array([np.sum(np.abs(entry[starts[r]:starts[r] + lens[r]] * x[col[starts[r]:starts[r] + lens[r]]])) for r in range(n_rows)])
+    w = rng.standard_normal(n_rows)
+    for variant in (K.SPMV_STREAM, K.SPMV_LANES, K.SPMV_AUTO):
+        y = torch.full((n_rows,), 5.0, dtype=torch.float64, device="cuda")
+        d = torch.zeros(1, dtype=torch.float64, device="cuda")
+        ctx.csr_spmv(n_rows, nnz, dev(entry), dev(col), K.rect_tensor(rowptr), 0, dev(x), 0, y, dot_w=dev(w), dot_out=d, variant=variant)
+        got = y.cpu().numpy()
+        if variant != K.SPMV_LANES:
+            np.testing.assert_array_equal(got, want)
+        else:
+            assert np.all(np.abs(got - want) <= REL * np.maximum(absrow, 1e-300))
+        assert abs(d.item() - float(want @ w)) <= 1e-11 * float(np.abs(want) @ np.abs(w))
 
 
 def test_csr_spmv_zero_rows_and_f32(ctx, oracle):
