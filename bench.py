@@ -1,30 +1,40 @@
 #!/usr/bin/env python
-"""bench.py -- the headline benchmark of the Krylov inner loop on B200.
+"""bench.py -- the benchmark of the Krylov inner loop on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|cusparse] [--workload c3] [--solver cg]
 
-Metric (BASELINE.json): CG iterations / second, fp64 CSR, 3-D 7-point Laplacian 256^3 (config C3),
-with the SpMV HBM GB/s of the dominant kernel reported in `roofline`.  The matrix is the reference's
-own benchmark matrix (BenchmarkStencil -dim 3 -nx 256 -ny 256 -nz 256), generated on the GPU by
-the same StencilGenerator rules; b = 1, x0 = 0, exactly the BenchmarkStencil / Test06 set-up.
+Headline (BASELINE.json): CG iterations / second, fp64 CSR, 3-D 7-point Laplacian 256^3 (config C3), with the SpMV
+HBM GB/s of the dominant kernel reported in `roofline`.  The matrix is the reference's own benchmark matrix
+(BenchmarkStencil -dim 3 -nx 256 -ny 256 -nz 256), generated on the GPU by the same StencilGenerator rules; b = 1,
+x0 = 0, exactly the BenchmarkStencil / Test06 set-up.
 
-A STEP is one replay of a recorded trace of `iters_per_step` CG iterations (BenchmarkStencil's
-`-pt`): `--steps 10` with the default 20 iterations per step is the reference protocol's 200 timed
-iterations after warm-up traces.  `value` is the whole-job rate with everything resident in HBM;
-`e2e` is the same rate through the host-buffer API (per step: H2D of the right-hand side from pinned
-memory, a fresh solve of `iters_per_step` iterations, D2H of the solution and the residual history).
+Workloads (`--workload`, BASELINE.json `configs`; each prints ONE JSON line of the same shape):
+    c3  3-D 7-point 256^3, CG (default; strong-scaled over --gpus)       c2  2-D 5-point 8192^2, CG
+    c4  3-D 27-point 192^3, BiCGStab                                      c5  COO power-law ~1e8 nnz, GMRES(30)
+    c1  2-D 5-point 256^2 (the CPU-runnable parity case)                  tiny  48^3 (smoke)
+`--solver` overrides the workload's solver; `--spaces 2` reproduces BenchmarkStencil's doubled block-diagonal system
+(test/BenchmarkStencil.cpp:199-207).
 
-At N > 1 (launched under torchrun) the FIXED 256^3 problem is row-partitioned over the N GPUs --
-strong scaling -- with the ghost-x halo exchange and the dot-product all-reduces over NVLink peer memory
-(fused into the kernels that produce the data; LSK_COMM=nccl keeps them on NCCL).  `--persistent` runs the
-whole CG step as one persistent kernel per trace instead of three leaf kernels per iteration.
+A STEP is one replay of a recorded trace of `iters_per_step` solver iterations (BenchmarkStencil's `-pt`; a GMRES
+"iteration" is one restart cycle, as there): `--steps 10` with the default 20 is the reference protocol's 200 timed
+iterations after warm-up traces.  `value` is the whole-job rate with everything resident in HBM; `e2e` is the same
+rate through the host-buffer API (per step: H2D of the right-hand side from pinned memory, a fresh solve of
+`iters_per_step` iterations, D2H of the solution and the solver's history), fully pipelined -- nothing is read
+back before the last step has been enqueued.  `parity` compares a fresh solve on the GPU(s) with the CPU oracle on
+the SAME full-size system (history and a strided sample of the solution), at every N.
 
-`--impl reference` times the reference's CPU task variants (the oracle restatement; the reference
-itself needs Legion and cannot be built here) on the host cores, on a bounded sample.
+At N > 1 (launched under torchrun) the FIXED problem is row-partitioned over the N GPUs -- strong scaling -- with the
+ghost-x halo exchange and the dot-product all-reduces over NVLink peer memory (fused into the kernels that produce
+the data; LSK_COMM=nccl keeps them on NCCL).
+
+`--impl reference` times the reference's CPU task variants (the oracle restatement; the reference itself needs
+Legion and cannot be built here) on the host cores, on a bounded sample.  `--impl cusparse` times the reference's GPU
+call sequence through cuSPARSE / cuBLAS (baseline/cusparse_ref.cu), the library path the hand-written kernels replace.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -36,19 +46,44 @@ if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
 WORKLOADS = {
-    # name: (dim_flag, (nx, ny, nz), description)
-    "c3": (3, (256, 256, 256), "BenchmarkStencil -dim 3: 3-D 7-point Laplacian 256^3, fp64 CSR, CG"),
-    "c2": (2, (8192, 8192, 1), "BenchmarkStencil -dim 2: 2-D 5-point Laplacian 8192^2, fp64 CSR, CG"),
-    "c4": (4, (192, 192, 192), "BenchmarkStencil -dim 4: 3-D 27-point stencil 192^3, fp64 CSR, CG"),
-    "c1": (2, (256, 256, 1), "2-D 5-point Laplacian 256^2 (the CPU-runnable parity case)"),
-    "tiny": (3, (48, 48, 48), "3-D 7-point Laplacian 48^3 (smoke)"),
+    # name: (kind, dim_flag, (nx, ny, nz), default solver, description)
+    "c3": ("stencil", 3, (256, 256, 256), "cg", "BenchmarkStencil -dim 3: 3-D 7-point Laplacian 256^3, fp64 CSR"),
+    "c2": ("stencil", 2, (8192, 8192, 1), "cg", "BenchmarkStencil -dim 2: 2-D 5-point Laplacian 8192^2, fp64 CSR"),
+    "c4": ("stencil", 4, (192, 192, 192), "bicgstab", "BenchmarkStencil -dim 4: 3-D 27-point stencil 192^3, fp64 CSR"),
+    "c5": ("coo", 0, (22, 0, 0), "gmres", "synthetic COO, power-law row lengths, N = 2^22, ~1e8 nnz, fp64"),
+    "c1": ("stencil", 2, (256, 256, 1), "cg", "2-D 5-point Laplacian 256^2 (the CPU-runnable parity case), fp64 CSR"),
+    "tiny": ("stencil", 3, (48, 48, 48), "cg", "3-D 7-point Laplacian 48^3 (smoke), fp64 CSR"),
 }
-METRIC = "cg_iterations_per_second"
+SOLVER_NAMES = {"cg": "CG", "bicgstab": "BiCGStab", "gmres": "GMRES(restart)"}
 UNIT = "it/s"
+GMRES_RESTART = {"c5": 30}  # BenchmarkStencil hard-codes 10; config C5 names GMRES(30)
+
+
+def metric_name(solver: str) -> str:
+    return f"{solver}_iterations_per_second"
+
+
+def workload_desc(args) -> str:
+    kind, dim_flag, shape, default_solver, desc = WORKLOADS[args.workload]
+    solver = args.solver or default_solver
+    name = SOLVER_NAMES[solver].replace("restart", str(gmres_restart(args)))
+    return f"{desc}, {name}"
+
+
+def gmres_restart(args) -> int:
+    return GMRES_RESTART.get(args.workload, 10)
+
+
+def shared_config(args, n, nnz) -> dict:
+    """The keys both arms print identically (the driver compares them)."""
+    kind, dim_flag, shape, default_solver, desc = WORKLOADS[args.workload]
+    return {"workload": workload_desc(args), "unknowns": int(n) * args.spaces, "nnz": int(nnz) * args.spaces,
+            "iters_per_step": args.iters_per_step, "spaces": args.spaces, "pieces": args.gpus,
+            "solver": args.solver or default_solver}
 
 
 # ---------------------------------------------------------------------------------------------------
-# clocks during the timed region (pynvml; the recipe's nvidia-smi line, in-process)
+# clocks during the timed region (the recipe's nvidia-smi line, in a separate process)
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
     """SM clock, power and clock-event reasons of one GPU while it is under load, sampled by `nvidia-smi -lms` in a
@@ -67,8 +102,7 @@ class ClockSampler:
         exe = shutil.which("nvidia-smi")
         if exe is None:
             return
-        # physical index of the device this process uses (CUDA_VISIBLE_DEVICES may remap)
-        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")  # physical index of the device this process uses
         ident = str(device_index)
         if vis:
             ids = [v.strip() for v in vis.split(",") if v.strip()]
@@ -81,15 +115,13 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def start(self):
-        pass  # sampling began in the constructor, before the warm-up
-
     def stop(self, t0: float | None = None, t1: float | None = None):
         """t0, t1: wall-clock bounds (time.time()) of the timed region."""
         import datetime
 
+        empty = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            return empty
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -112,7 +144,7 @@ class ClockSampler:
         except OSError:
             pass
         if not rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            return empty
         inside = [r for r in rows if t0 is not None and t1 is not None and t0 <= r[0] <= t1]
         # the GPU is under the same load from the warm-up on: samples of the timed region if there are any, else
         # the ones under load around it (power well above idle)
@@ -125,58 +157,182 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------
-# the reference arm / cpu_baseline: the reference's CPU task variants on the host cores
+# the workload on the host: oracle matrix (CPU arm, parity) -- and, for C5, the arrays uploaded to the GPU
 # ---------------------------------------------------------------------------------------------------
-def cpu_reference_run(dim_flag, shape, threads, its_warm, its_timed, steps=1):
-    """CG on the oracle (restated CPU task bodies, one piece per host thread -- one Legion CPU processor
-    per piece).  Returns (iterations/s, list of per-step seconds, description of the sample)."""
+_host_matrix_cache = {}
+
+
+def host_matrix(args):
+    """The workload's matrix in the oracle's representation (global arrays on the host)."""
     from oracle import oracle as orc
 
-    off, val = orc.benchmark_stencil(dim_flag)
-    dims = shape[:3] if dim_flag >= 3 else shape[:dim_flag]
-    m = orc.stencil_csr(dims, off, val)
+    kind, dim_flag, shape, _, _ = WORKLOADS[args.workload]
+    if args.shape:
+        shape = tuple(int(v) for v in args.shape.split(","))
+    key = (args.workload, shape)
+    if key not in _host_matrix_cache:
+        if kind == "stencil":
+            off, val = orc.benchmark_stencil(dim_flag)
+            dims = shape[:3] if dim_flag >= 3 else shape[:dim_flag]
+            _host_matrix_cache[key] = orc.stencil_csr(dims, off, val)
+        else:
+            from legionsolvers_b200.workloads import power_law_coo
+
+            n, entry, row, col = power_law_coo(shape[0])
+            _host_matrix_cache[key] = orc.Matrix(n, n, entry, col, row=row)
+    return _host_matrix_cache[key]
+
+
+def pin_cpu_threads():
+    """One oracle thread per core, pinned: must be set before libgomp starts."""
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
+
+
+def cpu_reference_run(args, threads, its_warm, its_timed, steps=1, sample_stride=None):
+    """The solver on the oracle (restated CPU task bodies, one piece per host thread -- one Legion CPU processor per
+    piece).  Returns a dict: rate (iterations/s), per-step seconds, description of the sample, the history after
+    its_warm + steps * its_timed iterations and a strided sample of the solution of space 0."""
+    pin_cpu_threads()
+    from oracle import oracle as orc
+
+    _, _, _, default_solver, _ = WORKLOADS[args.workload]
+    solver = args.solver or default_solver
+    m = host_matrix(args)
     orc.set_threads(threads)
-    pl = orc.Planner([m.n_rows], [threads])
+    pl = orc.Planner([m.n_rows] * args.spaces, [threads] * args.spaces)
     pl.fill(1, 1.0)
-    pl.add_matrix(m)
-    cg = orc.CGSolver(pl)
+    for s in range(args.spaces):
+        pl.add_matrix(m, s, s)
+    if solver == "cg":
+        sv = orc.CGSolver(pl)
+    elif solver == "bicgstab":
+        sv = orc.BiCGStabSolver(pl)
+    else:
+        sv = orc.GMRESSolver(pl, gmres_restart(args))
     for _ in range(its_warm):
-        cg.step()
+        sv.step()
     per_step = []
     for _ in range(steps):
         t0 = time.perf_counter()
         for _ in range(its_timed):
-            cg.step()
+            sv.step()
         per_step.append(time.perf_counter() - t0)
     total = sum(per_step)
-    sample = (f"{steps} x {its_timed} CG iterations of the FULL {'x'.join(map(str, dims))} system after {its_warm} warm-up "
-              f"iterations, {threads} pieces on {threads} host threads (reference-equivalent linear-time CSR body)")
-    return steps * its_timed / total, per_step, sample
+    if solver == "cg":
+        hist = {"residual_norm_squared": sv.residual_norm_squared.tolist()}
+    elif solver == "bicgstab":
+        hist = {"rho": sv.rho.tolist(), "alpha": sv.alpha.tolist(), "omega": sv.omega.tolist()}
+    else:
+        hist = {"hessenberg": sv.inner_products.tolist()}
+    x = pl.vector(0, 0)
+    stride = sample_stride or max(1, m.n_rows // 4096)
+    sample = (f"{steps} x {its_timed} {SOLVER_NAMES[solver].replace('restart', str(gmres_restart(args)))} iterations of the FULL system "
+              f"({m.n_rows} rows x {args.spaces} space(s), {m.nnz} nnz) after {its_warm} warm-up iterations, {threads} pieces on {threads} pinned host "
+              f"threads (reference-equivalent CPU task bodies; the CSR body is the linear-time form proven bit-identical to the reference's scan)")
+    return {"rate": steps * its_timed / total if total > 0 else 0.0, "per_step": per_step, "sample": sample, "history": hist,
+            "iterations": its_warm + steps * its_timed, "x_sample": x[::stride].copy(), "x_stride": stride, "x_absmax": float(abs(x).max()),
+            "threads": threads}
+
+
+def cpu_sample_sizes(args):
+    """(warm-up iterations, timed iterations) of the bounded CPU sample, sized for ~10-30 s of host work."""
+    _, _, _, default_solver, _ = WORKLOADS[args.workload]
+    solver = args.solver or default_solver
+    if args.workload in ("c1", "tiny"):
+        return (2, 20) if solver != "gmres" else (0, 2)
+    if solver == "gmres":
+        return 0, 1
+    if solver == "bicgstab":
+        return 1, 4
+    return 2, 6
+
+
+def reference_as_written_c1(threads=4):
+    """the reference's CSR body AS WRITTEN -- for every non-zero a linear scan of the piece's
+    rowptr (src/CSRMatrixTasks.cpp:73-91) -- is only runnable at C1 size: CG on the 256^2 system, 4 pieces."""
+    pin_cpu_threads()
+    from oracle import oracle as orc
+
+    off, val = orc.benchmark_stencil(2)
+    m = orc.stencil_csr((256, 256), off, val)
+    orc.set_threads(threads)
+    pl = orc.Planner([m.n_rows], [threads])
+    pl.fill(1, 1.0)
+    pl.add_matrix(m)
+    pl.use_literal_csr(True)
+    cg = orc.CGSolver(pl)
+    cg.step()
+    t0 = time.perf_counter()
+    its = 2
+    for _ in range(its):
+        cg.step()
+    return {"value": its / (time.perf_counter() - t0), "unit": UNIT, "what": "CG on 2-D 5-pt 256^2, 4 pieces, the quadratic rowptr scan as written",
+            "cores": threads}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0  # under torchrun only rank 0 runs the CPU arm
-    dim_flag, shape, desc = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
     threads = max(1, min(cores, 64))
     its = max(1, args.ref_iters_per_step)
-    rate, per_step, sample = cpu_reference_run(dim_flag, shape, threads, its_warm=max(1, args.warmup),
-                                               its_timed=its, steps=args.steps)
-    ms = 1e3 * sum(per_step) / len(per_step)
+    res = cpu_reference_run(args, threads, its_warm=max(1, min(args.warmup, 2)), its_timed=its, steps=args.steps)
+    m = host_matrix(args)
+    # a STEP of the CPU arm is a bounded sample (`its` iterations); ms_per_step is scaled to iters_per_step iterations
+    ms = 1e3 * (sum(res["per_step"]) / len(res["per_step"])) * (args.iters_per_step / its)
+    _, _, _, default_solver, _ = WORKLOADS[args.workload]
     line = {
-        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "impl": "reference", "metric": metric_name(args.solver or default_solver), "value": res["rate"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "iters_per_step": its, "spaces": 1, "pieces": threads,
-                   "note": "reference CPU task variants restated in C (oracle/): the reference needs Legion and cannot be built here"},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": shared_config(args, m.n_rows, m.nnz),
+        "cpu_baseline": {"value": res["rate"], "unit": UNIT, "cores": threads, "kind": "port", "sample": res["sample"],
+                         "iterations_per_timed_step": its,
+                         "note": "reference CPU task variants restated in C (oracle/): the reference needs Legion and cannot be built here"},
+        "e2e": {"value": res["rate"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# parity of a GPU history / solution against the oracle's
+# ---------------------------------------------------------------------------------------------------
+def parity_report(solver, gpu_hist, cpu, x_gpu_sample, restart):
+    """gpu_hist / cpu['history']: dicts of lists.  Tolerances: CG residual history 1e-10 relative over the window where
+    |r|^2 >= 1e-12 |b|^2 (north_star); BiCGStab rho/alpha/omega over the first 6 steps and GMRES Hessenberg over the first 10
+    columns 1e-9 (Lanczos-type recurrences amplify the dot-order difference ~3x per step; tests/ derive the windows)."""
+    import numpy as np
+
+    out = {"solver": solver}
+    if solver == "cg":
+        g, c = np.array(gpu_hist["residual_norm_squared"]), np.array(cpu["history"]["residual_norm_squared"])
+        k = min(g.size, c.size)
+        g, c = g[:k], c[:k]
+        err = float(np.max(np.abs(g - c) / np.maximum(np.abs(c), 1e-12 * abs(c[0]))))
+        out.update({"hist_rel_err": err, "tol": 1e-10, "entries": int(k)})
+    elif solver == "bicgstab":
+        err = 0.0
+        k = 0
+        for name in ("rho", "alpha", "omega"):
+            g, c = np.array(gpu_hist[name]), np.array(cpu["history"][name])
+            k = min(g.size, c.size, 7)
+            err = max(err, float(np.max(np.abs(g[1:k] - c[1:k]) / np.abs(c[1:k]))) if k > 1 else 0.0)
+        out.update({"hist_rel_err": err, "tol": 1e-9, "entries": int(k), "what": "rho, alpha, omega of the first steps"})
+    else:
+        g, c = np.array(gpu_hist["hessenberg"]), np.array(cpu["history"]["hessenberg"])
+        cols = min(10, restart)
+        err = float(np.max(np.abs(g[:, :cols] - c[:, :cols])) / np.max(np.abs(c)))
+        out.update({"hist_rel_err": err, "tol": 1e-9, "entries": int(cols), "what": "Hessenberg (inner_products), first columns of the last cycle"})
+    xs_c = cpu["x_sample"]
+    xerr = float(np.max(np.abs(x_gpu_sample - xs_c)) / max(cpu["x_absmax"], 1e-300)) if xs_c.size == x_gpu_sample.size else float("nan")
+    out.update({"x_rel_err": xerr, "x_tol": 1e-10 if solver == "cg" else 1e-8, "x_samples": int(xs_c.size),
+                "iterations": cpu["iterations"], "oracle_threads": cpu["threads"]})
+    out["ok"] = bool(out["hist_rel_err"] <= out["tol"] and xerr <= out["x_tol"])
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -201,11 +357,14 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        import datetime
+
         import torch.distributed as dist_
 
         dist = dist_
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(minutes=20))
 
     def barrier():
         torch.cuda.synchronize()
@@ -220,11 +379,13 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    dim_flag, shape, desc = WORKLOADS[args.workload]
+    kind, dim_flag, shape, default_solver, _ = WORKLOADS[args.workload]
+    solver = args.solver or default_solver
     if args.shape:
         shape = tuple(int(v) for v in args.shape.split(","))
-        desc += f" [grid overridden to {shape}]"
     ipt = args.iters_per_step
+    restart = gmres_restart(args)
+    spaces = args.spaces
     # everything (our kernels, NCCL, the timing events) goes on ONE explicit non-default stream: torch's
     # default stream has handle 0, which the runtime would read as "create a private stream"
     tstream = torch.cuda.Stream()
@@ -239,39 +400,54 @@ def run_ours(args):
         dist.broadcast(uid, src=0)
         rt.comm_init(bytes(uid.cpu().numpy().tobytes()))
 
-    # ---- problem set-up, all on the GPU: BenchmarkStencil's matrix, b = 1, x0 = 0 -------------------
+    # ---- problem set-up: BenchmarkStencil's matrix generated on the GPU (or the C5 arrays uploaded), b = 1, x0 = 0 ----
     t_setup = time.perf_counter()
-    st = S.benchmark_stencil(dim_flag, *shape)
-    n = shape[0] * shape[1] * shape[2]
     pieces = world  # -vp = total GPUs (bench_all.py:206-208)
-    mat = S.CSRMatrix.stencil(rt, st, pieces)
-    sol = S.PartitionedVector(rt, "sol", n, pieces)
-    rhs = S.PartitionedVector(rt, "rhs", n, pieces)
-    sol.zero_fill()
-    rhs.constant_fill(1.0)
-    pl = S.SquarePlanner(rt)
-    pl.add_sol_vector(sol)
-    pl.add_rhs_vector(rhs)
-    pl.add_row_partitioned_matrix(mat, 0, 0)
-    if args.solver == "cg":
-        cg = S.CGSolver(pl, fused=not args.unfused, persistent=True if args.persistent else None)
-    elif args.solver == "bicgstab":
-        cg = S.BiCGStabSolver(pl, fused=not args.unfused)
+    if kind == "stencil":
+        st = S.benchmark_stencil(dim_flag, *shape)
+        n = shape[0] * shape[1] * shape[2]
+        mat = S.CSRMatrix.stencil(rt, st, pieces)
     else:
-        cg = S.GMRESSolver(pl, 10, fused=not args.unfused)  # BenchmarkStencil hard-codes restart = 10
+        hm = host_matrix(args)
+        n = hm.n_rows
+        lo = (n * rank) // world
+        hi = (n * (rank + 1)) // world - 1
+        k_lo, k_hi = int(np.searchsorted(hm.row, lo, side="left")), int(np.searchsorted(hm.row, hi, side="right")) - 1
+        mat = S.COOMatrix.from_host(rt, n, n, hm.entry, hm.row, hm.col, k_range=(k_lo, k_hi), nnz_global=hm.nnz)
+    pl = S.SquarePlanner(rt)
+    sols, rhss = [], []
+    for s in range(spaces):
+        v = S.PartitionedVector(rt, f"sol{s}", n, pieces)
+        v.zero_fill()
+        pl.add_sol_vector(v)
+        sols.append(v)
+    for s in range(spaces):
+        v = S.PartitionedVector(rt, f"rhs{s}", n, pieces)
+        v.constant_fill(1.0)
+        pl.add_rhs_vector(v)
+        rhss.append(v)
+    for s in range(spaces):
+        pl.add_row_partitioned_matrix(mat, s, s)
+    if solver == "cg":
+        sv = S.CGSolver(pl, fused=not args.unfused, persistent=True if args.persistent else None)
+    elif solver == "bicgstab":
+        sv = S.BiCGStabSolver(pl, fused=not args.unfused)
+    else:
+        sv = S.GMRESSolver(pl, restart, fused=not args.unfused)
     rt.fence()
     setup_s = time.perf_counter() - t_setup
     nnz = mat.nnz
-    own_lo, own_hi = sol.owned_range()
+    own_lo, own_hi = sols[0].owned_range()
     n_local = own_hi - own_lo + 1
     nnz_local = mat.slab_k_hi - mat.slab_k_lo + 1
+    is_csr = bool(mat.is_csr)
 
     TRACE = 51  # the reference's trace id (test/BenchmarkStencil.cpp:218)
 
     def step():
         rt.begin_trace(TRACE)
         for _ in range(ipt):
-            cg.step()
+            sv.step()
         rt.end_trace(TRACE)
 
     # ---- warm-up, then EXACTLY K timed steps between barriers, CUDA events on the launching stream ---
@@ -294,7 +470,7 @@ def run_ours(args):
     rt.fence()
     launches0 = rt.kernel_launches
     cs0 = rt.comm_stats() if world > 1 else None
-    ph0 = rt.cg_phase_stats() if getattr(cg, "persistent", False) else None
+    ph0 = rt.cg_phase_stats() if getattr(sv, "persistent", False) else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     wall0 = time.time()
@@ -324,25 +500,31 @@ def run_ours(args):
         ph1 = rt.cg_phase_stats()
         its = max(1, ph1["iterations"] - ph0["iterations"])
         phase_us = {k[:-3] + "_us_per_iteration": round((ph1[k] - ph0[k]) / 1e3 / its, 2) for k in ph1 if k.endswith("_ns")}
-        if dist is not None:  # every rank's CTA-0 view, in the order of the keys above
-            mine_ph = torch.tensor(list(phase_us.values()), dtype=torch.float64, device="cuda")
-            all_ph = [torch.zeros_like(mine_ph) for _ in range(world)]
-            dist.all_gather(all_ph, mine_ph)
-            phase_us = {"keys": list(phase_us.keys()), "by_rank": [[round(float(x), 2) for x in v] for v in all_ph]}
 
-    # ---- roofline of the dominant kernel: the fused CSR SpMV + p.Ap, timed alone on the same stream ----
+    # ---- roofline of the dominant kernel: the (fused) mat-vec, timed alone on the same stream -----------------
     L = _abi.lib()
-    e_ptr, c_ptr, rp_ptr = mat.device_fields()
+    e_ptr, c_ptr, third_ptr = mat.device_fields()
     g_lo, g_hi = pl.ghost_bounds(0, pl.local_colors(0)[0])
     xg = torch.rand(g_hi - g_lo + 1, dtype=torch.float64, device="cuda")
     yv = torch.zeros(n_local, dtype=torch.float64, device="cuda")
-    dslot = torch.zeros(1, dtype=torch.float64, device="cuda")
+    dslot = torch.zeros(2, dtype=torch.float64, device="cuda")
     x_shifted = xg.data_ptr() - g_lo * 8
     w_ptr = xg.data_ptr() + (own_lo - g_lo) * 8
+    if is_csr:
+        kernel_name = ("csr_ws_kernel<NDOT=1> (warp-specialised TMA-pipelined CSR SpMV fused with y.w)")
+        spmv_bytes = 16 * nnz_local + 32 * n_local  # 16/nnz + rowptr 16 + x 8 + y 8 per row
 
-    def spmv():
-        _abi.check(L.lsk_csr_spmv_f64(rt.ctx, stream, n_local, nnz_local, e_ptr, c_ptr, rp_ptr, mat.slab_k_lo, x_shifted,
-                                      yv.data_ptr(), w_ptr, dslot.data_ptr(), None, 0), "lsk_csr_spmv_f64")
+        def spmv():
+            _abi.check(L.lsk_csr_spmv_f64(rt.ctx, stream, n_local, nnz_local, e_ptr, c_ptr, third_ptr, mat.slab_k_lo, x_shifted,
+                                          yv.data_ptr(), w_ptr, dslot.data_ptr(), None, 0), "lsk_csr_spmv_f64")
+    else:
+        kernel_name = "coo_segreduce_kernel (segmented warp-shuffle COO SpMV, beta = 1)"
+        spmv_bytes = 24 * nnz_local + 8 * (g_hi - g_lo + 1) + 16 * n_local  # 24/nnz + x 8 per column touched + y read-modify-write 16 per row
+        y_shifted = yv.data_ptr() - own_lo * 8
+
+        def spmv():
+            _abi.check(L.lsk_coo_spmv_f64(rt.ctx, stream, nnz_local, e_ptr, third_ptr, c_ptr, x_shifted, y_shifted, own_lo, own_hi, g_lo, g_hi),
+                       "lsk_coo_spmv_f64")
 
     for _ in range(5):
         spmv()
@@ -361,136 +543,191 @@ def run_ours(args):
         all_ms = [torch.zeros_like(mine_ms) for _ in range(world)]
         dist.all_gather(all_ms, mine_ms)
         spmv_ms_by_rank = [round(float(v[0]), 5) for v in all_ms]
-    spmv_bytes = 16 * nnz_local + 32 * n_local  # 16/nnz + rowptr 16 + x 8 + y 8 per row
     achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
     peaks_file = ROOT / "MEASURED_PEAKS.json"
     if peaks_file.exists():
         peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    traffic = None
+    # DRAM traffic of that kernel: from the committed ncu capture of the SAME kernel source, else unknown
+    traffic, traffic_src = None, "none: no ncu capture of this workload / kernel source committed"
     tf = ROOT / "profiles" / "spmv_traffic.json"
-    if tf.exists() and args.workload == "c3" and world == 1:
-        traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
-    # solver-iteration roofline: fused minimum 16 nnz + 104 N bytes per iteration
-    iter_bytes = 16 * nnz_local + 104 * n_local
+    if tf.exists() and world == 1:
+        rec = json.loads(tf.read_text()).get(args.workload)
+        if rec:
+            sha = hashlib.sha256(b"".join((ROOT / "legionsolvers_b200" / "csrc" / f).read_bytes() for f in rec.get("sources", []))).hexdigest()
+            if sha == rec.get("sources_sha256"):
+                traffic, traffic_src = rec["dram_bytes_per_launch"], f"{rec.get('from', 'profiles/')} (ncu --set full of this kernel source, not this run)"
+            else:
+                traffic_src = "stale: the kernel source changed since the committed ncu capture"
+    # solver-iteration roofline: fewest-pass bytes per iteration
+    mv = spmv_bytes + (8 * n_local if not is_csr else 0)  # the planner zero-fills before an accumulating (COO) mat-vec
+    if solver == "cg":
+        iter_bytes = mv + 72 * n_local
+    elif solver == "bicgstab":
+        iter_bytes = 2 * mv + 120 * n_local
+    else:  # one restart cycle: residual (mat-vec, xpay, dot, scal), m Arnoldi steps (mat-vec + (j + 1) fused axpy.dot + scal), m update axpys
+        m_ = restart
+        iter_bytes = (mv + 24 * n_local + 16 * n_local + 16 * n_local) + sum(mv + 32 * n_local * (j + 1) + 16 * n_local for j in range(m_)) + 24 * n_local * m_
+    iter_bytes *= spaces
     iter_frac = (iter_bytes * value / 1e9) / peak
 
-    if args.solver != "cg":
-        # secondary configs: device-resident rate only (a GMRES "iteration" is one restart cycle, as in BenchmarkStencil)
-        if rank == 0:
-            per_it = {"cg": 16 * nnz_local + 104 * n_local, "bicgstab": 32 * nnz_local + 184 * n_local}.get(args.solver)
-            print(json.dumps({
-                "metric": f"{args.solver}_iterations_per_second", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": desc, "solver": args.solver, "unknowns": n, "nnz": nnz, "iters_per_step": ipt, "pieces": pieces,
-                           "fused": not args.unfused,
-                           "iteration_roofline_frac": (per_it * value / 1e9 / peak) if per_it else None},
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None},
-                "gpu_launches": int(launches), "clocks": clocks}), flush=True)
-        barrier()
-        if dist is not None:
-            dist.destroy_process_group()
-        return 0
+    # ---- end to end through the host-buffer API, fully pipelined ---------------------------------------------------
+    # Every step is a FRESH solve of `ipt` iterations: its right-hand side comes from pinned host memory, its solution and
+    # history go back to the host.  Copies run on a second stream, double-buffered against the iterations (the H2D of step
+    # k + 1's right-hand side starts as soon as step k's reset has consumed the previous one; the D2H of step k's solution,
+    # staged device-to-device, overlaps step k + 1).  reset() and the iterations are recorded traces (CUDA graphs); the host
+    # enqueues all steps without reading anything back and synchronises once at the end.
+    e2e = None
+    if not args.no_e2e:
+        b_host = [torch.ones(n, dtype=torch.float64).pin_memory() for _ in range(spaces)]
+        x_host = [torch.zeros(n, dtype=torch.float64).pin_memory() for _ in range(spaces)]
+        x_stage = [torch.zeros(n_local, dtype=torch.float64, device="cuda") for _ in range(spaces)]
+        e2e_steps = max(2, min(args.steps, 10))
+        nh = {"cg": 1, "bicgstab": 3, "gmres": 0}[solver]
+        hist_len = ipt + 1
+        hist_stage = torch.zeros(max(1, nh) * hist_len, dtype=torch.float64, device="cuda")
+        hist_host = torch.zeros((e2e_steps + 2, max(1, nh) * hist_len), dtype=torch.float64).pin_memory()
+        TRACE_RESET, TRACE_ITERS = 52, 53
+        copy_stream = torch.cuda.Stream()
+        cs = copy_stream.cuda_stream
 
-    # ---- end to end through the host-buffer API ------------------------------------------------------
-    # Every step is a FRESH solve of `ipt` iterations: its right-hand side comes from pinned host memory, its solution
-    # and residual history go back to the host.  The copies run on a second stream and are double-buffered against the
-    # iterations -- the H2D of step k+1's right-hand side starts as soon as step k's reset has consumed the previous one,
-    # the D2H of step k's solution (staged device-to-device) overlaps step k+1 -- the way a production caller would
-    # drive independent solves.  All copies of all steps lie inside the timed region.
-    b_host = torch.ones(n, dtype=torch.float64).pin_memory()
-    x_host = torch.zeros(n, dtype=torch.float64).pin_memory()
-    x_stage = torch.zeros(n_local, dtype=torch.float64, device="cuda")
-    e2e_steps = max(2, min(args.steps, 10))
-    TRACE_E2E = 52
-    copy_stream = torch.cuda.Stream()
-    cs = copy_stream.cuda_stream
-    b_glob, x_stage_glob = b_host.data_ptr(), x_stage.data_ptr() - 8 * own_lo
-    x_host_own = x_host[own_lo:own_lo + n_local]
-
-    def e2e_run(nsteps):
-        ev_h2d, ev_reset, ev_solved, ev_d2h = (torch.cuda.Event() for _ in range(4))
-        copy_stream.wait_stream(tstream)
-        pl.vector_from_async(1, 0, b_glob, cs)       # H2D: right-hand side of the first step
-        ev_h2d.record(copy_stream)
-        ev_d2h.record(copy_stream)
-        hist = None
-        for k in range(nsteps):
-            tstream.wait_event(ev_h2d)                # this step's right-hand side has landed
-            pl.zero_fill(0)
-            cg.reset()                                # P <- RHS, R <- RHS, rr0: the last readers of RHS
-            ev_reset.record(tstream)
-            if k + 1 < nsteps:                        # H2D of the NEXT step's right-hand side, under this step's iterations
-                copy_stream.wait_event(ev_reset)
-                pl.vector_from_async(1, 0, b_glob, cs)
-                ev_h2d.record(copy_stream)
-            rt.begin_trace(TRACE_E2E)
-            for _ in range(ipt):
-                cg.step()
-            rt.end_trace(TRACE_E2E)
-            tstream.wait_event(ev_d2h)                # the staging buffer's previous content is on the host
-            pl.vector_to_async(0, 0, x_stage_glob, stream)   # solution -> staging buffer (device to device)
-            ev_solved.record(tstream)
-            copy_stream.wait_event(ev_solved)
-            with torch.cuda.stream(copy_stream):      # D2H: this step's solution, under the next step's iterations
-                x_host_own.copy_(x_stage, non_blocking=True)
+        def e2e_run(nsteps):
+            ev_h2d, ev_reset, ev_solved, ev_d2h = (torch.cuda.Event() for _ in range(4))
+            copy_stream.wait_stream(tstream)
+            for s in range(spaces):
+                pl.vector_from_async(1, s, b_host[s].data_ptr(), cs)       # H2D: right-hand side of the first step
+            ev_h2d.record(copy_stream)
             ev_d2h.record(copy_stream)
-            hist = cg.residual_norm_squared           # D2H: this step's residual history (waits for its iterations)
-        copy_stream.synchronize()
-        return hist
+            for k in range(nsteps):
+                tstream.wait_event(ev_h2d)                # this step's right-hand side has landed
+                rt.begin_trace(TRACE_RESET)
+                pl.zero_fill(0)
+                sv.reset()                                # the last readers of RHS
+                rt.end_trace(TRACE_RESET)
+                ev_reset.record(tstream)
+                if k + 1 < nsteps:                        # H2D of the NEXT step's right-hand side, under this step's iterations
+                    copy_stream.wait_event(ev_reset)
+                    for s in range(spaces):
+                        pl.vector_from_async(1, s, b_host[s].data_ptr(), cs)
+                    ev_h2d.record(copy_stream)
+                rt.begin_trace(TRACE_ITERS)
+                for _ in range(ipt):
+                    sv.step()
+                rt.end_trace(TRACE_ITERS)
+                tstream.wait_event(ev_d2h)                # the staging buffers' previous content is on the host
+                for s in range(spaces):                   # solution + history -> staging buffers (device to device)
+                    pl.vector_to_async(0, s, x_stage[s].data_ptr() - 8 * own_lo, stream)
+                for h in range(nh):
+                    sv.history_copy_async(h, hist_stage.data_ptr() + 8 * h * hist_len, hist_len, stream)
+                ev_solved.record(tstream)
+                copy_stream.wait_event(ev_solved)
+                with torch.cuda.stream(copy_stream):      # D2H under the next step's iterations
+                    for s in range(spaces):
+                        x_host[s][own_lo:own_lo + n_local].copy_(x_stage[s], non_blocking=True)
+                    hist_host[k].copy_(hist_stage, non_blocking=True)
+                ev_d2h.record(copy_stream)
+            copy_stream.synchronize()
+            torch.cuda.synchronize()
 
-    e2e_run(2)
-    barrier()
-    t0 = time.perf_counter()
-    hist = e2e_run(e2e_steps)
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = e2e_steps * ipt / e2e_s
-    rr_final = float(hist[-1])
-    x_check = float(x_host_own.abs().max())  # the solution really arrived
+        e2e_run(2)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_run(e2e_steps)
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        e2e_value = e2e_steps * ipt / e2e_s
+        e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n_local * spaces,
+               "d2h_bytes_per_step": 8 * n_local * spaces + 8 * nh * hist_len, "steps": e2e_steps,
+               "what": ("per step: H2D rhs (pinned) -> zero_fill + reset (trace) -> iters_per_step iterations (trace) -> D2H solution + history; copies on a "
+                        "second stream, double-buffered; nothing is read back until every step has been enqueued"),
+               "ratio_to_resident": e2e_value / value,
+               "solution_abs_max": float(x_host[0][own_lo:own_lo + n_local].abs().max()),
+               "history_last": float(hist_host[e2e_steps - 1][hist_len - 1]) if nh else None}
 
-    # ---- CPU baseline on the box's host cores (rank 0, N = 1 only), bounded sample ---------------------
-    cpu_baseline = None
-    if world == 1 and rank == 0 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        threads = max(1, min(cores, 64))
-        its = 6 if n >= 1 << 24 else 20
-        rate, _, sample = cpu_reference_run(dim_flag, shape, threads, its_warm=2, its_timed=its)
-        cpu_baseline = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+    # ---- parity at FULL size against the oracle, at every N; CPU baseline from the same oracle run at N = 1 ---------
+    # GPU side: a fresh solve of K iterations (K = the oracle's warm-up + timed iterations), history + strided solution sample
+    cpu_baseline, parity, as_written = None, None, None
+    if not args.no_parity:
+        its_warm, its_timed = cpu_sample_sizes(args)
+        K = its_warm + its_timed
+        for s in range(spaces):
+            rhss[s].constant_fill(1.0)
+        pl.zero_fill(0)
+        sv.reset()
+        for _ in range(K):
+            sv.step()
+        rt.fence()
+        if solver == "cg":
+            gpu_hist = {"residual_norm_squared": sv.residual_norm_squared.tolist()}
+        elif solver == "bicgstab":
+            gpu_hist = {"rho": sv.rho.tolist(), "alpha": sv.alpha.tolist(), "omega": sv.omega.tolist()}
+        else:
+            gpu_hist = {"hessenberg": sv.inner_products.tolist()}
+        stride = max(1, n // 4096)
+        xs_local = torch.zeros(n, dtype=torch.float64).pin_memory()
+        pl.vector_to_async(0, 0, xs_local.data_ptr(), stream)
+        rt.fence()
+        first = ((own_lo + stride - 1) // stride) * stride
+        mine_idx = np.arange(first, own_hi + 1, stride)
+        mine_val = xs_local.numpy()[mine_idx]
+        if dist is not None:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, (mine_idx, mine_val))
+            x_gpu = np.concatenate([v for _, v in gathered])
+        else:
+            x_gpu = mine_val
+        if rank == 0:
+            cores = os.cpu_count() or 1
+            threads = max(1, min(cores, 64))
+            cpu = cpu_reference_run(args, threads, its_warm=its_warm, its_timed=its_timed, sample_stride=stride)
+            parity = parity_report(solver, gpu_hist, cpu, x_gpu, restart)
+            if world == 1 and not args.no_cpu_baseline:
+                cpu_baseline = {"value": cpu["rate"], "unit": UNIT, "cores": threads, "kind": "port", "sample": cpu["sample"]}
+                if args.workload == "c3":
+                    cpu_baseline["reference_as_written_c1"] = reference_as_written_c1()
+
+    # ---- the library the kernels replace, on the same GPU (comparator only) ----------------------------------------------
+    vs_cusparse = None
+    if world == 1 and is_csr and not args.no_cusparse:
+        try:
+            from baseline import cusparse_ref
+
+            vs_cusparse = cusparse_ref.compare(rt, mat, n, nnz, stream, ours_spmv_ms=spmv_ms, ours_iteration_ms=ms_per_step / ipt, solver=solver)
+        except Exception as exc:  # the comparator is optional equipment: say why it is missing
+            vs_cusparse = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
 
     if rank == 0:
+        cfg = shared_config(args, n, nnz)
+        cfg.update({
+            "solver_form": ("persistent kernel (grid barriers instead of kernel boundaries, one launch per step)" if getattr(sv, "persistent", False)
+                            else "fused (fewest HBM passes: CG 3, BiCGStab 5)" if not args.unfused else "unfused (reference call sequence)"),
+            "gmres_restart": restart if solver == "gmres" else None,
+            "trace": "CUDA graph replay of iters_per_step iterations", "rhs": "b = 1, x0 = 0 (BenchmarkStencil)",
+            "l2": "working set per GPU exceeds the 126 MB L2 (matrix streamed once per iteration)" if (16 if is_csr else 24) * nnz_local > 2 * 126e6
+                  else "matrix slab of this rank fits the L2 only partly; vectors are L2-resident",
+            "halo_bytes_per_matvec_rank0": pl.halo_bytes_per_matvec, "setup_seconds": round(setup_s, 3),
+            "collectives": "none (1 GPU)" if world == 1 else rt.collectives,
+            "comm_error": rt.comm_error() if world > 1 else 0,
+            "time_inside_collectives": comm_us,
+            "persistent_kernel_phases": phase_us,
+            "spmv_ms_per_launch_by_rank": spmv_ms_by_rank,
+            "iteration_roofline": {"bytes_per_iteration_per_gpu": iter_bytes, "frac_of_peak": iter_frac,
+                                   "frac_of_nominal_8TBs": iter_bytes * value / 1e9 / 8000.0},
+        })
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": metric_name(solver), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {
-                "workload": desc, "unknowns": n, "nnz": nnz, "iters_per_step": ipt, "spaces": 1, "pieces": pieces,
-                "solver": ("CGSolver persistent kernel (3 HBM passes / iteration, grid barriers instead of kernel boundaries, one launch per step)"
-                           if getattr(cg, "persistent", False) else "CGSolver fused (3 HBM passes / iteration)" if not args.unfused
-                           else "CGSolver unfused (reference call sequence)"),
-                "trace": "CUDA graph replay of iters_per_step iterations", "rhs": "b = 1, x0 = 0 (BenchmarkStencil)",
-                "l2": "working set per GPU exceeds the 126 MB L2 (matrix streamed once per iteration)",
-                "halo_bytes_per_matvec_rank0": pl.halo_bytes_per_matvec, "setup_seconds": round(setup_s, 3),
-                "collectives": "none (1 GPU)" if world == 1 else rt.collectives,
-                "comm_error": rt.comm_error() if world > 1 else 0,
-                "time_inside_collectives": comm_us,
-                "persistent_kernel_phases": phase_us,
-                "spmv_ms_per_launch_by_rank": spmv_ms_by_rank,
-                "residual_norm_squared_last": rr_final,
-                "iteration_roofline": {"bytes_per_iteration_per_gpu": iter_bytes, "frac_of_peak": iter_frac},
-            },
-            "roofline": {"bound": "hbm", "kernel": "csr_tma_kernel<1> (fused CSR SpMV + p.Ap)", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+            "config": cfg,
+            "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "frac_of_nominal_8TBs": achieved / 8000.0,
                          "algorithmic_bytes_per_launch": spmv_bytes, "ms_per_launch": spmv_ms},
             "spmv_gbs": achieved,
+            "parity": parity,
             "cpu_baseline": cpu_baseline,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n_local,
-                    "d2h_bytes_per_step": 8 * n_local + 8 * (ipt + 1), "steps": e2e_steps,
-                    "what": ("per step: H2D rhs (pinned) -> reset -> iters_per_step CG iterations -> D2H solution + residual history; "
-                             "copies on a second stream, double-buffered against the iterations of the neighbouring steps"),
-                    "solution_abs_max": x_check},
+            "vs_cusparse": vs_cusparse,
+            "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
@@ -501,25 +738,43 @@ def run_ours(args):
     return 0
 
 
+def run_cusparse_arm(args):
+    """The reference's GPU call sequence through cuSPARSE / cuBLAS 12.9 (comparator; never reachable from the package)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from baseline import cusparse_ref
+
+    line = cusparse_ref.bench_line(args, WORKLOADS, shared_config, metric_name)
+    print(json.dumps(line), flush=True)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--impl", choices=["ours", "reference", "cusparse"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c3")
-    ap.add_argument("--iters-per-step", type=int, default=20, help="CG iterations per recorded trace (BenchmarkStencil -pt)")
-    ap.add_argument("--ref-iters-per-step", type=int, default=2, help="CPU reference arm: iterations per step (bounded sample)")
-    ap.add_argument("--solver", choices=["cg", "bicgstab", "gmres"], default="cg",
-                    help="cg is the headline; bicgstab / gmres (restart 10, as BenchmarkStencil) are reported for the other configs")
-    ap.add_argument("--shape", type=str, default=None, help="developer override nx,ny,nz of the workload's grid")
+    ap.add_argument("--iters-per-step", type=int, default=20, help="solver iterations per recorded trace (BenchmarkStencil -pt)")
+    ap.add_argument("--ref-iters-per-step", type=int, default=2, help="CPU reference arm: iterations per timed step (bounded sample)")
+    ap.add_argument("--solver", choices=["cg", "bicgstab", "gmres"], default=None, help="default: the workload's solver (c3/c2 cg, c4 bicgstab, c5 gmres)")
+    ap.add_argument("--spaces", type=int, default=1, choices=[1, 2], help="2 = BenchmarkStencil's doubled block-diagonal system")
+    ap.add_argument("--shape", type=str, default=None, help="developer override nx,ny,nz of the workload's grid (c5: log2 N)")
     ap.add_argument("--unfused", action="store_true", help="run the reference's unfused call sequence on the GPU")
-    ap.add_argument("--persistent", action="store_true",
-                    help="CG as one persistent kernel per step (default: three leaf kernels per iteration, ~2 %% faster; also LSK_CG_PERSISTENT=1)")
+    ap.add_argument("--persistent", action="store_true", help="CG as one persistent kernel per step (also LSK_CG_PERSISTENT=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the full-size comparison with the CPU oracle")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cusparse", action="store_true")
     args = ap.parse_args()
+    if args.workload == "c5" and args.iters_per_step == 20:
+        args.iters_per_step = 2  # a GMRES(30) restart cycle is ~30 iterations' worth of work
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.impl == "cusparse":
+        return run_cusparse_arm(args)
     return run_ours(args)
 
 

@@ -124,8 +124,13 @@ int lsk_solver_destroy(lsk_solver *s);
 int lsk_solver_step(lsk_solver *s);
 /* 1 if the solver's step runs as a persistent kernel (lsk_cg_steps_f64), 0 = one launch per pass */
 int lsk_solver_persistent(lsk_solver *s);
-/* CG only: start a new solve from the current RHS (re-runs the constructor's P <- RHS, R <- RHS, rr0) */
+/* start a new solve from the current RHS with SOL taken as 0: re-runs the constructor's initialisation (CG: P <- RHS,
+ * R <- RHS, rr0; BiCGStab: R, R~ <- RHS, P, V <- 0, rho = alpha' = omega = 1/0/1; GMRES keeps no state: no-op) */
 int lsk_solver_reset(lsk_solver *s);
+/* the first n entries of history `which` (as lsk_solver_history), copied with cudaMemcpyAsync(cudaMemcpyDefault) on
+ * `stream` (NULL = the runtime's stream) without synchronising: dst may be device or pinned host memory.  For callers
+ * that pipeline solves and read the histories once at the end (bench.py's end-to-end loop). */
+int lsk_solver_history_copy_async(lsk_solver *s, int which, double *dst, int64_t n, void *stream);
 /* which: CG 0 = residual_norm_squared; BiCGStab 0 = rho, 1 = alpha, 2 = omega; GMRES 0 = the
  * (restart+1) x restart inner_products table, row-major.  Copies up to `cap` values (oldest first),
  * *n = number available.  Synchronises. */

@@ -125,6 +125,17 @@ public:
           temp(planner_.get_runtime()), ru(planner_.get_runtime()), uu(planner_.get_runtime()), beta(planner_.get_runtime()),
           neg_omega(planner_.get_runtime()), q1(planner_.get_runtime()), q2(planner_.get_runtime()) {
         planner.allocate_workspace(5);
+        reset();
+    }
+
+    // start a new solve with the current RHS (and SOL taken as 0): the constructor's initialisation (:44-60)
+    void reset() {
+        rho.clear();
+        alpha.clear();
+        omega.clear();
+        rho_cur.assign_value(one);
+        alpha_cur.assign_value(zero);
+        omega_cur.assign_value(one);
         planner.copy(R, RHS);
         planner.copy(R_TILDE, RHS);
         rho.push_back(one);

@@ -180,6 +180,8 @@ public:
     explicit SquarePlanner(Runtime *rt_) : rt(rt_) {}
 
     Runtime *get_runtime() const { return rt; }
+    // a caller wrote vector `vec_idx` behind the planner's back (host upload): its ghost copies are stale
+    void vector_written(std::size_t vec_idx) { mark_dirty(vec_idx); }
 
     std::size_t add_sol_vector(const PartitionedVector<T> &v) {
         if (!workspace_vectors.empty()) rt->fail(LSK_E_INVALID, "add vectors before allocate_workspace");
@@ -219,6 +221,8 @@ public:
         // one space, one piece per rank: every reducing kernel is launched identically on every rank, so
         // the all-reduces can ride in the kernels' tails and the halo push in the producing xpay
         rt->set_fused_collectives(rt->p2p() && get_num_spaces() == 1 && canonical_index_partitions[0]->pieces == rt->nranks());
+        // the ghost-block flags of the gated mat-vec are computed now, outside any trace
+        for (Block &b : row_partitioned_matrices) (void) gate_ready(b);
     }
 
     // bring the ghost values of vector `vec_idx` up to date on every rank (stand-alone exchange)

@@ -374,17 +374,25 @@ int lsk_planner_vector_to_host(lsk_planner *pl, int vec, int space, double *glob
 int lsk_planner_vector_from_host(lsk_planner *pl, int vec, int space, const double *global) {
     REQUIRE(pl && global && vec >= 0 && space >= 0);
     return guard([&] {
+        pl->pl->vector_written((size_t) vec);  // its ghosts on the other ranks are stale from now on
         pl->pl->get_vector((size_t) vec, (size_t) space).copy_from_host(global);
         pl->rt->fence();
     });
 }
 int lsk_planner_vector_to_async(lsk_planner *pl, int vec, int space, double *global, void *stream) {
     REQUIRE(pl && global && vec >= 0 && space >= 0);
-    return guard([&] { pl->pl->get_vector((size_t) vec, (size_t) space).copy_to_async(global, static_cast<cudaStream_t>(stream)); });
+    return guard([&] {
+        pl->rt->flush_deferred();
+        pl->pl->get_vector((size_t) vec, (size_t) space).copy_to_async(global, static_cast<cudaStream_t>(stream));
+    });
 }
 int lsk_planner_vector_from_async(lsk_planner *pl, int vec, int space, const double *global, void *stream) {
     REQUIRE(pl && global && vec >= 0 && space >= 0);
-    return guard([&] { pl->pl->get_vector((size_t) vec, (size_t) space).copy_from_async(global, static_cast<cudaStream_t>(stream)); });
+    return guard([&] {
+        pl->rt->flush_deferred();  // steps a solver has deferred are issued before the copy can be ordered against them
+        pl->pl->vector_written((size_t) vec);
+        pl->pl->get_vector((size_t) vec, (size_t) space).copy_from_async(global, static_cast<cudaStream_t>(stream));
+    });
 }
 
 // ---- solvers -----------------------------------------------------------------------------------------------------
@@ -422,8 +430,22 @@ int lsk_solver_step(lsk_solver *s) {
 int lsk_solver_reset(lsk_solver *s) {
     REQUIRE(s);
     return guard([&] {
-        if (!s->cg) s->rt->fail(LSK_E_INVALID, "reset is implemented for CGSolver");
-        s->cg->reset();
+        if (s->cg) s->cg->reset();
+        else if (s->bicg) s->bicg->reset();
+        // GMRESSolver keeps no state between restart cycles: a new solve starts from whatever SOL and RHS hold
+    });
+}
+int lsk_solver_history_copy_async(lsk_solver *s, int which, double *dst, int64_t n, void *stream) {
+    REQUIRE(s && dst && n >= 0);
+    return guard([&] {
+        const ScalarHistory *h = nullptr;
+        if (s->cg) h = &s->cg->residual_norm_squared;
+        else if (s->bicg) h = which == 0 ? &s->bicg->rho : which == 1 ? &s->bicg->alpha : &s->bicg->omega;
+        else s->rt->fail(LSK_E_INVALID, "GMRESSolver keeps no history");
+        if (n > h->get_capacity()) s->rt->fail(LSK_E_INVALID, "history_copy_async: more entries than the history holds");
+        cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : s->rt->stream();
+        if (!stream) s->rt->flush_deferred();
+        if (n > 0) s->rt->check_cuda(cudaMemcpyAsync(dst, h->data(), sizeof(double) * (size_t) n, cudaMemcpyDefault, st), "history copy (async)");
     });
 }
 int lsk_solver_history(lsk_solver *s, int which, double *out, int64_t cap, int64_t *n) {

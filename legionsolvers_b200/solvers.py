@@ -359,6 +359,14 @@ class _Solver:
         _check(_abi.lib().lsk_solver_history(self.h, which, _np_ptr(out, np.float64), n.value, C.byref(n)), "history")
         return out
 
+    def reset(self):
+        """Start a new solve from the current RHS (SOL taken as 0, like the constructor)."""
+        _check(_abi.lib().lsk_solver_reset(self.h), "reset")
+
+    def history_copy_async(self, which: int, dst_ptr: int, n: int, stream: int | None = None):
+        """First n entries of history `which` -> dst_ptr (device or pinned host), asynchronously, no synchronisation."""
+        _check(_abi.lib().lsk_solver_history_copy_async(self.h, which, dst_ptr, n, stream), "history_copy_async")
+
     def destroy(self):
         if getattr(self, "h", None):
             _abi.lib().lsk_solver_destroy(self.h)
@@ -379,10 +387,6 @@ class CGSolver(_Solver):
     def persistent(self) -> bool:
         """True when step() runs as the persistent CG kernel (steps are deferred and batched per launch)."""
         return bool(_abi.lib().lsk_solver_persistent(self.h))
-
-    def reset(self):
-        """Start a new solve from the current RHS (SOL taken as 0, like the constructor)."""
-        _check(_abi.lib().lsk_solver_reset(self.h), "reset")
 
     @property
     def residual_norm_squared(self) -> np.ndarray:
