@@ -819,7 +819,7 @@ int lsk_cg_update_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, const double *rr_ol
         const int64_t cap = (int64_t) ctx->sm_count * 3;
         const int grid = (int) (nchunks < cap ? nchunks : cap);
         const RedScratch rs = next_scratch(ctx);
-        LSK_RETURN_IF_CUDA(launch_pdl(cg_update_tma_kernel, grid, kBlock, (size_t) kVecStages * kVecStageBytes, (cudaStream_t) s, rr_old, pq,
+        LSK_RETURN_IF_CUDA(launch_pdl(kPdlUpdate, cg_update_tma_kernel, grid, kBlock, (size_t) kVecStages * kVecStageBytes, (cudaStream_t) s, rr_old, pq,
                                       (const double *) (ctx->consts + 1), p, q, x, r, rr_new, n, sp.head, sp.npacks, rs));
         return after_launch(ctx);
     }
@@ -858,7 +858,7 @@ int lsk_cg_direction_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, double *rr_cur, 
     const int grid = (int) (nchunks < cap ? nchunks : cap);
     RedScratch rs = next_scratch(ctx);
     if (nmoves == 0) rs.peers = nullptr;
-    LSK_RETURN_IF_CUDA(launch_pdl(cg_direction_tma_kernel, grid, kBlock, (size_t) kVecStages * kVecStageBytes, (cudaStream_t) s, rr_cur, rr_new,
+    LSK_RETURN_IF_CUDA(launch_pdl(kPdlDirection, cg_direction_tma_kernel, grid, kBlock, (size_t) kVecStages * kVecStageBytes, (cudaStream_t) s, rr_cur, rr_new,
                                   r, p, n, sp.head, sp.npacks, h, rs, history, (long long) history_capacity,
                                   reinterpret_cast<long long *>(history_count)));
     return after_launch(ctx);

@@ -320,7 +320,7 @@ __device__ __forceinline__ void halo_publish(const lsk_peers *peers, const lsk_h
         me->halo_sent[mv.peer] = e;
     }
     __syncthreads();
-    __threadfence_system();
+    if (wait) __threadfence_system();  // acquire side: the neighbours' data is visible to whatever runs next on this stream
     if (threadIdx.x == 0) {
         me->halo_calls += 1;
         me->halo_wait_ns += global_ns() - t0;
@@ -425,12 +425,21 @@ __device__ __forceinline__ void grid_reduce_finish(const double (&acc)[NRED], do
 // iteration whose x/r update is the grid-stride kernel gains 1 %, but the chain mat-vec -> cg_update_tma ->
 // cg_direction_tma with all three edges programmatic drops from 1618 to 1180 it/s (power 630 -> 520 W: the GPU idles
 // ~65 us per boundary).  Not understood yet, so the attribute is only set when LSK_PDL=1.
+#ifndef LSK_PDL_DEFAULT
+#define LSK_PDL_DEFAULT 1  // the mat-vec only (kPdlSpmv): measured +3 % on an 8-GPU slab; the vector kernels lose with it
+#endif
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// kernel classes for the LSK_PDL bit mask (developer switch): which launches carry the programmatic attribute
+enum PdlClass { kPdlSpmv = 1, kPdlUpdate = 2, kPdlDirection = 4 };
+inline int pdl_mask() {
+    static const int m = [] { const char *e = getenv("LSK_PDL"); return e ? atoi(e) : LSK_PDL_DEFAULT; }();
+    return m;
+}
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+inline cudaError_t launch_pdl(int cls, void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned) grid);
     cfg.blockDim = dim3((unsigned) block);
@@ -440,8 +449,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, siz
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    static const bool on = [] { const char *e = getenv("LSK_PDL"); return e && e[0] == '1'; }();
-    cfg.numAttrs = on ? 1 : 0;
+    cfg.numAttrs = (pdl_mask() & cls) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 #endif

@@ -507,11 +507,11 @@ static int launch_tma_kernel_lpr(lsk_ctx *ctx, int ndot, int grid, cudaStream_t 
     if (rc != 0) return rc;
     cudaError_t e;
     if (ndot == 0)
-        e = launch_pdl(csr_tma_kernel<0, LPR>, grid, kBlock, kTmaSmem, st, a, rs.partials, rs.ticket, o0, o1, rs.peers);
+        e = launch_pdl(kPdlSpmv, csr_tma_kernel<0, LPR>, grid, kBlock, kTmaSmem, st, a, rs.partials, rs.ticket, o0, o1, rs.peers);
     else if (ndot == 1)
-        e = launch_pdl(csr_tma_kernel<1, LPR>, grid, kBlock, kTmaSmem, st, a, rs.partials, rs.ticket, o0, o1, rs.peers);
+        e = launch_pdl(kPdlSpmv, csr_tma_kernel<1, LPR>, grid, kBlock, kTmaSmem, st, a, rs.partials, rs.ticket, o0, o1, rs.peers);
     else
-        e = launch_pdl(csr_tma_kernel<2, LPR>, grid, kBlock, kTmaSmem, st, a, rs.partials, rs.ticket, o0, o1, rs.peers);
+        e = launch_pdl(kPdlSpmv, csr_tma_kernel<2, LPR>, grid, kBlock, kTmaSmem, st, a, rs.partials, rs.ticket, o0, o1, rs.peers);
     return (int) e;
 }
 
@@ -552,9 +552,9 @@ static int launch_ws_kernel_cfg(lsk_ctx *ctx, int ndot, int grid, cudaStream_t s
     });
     if (rc != 0) return rc;
     cudaError_t e;
-    if (ndot == 0) e = launch_pdl(csr_ws_kernel<0, LPR, GATED>, grid, kWsThreads, kWsSmem, st, a, g, rs, o0, o1);
-    else if (ndot == 1) e = launch_pdl(csr_ws_kernel<1, LPR, GATED>, grid, kWsThreads, kWsSmem, st, a, g, rs, o0, o1);
-    else e = launch_pdl(csr_ws_kernel<2, LPR, GATED>, grid, kWsThreads, kWsSmem, st, a, g, rs, o0, o1);
+    if (ndot == 0) e = launch_pdl(kPdlSpmv, csr_ws_kernel<0, LPR, GATED>, grid, kWsThreads, kWsSmem, st, a, g, rs, o0, o1);
+    else if (ndot == 1) e = launch_pdl(kPdlSpmv, csr_ws_kernel<1, LPR, GATED>, grid, kWsThreads, kWsSmem, st, a, g, rs, o0, o1);
+    else e = launch_pdl(kPdlSpmv, csr_ws_kernel<2, LPR, GATED>, grid, kWsThreads, kWsSmem, st, a, g, rs, o0, o1);
     return (int) e;
 }
 

@@ -255,8 +255,14 @@ double *Runtime::new_slot() {
 // ---- tracing ---------------------------------------------------------------------------------------------
 void Runtime::begin_trace(int id) {
     flush_deferred();  // work deferred before the trace does not belong to it
-    if (mode_ != Mode::Eager) fail(LSK_E_INVALID, "begin_trace: traces do not nest");
+    if (mode_ != Mode::Eager || eager_trace_) fail(LSK_E_INVALID, "begin_trace: traces do not nest");
     active_trace_ = id;
+    static const bool eager = [] { const char *e = std::getenv("LSK_TRACE"); return e && std::string(e) == "eager"; }();
+    if (eager) {  // developer switch: run traced regions launch by launch (no CUDA graph)
+        mode_ = Mode::Eager;
+        eager_trace_ = true;
+        return;
+    }
     if (traces_.count(id)) {
         mode_ = Mode::Replay;
         return;
@@ -268,6 +274,11 @@ void Runtime::begin_trace(int id) {
 
 void Runtime::end_trace(int id) {
     flush_deferred();  // work deferred inside the trace is recorded (or, on replay, skipped) now
+    if (eager_trace_ && id == active_trace_) {
+        eager_trace_ = false;
+        active_trace_ = -1;
+        return;
+    }
     if (mode_ == Mode::Eager || id != active_trace_) fail(LSK_E_INVALID, "end_trace without matching begin_trace");
     if (mode_ == Mode::Capture) {
         cudaGraph_t graph = nullptr;

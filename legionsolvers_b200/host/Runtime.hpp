@@ -157,6 +157,7 @@ private:
     const void *deferred_owner_ = nullptr;
     std::function<void()> deferred_;
     int active_trace_ = -1;
+    bool eager_trace_ = false;
     uint64_t capture_mark_ = 0;
     uint64_t replayed_kernels_ = 0;
     std::map<int, Trace> traces_;
