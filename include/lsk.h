@@ -189,6 +189,35 @@ int lsk_coo_spmv_f32(lsk_ctx *ctx, lsk_stream s, int64_t nnz, const float *entry
                      int64_t col_hi);
 
 /* ------------------------------------------------------------------------------------------------
+ * Transposed mat-vecs -- CSRRmatvecTask / COORmatvecTask (TaskIDs reserved at src/TaskIDs.hpp:40-45, bodies
+ * `assert(false)` in the reference: src/CSRMatrixTasks.cpp:94-100, src/COOMatrixTasks.cpp:77-83):
+ *   y_shifted[col[k]] += entry[k] * x[row of k]      for every stored non-zero k of the piece
+ * accumulating (the caller zero-fills, as SquarePlanner::matvec does), guarded by col in [col_lo, col_hi] (and, COO,
+ * row in [row_lo, row_hi]).  CSR: x is the piece's own rows (x[0] <-> first row of `rowptr`); COO: x_shifted is
+ * indexable by GLOBAL row.  y_shifted is indexable by GLOBAL column.  fp64 atomics: <= 1e-12, not bit-reproducible.
+ * ---------------------------------------------------------------------------------------------- */
+int lsk_csr_rspmv_f64(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const double *entry, const int64_t *col,
+                      const lsk_rect *rowptr, int64_t k_base, const double *x, double *y_shifted, int64_t col_lo,
+                      int64_t col_hi);
+int lsk_coo_rspmv_f64(lsk_ctx *ctx, lsk_stream s, int64_t nnz, const double *entry, const int64_t *row,
+                      const int64_t *col, const double *x_shifted, double *y_shifted, int64_t row_lo, int64_t row_hi,
+                      int64_t col_lo, int64_t col_hi);
+
+/* ------------------------------------------------------------------------------------------------
+ * The end of a GMRES restart cycle, finished.  The reference stops at a placeholder (DummyTask returns 1:
+ * SOL += 1 * v_j, src/GMRESSolver.hpp:109-126); these two are what the algorithm needs instead:
+ *   lsk_gmres_solve_f64   y = argmin || sqrt(*beta_sq) e1 - H y ||_2 for the (m + 1) x m upper Hessenberg H (row-major,
+ *                         leading dimension ld, DEVICE memory) by Givens rotations; *resid (optional) = the minimum,
+ *                         i.e. the norm of the new residual.  m <= 64.  One thread: it is ~m^2 flops.
+ *   lsk_multi_axpy_f64    x = x + sum_j y[j] V[j], added in ascending j with one fma per term -- bit-identical to m
+ *                         AxpyTasks -- in ONE pass: 8 (m + 2) instead of 24 m bytes per element.  y and the pointer
+ *                         table V live on the device.
+ * ---------------------------------------------------------------------------------------------- */
+int lsk_gmres_solve_f64(lsk_ctx *ctx, lsk_stream s, int m, const double *H, int ld, const double *beta_sq, double *y,
+                        double *resid);
+int lsk_multi_axpy_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, int m, const double *y, const double *const *V, double *x);
+
+/* ------------------------------------------------------------------------------------------------
  * Fused solver passes.  Each equals a fixed sequence of the leaf tasks above with identical
  * element-wise arithmetic (same fma / rounding per element), saving HBM passes.
  * ---------------------------------------------------------------------------------------------- */

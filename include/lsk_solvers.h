@@ -101,6 +101,9 @@ int lsk_planner_axpy(lsk_planner *pl, int dst, double alpha, int src);
 int lsk_planner_xpay(lsk_planner *pl, int dst, double alpha, int src);
 int lsk_planner_dot(lsk_planner *pl, int v, int w, double *out); /* synchronises */
 int lsk_planner_matvec(lsk_planner *pl, int dst, int src);
+/* dst = A^T src over all registered blocks (CSRRmatvecTask / COORmatvecTask: reserved, unimplemented in the reference).
+ * Fails on several ranks when a local piece references columns owned by another rank (no reverse halo exchange yet). */
+int lsk_planner_rmatvec(lsk_planner *pl, int dst, int src);
 /* fused dst = A src with out_yw = dst . vec(w) (and out_yy = dst . dst if not NULL); synchronises */
 int lsk_planner_matvec_dot(lsk_planner *pl, int dst, int src, int w, double *out_yw, double *out_yy);
 int lsk_planner_vector_to_host(lsk_planner *pl, int vec, int space, double *global);
@@ -127,12 +130,17 @@ int lsk_solver_persistent(lsk_solver *s);
 /* start a new solve from the current RHS with SOL taken as 0: re-runs the constructor's initialisation (CG: P <- RHS,
  * R <- RHS, rr0; BiCGStab: R, R~ <- RHS, P, V <- 0, rho = alpha' = omega = 1/0/1; GMRES keeps no state: no-op) */
 int lsk_solver_reset(lsk_solver *s);
+/* options: LSK_OPT_GMRES_REAL_UPDATE (GMRES): 0 (default) = the reference's placeholder update SOL += 1 * v_j
+ * (DummyTask, src/GMRESSolver.hpp:109-126); 1 = the finished algorithm: Givens least squares on the Hessenberg, SOL += V y
+ * in one pass, and history `which` = 1 then holds || b - A x || after each cycle.  Set outside any trace. */
+enum lsk_solver_option { LSK_OPT_GMRES_REAL_UPDATE = 1 };
+int lsk_solver_set_option(lsk_solver *s, int option, int value);
 /* the first n entries of history `which` (as lsk_solver_history), copied with cudaMemcpyAsync(cudaMemcpyDefault) on
  * `stream` (NULL = the runtime's stream) without synchronising: dst may be device or pinned host memory.  For callers
  * that pipeline solves and read the histories once at the end (bench.py's end-to-end loop). */
 int lsk_solver_history_copy_async(lsk_solver *s, int which, double *dst, int64_t n, void *stream);
 /* which: CG 0 = residual_norm_squared; BiCGStab 0 = rho, 1 = alpha, 2 = omega; GMRES 0 = the
- * (restart+1) x restart inner_products table, row-major.  Copies up to `cap` values (oldest first),
+ * (restart+1) x restart inner_products table, row-major, 1 = residual norms (real update only).  Copies up to `cap` values (oldest first),
  * *n = number available.  Synchronises. */
 int lsk_solver_history(lsk_solver *s, int which, double *out, int64_t cap, int64_t *n);
 

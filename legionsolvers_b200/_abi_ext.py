@@ -114,3 +114,9 @@ def declare(L) -> None:
     L.lsk_solver_reset.argtypes = [vp]
     L.lsk_solver_history.argtypes = [vp, ci, vp, i64, C.POINTER(i64)]
     L.lsk_solver_history_copy_async.argtypes = [vp, ci, vp, i64, vp]
+    L.lsk_solver_set_option.argtypes = [vp, ci, ci]
+    L.lsk_planner_rmatvec.argtypes = [vp, ci, ci]
+    L.lsk_csr_rspmv_f64.argtypes = [vp, vp, i64, i64, vp, vp, vp, i64, vp, vp, i64, i64]
+    L.lsk_coo_rspmv_f64.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, i64, i64, i64, i64]
+    L.lsk_gmres_solve_f64.argtypes = [vp, vp, ci, vp, ci, vp, vp, vp]
+    L.lsk_multi_axpy_f64.argtypes = [vp, vp, i64, ci, vp, vp, vp]

@@ -57,6 +57,10 @@ public:
     virtual void matvec(PartitionedVector<T> &dst, const PartitionedVector<T> &src, const IntervalPartition &kernel_partition,
                         const IntervalPartition &ghost_partition, const MatvecFusion<T> *fusion = nullptr,
                         const MatvecGate *gate = nullptr) const = 0;
+    // dst += A^T src (CSRRmatvecTask / COORmatvecTask, reserved but unimplemented in the reference): dst lives on the DOMAIN
+    // space, src on the range space; accumulates.  dst must hold every column the local pieces reference.
+    virtual void rmatvec(PartitionedVector<T> &dst, const PartitionedVector<T> &src, const IntervalPartition &kernel_partition,
+                         const IntervalPartition &ghost_partition) const = 0;
     virtual bool overwrites_output() const = 0;  // CSR: beta = 0; COO: beta = 1 (reference GPU variants)
     // gated mat-vec of the piece of colour c (rows [r_lo, r_lo + nrow)): 0 = not available for this matrix / piece,
     // else the number of row-block flags; gate_flags computes them (which row blocks reference a column outside the rows)
@@ -200,6 +204,29 @@ public:
         }
     }
 
+    void rmatvec(PartitionedVector<T> &dst, const PartitionedVector<T> &src, const IntervalPartition &kp,
+                 const IntervalPartition &gp) const override {
+        if constexpr (!std::is_same<T, double>::value) {
+            rt->fail(LSK_E_INVALID, "transposed mat-vec is instantiated for fp64");
+        } else {
+            const IndexPartition &p = src.partition();  // rows
+            for (int c = p.first_color; c < p.end_color; ++c) {
+                const int64_t r_lo = p.lo[(size_t) c], nrow = p.piece_size(c);
+                const int64_t k_lo = kp.lo[(size_t) c], nk = kp.hi[(size_t) c] - k_lo + 1;
+                if (nk <= 0 || nrow <= 0) continue;
+                if (gp.lo[(size_t) c] < dst.buf_lo() || gp.hi[(size_t) c] > dst.buf_hi())
+                    rt->fail(LSK_E_INVALID, "destination vector does not hold the columns of the piece");
+                const T *e = entry.ptr + (k_lo - slab_k_lo);
+                const int64_t *cc = col.ptr + (k_lo - slab_k_lo);
+                const lsk_rect *rp = rowptr.ptr + (r_lo - slab_r_lo);
+                const T *x = src.ptr(r_lo);
+                T *y = dst.shifted();
+                const int64_t cl = gp.lo[(size_t) c], ch = gp.hi[(size_t) c];
+                rt->enqueue("csr rmatvec", [&] { return lsk_csr_rspmv_f64(rt->ctx(), rt->stream(), nrow, nk, e, cc, rp, k_lo, x, y, cl, ch); });
+            }
+        }
+    }
+
     int64_t gate_row_blocks(int c, int64_t r_lo, int64_t nrow, const IntervalPartition &kp) const override {
         if constexpr (!std::is_same<T, double>::value) {
             return 0;
@@ -320,6 +347,27 @@ public:
             gp.hi[(size_t) c] = std::min<int64_t>(domain_volume - 1, s.mx);
         }
         return gp;
+    }
+
+    void rmatvec(PartitionedVector<T> &dst, const PartitionedVector<T> &src, const IntervalPartition &kp,
+                 const IntervalPartition &gp) const override {
+        if constexpr (!std::is_same<T, double>::value) {
+            rt->fail(LSK_E_INVALID, "transposed mat-vec is instantiated for fp64");
+        } else {
+            const IndexPartition &p = src.partition();  // rows
+            for (int c = p.first_color; c < p.end_color; ++c) {
+                const int64_t k_lo = kp.lo[(size_t) c], nk = kp.hi[(size_t) c] - k_lo + 1;
+                if (nk <= 0) continue;
+                if (gp.lo[(size_t) c] < dst.buf_lo() || gp.hi[(size_t) c] > dst.buf_hi())
+                    rt->fail(LSK_E_INVALID, "destination vector does not hold the columns of the piece");
+                const T *e = entry.ptr + (k_lo - slab_k_lo);
+                const int64_t *rr = row.ptr + (k_lo - slab_k_lo), *cc = col.ptr + (k_lo - slab_k_lo);
+                const T *x = src.shifted();
+                T *y = dst.shifted();
+                const int64_t rl = p.lo[(size_t) c], rh = p.hi[(size_t) c], cl = gp.lo[(size_t) c], ch = gp.hi[(size_t) c];
+                rt->enqueue("coo rmatvec", [&] { return lsk_coo_rspmv_f64(rt->ctx(), rt->stream(), nk, e, rr, cc, x, y, rl, rh, cl, ch); });
+            }
+        }
     }
 
     // COOMatrix::matvec (src/COOMatrix.cpp:144-191): accumulates into dst (beta = 1)

@@ -202,32 +202,46 @@ public:
     Scalar<T> negative_one, one;
     std::vector<std::vector<Scalar<T>>> inner_products;  // (restart + 1) x restart, as in the reference
     const bool fused;
+    // false (default): the reference's placeholder update SOL += 1 * v_j (DummyTask), for parity with it.
+    // true (set_real_update): the finished algorithm -- y = argmin || beta e1 - H y || by Givens rotations, SOL += V y in one pass.
+    bool real_update = false;
+    ScalarHistory residual_norm;  // real update only: || b - A x || after each cycle (the least-squares minimum)
 
 private:
     Scalar<T> d, scale, neg_h, coeff;
+    DeviceBuffer<T> hess;         // the inner_products table, contiguous: (restart + 1) x restart, row-major
+    DeviceBuffer<T> ls;           // beta^2, y[0 .. restart), residual
+    DeviceBuffer<const T *> basis_table;
 
 public:
     // constructor (src/GMRESSolver.hpp:32-77)
     explicit GMRESSolver(SquarePlanner<T> &planner_, std::size_t restart_, bool fused_ = true)
         : planner(planner_), restart(restart_), negative_one(planner_.get_runtime(), static_cast<T>(-1)),
-          one(planner_.get_runtime(), static_cast<T>(1)), fused(fused_), d(planner_.get_runtime()), scale(planner_.get_runtime()),
-          neg_h(planner_.get_runtime()), coeff(planner_.get_runtime()) {
+          one(planner_.get_runtime(), static_cast<T>(1)), fused(fused_), residual_norm(planner_.get_runtime(), 1 << 12),
+          d(planner_.get_runtime()), scale(planner_.get_runtime()), neg_h(planner_.get_runtime()), coeff(planner_.get_runtime()),
+          hess(planner_.get_runtime(), (restart_ + 1) * restart_), ls(planner_.get_runtime(), restart_ + 2) {
+        Runtime *rt = planner.get_runtime();
+        if (restart == 0 || restart > 64) rt->fail(LSK_E_INVALID, "GMRES restart must be 1 .. 64");
         planner.allocate_workspace(restart + 1);
+        rt->check_cuda(cudaMemsetAsync(hess.ptr, 0, sizeof(T) * hess.count, rt->stream()), "hessenberg init");
+        rt->check_cuda(cudaMemsetAsync(ls.ptr, 0, sizeof(T) * ls.count, rt->stream()), "least-squares init");
         for (std::size_t i = 0; i <= restart; ++i) {
             std::vector<Scalar<T>> row;
-            for (std::size_t j = 0; j < restart; ++j) row.emplace_back(planner.get_runtime(), static_cast<T>(0));
+            for (std::size_t j = 0; j < restart; ++j) row.emplace_back(rt, hess.ptr + i * restart + j);  // views into the table
             inner_products.push_back(std::move(row));
         }
     }
 
     static constexpr std::size_t krylov_basis(std::size_t i) noexcept { return i + 2; }
 
-    // step (src/GMRESSolver.hpp:83-127) = one restart cycle: residual, Arnoldi with modified
-    // Gram-Schmidt, then the reference's PLACEHOLDER update (DummyTask returns 1: SOL += 1 * V_j).
+    // step (src/GMRESSolver.hpp:83-127) = one restart cycle: residual, Arnoldi with modified Gram-Schmidt, then the
+    // update (the reference's placeholder, or the real one).
     void step() {
+        Runtime *rt = planner.get_runtime();
         planner.matvec(krylov_basis(0), SOL);
         planner.xpay(krylov_basis(0), negative_one, RHS);
         planner.dot_into(krylov_basis(0), krylov_basis(0), d);
+        if (real_update) Scalar<T>(rt, ls.ptr).assign_value(d);  // beta^2 = || b - A x ||^2
         scale.set(LSK_OP_RSQRT, d);
         planner.scal(krylov_basis(0), scale);
         for (std::size_t j = 0; j < restart; ++j) {
@@ -255,8 +269,31 @@ public:
                 planner.scal(w, scale);
             }
         }
-        coeff.set(LSK_OP_DUMMY, one);
-        for (std::size_t j = 0; j < restart; ++j) planner.axpy(SOL, coeff, krylov_basis(j));
+        if (!real_update) {
+            coeff.set(LSK_OP_DUMMY, one);
+            for (std::size_t j = 0; j < restart; ++j) planner.axpy(SOL, coeff, krylov_basis(j));
+            return;
+        }
+        // y = argmin || beta e1 - H y ||: one single-thread kernel; SOL += V y: one pass over the basis
+        T *y = ls.ptr + 1, *res = ls.ptr + 1 + restart;
+        const T *H = hess.ptr, *beta_sq = ls.ptr;
+        const int m = (int) restart;
+        rt->enqueue("gmres least squares", [&] { return lsk_gmres_solve_f64(rt->ctx(), rt->stream(), m, H, m, beta_sq, y, res); });
+        planner.multi_axpy(SOL, y, basis_ids(), basis_table);
+        residual_norm.push_back(Scalar<T>(rt, res));
+    }
+
+    // switch between the reference's placeholder update and the finished one (outside any trace)
+    void set_real_update(bool on) {
+        real_update = on;
+        if (on) planner.prepare_basis_table(basis_ids(), basis_table);
+    }
+
+private:
+    std::vector<std::size_t> basis_ids() const {
+        std::vector<std::size_t> basis;
+        for (std::size_t j = 0; j < restart; ++j) basis.push_back(krylov_basis(j));
+        return basis;
     }
 };
 

@@ -489,6 +489,46 @@ public:
     // skipped for range spaces written by a CSR block; COO blocks accumulate (beta = 1).
     void matvec(std::size_t dst_idx, std::size_t src_idx) { matvec_impl(dst_idx, src_idx, nullptr, nullptr, 0); }
 
+    // rmatvec: dst = A^T src over all registered blocks -- the transposed operator the reference reserves TaskIDs for
+    // (CSRRmatvecTask / COORmatvecTask) and never implemented.  zero_fill(dst), then every block accumulates its piece's
+    // contribution into the columns it references.  On several ranks the contributions to columns owned by OTHER ranks
+    // would have to travel back (a reverse halo exchange); that is not built: the call fails loudly when a local piece
+    // references a ghost column.
+    void rmatvec(std::size_t dst_idx, std::size_t src_idx) {
+        mark_dirty(dst_idx);
+        close_halo(src_idx);
+        for (std::size_t i = 0; i < get_num_spaces(); ++i) get_vector(dst_idx, i).zero_fill();
+        for (const Block &b : row_partitioned_matrices) {
+            if (rt->nranks() > 1 && !b.halo.empty()) rt->fail(LSK_E_INVALID, "rmatvec on several ranks needs a reverse halo exchange (not implemented)");
+            b.matrix->rmatvec(get_vector(dst_idx, b.domain_index), get_vector(src_idx, b.range_index), b.kernel_partition, b.ghost_partition);
+        }
+    }
+
+    // SOL-style update x += sum_j y[j] v_j in one pass per piece (GMRES's real update): y = m device doubles,
+    // basis = the vector ids of v_0 .. v_{m-1}
+    void prepare_basis_table(const std::vector<std::size_t> &basis, DeviceBuffer<const T *> &table) {
+        const size_t m = basis.size(), pieces = total_local_pieces();
+        if (rt->capturing() || rt->replaying()) rt->fail(LSK_E_INVALID, "the basis pointer table must be built outside a trace");
+        std::vector<const T *> host(m * pieces);
+        for_each_local_piece([&](size_t s, int, int64_t lo, int64_t, size_t flat) {
+            for (size_t j = 0; j < m; ++j) host[flat * m + j] = get_vector(basis[j], s).ptr(lo);
+        });
+        table = DeviceBuffer<const T *>(rt, m * pieces);
+        rt->check_cuda(cudaMemcpyAsync(table.ptr, host.data(), sizeof(const T *) * host.size(), cudaMemcpyHostToDevice, rt->stream()), "basis table");
+        rt->fence();
+    }
+    void multi_axpy(std::size_t dst, const T *y_dev, const std::vector<std::size_t> &basis, DeviceBuffer<const T *> &table) {
+        static_assert(std::is_same<T, double>::value, "fused passes are instantiated for fp64");
+        mark_dirty(dst);
+        const size_t m = basis.size();
+        if (table.count != m * total_local_pieces()) rt->fail(LSK_E_INVALID, "multi_axpy: prepare_basis_table first");
+        for_each_local_piece([&](size_t s, int, int64_t lo, int64_t n, size_t flat) {
+            T *x = get_vector(dst, s).ptr(lo);
+            const T *const *V = table.ptr + flat * m;
+            rt->enqueue("multi_axpy", [&] { return lsk_multi_axpy_f64(rt->ctx(), rt->stream(), n, (int) m, y_dev, V, x); });
+        });
+    }
+
     // ---- fused fast path (fp64) --------------------------------------------------------------------------------
     bool can_fuse_matvec_dot() const {
         std::set<size_t> seen;

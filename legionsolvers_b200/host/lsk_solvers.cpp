@@ -355,6 +355,10 @@ int lsk_planner_matvec(lsk_planner *pl, int dst, int src) {
     REQUIRE(pl && dst >= 0 && src >= 0);
     return guard([&] { pl->pl->matvec((size_t) dst, (size_t) src); });
 }
+int lsk_planner_rmatvec(lsk_planner *pl, int dst, int src) {
+    REQUIRE(pl && dst >= 0 && src >= 0);
+    return guard([&] { pl->pl->rmatvec((size_t) dst, (size_t) src); });
+}
 int lsk_planner_matvec_dot(lsk_planner *pl, int dst, int src, int w, double *out_yw, double *out_yy) {
     REQUIRE(pl && out_yw && dst >= 0 && src >= 0 && w >= 0);
     return guard([&] {
@@ -435,6 +439,13 @@ int lsk_solver_reset(lsk_solver *s) {
         // GMRESSolver keeps no state between restart cycles: a new solve starts from whatever SOL and RHS hold
     });
 }
+int lsk_solver_set_option(lsk_solver *s, int option, int value) {
+    REQUIRE(s);
+    return guard([&] {
+        if (option == LSK_OPT_GMRES_REAL_UPDATE && s->gmres) s->gmres->set_real_update(value != 0);
+        else s->rt->fail(LSK_E_INVALID, "unknown solver option");
+    });
+}
 int lsk_solver_history_copy_async(lsk_solver *s, int which, double *dst, int64_t n, void *stream) {
     REQUIRE(s && dst && n >= 0);
     return guard([&] {
@@ -456,6 +467,8 @@ int lsk_solver_history(lsk_solver *s, int which, double *out, int64_t cap, int64
             h = s->cg->residual_norm_squared.to_host();
         } else if (s->bicg) {
             h = which == 0 ? s->bicg->rho.to_host() : which == 1 ? s->bicg->alpha.to_host() : s->bicg->omega.to_host();
+        } else if (which == 1) {
+            h = s->gmres->residual_norm.to_host();
         } else {
             for (auto &row : s->gmres->inner_products)
                 for (auto &sc : row) h.push_back(sc.get_value());

@@ -313,6 +313,10 @@ class SquarePlanner:
     def matvec(self, dst, src):
         _check(_abi.lib().lsk_planner_matvec(self.h, dst, src), "matvec")
 
+    def rmatvec(self, dst, src):
+        """dst = A^T src (CSRRmatvecTask / COORmatvecTask)."""
+        _check(_abi.lib().lsk_planner_rmatvec(self.h, dst, src), "rmatvec")
+
     def matvec_dot(self, dst, src, w, want_yy=False):
         a, b = C.c_double(), C.c_double()
         _check(_abi.lib().lsk_planner_matvec_dot(self.h, dst, src, w, C.byref(a), C.byref(b) if want_yy else None),
@@ -407,8 +411,16 @@ class BiCGStabSolver(_Solver):
 class GMRESSolver(_Solver):
     KIND = SOLVER_GMRES
 
-    def __init__(self, planner, restart, fused=True):
+    def __init__(self, planner, restart, fused=True, real_update=False):
+        """real_update=False: the reference's placeholder update (DummyTask); True: Givens least squares + SOL += V y."""
         super().__init__(planner, restart, fused)
+        if real_update:
+            _check(_abi.lib().lsk_solver_set_option(self.h, 1, 1), "set_option")
+
+    @property
+    def residual_norm(self) -> np.ndarray:
+        """|| b - A x || after each cycle (real update only)."""
+        return self._history(1)
 
     @property
     def inner_products(self) -> np.ndarray:

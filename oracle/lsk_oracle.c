@@ -153,6 +153,29 @@ void orc_coo_matvec(int64_t k_lo, int64_t k_hi, int64_t r_lo, int64_t r_hi, int6
     }
 }
 
+/* CSRRmatvecTask / COORmatvecTask: the reference reserves the tasks (src/TaskIDs.hpp:40-45) but their bodies are
+ * `assert(false)` (src/CSRMatrixTasks.cpp:94-100, src/COOMatrixTasks.cpp:77-83) -- there is no reference arithmetic to
+ * restate.  The transposed products are defined by analogy with the forward bodies above: the same loop over the
+ * piece's stored non-zeros in ascending k, the same guards, product rounded then added, with the roles of row and
+ * column exchanged:  y[col_k] += entry_k * x[row_k].  PARITY UNPINNED by any reference vector; pinned in the tests by
+ * an independent check against scipy's A^T x. */
+void orc_coo_rmatvec(int64_t k_lo, int64_t k_hi, int64_t r_lo, int64_t r_hi, int64_t out_lo, int64_t out_hi,
+                     const double *entry, const int64_t *row, const int64_t *col, const double *x, double *y) {
+    for (int64_t k = k_lo; k <= k_hi; ++k) {
+        const int64_t r = row[k], c = col[k];
+        if (out_lo <= c && c <= out_hi && r_lo <= r && r <= r_hi) y[c] += entry[k] * x[r];
+    }
+}
+
+void orc_csr_rmatvec(int64_t r_lo, int64_t r_hi, int64_t out_lo, int64_t out_hi, const double *entry,
+                     const int64_t *col, const orc_rect *rowptr, const double *x, double *y) {
+    for (int64_t r = r_lo; r <= r_hi; ++r)
+        for (int64_t k = rowptr[r].lo; k <= rowptr[r].hi; ++k) {
+            const int64_t c = col[k];
+            if (out_lo <= c && c <= out_hi) y[c] += entry[k] * x[r];
+        }
+}
+
 /* ============================================================================================
  * Problem generators
  * ============================================================================================ */

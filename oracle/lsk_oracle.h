@@ -73,6 +73,12 @@ void orc_coo_matvec(int64_t k_lo, int64_t k_hi, int64_t r_lo, int64_t r_hi, int6
                     int64_t in_hi, const double *entry, const int64_t *row, const int64_t *col,
                     const double *x, double *y);
 
+/* transposed products y[col_k] += entry_k * x[row_k] (no reference body exists: see lsk_oracle.c) */
+void orc_coo_rmatvec(int64_t k_lo, int64_t k_hi, int64_t r_lo, int64_t r_hi, int64_t out_lo, int64_t out_hi,
+                     const double *entry, const int64_t *row, const int64_t *col, const double *x, double *y);
+void orc_csr_rmatvec(int64_t r_lo, int64_t r_hi, int64_t out_lo, int64_t out_hi, const double *entry,
+                     const int64_t *col, const orc_rect *rowptr, const double *x, double *y);
+
 /* ---- problem generators ---------------------------------------------------------------------- */
 void orc_laplacian_1d_coo(int64_t k_lo, int64_t k_hi, double *entry, int64_t *row, int64_t *col);
 void orc_laplacian_1d_csr(int64_t k_lo, int64_t k_hi, double *entry, int64_t *col);

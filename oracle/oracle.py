@@ -79,6 +79,8 @@ def _declare(L):
     L.orc_csr_matvec.argtypes = [i64] * 6 + [vp] * 5
     L.orc_csr_matvec.restype = ci
     L.orc_coo_matvec.argtypes = [i64] * 6 + [vp] * 5
+    L.orc_coo_rmatvec.argtypes = [i64] * 6 + [vp] * 5
+    L.orc_csr_rmatvec.argtypes = [i64] * 4 + [vp] * 5
     L.orc_laplacian_1d_coo.argtypes = [i64, i64, vp, vp, vp]
     L.orc_laplacian_1d_csr.argtypes = [i64, i64, vp, vp]
     L.orc_laplacian_1d_rowptr.argtypes = [i64, i64, i64, vp]
@@ -327,6 +329,15 @@ def coo_matvec(m: Matrix, x, y, k=None, r=None, cols=None):
     c_lo, c_hi = cols if cols else (0, m.n_cols - 1)
     lib().orc_coo_matvec(k_lo, k_hi, r_lo, r_hi, c_lo, c_hi, _p(m.entry), _p(m.row), _p(m.col),
                          _p(x, np.float64), _p(y, np.float64))
+
+
+def rmatvec(m: Matrix, x, y):
+    """y += A^T x over the whole matrix (CSRRmatvecTask / COORmatvecTask: no reference body, see lsk_oracle.c)."""
+    if m.is_csr:
+        lib().orc_csr_rmatvec(0, m.n_rows - 1, 0, m.n_cols - 1, _p(m.entry), _p(m.col), _p(m.rowptr), _p(x, np.float64), _p(y, np.float64))
+    else:
+        lib().orc_coo_rmatvec(0, m.nnz - 1, 0, m.n_rows - 1, 0, m.n_cols - 1, _p(m.entry), _p(m.row), _p(m.col), _p(x, np.float64),
+                              _p(y, np.float64))
 
 
 # --------------------------------------------------------------------------------------------

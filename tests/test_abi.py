@@ -1,11 +1,14 @@
 """CPU-side checks of the drop-in boundary: liblsk.so loads and exports every symbol that
 include/*.h declares, and fails loudly (no fallback) when there is no GPU."""
 import ctypes as C
+from pathlib import Path
 
 import pytest
 import torch
 
 from legionsolvers_b200 import _abi, build
+
+ROOT = Path(__file__).resolve().parents[1]
 
 
 def test_library_is_built_for_sm100a_only():
@@ -98,3 +101,52 @@ def test_host_only_entry_points_of_the_cg_step():
     assert L.lsk_csr_spmv_gated_supported(100, 100000, 0x1000, 0x2000, 0x3000, 0) == 0  # warp-per-row variant has no gate
     assert L.lsk_csr_spmv_gated_f64(None, None, 1, 1, None, None, None, 0, None, None, None, None, None, 0, None, None, 0) == -1
     assert L.lsk_halo_wait_f64(None, None, None, None, 0) == -1
+
+
+# ---- integration/: the reference-side binding is real code, not prose ----------------------------------------------------
+def _compile_and_run(src: str, tmp_path, extra=()):
+    import subprocess
+
+    c = tmp_path / "t.c"
+    c.write_text(src)
+    exe = tmp_path / "t"
+    subprocess.check_call(["gcc", "-std=c11", "-I", str(ROOT / "integration"), "-I", str(ROOT / "include"), *extra, str(c), "-o", str(exe)])
+    return subprocess.check_output([str(exe)]).decode().split()
+
+
+def test_task_ids_known_answers(tmp_path):
+    """integration/lsk_task_ids.h restates src/TaskIDs.hpp:17-53 + src/TaskBaseClasses.hpp:61-103,196-209,262-285; the literal ids
+    are the ones a build of the reference prints at registration."""
+    src = r'''
+#include <stdio.h>
+#include "lsk_task_ids.h"
+int main(void) {
+    printf("%d %d %d %d ", LSK_TID_F64_1D_S64(LSK_BLOCK_SCAL), LSK_TID_F64_1D_S64(LSK_BLOCK_AXPY), LSK_TID_F64_1D_S64(LSK_BLOCK_XPAY), LSK_TID_F64_1D_S64(LSK_BLOCK_DOT));
+    printf("%d %d %d %d ", LSK_TID_MATVEC_F64_1D_S64(LSK_BLOCK_COO_MATVEC), LSK_TID_MATVEC_F64_1D_S64(LSK_BLOCK_COO_RMATVEC),
+           LSK_TID_MATVEC_F64_1D_S64(LSK_BLOCK_CSR_MATVEC), LSK_TID_MATVEC_F64_1D_S64(LSK_BLOCK_CSR_RMATVEC));
+    for (int b = LSK_BLOCK_PRINT_SCALAR; b <= LSK_BLOCK_DUMMY; ++b) printf("%d ", lsk_task_id_t(b, LSK_ENTRY_F64));
+    printf("%d %d %d ", LSK_LOAD_CUDA_LIBS_TASK_ID, LSK_TASK_BLOCK_SIZE,
+           lsk_task_id_tdi(LSK_BLOCK_SCAL, LSK_ENTRY_F32, 1, LSK_INDEX_S64));
+    return 0;
+}'''
+    got = [int(v) for v in _compile_and_run(src, tmp_path)]
+    assert got[:4] == [557044, 562228, 567412, 572596]                       # Scal, Axpy, Xpay, Dot
+    assert got[4:8] == [577888, 583072, 593440, 598624]                      # COOMatvec, COORmatvec, CSRMatvec, CSRRmatvec
+    assert got[8:17] == [500002, 505186, 510370, 515554, 520738, 525922, 531106, 536290, 541474]  # Print .. Dummy (fp64)
+    assert got[17:] == [500000, 5184, 557043]                                # LoadCUDALibs, block size, fp32 = fp64 - 1
+
+
+def test_patched_cuda_task_bodies_type_check():
+    """integration/cuda_task_bodies.cpp -- the six cuda_task_body bodies of INTEGRATION.md as code -- compiles against the
+    <= 150-line stub of the Legion types they touch, with lsk.h's real prototypes."""
+    import subprocess
+
+    stub = (ROOT / "integration" / "legion_stub.h").read_text().splitlines()
+    assert len(stub) <= 150
+    proc = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-I", str(ROOT / "include"), "-I", str(ROOT / "integration"),
+                           str(ROOT / "integration" / "cuda_task_bodies.cpp")], capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr
+    body = (ROOT / "integration" / "cuda_task_bodies.cpp").read_text()
+    assert "static_assert(sizeof(Legion::Rect<1, long long>) == sizeof(lsk_rect)" in body
+    for fn in ("lsk_scal_f64", "lsk_axpy_f64", "lsk_xpay_f64", "lsk_dot_f64", "lsk_csr_spmv_f64", "lsk_coo_spmv_f64", "lsk_csr_rspmv_f64"):
+        assert fn in body

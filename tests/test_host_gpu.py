@@ -417,3 +417,84 @@ def test_kernel_launch_accounting(rt, oracle):
     rt.fence()
     # per step: 4 pieces x (spmv+dot, cg_update, xpay) + 2 colour-order folds of 4 partials (copy + 3 adds) + append
     assert rt.kernel_launches - before == 5 * (4 * 3 + 2 * 4 + 1)
+
+
+# ---- transposed mat-vecs and the finished GMRES update ----------------------------------------
+@pytest.mark.parametrize("fmt", ["csr", "coo"])
+@pytest.mark.parametrize("pieces", [1, 4])
+def test_rmatvec_vs_oracle_and_scipy(rt, oracle, fmt, pieces):
+    """dst = A^T src through the planner (CSRRmatvecTask / COORmatvecTask, reserved but `assert(false)` in the reference):
+    against the oracle's definition and, independently, scipy's transpose.  Non-symmetric matrix, random values."""
+    rng = np.random.default_rng(3)
+    n = 5000
+    lens = rng.integers(1, 12, n)
+    lens[[7, 3000]] = [400, 1500]
+    starts = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    col = np.concatenate([np.sort(rng.choice(n, size=l, replace=False)) for l in lens]).astype(np.int64)
+    entry = rng.standard_normal(col.size)
+    rowptr = np.empty(n, dtype=oracle.RECT_DTYPE)
+    rowptr["lo"], rowptr["hi"] = starts, starts + lens - 1
+    m = oracle.Matrix(n, n, entry, col, rowptr=rowptr)
+    if fmt == "coo":
+        m = m.to_coo()
+    x = rng.standard_normal(n)
+    pl, _, _, _ = build_system(rt, oracle, m, pieces, rhs=[x])
+    pl.allocate_workspace(1)
+    pl.rmatvec(2, 1)
+    got = pl.vector_to_numpy(2, 0, n)
+    want = np.zeros(n)
+    oracle.rmatvec(m, x, want)
+    At = m.to_scipy().T.tocsr()
+    scale = np.abs(At) @ np.abs(x)
+    assert np.all(np.abs(got - want) <= 1e-12 * np.maximum(scale, 1e-300))
+    assert np.all(np.abs(got - At @ x) <= 1e-12 * np.maximum(scale, 1e-300))
+    # adjoint identity through both products of the planner: <A^T x, z> = <x, A z>
+    z = rng.standard_normal(n)
+    pl.vector_from_numpy(0, 0, z)
+    pl.matvec(2, 0)
+    Az = pl.vector_to_numpy(2, 0, n)
+    assert abs(float(got @ z) - float(x @ Az)) <= 1e-11 * float(np.abs(got) @ np.abs(z))
+
+
+@pytest.mark.parametrize("case,restart", [("7pt", 10), ("7pt", 30), ("coo", 30)])
+@pytest.mark.parametrize("traced", [False, True])
+def test_gmres_real_update_reduces_the_true_residual(rt, oracle, case, restart, traced):
+    """GMRES with the FINISHED update (Givens least squares + SOL += V y): the true residual || b - A x || equals the
+    least-squares minimum the kernel reports, decreases from cycle to cycle, and the update is what numpy's lstsq gives.
+    The default (placeholder) mode is covered by test_gmres_hessenberg_vs_oracle."""
+    from legionsolvers_b200.solvers import GMRESSolver
+    from legionsolvers_b200.workloads import power_law_coo
+
+    if case == "7pt":
+        off, val = oracle.benchmark_stencil(3)
+        m = oracle.stencil_csr((18, 18, 18), off, val)
+    else:
+        n_, e_, r_, c_ = power_law_coo(13)
+        m = oracle.Matrix(n_, n_, e_, c_, row=r_)
+    n = m.n_rows
+    rng = np.random.default_rng(9)
+    b = rng.uniform(0.5, 1.5, n)
+    pl, _, _, _ = build_system(rt, oracle, m, 2, rhs=[b])
+    s = GMRESSolver(pl, restart, real_update=True)
+    A = m.to_scipy()
+    res = [np.linalg.norm(b)]
+    tid = new_trace_id()
+    for cycle in range(3):
+        x_before = pl.vector_to_numpy(0, 0, n)
+        if traced:
+            rt.begin_trace(tid)
+        s.step()
+        if traced:
+            rt.end_trace(tid)
+        x = pl.vector_to_numpy(0, 0, n)
+        H = s.inner_products
+        V = np.stack([pl.vector_to_numpy(2 + j, 0, n) for j in range(restart)], axis=1)
+        beta = np.linalg.norm(b - A @ x_before)
+        e1 = np.zeros(restart + 1)
+        e1[0] = beta
+        y, *_ = np.linalg.lstsq(H, e1, rcond=None)
+        np.testing.assert_allclose(x - x_before, V @ y, rtol=0, atol=1e-9 * np.max(np.abs(V @ y)))
+        res.append(np.linalg.norm(b - A @ x))
+        assert res[-1] < 0.9 * res[-2]
+        assert abs(s.residual_norm[-1] - res[-1]) <= 1e-7 * res[0]
+    assert res[-1] <= 1e-3 * res[0]

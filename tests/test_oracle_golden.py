@@ -275,3 +275,22 @@ def test_bicgstab_and_gmres_run_and_reduce_residual(oracle):
     np.testing.assert_allclose(V.T @ V, np.eye(mres + 1), atol=1e-10)
     # placeholder update: SOL += 1 * V_j for j < m (DummyTask returns 1)
     np.testing.assert_allclose(pl2.vector(0), V[:, :mres].sum(axis=1), rtol=1e-12, atol=1e-12)
+
+
+def test_transposed_products_match_scipy(oracle):
+    """orc_csr_rmatvec / orc_coo_rmatvec (no reference body exists: the tasks are `assert(false)`) against scipy's A^T x."""
+    rng = np.random.default_rng(2)
+    n = 400
+    lens = rng.integers(0, 9, n)
+    starts = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    col = np.concatenate([np.sort(rng.choice(n, size=l, replace=False)) for l in lens]).astype(np.int64)
+    entry = rng.standard_normal(col.size)
+    rowptr = np.empty(n, dtype=oracle.RECT_DTYPE)
+    rowptr["lo"], rowptr["hi"] = starts, starts + lens - 1
+    m = oracle.Matrix(n, n, entry, col, rowptr=rowptr)
+    x = rng.standard_normal(n)
+    want = m.to_scipy().T @ x
+    for mm in (m, m.to_coo()):
+        y = np.zeros(n)
+        oracle.rmatvec(mm, x, y)
+        np.testing.assert_allclose(y, want, rtol=0, atol=1e-13 * np.max(np.abs(want)))
