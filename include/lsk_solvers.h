@@ -26,6 +26,13 @@ typedef struct lsk_solver lsk_solver;
 
 const char *lsk_last_error(void);
 
+/* ---- halo plan: the host arithmetic of SquarePlanner::add_row_partitioned_matrix (src/SquarePlanner.hpp:209-235 derives the
+ * ghost partition; Realm then moves the ghost instances implicitly -- here the moves are explicit).  ranges4[r] = {first owned
+ * row, last owned row, ghost lo, ghost hi} of rank r (inclusive; ghost lo > ghost hi = none).  Output: moves5[i] = {peer,
+ * send_lo, send_n, recv_lo, recv_n} for every peer this rank trades with, *nmoves of them (<= nranks - 1).  No CUDA, no
+ * runtime needed: the multi-process CPU tests call it directly. */
+int lsk_halo_plan(int rank, int nranks, const int64_t *ranges4, int64_t *moves5, int *nmoves);
+
 /* ---- runtime: one per process / GPU (replaces Legion::Runtime + mapper for this path) ------------ */
 /* external_stream: a cudaStream_t to enqueue on, or NULL for a private stream */
 int lsk_rt_create(int device, int rank, int nranks, void *external_stream, lsk_runtime **out);

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstring>
 #include <cstdlib>
+#include <set>
 #include <sstream>
 
 namespace LegionSolvers {
@@ -31,7 +32,20 @@ Runtime::~Runtime() {
     cudaStreamSynchronize(stream_);
     for (auto &kv : traces_)
         if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    // Exported allocations must outlive every importer's mapping (freeing IPC-exported memory that a peer still has
+    // open is undefined): close MY mappings of the peers' buffers, then meet the peers at a barrier -- after it, nobody
+    // maps my buffers any more -- and only then free.
     for (void *p : ipc_opened_) cudaIpcCloseMemHandle(p);
+    if (comm_ && p2p_ && nranks_ > 1) {
+        int *flag = nullptr;
+        if (cudaMalloc(&flag, sizeof(int)) == cudaSuccess) {
+            cudaMemsetAsync(flag, 0, sizeof(int), stream_);
+            if (ncclAllReduce(flag, flag, 1, ncclInt, ncclSum, reinterpret_cast<ncclComm_t>(comm_), stream_) == ncclSuccess)
+                cudaStreamSynchronize(stream_);
+            cudaFree(flag);
+        }
+    }
+    for (void *p : retired_) cudaFree(p);
     if (comm_) ncclCommDestroy(reinterpret_cast<ncclComm_t>(comm_));
     if (window_) cudaFree(window_);
     for (void *p : allocations_) cudaFree(p);
@@ -108,6 +122,7 @@ Runtime::Exported Runtime::export_allocation(void *raw, int64_t tag0, int64_t ta
     std::vector<int64_t> all((size_t) W * nranks_);
     check_cuda(cudaMemcpyAsync(all.data(), recv.ptr, sizeof(int64_t) * all.size(), cudaMemcpyDeviceToHost, stream_), "export D2H");
     fence();
+    if (ge == cudaSuccess) exported_.insert(raw);
     Exported ex;
     ex.base.assign((size_t) nranks_, nullptr);
     ex.tag0.assign((size_t) nranks_, 0);
@@ -235,6 +250,10 @@ void Runtime::free(void *p) {
     if (it != allocations_.end()) {
         allocations_.erase(it);
         cudaStreamSynchronize(stream_);
+        if (exported_.count(p)) {  // peers may still map it (CUDA IPC): keep it until the collective teardown in ~Runtime
+            retired_.push_back(p);
+            return;
+        }
         cudaFree(p);
     }
 }
@@ -302,6 +321,14 @@ void Runtime::end_trace(int id) {
 void Runtime::fence() {
     flush_deferred();
     check_cuda(cudaStreamSynchronize(stream_), "cudaStreamSynchronize");
+    // A spin-wait of a peer-memory collective (or of a persistent kernel's barrier) that gave up only raises a device
+    // flag (and poisons the reduced value with NaN): surface it here, at the first host synchronisation after it, instead
+    // of returning numbers computed from stale ghosts with status 0.
+    if (nranks_ > 1 && p2p_ && mode_ == Mode::Eager) {
+        int e = 0, g = 0;
+        if (lsk_comm_error(ctx_, stream_, &peers_, &e) == 0 && lsk_ctx_error(ctx_, stream_, &g) == 0 && (e | g) != 0)
+            fail(LSK_E_NCCL, "a peer-memory collective timed out (dead or diverged peer): results are invalid");
+    }
 }
 
 uint64_t Runtime::kernel_launches() const {

@@ -23,6 +23,7 @@
 #include <functional>
 #include <map>
 #include <memory>
+#include <set>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -162,6 +163,8 @@ private:
     uint64_t replayed_kernels_ = 0;
     std::map<int, Trace> traces_;
     std::vector<void *> allocations_;
+    std::set<void *> exported_;     // allocations some peer may have mapped (CUDA IPC)
+    std::vector<void *> retired_;   // exported allocations released by their owner: freed at the collective teardown
     std::vector<double *> arena_chunks_;
     size_t arena_used_ = 0;
     static constexpr size_t kArenaChunk = 1 << 16;

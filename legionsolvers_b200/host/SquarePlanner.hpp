@@ -400,21 +400,20 @@ public:
             rt->check_cuda(cudaMemcpyAsync(all.data(), recv.ptr, sizeof(int64_t) * all.size(), cudaMemcpyDeviceToHost, rt->stream()), "halo plan D2H");
             rt->fence();
         }
-        const int me = rt->rank();
-        for (int q = 0; q < R; ++q) {
-            if (q == me) continue;
-            const int64_t q_own_lo = all[(size_t) q * 4], q_own_hi = all[(size_t) q * 4 + 1];
-            const int64_t q_g_lo = all[(size_t) q * 4 + 2], q_g_hi = all[(size_t) q * 4 + 3];
+        // the plan itself is host arithmetic with a C entry point of its own (lsk_halo_plan): the multi-process CPU tests
+        // drive exactly this code
+        std::vector<int64_t> moves((size_t) R * 5);
+        int nmoves = 0;
+        if (lsk_halo_plan(rt->rank(), R, all.data(), moves.data(), &nmoves) != 0) rt->fail(LSK_E_INVALID, "lsk_halo_plan");
+        for (int i = 0; i < nmoves; ++i) {
             HaloMove m;
-            m.peer = q;
-            m.recv_lo = std::max(g_lo, q_own_lo);
-            m.recv_n = std::max<int64_t>(0, std::min(g_hi, q_own_hi) - m.recv_lo + 1);
-            m.send_lo = std::max(q_g_lo, domain.own_lo());
-            m.send_n = std::max<int64_t>(0, std::min(q_g_hi, domain.own_hi()) - m.send_lo + 1);
-            if (m.recv_n > 0 || m.send_n > 0) {
-                b.halo.push_back(m);
-                halo_bytes_per_matvec += (uint64_t) m.recv_n * sizeof(T);
-            }
+            m.peer = (int) moves[(size_t) i * 5];
+            m.send_lo = moves[(size_t) i * 5 + 1];
+            m.send_n = moves[(size_t) i * 5 + 2];
+            m.recv_lo = moves[(size_t) i * 5 + 3];
+            m.recv_n = moves[(size_t) i * 5 + 4];
+            b.halo.push_back(m);
+            halo_bytes_per_matvec += (uint64_t) m.recv_n * sizeof(T);
         }
         // every vector of the domain space must be able to hold the ghost interval
         if (g_hi >= g_lo) {

@@ -65,6 +65,32 @@ extern "C" {
 
 const char *lsk_last_error(void) { return g_last_error.c_str(); }
 
+// ---- halo plan (host arithmetic, no CUDA): what SquarePlanner::add_row_partitioned_matrix derives from the all-gathered
+// {owned rows, ghost interval} of every rank -- for each peer, the sub-range of MY owned rows inside ITS ghost interval
+// (send) and the sub-range of MY ghost interval that IT owns (recv) ------------------------------------------------------
+int lsk_halo_plan(int rank, int nranks, const int64_t *ranges4, int64_t *moves5, int *nmoves) {
+    if (rank < 0 || nranks < 1 || rank >= nranks || !ranges4 || !moves5 || !nmoves) return LSK_E_INVALID;
+    const int64_t own_lo = ranges4[(size_t) rank * 4], own_hi = ranges4[(size_t) rank * 4 + 1];
+    const int64_t g_lo = ranges4[(size_t) rank * 4 + 2], g_hi = ranges4[(size_t) rank * 4 + 3];
+    int n = 0;
+    for (int q = 0; q < nranks; ++q) {
+        if (q == rank) continue;
+        const int64_t q_own_lo = ranges4[(size_t) q * 4], q_own_hi = ranges4[(size_t) q * 4 + 1];
+        const int64_t q_g_lo = ranges4[(size_t) q * 4 + 2], q_g_hi = ranges4[(size_t) q * 4 + 3];
+        const int64_t recv_lo = std::max(g_lo, q_own_lo);
+        const int64_t recv_n = std::max<int64_t>(0, std::min(g_hi, q_own_hi) - recv_lo + 1);
+        const int64_t send_lo = std::max(q_g_lo, own_lo);
+        const int64_t send_n = std::max<int64_t>(0, std::min(q_g_hi, own_hi) - send_lo + 1);
+        if (recv_n > 0 || send_n > 0) {
+            int64_t *m = moves5 + (size_t) n * 5;
+            m[0] = q; m[1] = send_lo; m[2] = send_n; m[3] = recv_lo; m[4] = recv_n;
+            ++n;
+        }
+    }
+    *nmoves = n;
+    return 0;
+}
+
 // ---- runtime ---------------------------------------------------------------------------------------------------
 int lsk_rt_create(int device, int rank, int nranks, void *external_stream, lsk_runtime **out) {
     REQUIRE(out);

@@ -80,7 +80,25 @@ void orc_xpay(int64_t n, double alpha, const double *x, double *y) {
 }
 
 /* DotTask::task_body, src/LinearAlgebraTasks.cpp:135-175: sequential result += v*w */
+/* Test-only switch (orc_set_dot_order): 0 = the reference's sequential sum below (default); 1 = a pairwise tree over
+ * blocks of 256 sequential products -- ANOTHER valid evaluation order of the same dot product.  The tests use the
+ * spread between the two to measure how strongly a Lanczos-type recurrence (BiCGStab, GMRES on symmetric matrices)
+ * amplifies a change of summation order, and bound the GPU's deviation by that measured sensitivity. */
+static int g_dot_order = 0;
+void orc_set_dot_order(int order) { g_dot_order = order; }
+
+static double dot_pairwise(int64_t n, const double *v, const double *w) {
+    if (n <= 256) {
+        double r = 0.0;
+        for (int64_t i = 0; i < n; ++i) r += v[i] * w[i];
+        return r;
+    }
+    const int64_t h = n / 2;
+    return dot_pairwise(h, v, w) + dot_pairwise(n - h, v + h, w + h);
+}
+
 double orc_dot(int64_t n, const double *v, const double *w) {
+    if (g_dot_order == 1) return dot_pairwise(n, v, w);
     double result = 0.0;
     for (int64_t i = 0; i < n; ++i) result += v[i] * w[i];
     return result;

@@ -55,6 +55,8 @@ void orc_scal(int64_t n, double alpha, double *x);
 void orc_axpy(int64_t n, double alpha, const double *x, double *y);
 void orc_xpay(int64_t n, double alpha, const double *x, double *y);
 double orc_dot(int64_t n, const double *v, const double *w);
+/* test-only: 0 = the reference's sequential order (default), 1 = pairwise tree (sensitivity measurements) */
+void orc_set_dot_order(int order);
 
 void orc_scal_f32(int64_t n, float alpha, float *x);
 void orc_axpy_f32(int64_t n, float alpha, const float *x, float *y);

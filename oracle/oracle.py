@@ -55,6 +55,7 @@ def _p(a, dtype=None):
 def _declare(L):
     i64, dbl, vp, ci = C.c_int64, C.c_double, C.c_void_p, C.c_int
     L.orc_set_threads.argtypes = [ci]
+    L.orc_set_dot_order.argtypes = [ci]
     L.orc_get_threads.restype = ci
     L.orc_get_alpha.argtypes = [ci, vp]
     L.orc_get_alpha.restype = dbl
@@ -142,6 +143,11 @@ def _declare(L):
 # --------------------------------------------------------------------------------------------
 def set_threads(n: int) -> None:
     lib().orc_set_threads(int(n))
+
+
+def set_dot_order(order: int) -> None:
+    """0 = the reference's sequential dot (default); 1 = pairwise tree -- another valid order, for sensitivity measurements."""
+    lib().orc_set_dot_order(int(order))
 
 
 def get_alpha(terms) -> float:

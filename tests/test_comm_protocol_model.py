@@ -159,3 +159,63 @@ def test_model_detects_a_broken_protocol():
         except AssertionError:
             caught += 1
     assert caught > 0
+
+
+# ---- exchanges are numbered PER PAIR of ranks (CommWindow::halo_sent) ------------------------------------------------------
+def _pair_counter_program(me, nranks, wins_done, plans, use_pair_counters, log):
+    """One rank issuing a sequence of halo exchanges; plans[x][me] = peers `me` trades with in exchange x (possibly none:
+    the stand-alone exchange kernel is not even launched then).  Yields at every store / poll."""
+    sent = [0] * nranks  # halo_sent[peer]
+    single = 0           # the round-1 scheme: ONE epoch per rank, compared with per-peer flags
+    for x, plan in enumerate(plans):
+        peers = plan[me]
+        if not peers:
+            continue     # lsk_halo_exchange_f64 returns without a launch: no counter moves
+        single += 1
+        for p in peers:  # publish "exchange #e of our pair has landed"
+            e = sent[p] + 1 if use_pair_counters else single
+            wins_done[p][me] = e
+            yield
+        for p in peers:  # wait for the peer's
+            e = sent[p] + 1 if use_pair_counters else single
+            spins = 0
+            while wins_done[me][p] < e:
+                spins += 1
+                if spins > 2000:
+                    log.append((me, x, p, "timeout"))
+                    return
+                yield
+            sent[p] = e
+    log.append((me, "done"))
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_per_pair_exchange_counters_survive_asymmetric_plans(seed):
+    """Three ranks, blocks whose halos differ: exchange 0 involves only the pair (0, 1), exchange 1 only (1, 2), exchange 2
+    everybody.  With ONE epoch per rank (round 1) rank 1 has counted two exchanges when rank 0 and rank 2 have counted one:
+    in exchange 2 it waits for epoch 3 from peers that publish 2 -- a dead wait (the 4 s timeout, then stale ghosts).  With
+    a counter per PAIR both ends of every pair have always counted the same number of exchanges."""
+    plans = [
+        {0: [1], 1: [0], 2: []},
+        {0: [], 1: [2], 2: [1]},
+        {0: [1], 1: [0, 2], 2: [1]},
+        {0: [1], 1: [0], 2: []},
+        {0: [1], 1: [0, 2], 2: [1]},
+    ]
+    for use_pair, expect_ok in ((True, True), (False, False)):
+        rng = random.Random(seed)
+        wins_done = [[0] * 3 for _ in range(3)]
+        log = []
+        progs = [_pair_counter_program(r, 3, wins_done, plans, use_pair, log) for r in range(3)]
+        live = list(range(3))
+        while live:
+            r = rng.choice(live)
+            try:
+                next(progs[r])
+            except StopIteration:
+                live.remove(r)
+        timeouts = [e for e in log if e[-1] == "timeout"]
+        if expect_ok:
+            assert not timeouts and sorted(e[0] for e in log) == [0, 1, 2]
+        else:
+            assert timeouts, "the single-epoch scheme should have diverged on this plan"

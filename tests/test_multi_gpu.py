@@ -1,5 +1,6 @@
-"""N > 1: (gpu) torchrun with 2 ranks on 2 GPUs when the box has them; (cpu) world_size-2 gloo tests
-of the host-side logic of the same path: partition -> ghost intervals -> halo plan -> SpMV/CG."""
+"""N > 1: (gpu) torchrun with 2 ranks on 2 GPUs when the box has them; (cpu) world_size-2 / -4 gloo tests of the
+host-side logic of the same path, THROUGH THE PRODUCT'S OWN entry points (lsk_equal_partition, lsk_shard, lsk_halo_plan --
+the function SquarePlanner::add_row_partitioned_matrix calls): partition -> ghost intervals -> halo plan -> SpMV / CG."""
 import json
 import os
 import subprocess
@@ -55,14 +56,22 @@ def _gloo_worker(rank, world, port, q):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
+        import ctypes as C
+
+        from legionsolvers_b200 import _abi
+
+        L = _abi.lib()  # the PRODUCT's host-side entry points (no GPU needed for these)
         off, val = orc.benchmark_stencil(3)
         shape = (8, 6, 5)
         m = orc.stencil_csr(shape, off, val)
         n, pieces = m.n_rows, world
-        lo, hi = orc.equal_partition(n, pieces)
-        # blocked sharding: colour c -> rank c / ceil(P / world)
-        mine = [c for c in range(pieces) if orc.shard(c, pieces, world) == rank]
-        assert mine == [rank]
+        # create_equal_partition and the blocked sharding rule: the product's functions, checked against the oracle's
+        lo, hi = np.zeros(pieces, dtype=np.int64), np.zeros(pieces, dtype=np.int64)
+        assert L.lsk_equal_partition(n, pieces, lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p)) == 0
+        olo, ohi = orc.equal_partition(n, pieces)
+        assert np.array_equal(lo, olo) and np.array_equal(hi, ohi)
+        mine = [c for c in range(pieces) if L.lsk_shard(c, pieces, world) == rank]
+        assert mine == [rank] == [c for c in range(pieces) if orc.shard(c, pieces, world) == rank]
         pl = orc.Planner([n], [pieces])
         b = pl.add_matrix(m)
         own_lo, own_hi = int(lo[rank]), int(hi[rank])
@@ -72,15 +81,14 @@ def _gloo_worker(rank, world, port, q):
         allr = [torch.zeros(4, dtype=torch.int64) for _ in range(world)]
         dist.all_gather(allr, mine_t)
         allr = [tuple(int(v) for v in t) for t in allr]
-        # halo plan, same arithmetic as SquarePlanner::add_row_partitioned_matrix
-        moves = []
-        for q_ in range(world):
-            if q_ == rank:
-                continue
-            qo_lo, qo_hi, qg_lo, qg_hi = allr[q_]
-            recv_lo = max(g_lo, qo_lo); recv_n = max(0, min(g_hi, qo_hi) - recv_lo + 1)
-            send_lo = max(qg_lo, own_lo); send_n = max(0, min(qg_hi, own_hi) - send_lo + 1)
-            moves.append((q_, send_lo, send_n, recv_lo, recv_n))
+        # the halo plan: SquarePlanner::add_row_partitioned_matrix's own arithmetic, through its C entry point
+        ranges = np.ascontiguousarray(np.array(allr, dtype=np.int64).reshape(world, 4))
+        moves5 = np.zeros((world, 5), dtype=np.int64)
+        nmoves = C.c_int(0)
+        assert L.lsk_halo_plan(rank, world, ranges.ctypes.data_as(C.c_void_p), moves5.ctypes.data_as(C.c_void_p), C.byref(nmoves)) == 0
+        planned = {int(r[0]): tuple(int(v) for v in r[1:]) for r in moves5[:nmoves.value]}
+        # (peers with nothing to trade are not in the plan; the checks below want one entry per peer)
+        moves = [(q_,) + planned.get(q_, (0, 0, 0, 0)) for q_ in range(world) if q_ != rank]
         # run 12 CG iterations with a DISTRIBUTED x: each rank holds only [g_lo, g_hi] of p
         x_full = np.zeros(n); r = np.ones(n); p = np.ones(n); qv = np.zeros(n)
         own = slice(own_lo, own_hi + 1)
