@@ -589,16 +589,21 @@ def run_ours(args):
         hist_stage = torch.zeros(max(1, nh) * hist_len, dtype=torch.float64, device="cuda")
         hist_host = torch.zeros((e2e_steps + 2, max(1, nh) * hist_len), dtype=torch.float64).pin_memory()
         TRACE_RESET, TRACE_ITERS = 52, 53
+        # two copy streams: H2D and D2H run concurrently (PCIe is full duplex); on ONE stream the H2D of step k + 2 queues
+        # behind the D2H of step k and the step period becomes the SUM of the two copies (measured at 8 GPUs, where eight
+        # ranks share the host's PCIe fabric: e2e 0.48 of the resident rate)
         copy_stream = torch.cuda.Stream()
+        d2h_stream = torch.cuda.Stream()
         cs = copy_stream.cuda_stream
 
         def e2e_run(nsteps):
             ev_h2d, ev_reset, ev_solved, ev_d2h = (torch.cuda.Event() for _ in range(4))
             copy_stream.wait_stream(tstream)
+            d2h_stream.wait_stream(tstream)
             for s in range(spaces):
                 pl.vector_from_async(1, s, b_host[s].data_ptr(), cs)       # H2D: right-hand side of the first step
             ev_h2d.record(copy_stream)
-            ev_d2h.record(copy_stream)
+            ev_d2h.record(d2h_stream)
             for k in range(nsteps):
                 tstream.wait_event(ev_h2d)                # this step's right-hand side has landed
                 rt.begin_trace(TRACE_RESET)
@@ -621,13 +626,14 @@ def run_ours(args):
                 for h in range(nh):
                     sv.history_copy_async(h, hist_stage.data_ptr() + 8 * h * hist_len, hist_len, stream)
                 ev_solved.record(tstream)
-                copy_stream.wait_event(ev_solved)
-                with torch.cuda.stream(copy_stream):      # D2H under the next step's iterations
+                d2h_stream.wait_event(ev_solved)
+                with torch.cuda.stream(d2h_stream):       # D2H under the next step's iterations
                     for s in range(spaces):
                         x_host[s][own_lo:own_lo + n_local].copy_(x_stage[s], non_blocking=True)
                     hist_host[k].copy_(hist_stage, non_blocking=True)
-                ev_d2h.record(copy_stream)
+                ev_d2h.record(d2h_stream)
             copy_stream.synchronize()
+            d2h_stream.synchronize()
             torch.cuda.synchronize()
 
         e2e_run(2)
@@ -639,7 +645,7 @@ def run_ours(args):
         e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n_local * spaces,
                "d2h_bytes_per_step": 8 * n_local * spaces + 8 * nh * hist_len, "steps": e2e_steps,
                "what": ("per step: H2D rhs (pinned) -> zero_fill + reset (trace) -> iters_per_step iterations (trace) -> D2H solution + history; copies on a "
-                        "second stream, double-buffered; nothing is read back until every step has been enqueued"),
+                        "H2D and a D2H stream, double-buffered; nothing is read back until every step has been enqueued"),
                "ratio_to_resident": e2e_value / value,
                "solution_abs_max": float(x_host[0][own_lo:own_lo + n_local].abs().max()),
                "history_last": float(hist_host[e2e_steps - 1][hist_len - 1]) if nh else None}

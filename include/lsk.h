@@ -159,7 +159,13 @@ enum lsk_spmv_variant {
     LSK_SPMV_STREAM = 1, /* block streams a contiguous run of non-zeros through shared memory */
     LSK_SPMV_VECTOR = 2, /* 2..16 lanes per row */
     LSK_SPMV_WARP = 3,   /* one warp per row */
-    LSK_SPMV_LANES = 4   /* the STREAM kernel's TMA-staged tiles with 2, 4 or 8 lanes per row (by mean row length) */
+    LSK_SPMV_LANES = 4,  /* the STREAM kernel's TMA-staged tiles with 2, 4 or 8 lanes per row (by mean row length) */
+    /* flag, OR-ed into `variant`: y = y + A x instead of y = A x.  For a further operator block on rows that an earlier
+     * block of the same planner mat-vec has already written (the reference's CPU bodies accumulate onto the zero-filled
+     * destination through a sum-reduction accessor, src/CSRMatrixTasks.cpp:29-31; its cuSPARSE variant overwrites,
+     * beta = 0, which is only right for one block per range space).  STREAM: the products are added one by one onto
+     * the row's current value, in ascending k -- bit-identical to the CPU body. */
+    LSK_SPMV_ACCUMULATE = 0x100
 };
 int lsk_csr_spmv_f64(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const double *entry,
                      const int64_t *col, const lsk_rect *rowptr, int64_t k_base,

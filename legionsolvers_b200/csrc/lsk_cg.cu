@@ -433,6 +433,7 @@ int lsk_cg_steps_f64(lsk_ctx *ctx, lsk_stream s, const lsk_cg_problem *pb, int n
     a.mv.y = pb->q;
     a.p = pb->p_shifted + pb->own_lo;
     a.mv.dot_w = a.p;
+    a.mv.accumulate = 0;
     a.q = pb->q;
     a.x = pb->x;
     a.r = pb->r;

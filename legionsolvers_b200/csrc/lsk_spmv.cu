@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(kBlock, 4)
 csr_stream_kernel(int64_t rows, int rpb, int64_t n_row_blocks, const T *__restrict__ entry,
                   const long long *__restrict__ col, const lsk_rect *__restrict__ rowptr, int64_t k_base,
                   const T *__restrict__ x, T *__restrict__ y, const T *__restrict__ dot_w,
-                  double *partials, unsigned int *ticket, T *out_yw, T *out_yy, const lsk_peers *peers) {
+                  double *partials, unsigned int *ticket, T *out_yw, T *out_yy, const lsk_peers *peers, bool accumulate) {
     __shared__ __align__(16) T s_prod[kTile];
     __shared__ long long s_lo[kWarps], s_hi[kWarps];
     const int tid = threadIdx.x;
@@ -154,6 +154,7 @@ csr_stream_kernel(int64_t rows, int rpb, int64_t n_row_blocks, const T *__restri
             __syncthreads();  // s_lo/s_hi are rewritten by the next row block
         }
         if (have) {
+            if (accumulate) acc = add_rn(y[r0 + tid], acc);  // a further block on the same rows (beta = 1)
             y[r0 + tid] = acc;
             if constexpr (NDOT >= 1) dacc[0] = fma((double) acc, dot_w != y ? (double) __ldg(dot_w + r0 + tid) : (double) acc, dacc[0]);
             if constexpr (NDOT >= 2) dacc[NDOT - 1] = fma((double) acc, (double) acc, dacc[NDOT - 1]);
@@ -181,7 +182,7 @@ csr_stream_pipe_kernel(int64_t rows, int rpb, int64_t n_row_blocks, const T *__r
                        const long long *__restrict__ col, const lsk_rect *__restrict__ rowptr,
                        int64_t k_base, const T *__restrict__ x, T *__restrict__ y,
                        const T *__restrict__ dot_w, double *partials, unsigned int *ticket, T *out_yw,
-                       T *out_yy, const lsk_peers *peers) {
+                       T *out_yy, const lsk_peers *peers, bool accumulate) {
     constexpr int U = kTile / (4 * kBlock);
     __shared__ __align__(16) T s_prod[kTile];
     __shared__ long long s_lo[kWarps], s_hi[kWarps];
@@ -297,6 +298,7 @@ csr_stream_pipe_kernel(int64_t rows, int rpb, int64_t n_row_blocks, const T *__r
         if (last_tile) {
             const int64_t r = rb * rpb + tid;
             if (tid < rpb && r < rows) {
+                if (accumulate) acc = add_rn(y[r], acc);
                 y[r] = acc;
                 if constexpr (NDOT >= 1) dacc[0] = fma((double) acc, dot_w != y ? (double) __ldg(dot_w + r) : (double) acc, dacc[0]);
                 if constexpr (NDOT >= 2) dacc[NDOT - 1] = fma((double) acc, (double) acc, dacc[NDOT - 1]);
@@ -372,7 +374,7 @@ __global__ void __launch_bounds__(kBlock)
 csr_vector_kernel(int64_t rows, const T *__restrict__ entry, const long long *__restrict__ col,
                   const lsk_rect *__restrict__ rowptr, int64_t k_base, const T *__restrict__ x,
                   T *__restrict__ y, const T *__restrict__ dot_w, double *partials, unsigned int *ticket,
-                  T *out_yw, T *out_yy, const lsk_peers *peers) {
+                  T *out_yw, T *out_yy, const lsk_peers *peers, bool accumulate) {
     constexpr int RPC = kBlock / V;  // rows per CTA pass
     const int sub = threadIdx.x % V;
     double dacc[NDOT > 0 ? NDOT : 1];
@@ -392,6 +394,7 @@ csr_vector_kernel(int64_t rows, const T *__restrict__ entry, const long long *__
 #pragma unroll
         for (int o = V / 2; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o, V);
         if (active && sub == 0) {
+            if (accumulate) sum = add_rn(y[row], sum);
             y[row] = sum;
             if constexpr (NDOT >= 1) dacc[0] = fma((double) sum, dot_w != y ? (double) __ldg(dot_w + row) : (double) sum, dacc[0]);
             if constexpr (NDOT >= 2) dacc[NDOT - 1] = fma((double) sum, (double) sum, dacc[NDOT - 1]);
@@ -473,25 +476,25 @@ template <typename T, bool VEC>
 static void launch_stream_kernel(int ndot, int grid, cudaStream_t st, int64_t rows, int rpb, int64_t nrb,
                                  const T *entry, const long long *col, const lsk_rect *rowptr,
                                  int64_t k_base, const T *x, T *y, const T *dot_w, RedScratch rs, T *o0,
-                                 T *o1) {
+                                 T *o1, bool accumulate) {
     if (ndot == 0)
-        csr_stream_kernel<T, VEC, 0><<<grid, kBlock, 0, st>>>(rows, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers);
+        csr_stream_kernel<T, VEC, 0><<<grid, kBlock, 0, st>>>(rows, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers, accumulate);
     else if (ndot == 1)
-        csr_stream_kernel<T, VEC, 1><<<grid, kBlock, 0, st>>>(rows, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers);
+        csr_stream_kernel<T, VEC, 1><<<grid, kBlock, 0, st>>>(rows, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers, accumulate);
     else
-        csr_stream_kernel<T, VEC, 2><<<grid, kBlock, 0, st>>>(rows, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers);
+        csr_stream_kernel<T, VEC, 2><<<grid, kBlock, 0, st>>>(rows, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers, accumulate);
 }
 
 template <typename T>
 static void launch_pipe_kernel(int ndot, int grid, cudaStream_t st, int64_t rows, int rpb, int64_t nrb,
                                const T *entry, const long long *col, const lsk_rect *rowptr, int64_t k_base,
-                               const T *x, T *y, const T *dot_w, RedScratch rs, T *o0, T *o1) {
+                               const T *x, T *y, const T *dot_w, RedScratch rs, T *o0, T *o1, bool accumulate) {
     if (ndot == 0)
-        csr_stream_pipe_kernel<T, 0><<<grid, kBlock, 0, st>>>(rows, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers);
+        csr_stream_pipe_kernel<T, 0><<<grid, kBlock, 0, st>>>(rows, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers, accumulate);
     else if (ndot == 1)
-        csr_stream_pipe_kernel<T, 1><<<grid, kBlock, 0, st>>>(rows, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers);
+        csr_stream_pipe_kernel<T, 1><<<grid, kBlock, 0, st>>>(rows, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers, accumulate);
     else
-        csr_stream_pipe_kernel<T, 2><<<grid, kBlock, 0, st>>>(rows, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers);
+        csr_stream_pipe_kernel<T, 2><<<grid, kBlock, 0, st>>>(rows, rpb, nrb, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers, accumulate);
 }
 
 template <int LPR>
@@ -518,7 +521,7 @@ static int launch_tma_kernel_lpr(lsk_ctx *ctx, int ndot, int grid, cudaStream_t 
 // lanes per row 1 (thread per row) .. 8; the row block is sized so that its non-zeros fill about one tile
 static int launch_tma_kernel(lsk_ctx *ctx, int lpr, int ndot, cudaStream_t st, int64_t rows, int64_t nnz, const double *entry,
                              const long long *col, const lsk_rect *rowptr, int64_t k_base, const double *x, double *y,
-                             const double *dot_w, RedScratch rs, double *o0, double *o1) {
+                             const double *dot_w, RedScratch rs, double *o0, double *o1, bool accumulate) {
     const double mean = rows > 0 ? (double) nnz / (double) rows : 1.0;
     const int unit = 32 / lpr;  // rows per warp
     int rpb = (int) ((double) kTmaTile / (mean < 1.0 ? 1.0 : mean));
@@ -530,7 +533,7 @@ static int launch_tma_kernel(lsk_ctx *ctx, int lpr, int ndot, cudaStream_t st, i
     const int grid = (int) (nrb < cap ? nrb : cap);
     TmaSpmvArgs a;
     a.rows = rows; a.nnz = nnz; a.rpb = rpb; a.n_row_blocks = nrb; a.entry = entry; a.col = col; a.rowptr = rowptr;
-    a.k_base = k_base; a.x = x; a.y = y; a.dot_w = dot_w;
+    a.k_base = k_base; a.x = x; a.y = y; a.dot_w = dot_w; a.accumulate = accumulate ? 1 : 0;
     switch (lpr) {
     case 1: return launch_tma_kernel_lpr<1>(ctx, ndot, grid, st, a, rs, o0, o1);
     case 2: return launch_tma_kernel_lpr<2>(ctx, ndot, grid, st, a, rs, o0, o1);
@@ -574,7 +577,7 @@ static int ws_lanes_per_row(int64_t rows, int64_t nnz, int variant) {
 
 static int launch_ws_kernel(lsk_ctx *ctx, int lpr, int ndot, cudaStream_t st, int64_t rows, int64_t nnz, const double *entry,
                             const long long *col, const lsk_rect *rowptr, int64_t k_base, const double *x, double *y,
-                            const double *dot_w, const WsGate *gate, double *o0, double *o1) {
+                            const double *dot_w, const WsGate *gate, double *o0, double *o1, bool accumulate) {
     const int rpb = ws_rows_per_block(rows, nnz, lpr);
     const int64_t nrb = rows > 0 ? (rows + rpb - 1) / rpb : 0;  // no rows: one CTA that only finishes the fused dots (0)
     static const char *cta_env = getenv("LSK_WS_CTAS");  // developer knob: CTAs per SM
@@ -582,7 +585,7 @@ static int launch_ws_kernel(lsk_ctx *ctx, int lpr, int ndot, cudaStream_t st, in
     const int grid = (int) (nrb < 1 ? 1 : nrb < cap ? nrb : cap);
     TmaSpmvArgs a;
     a.rows = rows; a.nnz = nnz; a.rpb = rpb; a.n_row_blocks = nrb; a.entry = entry; a.col = col; a.rowptr = rowptr;
-    a.k_base = k_base; a.x = x; a.y = y; a.dot_w = dot_w;
+    a.k_base = k_base; a.x = x; a.y = y; a.dot_w = dot_w; a.accumulate = accumulate ? 1 : 0;
     RedScratch rs = {nullptr, nullptr, nullptr, nullptr};
     if (ndot > 0) rs = next_scratch(ctx);
     switch (lpr) {
@@ -609,13 +612,13 @@ __global__ void __launch_bounds__(kBlock) csr_ghost_blocks_kernel(int64_t rows, 
 template <typename T, int V>
 static void launch_vector_kernel(int ndot, int grid, cudaStream_t st, int64_t rows, const T *entry,
                                  const long long *col, const lsk_rect *rowptr, int64_t k_base, const T *x,
-                                 T *y, const T *dot_w, RedScratch rs, T *o0, T *o1) {
+                                 T *y, const T *dot_w, RedScratch rs, T *o0, T *o1, bool accumulate) {
     if (ndot == 0)
-        csr_vector_kernel<T, V, 0><<<grid, kBlock, 0, st>>>(rows, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers);
+        csr_vector_kernel<T, V, 0><<<grid, kBlock, 0, st>>>(rows, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers, accumulate);
     else if (ndot == 1)
-        csr_vector_kernel<T, V, 1><<<grid, kBlock, 0, st>>>(rows, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers);
+        csr_vector_kernel<T, V, 1><<<grid, kBlock, 0, st>>>(rows, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers, accumulate);
     else
-        csr_vector_kernel<T, V, 2><<<grid, kBlock, 0, st>>>(rows, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers);
+        csr_vector_kernel<T, V, 2><<<grid, kBlock, 0, st>>>(rows, entry, col, rowptr, k_base, x, y, dot_w, rs.partials, rs.ticket, o0, o1, rs.peers, accumulate);
 }
 
 template <typename T>
@@ -626,6 +629,8 @@ static int csr_spmv(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const
     if (rows > 0 && (!rowptr || !y || !x_shifted)) return LSK_E_INVALID;
     if (nnz > 0 && (!entry || !col)) return LSK_E_INVALID;
     if ((dot_w == nullptr) != (dot_out == nullptr)) return LSK_E_INVALID;
+    const bool accumulate = (variant & LSK_SPMV_ACCUMULATE) != 0;
+    variant &= ~LSK_SPMV_ACCUMULATE;
     if (variant < LSK_SPMV_AUTO || variant > LSK_SPMV_LANES) return LSK_E_INVALID;
     // the fused reductions share one kernel shape: {} | {y.w} | {y.w, y.y}; y.y alone rides on a
     // y.w slot pointed at y itself (the kernels then use the row's own result for w)
@@ -654,7 +659,7 @@ static int csr_spmv(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const
         // the warp-specialised TMA pipeline: thread per row (bit-exact) or 2-8 lanes per row
         const int rc = launch_ws_kernel(ctx, ws_lanes_per_row(rows, nnz, variant), ndot, st, rows, nnz, reinterpret_cast<const double *>(entry),
                                         colp, rowptr, k_base, reinterpret_cast<const double *>(x_shifted), reinterpret_cast<double *>(y),
-                                        reinterpret_cast<const double *>(w), gate, reinterpret_cast<double *>(o0), reinterpret_cast<double *>(o1));
+                                        reinterpret_cast<const double *>(w), gate, reinterpret_cast<double *>(o0), reinterpret_cast<double *>(o1), accumulate);
         if (rc != 0) return rc;
         return after_launch(ctx);
     }
@@ -667,7 +672,7 @@ static int csr_spmv(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const
             const int rc = launch_tma_kernel(ctx, lpr, ndot, st, rows, nnz, reinterpret_cast<const double *>(entry), colp, rowptr, k_base,
                                              reinterpret_cast<const double *>(x_shifted), reinterpret_cast<double *>(y),
                                              reinterpret_cast<const double *>(w), rs, reinterpret_cast<double *>(o0),
-                                             reinterpret_cast<double *>(o1));
+                                             reinterpret_cast<double *>(o1), accumulate);
             if (rc != 0) return rc;
             return after_launch(ctx);
         }
@@ -693,14 +698,14 @@ static int csr_spmv(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const
             const int rc = launch_tma_kernel(ctx, 1, ndot, st, rows, nnz, reinterpret_cast<const double *>(entry), colp, rowptr, k_base,
                                              reinterpret_cast<const double *>(x_shifted), reinterpret_cast<double *>(y),
                                              reinterpret_cast<const double *>(w), rs, reinterpret_cast<double *>(o0),
-                                             reinterpret_cast<double *>(o1));
+                                             reinterpret_cast<double *>(o1), accumulate);
             if (rc != 0) return rc;
         } else if (vec && impl != 2)
-            launch_pipe_kernel<T>(ndot, grid, st, rows, rpb, nrb, entry, colp, rowptr, k_base, x_shifted, y, w, rs, o0, o1);
+            launch_pipe_kernel<T>(ndot, grid, st, rows, rpb, nrb, entry, colp, rowptr, k_base, x_shifted, y, w, rs, o0, o1, accumulate);
         else if (vec)
-            launch_stream_kernel<T, true>(ndot, grid, st, rows, rpb, nrb, entry, colp, rowptr, k_base, x_shifted, y, w, rs, o0, o1);
+            launch_stream_kernel<T, true>(ndot, grid, st, rows, rpb, nrb, entry, colp, rowptr, k_base, x_shifted, y, w, rs, o0, o1, accumulate);
         else
-            launch_stream_kernel<T, false>(ndot, grid, st, rows, rpb, nrb, entry, colp, rowptr, k_base, x_shifted, y, w, rs, o0, o1);
+            launch_stream_kernel<T, false>(ndot, grid, st, rows, rpb, nrb, entry, colp, rowptr, k_base, x_shifted, y, w, rs, o0, o1, accumulate);
     } else {
         int V = 32;
         if (variant == LSK_SPMV_VECTOR) {
@@ -710,11 +715,11 @@ static int csr_spmv(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const
         const int64_t passes = (rows * V + kBlock - 1) / kBlock;
         const int grid = stream_grid(ctx, (passes > 0 ? passes : 1) * kBlock, 8);
         switch (V) {
-        case 2: launch_vector_kernel<T, 2>(ndot, grid, st, rows, entry, colp, rowptr, k_base, x_shifted, y, w, rs, o0, o1); break;
-        case 4: launch_vector_kernel<T, 4>(ndot, grid, st, rows, entry, colp, rowptr, k_base, x_shifted, y, w, rs, o0, o1); break;
-        case 8: launch_vector_kernel<T, 8>(ndot, grid, st, rows, entry, colp, rowptr, k_base, x_shifted, y, w, rs, o0, o1); break;
-        case 16: launch_vector_kernel<T, 16>(ndot, grid, st, rows, entry, colp, rowptr, k_base, x_shifted, y, w, rs, o0, o1); break;
-        default: launch_vector_kernel<T, 32>(ndot, grid, st, rows, entry, colp, rowptr, k_base, x_shifted, y, w, rs, o0, o1); break;
+        case 2: launch_vector_kernel<T, 2>(ndot, grid, st, rows, entry, colp, rowptr, k_base, x_shifted, y, w, rs, o0, o1, accumulate); break;
+        case 4: launch_vector_kernel<T, 4>(ndot, grid, st, rows, entry, colp, rowptr, k_base, x_shifted, y, w, rs, o0, o1, accumulate); break;
+        case 8: launch_vector_kernel<T, 8>(ndot, grid, st, rows, entry, colp, rowptr, k_base, x_shifted, y, w, rs, o0, o1, accumulate); break;
+        case 16: launch_vector_kernel<T, 16>(ndot, grid, st, rows, entry, colp, rowptr, k_base, x_shifted, y, w, rs, o0, o1, accumulate); break;
+        default: launch_vector_kernel<T, 32>(ndot, grid, st, rows, entry, colp, rowptr, k_base, x_shifted, y, w, rs, o0, o1, accumulate); break;
         }
     }
     return after_launch(ctx);
@@ -750,6 +755,7 @@ int lsk_csr_spmv_f64(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, cons
 }
 // ---- gated form (several GPUs): ghost columns guarded per row block --------------------------------------------------
 static int gated_variant(int64_t rows, int64_t nnz, int variant) {
+    variant &= ~LSK_SPMV_ACCUMULATE;
     if (variant == LSK_SPMV_AUTO) variant = pick_variant(rows, nnz);
     return variant;
 }

@@ -125,6 +125,7 @@ struct TmaSpmvArgs {
     const double *x;         // shifted to global column 0
     double *y;
     const double *dot_w;     // NDOT >= 1
+    int accumulate;          // non-zero: y = y + A x (a further block of a multi-operator system on the same rows)
 };
 
 // Ghost columns (outside the owned rows) are written by peer GPUs while the kernel runs.  Before a CTA
@@ -431,6 +432,7 @@ __device__ __forceinline__ void csr_tma_run(const TmaSpmvArgs &a, TmaSpmvState &
             }
             const int64_t r = rb * rpb + trow;
             if (tsub == 0 && trow < rpb && r < rows) {
+                if (a.accumulate) acc = add_rn(a.y[r], acc);
                 a.y[r] = acc;
                 if constexpr (NDOT >= 1) dacc[0] = fma(acc, a.dot_w != a.y ? wv : acc, dacc[0]);  // w == y: the y.y-only form
                 if constexpr (NDOT >= 2) dacc[NDOT - 1] = fma(acc, acc, dacc[NDOT - 1]);

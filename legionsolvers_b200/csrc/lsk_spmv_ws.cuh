@@ -309,7 +309,10 @@ csr_ws_kernel(TmaSpmvArgs a, WsGate gate, RedScratch rs, double *out_yw, double 
                     hi1 = rc.y + 1 - k_base;
                     direct = lo < s_meta[stage].jb || hi1 > s_meta[stage].je;
                 }
-                acc = 0.0;
+                // beta = 0; or the row's current value when a further block of a multi-operator system accumulates onto the
+                // same rows: the products are then added one by one onto it, exactly as the reference's CPU body adds them
+                // onto the zero-filled (or already partly summed) destination
+                acc = (a.accumulate && tsub == 0 && have) ? a.y[r] : 0.0;
                 if constexpr (NDOT >= 1) {  // requested now: its latency hides behind the gathers
                     // (w == y: the y.y-only form of the C ABI; the row's own result is used instead, below)
                     if (tsub == 0 && have && a.dot_w != a.y) wv = GATED ? ld_f64(a.dot_w + r) : __ldg(a.dot_w + r);

@@ -54,9 +54,10 @@ public:
     virtual IntervalPartition create_domain_partition_from_kernel_partition(int64_t domain_volume,
                                                                             const IntervalPartition &kernel_partition,
                                                                             const IndexPartition &colors) const = 0;
+    // accumulate: dst += A src instead of dst = A src (matrices that overwrite, i.e. CSR: a further block on the same rows)
     virtual void matvec(PartitionedVector<T> &dst, const PartitionedVector<T> &src, const IntervalPartition &kernel_partition,
                         const IntervalPartition &ghost_partition, const MatvecFusion<T> *fusion = nullptr,
-                        const MatvecGate *gate = nullptr) const = 0;
+                        const MatvecGate *gate = nullptr, bool accumulate = false) const = 0;
     // dst += A^T src (CSRRmatvecTask / COORmatvecTask, reserved but unimplemented in the reference): dst lives on the DOMAIN
     // space, src on the range space; accumulates.  dst must hold every column the local pieces reference.
     virtual void rmatvec(PartitionedVector<T> &dst, const PartitionedVector<T> &src, const IntervalPartition &kernel_partition,
@@ -98,8 +99,8 @@ struct SpmvKernels;
 template <>
 struct SpmvKernels<double> {
     static int csr(lsk_ctx *c, cudaStream_t s, int64_t rows, int64_t nnz, const double *e, const int64_t *col,
-                   const lsk_rect *rp, int64_t kb, const double *x, double *y, const double *w, double *o, double *oyy) {
-        return lsk_csr_spmv_f64(c, s, rows, nnz, e, col, rp, kb, x, y, w, o, oyy, LSK_SPMV_AUTO);
+                   const lsk_rect *rp, int64_t kb, const double *x, double *y, const double *w, double *o, double *oyy, bool acc = false) {
+        return lsk_csr_spmv_f64(c, s, rows, nnz, e, col, rp, kb, x, y, w, o, oyy, LSK_SPMV_AUTO | (acc ? LSK_SPMV_ACCUMULATE : 0));
     }
     static int coo(lsk_ctx *c, cudaStream_t s, int64_t nnz, const double *e, const int64_t *row, const int64_t *col,
                    const double *x, double *y, int64_t rl, int64_t rh, int64_t cl, int64_t ch) {
@@ -109,8 +110,8 @@ struct SpmvKernels<double> {
 template <>
 struct SpmvKernels<float> {
     static int csr(lsk_ctx *c, cudaStream_t s, int64_t rows, int64_t nnz, const float *e, const int64_t *col,
-                   const lsk_rect *rp, int64_t kb, const float *x, float *y, const float *w, float *o, float *oyy) {
-        return lsk_csr_spmv_f32(c, s, rows, nnz, e, col, rp, kb, x, y, w, o, oyy, LSK_SPMV_AUTO);
+                   const lsk_rect *rp, int64_t kb, const float *x, float *y, const float *w, float *o, float *oyy, bool acc = false) {
+        return lsk_csr_spmv_f32(c, s, rows, nnz, e, col, rp, kb, x, y, w, o, oyy, LSK_SPMV_AUTO | (acc ? LSK_SPMV_ACCUMULATE : 0));
     }
     static int coo(lsk_ctx *c, cudaStream_t s, int64_t nnz, const float *e, const int64_t *row, const int64_t *col,
                    const float *x, float *y, int64_t rl, int64_t rh, int64_t cl, int64_t ch) {
@@ -251,7 +252,8 @@ public:
     // CSRMatrix::matvec (src/CSRMatrix.cpp:158-214): one CSRMatvecTask per piece of dst with regions
     // {dst piece, kernel piece, rowptr piece, ghost piece of src}
     void matvec(PartitionedVector<T> &dst, const PartitionedVector<T> &src, const IntervalPartition &kp,
-                const IntervalPartition &gp, const MatvecFusion<T> *fusion = nullptr, const MatvecGate *gate = nullptr) const override {
+                const IntervalPartition &gp, const MatvecFusion<T> *fusion = nullptr, const MatvecGate *gate = nullptr,
+                bool accumulate = false) const override {
         const IndexPartition &p = dst.partition();
         for (int c = p.first_color; c < p.end_color; ++c) {
             const int64_t r_lo = p.lo[(size_t) c], nrow = p.piece_size(c);
@@ -267,7 +269,7 @@ public:
             T *ow = w ? fusion->yw[(size_t) c] : nullptr;
             T *oyy = (fusion && !fusion->yy.empty()) ? fusion->yy[(size_t) c] : nullptr;
             if constexpr (std::is_same<T, double>::value) {
-                if (gate != nullptr) {  // the halo of src is still in flight: the kernel waits per row block
+                if (gate != nullptr && !accumulate) {  // the halo of src is still in flight: the kernel waits per row block
                     rt->enqueue("csr matvec (gated)", [&] {
                         return lsk_csr_spmv_gated_f64(rt->ctx(), rt->stream(), nrow, nk, e, cc, rp, k_lo, x, y, w, ow, oyy, LSK_SPMV_AUTO,
                                                       gate->blocks, gate->moves, gate->nmoves);
@@ -276,7 +278,7 @@ public:
                 }
             }
             rt->enqueue("csr matvec", [&] {
-                return SpmvKernels<T>::csr(rt->ctx(), rt->stream(), nrow, nk > 0 ? nk : 0, e, cc, rp, nk > 0 ? k_lo : 0, x, y, w, ow, oyy);
+                return SpmvKernels<T>::csr(rt->ctx(), rt->stream(), nrow, nk > 0 ? nk : 0, e, cc, rp, nk > 0 ? k_lo : 0, x, y, w, ow, oyy, accumulate);
             });
         }
     }
@@ -372,7 +374,7 @@ public:
 
     // COOMatrix::matvec (src/COOMatrix.cpp:144-191): accumulates into dst (beta = 1)
     void matvec(PartitionedVector<T> &dst, const PartitionedVector<T> &src, const IntervalPartition &kp,
-                const IntervalPartition &gp, const MatvecFusion<T> * = nullptr, const MatvecGate * = nullptr) const override {
+                const IntervalPartition &gp, const MatvecFusion<T> * = nullptr, const MatvecGate * = nullptr, bool = false) const override {
         const IndexPartition &p = dst.partition();
         for (int c = p.first_color; c < p.end_color; ++c) {
             const int64_t k_lo = kp.lo[(size_t) c], nk = kp.hi[(size_t) c] - k_lo + 1;

@@ -636,7 +636,10 @@ private:
             if (!overwritten[s]) get_vector(dst_idx, s).zero_fill();
         std::set<size_t> exchanged;
         std::vector<T *> parts_yw, parts_yy;
+        std::vector<bool> csr_written(S, false);  // a range space's FIRST overwriting block overwrites, further ones accumulate
         auto run = [&](const Block &b) {
+            const bool accumulate = b.matrix->overwrites_output() && csr_written[b.range_index];
+            if (b.matrix->overwrites_output()) csr_written[b.range_index] = true;
             PartitionedVector<T> &src = get_vector(src_idx, b.domain_index);
             if (!src_fresh && exchanged.insert(b.domain_index).second) exchange_halo(b, src);
             if (yw) {
@@ -657,7 +660,8 @@ private:
                 }
                 b.matrix->matvec(get_vector(dst_idx, b.range_index), src, b.kernel_partition, b.ghost_partition, &fz, gated ? &gate : nullptr);
             } else {
-                b.matrix->matvec(get_vector(dst_idx, b.range_index), src, b.kernel_partition, b.ghost_partition, nullptr, gated ? &gate : nullptr);
+                b.matrix->matvec(get_vector(dst_idx, b.range_index), src, b.kernel_partition, b.ghost_partition, nullptr, gated ? &gate : nullptr,
+                                 accumulate);
             }
         };
         // overwriting (CSR) blocks first, accumulating (COO) blocks after

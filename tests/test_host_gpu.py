@@ -525,3 +525,82 @@ def test_gmres_real_update_reduces_the_true_residual(rt, oracle, case, restart, 
         assert res[-1] < 0.9 * res[-2] or res[-1] <= 1e-9 * res[0]
         assert abs(s.residual_norm[-1] - res[-1]) <= 1e-7 * res[0]
     assert res[-1] <= 0.1 * res[0]  # three restart cycles
+
+
+# ---- several operators on one system, off-diagonal blocks ---------------------------------------
+@pytest.mark.parametrize("pieces", [1, 3])
+def test_multi_operator_planner_with_off_diagonal_blocks(rt, oracle, pieces):
+    """A 2 x 2 block system [[A, B], [C, A + D]] on two index spaces, registered block by block the way the reference's
+    SquarePlanner takes (matrix, domain_index, range_index) (src/SquarePlanner.hpp:209-235): two CSR blocks and one COO block
+    land on the same range space, so the first overwrites and the others accumulate.  planner.matvec is bit-exact against the
+    oracle's planner (which zero-fills and accumulates, like the reference's CPU bodies), and BiCGStab solves the coupled system."""
+    from legionsolvers_b200 import solvers as S
+
+    off, val = oracle.benchmark_stencil(3)
+    A = oracle.stencil_csr((12, 10, 8), off, val)
+    n = A.n_rows
+    rng = np.random.default_rng(21)
+
+    def random_csr(density_per_row, scale):
+        lens = rng.integers(0, density_per_row + 1, n)
+        starts = np.concatenate([[0], np.cumsum(lens)[:-1]])
+        col = np.concatenate([np.sort(rng.choice(n, size=l, replace=False)) for l in lens] + [np.zeros(0, dtype=np.int64)]).astype(np.int64)
+        rp = np.empty(n, dtype=oracle.RECT_DTYPE)
+        rp["lo"], rp["hi"] = starts, starts + lens - 1
+        return oracle.Matrix(n, n, scale * rng.standard_normal(col.size), col, rowptr=rp)
+
+    B, Cm, D = random_csr(3, 0.05), random_csr(2, 0.05), random_csr(2, 0.05)
+    blocks = [(A, 0, 0), (B, 1, 0), (Cm.to_coo(), 0, 1), (A, 1, 1), (D, 1, 1)]  # (matrix, domain space, range space)
+    x = [rng.standard_normal(n), rng.standard_normal(n)]
+    pl = S.SquarePlanner(rt)
+    opl = oracle.Planner([n, n], [pieces, pieces])
+    keep = []
+    for sidx in range(2):
+        v = S.PartitionedVector(rt, f"sol{sidx}", n, pieces)
+        v.zero_fill()
+        pl.add_sol_vector(v)
+        keep.append(v)
+    for sidx in range(2):
+        v = S.PartitionedVector(rt, f"rhs{sidx}", n, pieces)
+        v.from_numpy(x[sidx])
+        pl.add_rhs_vector(v)
+        opl.vector(1, sidx)[:] = x[sidx]
+        keep.append(v)
+    for m, d, r in blocks:
+        gm = (S.CSRMatrix.from_host(rt, n, n, m.entry, m.col, m.rowptr) if m.is_csr else S.COOMatrix.from_host(rt, n, n, m.entry, m.row, m.col))
+        keep.append(gm)
+        pl.add_row_partitioned_matrix(gm, d, r)
+        opl.add_matrix(m, d, r)
+    pl.allocate_workspace(1)
+    opl.allocate_workspace(1)
+    pl.matvec(2, 1)
+    opl.matvec(2, 1)
+    for sidx in range(2):
+        got, want = pl.vector_to_numpy(2, sidx, n), opl.vector(2, sidx)
+        if sidx == 0:
+            np.testing.assert_array_equal(got, want)  # CSR + CSR on one range space: products added one by one, as the CPU bodies do
+        else:
+            np.testing.assert_allclose(got, want, rtol=0, atol=1e-12 * np.max(np.abs(want)))  # a COO block (atomics) takes part
+    # and the coupled system is solvable through the same planner
+    pl2, opl2 = S.SquarePlanner(rt), None
+    for sidx in range(2):
+        v = S.PartitionedVector(rt, f"s{sidx}", n, pieces)
+        v.zero_fill()
+        pl2.add_sol_vector(v)
+        keep.append(v)
+    for sidx in range(2):
+        v = S.PartitionedVector(rt, f"b{sidx}", n, pieces)
+        v.from_numpy(x[sidx])
+        pl2.add_rhs_vector(v)
+        keep.append(v)
+    for gm, (m, d, r) in zip([k for k in keep if isinstance(k, (S.CSRMatrix, S.COOMatrix))], blocks):
+        pl2.add_row_partitioned_matrix(gm, d, r)
+    sv = S.BiCGStabSolver(pl2)
+    for _ in range(45):  # (scipy's BiCGStab needs 37 iterations for 1e-8 on this system)
+        sv.step()
+    import scipy.sparse as sp
+
+    full = sp.bmat([[A.to_scipy(), B.to_scipy()], [Cm.to_scipy(), A.to_scipy() + D.to_scipy()]]).tocsr()
+    sol = np.concatenate([pl2.vector_to_numpy(0, 0, n), pl2.vector_to_numpy(0, 1, n)])
+    rhs = np.concatenate(x)
+    assert np.linalg.norm(rhs - full @ sol) <= 1e-6 * np.linalg.norm(rhs)
