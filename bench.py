@@ -596,6 +596,15 @@ def run_ours(args):
         d2h_stream = torch.cuda.Stream()
         cs = copy_stream.cuda_stream
 
+        e2e_trace = os.environ.get("LSK_E2E_TRACE") == "1"  # developer switch: device-side timeline of the e2e loop
+        marks = []
+
+        def mark(stream_, what, k):
+            if e2e_trace:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(stream_)
+                marks.append((what, k, ev, time.perf_counter()))
+
         def e2e_run(nsteps):
             ev_h2d, ev_reset, ev_solved, ev_d2h = (torch.cuda.Event() for _ in range(4))
             copy_stream.wait_stream(tstream)
@@ -606,20 +615,25 @@ def run_ours(args):
             ev_d2h.record(d2h_stream)
             for k in range(nsteps):
                 tstream.wait_event(ev_h2d)                # this step's right-hand side has landed
+                mark(tstream, "reset_begin", k)
                 rt.begin_trace(TRACE_RESET)
                 pl.zero_fill(0)
                 sv.reset()                                # the last readers of RHS
                 rt.end_trace(TRACE_RESET)
                 ev_reset.record(tstream)
+                mark(tstream, "iters_begin", k)
                 if k + 1 < nsteps:                        # H2D of the NEXT step's right-hand side, under this step's iterations
                     copy_stream.wait_event(ev_reset)
+                    mark(copy_stream, "h2d_begin", k + 1)
                     for s in range(spaces):
                         pl.vector_from_async(1, s, b_host[s].data_ptr(), cs)
+                    mark(copy_stream, "h2d_end", k + 1)
                     ev_h2d.record(copy_stream)
                 rt.begin_trace(TRACE_ITERS)
                 for _ in range(ipt):
                     sv.step()
                 rt.end_trace(TRACE_ITERS)
+                mark(tstream, "iters_end", k)
                 tstream.wait_event(ev_d2h)                # the staging buffers' previous content is on the host
                 for s in range(spaces):                   # solution + history -> staging buffers (device to device)
                     pl.vector_to_async(0, s, x_stage[s].data_ptr() - 8 * own_lo, stream)
@@ -627,10 +641,12 @@ def run_ours(args):
                     sv.history_copy_async(h, hist_stage.data_ptr() + 8 * h * hist_len, hist_len, stream)
                 ev_solved.record(tstream)
                 d2h_stream.wait_event(ev_solved)
+                mark(d2h_stream, "d2h_begin", k)
                 with torch.cuda.stream(d2h_stream):       # D2H under the next step's iterations
                     for s in range(spaces):
                         x_host[s][own_lo:own_lo + n_local].copy_(x_stage[s], non_blocking=True)
                     hist_host[k].copy_(hist_stage, non_blocking=True)
+                mark(d2h_stream, "d2h_end", k)
                 ev_d2h.record(d2h_stream)
             copy_stream.synchronize()
             d2h_stream.synchronize()
@@ -638,9 +654,14 @@ def run_ours(args):
 
         e2e_run(2)
         barrier()
+        marks.clear()
         t0 = time.perf_counter()
         e2e_run(e2e_steps)
         e2e_s = max_over_ranks(time.perf_counter() - t0)
+        if e2e_trace and rank == 0 and marks:
+            base_ev, base_t = marks[0][2], marks[0][3]
+            for what, k, ev, th in marks:
+                print(f"e2e-trace step {k:2d} {what:12s} device {base_ev.elapsed_time(ev):9.3f} ms   host-enqueue {1e3 * (th - base_t):9.3f} ms", file=sys.stderr)
         e2e_value = e2e_steps * ipt / e2e_s
         e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n_local * spaces,
                "d2h_bytes_per_step": 8 * n_local * spaces + 8 * nh * hist_len, "steps": e2e_steps,

@@ -366,6 +366,17 @@ int lsk_halo_exchange_f64(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, co
  * its last CTA: the value it writes is already the global one.  Every rank must then launch the same
  * reducing kernels in the same order.  NULL switches back to rank-local reductions. */
 int lsk_ctx_set_peers(lsk_ctx *ctx, const lsk_peers *peers);
+/* DEFERRED form of the fused all-reduce, for a reduction whose only consumer is the next kernel on the stream (the p.q and
+ * r.r of a fused CG step).  lsk_ctx_defer_next_allreduce(ctx) applies to the NEXT reducing launch through ctx, if it is
+ * lsk_csr_spmv_f64 / lsk_csr_spmv_gated_f64 with dot_out only, or lsk_cg_update_f64: its last CTA only SENDS the rank's sum to
+ * the peers (the value it stores to the output slot is the rank-local one) and the kernel ends; the cross-rank sum is formed
+ * by the next lsk_cg_update_f64 whose `pq`, or lsk_cg_direction_f64 whose `rr_new`, is that same slot -- every CTA of it polls
+ * the packets in its own window at its start, and the global value is stored back to the slot.  The NVLink flight and the
+ * wait for the slowest rank then overlap the kernel boundary.  Any other entry point that reads device scalars, called in
+ * between, first finishes the reduction with a one-warp kernel (so does lsk_ctx_settle), i.e. a wrong guess costs a launch,
+ * never a wrong number.  No-op without lsk_ctx_set_peers. */
+int lsk_ctx_defer_next_allreduce(lsk_ctx *ctx);
+int lsk_ctx_settle(lsk_ctx *ctx, lsk_stream s);
 /* XpayTask fused with the halo push of its result: y = fma(alpha, y, x), and the elements of y that lie
  * in moves[i].src[0..n) (sub-ranges of y) are also stored to moves[i].dst in the neighbour's memory;
  * when the kernel completes every rank's ghosts of y are current.  There is NO ready-handshake: the

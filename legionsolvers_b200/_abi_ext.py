@@ -43,6 +43,8 @@ def declare(L) -> None:
     L.lsk_halo_exchange_f64.argtypes = [vp, vp, vp, vp, ci]
     L.lsk_comm_error.argtypes = [vp, vp, vp, vp]
     L.lsk_ctx_set_peers.argtypes = [vp, vp]
+    L.lsk_ctx_defer_next_allreduce.argtypes = [vp]
+    L.lsk_ctx_settle.argtypes = [vp, vp]
     L.lsk_xpay_halo_f64.argtypes = [vp, vp, i64, ci, vp, vp, vp, vp, vp, vp, vp, ci]
     L.lsk_halo_plan.argtypes = [ci, ci, vp, vp, C.POINTER(ci)]
     L.lsk_last_error.restype = C.c_char_p

@@ -22,7 +22,7 @@ namespace lsk {
 template <typename F>
 __global__ void __launch_bounds__(kBlock)
 stream_kernel(F f, int64_t n, int64_t head, int64_t npacks, double *partials, unsigned int *ticket,
-              const lsk_peers *peers) {
+              const lsk_peers *peers, bool defer) {
     using T = typename F::T;
     constexpr int NRED = F::NRED;
     constexpr int EPP = PackOf<T>::N;
@@ -43,7 +43,7 @@ stream_kernel(F f, int64_t n, int64_t head, int64_t npacks, double *partials, un
     if constexpr (NRED > 0) {
         T *out[NRED];
         f.outs(out);
-        grid_reduce_finish<NRED, T>(acc, partials, ticket, out, peers);
+        grid_reduce_finish<NRED, T>(acc, partials, ticket, out, peers, nullptr, defer);
     }
 }
 
@@ -96,11 +96,16 @@ static int tma_stream_configure(lsk_ctx *ctx) {
     });
 }
 
+// defer: the reduction's cross-rank sum is left to the consumer kernel (grid-stride form only; see lsk_cg_update_f64)
 template <typename F>
-static int launch_stream(lsk_ctx *ctx, lsk_stream s, F f, int64_t n, Span sp) {
+static int launch_stream(lsk_ctx *ctx, lsk_stream s, F f, int64_t n, Span sp, bool defer = false, bool settled = false) {
     if (n == 0 && F::NRED == 0) return 0;
+    if (!settled) {  // a deferred reduction whose designated consumer is not this launch is finished first
+        const int rc = settle_pending(ctx, (cudaStream_t) s);
+        if (rc != 0) return rc;
+    }
     if constexpr (HasTmaForm<F>::value) {
-        if (sp.npacks >= tma_stream_min_packs() && tma_stream_configure<F>(ctx) == 0) {
+        if (!defer && sp.npacks >= tma_stream_min_packs() && tma_stream_configure<F>(ctx) == 0) {
             const int64_t nchunks = (sp.npacks * 4 + VecChunk<F::NIN>::value - 1) / VecChunk<F::NIN>::value;
             const int64_t cap = (int64_t) ctx->sm_count * 3;
             const int grid = (int) (nchunks < cap ? nchunks : cap);
@@ -111,10 +116,10 @@ static int launch_stream(lsk_ctx *ctx, lsk_stream s, F f, int64_t n, Span sp) {
     }
     const int64_t items = sp.npacks > 0 ? sp.npacks : n;
     const int grid = stream_grid(ctx, items > 0 ? items : 1, 8);
-    RedScratch rs = {nullptr, nullptr, nullptr, nullptr};
+    RedScratch rs = {nullptr, nullptr, nullptr, nullptr, 0};
     if (F::NRED > 0) rs = next_scratch(ctx);
     stream_kernel<F><<<grid, kBlock, 0, (cudaStream_t) s>>>(f, n, sp.head, sp.npacks, rs.partials, rs.ticket,
-                                                            F::NRED > 0 ? ctx->d_peers : nullptr);
+                                                            F::NRED > 0 ? ctx->d_peers : nullptr, defer);
     return after_launch(ctx);
 }
 
@@ -224,16 +229,24 @@ __device__ __forceinline__ void for_each_edge(int64_t n, int64_t head, int64_t n
 
 // src/CGSolver.hpp:50-52: x = fma(rr/pq, p, x); r = fma((-1*rr)/pq, q, r); rr_new = r.r
 __global__ void __launch_bounds__(kBlock, 3)
-cg_update_tma_kernel(const double *rr_old, const double *pq, const double *neg_one, const double *p, const double *q, double *x,
-                     double *r, double *rr_new, int64_t n, int64_t head, int64_t npacks, RedScratch rs) {
+cg_update_tma_kernel(const double *rr_old, double *pq, const double *neg_one, const double *p, const double *q, double *x,
+                     double *r, double *rr_new, int64_t n, int64_t head, int64_t npacks, RedScratch rs, bool resolve) {
     extern __shared__ __align__(128) unsigned char s_dyn[];
     __shared__ __align__(8) VecKernelShared sh;
     pdl_launch_dependents();
     VecRing ring;
     vec_ring_init(ring, s_dyn, sh);
     pdl_wait();  // everything below reads what the mat-vec before this kernel produced (q, p.q)
-    const double a1 = div_rn(*rr_old, *pq);
-    const double a2 = div_rn(mul_rn(*neg_one, *rr_old), *pq);
+    __shared__ double s_pq[kMaxRed];
+    double pqv;
+    if (resolve) {  // the mat-vec only SENT its rank's p.q: sum the ranks' packets (and leave the global value in the slot)
+        allreduce_resolve(*rs.peers, s_pq, 1, pq);
+        pqv = s_pq[0];
+    } else {
+        pqv = *pq;
+    }
+    const double a1 = div_rn(*rr_old, pqv);
+    const double a2 = div_rn(mul_rn(*neg_one, *rr_old), pqv);
     double racc = 0.0;
     const double *const in[4] = {p, q, x, r};
     vec_stream<4>(ring, in, head, npacks * 4, rs.work, 0, [](int64_t, int) {}, [&](int64_t i, const double (&v)[4][2]) {
@@ -252,15 +265,16 @@ cg_update_tma_kernel(const double *rr_old, const double *pq, const double *neg_o
     });
     const double acc[1] = {racc};
     double *const out[1] = {rr_new};
-    grid_reduce_finish<1, double>(acc, rs.partials, rs.ticket, out, rs.peers, rs.work);
+    grid_reduce_finish<1, double>(acc, rs.partials, rs.ticket, out, rs.peers, rs.work, rs.defer != 0);
 }
 
 // src/CGSolver.hpp:53-54: residual_norm_squared.push_back(rr_new); p = fma(rr_new/rr_cur, p, r) -- plus, on several
 // ranks, p's boundary stored into the neighbours' ghost regions and the exchange epoch closed (as xpay_halo_kernel),
 // and rr_cur <- rr_new for the next step.  Everything after the element loop is done by the last CTA to finish.
 __global__ void __launch_bounds__(kBlock, 3)
-cg_direction_tma_kernel(double *rr_cur, const double *rr_new, const double *r, double *p, int64_t n, int64_t head, int64_t npacks,
-                        HaloSpec h, RedScratch rs, double *hist, long long hist_cap, long long *hist_count) {
+cg_direction_tma_kernel(double *rr_cur, double *rr_new, const double *r, double *p, int64_t n, int64_t head, int64_t npacks,
+                        HaloSpec h, RedScratch rs, double *hist, long long hist_cap, long long *hist_count, bool resolve,
+                        const lsk_peers *resolve_peers) {
     extern __shared__ __align__(128) unsigned char s_dyn[];
     __shared__ __align__(8) VecKernelShared sh;
     __shared__ bool s_last;
@@ -270,7 +284,10 @@ cg_direction_tma_kernel(double *rr_cur, const double *rr_new, const double *r, d
     pdl_wait();  // rr_new and r come from the update kernel before this one
     const lsk_peers *peers = rs.peers;
     const bool multi = (peers != nullptr && h.nmoves > 0);
-    const double beta = div_rn(*rr_new, *rr_cur);  // xpay(P, rr_new, rr_cur, R): alpha = f0 / f1
+    __shared__ double s_rr[kMaxRed];
+    if (resolve) allreduce_resolve(*resolve_peers, s_rr, 1, rr_new);  // the update kernel only SENT its rank's r.r
+    const double rr_new_v = resolve ? s_rr[0] : *rr_new;
+    const double beta = div_rn(rr_new_v, *rr_cur);  // xpay(P, rr_new, rr_cur, R): alpha = f0 / f1
     bool remote = false, chunk_halo = false;
     const double *const in[2] = {p, r};
     const int64_t rot = multi ? halo_first_chunk(h, head, kVecStageBytes / 16) : 0;
@@ -297,7 +314,7 @@ cg_direction_tma_kernel(double *rr_cur, const double *rr_new, const double *r, d
     if (!s_last) return;
     if (multi) halo_publish(peers, h.m, h.nmoves, h.open == 0);  // publish; wait for the neighbours' unless the exchange stays open
     if (threadIdx.x == 0) {
-        const double v = *rr_new;
+        const double v = rr_new_v;
         if (hist != nullptr) {
             const long long c = *hist_count;
             hist[c % hist_cap] = v;
@@ -489,11 +506,20 @@ struct Dot2F {  // r.u and u.u in one pass (src/BiCGStabSolver.hpp:75-76)
 struct CgUpdateF {  // src/CGSolver.hpp:50-52: two axpys and the r.r dot in one pass
     using T = double;
     static constexpr int NRED = 1;
-    const double *rr_old, *pq, *neg_one; const double *p, *q; double *x, *r; double *rr_new;
+    const double *rr_old; double *pq; const double *neg_one; const double *p, *q; double *x, *r; double *rr_new;
+    const lsk_peers *resolve_peers;  // non-null: p.q was only SENT by the mat-vec; sum the ranks' packets first
     double a1, a2;
     __device__ void init() {
-        a1 = div_rn(*rr_old, *pq);                      // axpy(SOL, rr_old, p_norm, P): f0/f1
-        a2 = div_rn(mul_rn(*neg_one, *rr_old), *pq);    // axpy(R, -1, rr_old, p_norm, Q): (f0*f1)/f2
+        __shared__ double s_pq[kMaxRed];
+        double pqv;
+        if (resolve_peers != nullptr) {
+            allreduce_resolve(*resolve_peers, s_pq, 1, pq);
+            pqv = s_pq[0];
+        } else {
+            pqv = *pq;
+        }
+        a1 = div_rn(*rr_old, pqv);                      // axpy(SOL, rr_old, p_norm, P): f0/f1
+        a2 = div_rn(mul_rn(*neg_one, *rr_old), pqv);    // axpy(R, -1, rr_old, p_norm, Q): (f0*f1)/f2
     }
     __device__ void outs(double **o) { o[0] = rr_new; }
     __device__ void scalar(int64_t i, double *acc) {
@@ -664,6 +690,10 @@ static int scalar_op(lsk_ctx *ctx, lsk_stream s, int op, const T *a, const T *b,
     const bool binary = (op >= LSK_OP_ADD && op <= LSK_OP_DIV);
     if (op != LSK_OP_DUMMY && !a) return LSK_E_INVALID;
     if (binary && !b) return LSK_E_INVALID;
+    {
+        const int rc = settle_pending(ctx, (cudaStream_t) s);
+        if (rc != 0) return rc;
+    }
     scalar_op_kernel<T><<<1, 1, 0, (cudaStream_t) s>>>(op, a, b, out);
     return after_launch(ctx);
 }
@@ -740,6 +770,10 @@ int lsk_xpay_halo_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, int nt, const doubl
     if (!ctx || n < 0 || !alpha_ok(al) || (n > 0 && (!x || !y)) || nmoves < 0 || nmoves > 4 || (nmoves > 0 && !moves))
         return LSK_E_INVALID;
     if (!ctx->d_peers) return LSK_E_INVALID;  // needs lsk_ctx_set_peers
+    {
+        const int rc = settle_pending(ctx, (cudaStream_t) s);
+        if (rc != 0) return rc;
+    }
     HaloSpec h;
     h.nmoves = nmoves;
     h.open = 0;
@@ -804,6 +838,10 @@ int lsk_scalar_op_f32(lsk_ctx *ctx, lsk_stream s, int op, const float *a, const 
 int lsk_scalar_append_f64(lsk_ctx *ctx, lsk_stream s, const double *value, double *hist, int64_t capacity,
                           int64_t *count, double *also) {
     if (!ctx || !value || !hist || !count || capacity <= 0) return LSK_E_INVALID;
+    {
+        const int rc = settle_pending(ctx, (cudaStream_t) s);
+        if (rc != 0) return rc;
+    }
     scalar_append_kernel<<<1, 1, 0, (cudaStream_t) s>>>(value, hist, capacity, reinterpret_cast<long long *>(count), also);
     return after_launch(ctx);
 }
@@ -811,6 +849,16 @@ int lsk_scalar_append_f64(lsk_ctx *ctx, lsk_stream s, const double *value, doubl
 int lsk_cg_update_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, const double *rr_old, const double *pq,
                       const double *p, const double *q, double *x, double *r, double *rr_new) {
     if (!ctx || n < 0 || !rr_old || !pq || !rr_new || (n > 0 && (!p || !q || !x || !r))) return LSK_E_INVALID;
+    // deferred all-reduces (lsk_ctx_defer_next_allreduce): this kernel is the designated consumer of a p.q still in flight,
+    // and may itself leave the cross-rank sum of r.r to the next lsk_cg_direction_f64
+    const bool resolve = ctx->pending_slot != nullptr && ctx->pending_slot == pq && ctx->d_peers != nullptr;
+    if (resolve) ctx->pending_slot = nullptr;
+    if (!resolve) {
+        const int rc = settle_pending(ctx, (cudaStream_t) s);
+        if (rc != 0) return rc;
+    }
+    const bool defer = take_defer(ctx);
+    double *pq_rw = const_cast<double *>(pq);  // the global value is stored back into the slot by the resolving kernel
     const Span sp = plan_span<double>(n, {p, q, x, r});
     // Streamed form for passes that do not fit the L2 (measured: 805 MB pass 6.3 -> 7.0 TB/s); for an L2-resident
     // 2 M-row slab the grid-stride kernel with 2048 threads per SM is the faster one (16 vs 14 us).
@@ -818,15 +866,20 @@ int lsk_cg_update_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, const double *rr_ol
         const int64_t nchunks = (sp.npacks * 4 + 511) / 512;
         const int64_t cap = (int64_t) ctx->sm_count * 3;
         const int grid = (int) (nchunks < cap ? nchunks : cap);
-        const RedScratch rs = next_scratch(ctx);
-        LSK_RETURN_IF_CUDA(launch_pdl(kPdlUpdate, cg_update_tma_kernel, grid, kBlock, (size_t) kVecStages * kVecStageBytes, (cudaStream_t) s, rr_old, pq,
-                                      (const double *) (ctx->consts + 1), p, q, x, r, rr_new, n, sp.head, sp.npacks, rs));
+        RedScratch rs = next_scratch(ctx);
+        if (defer) rs.defer = 1;
+        if (defer) ctx->pending_slot = rr_new;
+        LSK_RETURN_IF_CUDA(launch_pdl(kPdlUpdate, cg_update_tma_kernel, grid, kBlock, (size_t) kVecStages * kVecStageBytes, (cudaStream_t) s, rr_old, pq_rw,
+                                      (const double *) (ctx->consts + 1), p, q, x, r, rr_new, n, sp.head, sp.npacks, rs, resolve));
         return after_launch(ctx);
     }
     CgUpdateF f;
-    f.rr_old = rr_old; f.pq = pq; f.neg_one = ctx->consts + 1;
+    f.rr_old = rr_old; f.pq = pq_rw; f.neg_one = ctx->consts + 1;
     f.p = p; f.q = q; f.x = x; f.r = r; f.rr_new = rr_new;
-    return launch_stream(ctx, s, f, n, sp);
+    f.resolve_peers = resolve ? ctx->d_peers : nullptr;
+    const int rc = launch_stream(ctx, s, f, n, sp, defer, true);
+    if (rc == 0 && defer) ctx->pending_slot = rr_new;
+    return rc;
 }
 
 int lsk_cg_direction_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, double *rr_cur, const double *rr_new, const double *r, double *p,
@@ -838,6 +891,14 @@ int lsk_cg_direction_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, double *rr_cur, 
     if (nmoves > 0 && !ctx->d_peers) return LSK_E_INVALID;  // needs lsk_ctx_set_peers
     const Span sp = plan_span<double>(n, {r, p});
     if (sp.npacks < 1 || vec_kernels_configure(ctx) != 0) return LSK_E_INVALID;  // callers check lsk_cg_direction_supported
+    // the designated consumer of an r.r whose cross-rank sum is still in flight (lsk_ctx_defer_next_allreduce)
+    const bool resolve = ctx->pending_slot != nullptr && ctx->pending_slot == rr_new && ctx->d_peers != nullptr;
+    if (resolve) {
+        ctx->pending_slot = nullptr;
+    } else {
+        const int rc = settle_pending(ctx, (cudaStream_t) s);
+        if (rc != 0) return rc;
+    }
     HaloSpec h;
     h.nmoves = nmoves;
     h.open = halo_open ? 1 : 0;
@@ -858,9 +919,9 @@ int lsk_cg_direction_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, double *rr_cur, 
     const int grid = (int) (nchunks < cap ? nchunks : cap);
     RedScratch rs = next_scratch(ctx);
     if (nmoves == 0) rs.peers = nullptr;
-    LSK_RETURN_IF_CUDA(launch_pdl(kPdlDirection, cg_direction_tma_kernel, grid, kBlock, (size_t) kVecStages * kVecStageBytes, (cudaStream_t) s, rr_cur, rr_new,
-                                  r, p, n, sp.head, sp.npacks, h, rs, history, (long long) history_capacity,
-                                  reinterpret_cast<long long *>(history_count)));
+    LSK_RETURN_IF_CUDA(launch_pdl(kPdlDirection, cg_direction_tma_kernel, grid, kBlock, (size_t) kVecStages * kVecStageBytes, (cudaStream_t) s, rr_cur,
+                                  const_cast<double *>(rr_new), r, p, n, sp.head, sp.npacks, h, rs, history, (long long) history_capacity,
+                                  reinterpret_cast<long long *>(history_count), resolve, (const lsk_peers *) ctx->d_peers));
     return after_launch(ctx);
 }
 

@@ -19,6 +19,21 @@ __global__ void __launch_bounds__(32) allreduce_kernel(lsk_peers peers, double *
         for (int j = 0; j < count; ++j) slots[j] = v[j];
 }
 
+// finishes a deferred all-reduce whose designated consumer did not come: one warp polls, sums, stores the slot
+__global__ void __launch_bounds__(32) allreduce_resolve_kernel(const lsk_peers *peers, double *slot) {
+    __shared__ double s_v[kMaxRed];
+    allreduce_resolve(*peers, s_v, 1, slot);
+}
+
+int settle_pending(lsk_ctx *ctx, cudaStream_t st) {
+    if (ctx->pending_slot == nullptr) return 0;
+    double *slot = const_cast<double *>(static_cast<const double *>(ctx->pending_slot));
+    ctx->pending_slot = nullptr;
+    if (ctx->d_peers == nullptr) return 0;
+    allreduce_resolve_kernel<<<1, 32, 0, st>>>(ctx->d_peers, slot);
+    return after_launch(ctx);
+}
+
 // ---- halo exchange -------------------------------------------------------------------------------------
 struct HaloArgs {
     int nmoves;

@@ -33,6 +33,8 @@ struct lsk_ctx {
     unsigned long long launches;
     lsk_peers *d_peers;        // device copy of the peer windows; non-null = reducing kernels all-reduce in their tail
     lsk_peers h_peers;         // host copy (valid while d_peers is non-null): window addresses for the gated mat-vec
+    int defer_next;            // lsk_ctx_defer_next_allreduce: the next fused reduction sends without waiting
+    const void *pending_slot;  // device scalar whose cross-rank sum is still in flight (resolved by its consumer)
     unsigned long long *work;  // [kScratchSets] dynamic work counters of the TMA-streamed vector kernels, zero between launches
     unsigned long long configured;  // one bit per kernel family whose dynamic shared-memory opt-in was done on THIS device
                                     // (function attributes are per device: a process may hold contexts on several GPUs)
@@ -47,6 +49,7 @@ struct RedScratch {
     unsigned int *ticket;
     const lsk_peers *peers;  // non-null: finish the reduction with a cross-rank sum
     unsigned long long *work;  // dynamic work counter (zero at launch; the last CTA resets it)
+    int defer;                 // with peers: send the rank sums to the peers and return; the consumer kernel sums them up
 };
 
 inline RedScratch next_scratch(lsk_ctx *ctx) {
@@ -57,6 +60,8 @@ inline RedScratch next_scratch(lsk_ctx *ctx) {
     r.ticket = ctx->tickets + set;
     r.peers = ctx->d_peers;
     r.work = ctx->work + set;
+    r.defer = 0;
+    ctx->defer_next = 0;  // a request nobody claimed (take_defer) does not carry over to a later launch
     return r;
 }
 
@@ -292,6 +297,76 @@ __device__ __forceinline__ void allreduce_warp(const lsk_peers &peers, double *v
     __syncwarp();
 }
 
+// The same all-reduce SPLIT in two, for a reduction whose only consumer is the next kernel on the stream (the p.q and
+// r.r of a fused CG step): the producing kernel's last CTA only SENDS (allreduce_send: packets to every peer, epoch
+// advanced, no polling) and exits; every CTA of the consuming kernel polls the packets in its OWN window at its start
+// (allreduce_resolve) and adds them in rank order -- identical bits in every CTA of every rank.  The NVLink flight and
+// the wait for the slowest rank then overlap the kernel boundary instead of extending the producer's tail.
+__device__ __forceinline__ void allreduce_send(const lsk_peers &peers, const double *v, int count) {
+    CommWindow *me = static_cast<CommWindow *>(peers.window[peers.rank]);
+    const int r = threadIdx.x & 31;
+    const unsigned long long e = me->ar_epoch + 1;
+    const unsigned long long tag = (e & 0xffffffffull) << 32;
+    const int par = (int) (e & 1);
+    if (r < peers.nranks) {
+        CommWindow *dst = static_cast<CommWindow *>(peers.window[r]);
+        for (int j = 0; j < count; ++j) {
+            const unsigned long long bits = (unsigned long long) __double_as_longlong(v[j]);
+            volatile unsigned long long *pk = &dst->ar_pkt[par][peers.rank][j][0];
+            pk[0] = tag | (bits & 0xffffffffull);
+            pk[1] = tag | (bits >> 32);
+        }
+    }
+    __syncwarp();
+    if (r == 0) {
+        me->ar_epoch = e;
+        me->ar_calls += 1;
+    }
+}
+// all threads of the CTA call it; s_out[count] is shared memory; `slot` (may be null): CTA 0 also stores the sums there
+__device__ __forceinline__ void allreduce_resolve(const lsk_peers &peers, double *s_out, int count, double *slot) {
+    if (threadIdx.x < 32) {
+        CommWindow *me = static_cast<CommWindow *>(peers.window[peers.rank]);
+        const int r = threadIdx.x;
+        const unsigned long long e = *reinterpret_cast<volatile unsigned long long *>(&me->ar_epoch);  // advanced by the sender kernel
+        const unsigned long long tag = (e & 0xffffffffull) << 32;
+        const int par = (int) (e & 1);
+        const unsigned long long t0 = (r == 0 && blockIdx.x == 0) ? global_ns() : 0ull;
+        double got[kMaxRed];
+        for (int j = 0; j < kMaxRed; ++j) got[j] = 0.0;
+        if (r < peers.nranks) {
+            for (int j = 0; j < count; ++j) {
+                const volatile unsigned long long *pk = &me->ar_pkt[par][r][j][0];
+                unsigned long long a, b;
+                unsigned int polls = 0;
+                unsigned long long t_start = 0;
+                bool timed_out = false;
+                do {
+                    a = pk[0];
+                    b = pk[1];
+                    if (spin_expired(polls, t_start)) {
+                        me->error = 1;
+                        timed_out = true;
+                        break;
+                    }
+                } while ((a >> 32) != (tag >> 32) || (b >> 32) != (tag >> 32));
+                got[j] = timed_out ? __longlong_as_double(0x7ff8000000000000ll)
+                                   : __longlong_as_double((long long) ((a & 0xffffffffull) | (b << 32)));
+            }
+        }
+        for (int j = 0; j < count; ++j) {
+            double sum = 0.0;
+            for (int q = 0; q < peers.nranks; ++q) sum += __shfl_sync(0xffffffffu, got[j], q);
+            if (r == 0) {
+                s_out[j] = sum;
+                if (slot != nullptr && blockIdx.x == 0) slot[j] = sum;
+            }
+        }
+        if (r == 0 && blockIdx.x == 0) me->ar_wait_ns += global_ns() - t0;
+    }
+    __syncthreads();
+}
+
 // boundary sub-ranges of a vector y that are mirrored into the neighbours' ghost regions (xpay_halo, CG kernel)
 struct HaloSpec {
     int nmoves;
@@ -361,7 +436,7 @@ __device__ __forceinline__ double block_sum(double v, double *smem /*[NT / 32]*/
 template <int NRED, typename T, int NT = kBlock>
 __device__ __forceinline__ void grid_reduce_finish(const double (&acc)[NRED], double *partials,
                                                    unsigned int *ticket, T *const (&out)[NRED],
-                                                   const lsk_peers *peers = nullptr, unsigned long long *reset = nullptr) {
+                                                   const lsk_peers *peers = nullptr, unsigned long long *reset = nullptr, bool defer = false) {
     __shared__ double s_red[NT / 32];
     __shared__ double s_tot[NRED];
     __shared__ bool s_last;
@@ -395,10 +470,14 @@ __device__ __forceinline__ void grid_reduce_finish(const double (&acc)[NRED], do
             double v[NRED];
 #pragma unroll
             for (int j = 0; j < NRED; ++j) v[j] = s_tot[j];
-            allreduce_warp(*peers, v, NRED);
-            if (threadIdx.x == 0) {
+            if (defer) {
+                allreduce_send(*peers, v, NRED);  // the consumer kernel forms the cross-rank sum (allreduce_resolve)
+            } else {
+                allreduce_warp(*peers, v, NRED);
+                if (threadIdx.x == 0) {
 #pragma unroll
-                for (int j = 0; j < NRED; ++j) s_tot[j] = v[j];
+                    for (int j = 0; j < NRED; ++j) s_tot[j] = v[j];
+                }
             }
         }
         __syncthreads();
@@ -484,6 +563,15 @@ inline int configure_once(lsk_ctx *ctx, int family, Setup setup) {
     ctx->configured |= bit;
     return 0;
 }
+
+// claim a pending lsk_ctx_defer_next_allreduce request for this launch (only meaningful with peers)
+inline bool take_defer(lsk_ctx *ctx) {
+    const bool d = ctx->defer_next != 0 && ctx->d_peers != nullptr;
+    ctx->defer_next = 0;
+    return d;
+}
+// if a deferred reduction is still in flight and THIS launch is not its designated consumer, finish it first
+int settle_pending(lsk_ctx *ctx, cudaStream_t st);  // lsk_comm.cu
 
 inline int after_launch(lsk_ctx *ctx) {
     ctx->launches += 1;

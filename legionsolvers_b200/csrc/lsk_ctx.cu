@@ -51,6 +51,8 @@ int lsk_ctx_create(int device, lsk_ctx **out) {
     ctx->work = nullptr;
     ctx->configured = 0;
     ctx->cg_blocks_per_sm = 0;
+    ctx->defer_next = 0;
+    ctx->pending_slot = nullptr;
     const size_t pbytes = sizeof(double) * (size_t) kScratchSets * kMaxRed * kMaxPartials;
     cudaError_t e = cudaMalloc(&ctx->partials, pbytes);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->tickets, sizeof(unsigned int) * kScratchSets);
@@ -100,6 +102,16 @@ int lsk_ctx_set_peers(lsk_ctx *ctx, const lsk_peers *peers) {
     LSK_RETURN_IF_CUDA(cudaMemcpy(ctx->d_peers, peers, sizeof(lsk_peers), cudaMemcpyHostToDevice));
     ctx->h_peers = *peers;
     return 0;
+}
+
+int lsk_ctx_defer_next_allreduce(lsk_ctx *ctx) {
+    if (!ctx) return LSK_E_INVALID;
+    ctx->defer_next = ctx->d_peers != nullptr ? 1 : 0;
+    return 0;
+}
+int lsk_ctx_settle(lsk_ctx *ctx, lsk_stream s) {
+    if (!ctx) return LSK_E_INVALID;
+    return lsk::settle_pending(ctx, (cudaStream_t) s);
 }
 
 int lsk_ctx_device(const lsk_ctx *ctx) { return ctx ? ctx->device : -1; }

@@ -571,6 +571,11 @@ static int launch_ws_kernel_lpr(lsk_ctx *ctx, int ndot, int grid, cudaStream_t s
 
 static int ws_lanes_per_row(int64_t rows, int64_t nnz, int variant) {
     if (variant != LSK_SPMV_LANES) return 1;
+    static const char *lpr_env = getenv("LSK_WS_LPR");  // developer knob: 2, 4 or 8 lanes per row for the LANES variant
+    if (lpr_env) {
+        const int v = atoi(lpr_env);
+        if (v == 2 || v == 4 || v == 8) return v;
+    }
     const double mean = rows > 0 ? (double) nnz / (double) rows : 1.0;
     return mean <= 16.0 ? 2 : mean <= 40.0 ? 4 : 8;
 }
@@ -586,8 +591,14 @@ static int launch_ws_kernel(lsk_ctx *ctx, int lpr, int ndot, cudaStream_t st, in
     TmaSpmvArgs a;
     a.rows = rows; a.nnz = nnz; a.rpb = rpb; a.n_row_blocks = nrb; a.entry = entry; a.col = col; a.rowptr = rowptr;
     a.k_base = k_base; a.x = x; a.y = y; a.dot_w = dot_w; a.accumulate = accumulate ? 1 : 0;
-    RedScratch rs = {nullptr, nullptr, nullptr, nullptr};
+    // a reduction whose consumer is the next cg_update (lsk_ctx_defer_next_allreduce): only the y.w form
+    const bool defer = take_defer(ctx) && ndot == 1 && o0 != nullptr;
+    RedScratch rs = {nullptr, nullptr, nullptr, nullptr, 0};
     if (ndot > 0) rs = next_scratch(ctx);
+    if (defer) {
+        rs.defer = 1;
+        ctx->pending_slot = o0;
+    }
     switch (lpr) {
     case 1: return launch_ws_kernel_lpr<1>(ctx, ndot, grid, st, a, gate, rs, o0, o1);
     case 2: return launch_ws_kernel_lpr<2>(ctx, ndot, grid, st, a, gate, rs, o0, o1);
@@ -645,6 +656,10 @@ static int csr_spmv(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const
     if (variant == LSK_SPMV_AUTO) variant = pick_variant(rows, nnz);
     const cudaStream_t st = (cudaStream_t) s;
     const long long *colp = reinterpret_cast<const long long *>(col);
+    {
+        const int rc = settle_pending(ctx, st);
+        if (rc != 0) return rc;
+    }
 
     // the TMA kernels need fp64 and col / entry 16-byte aligned at the same elements
     const bool tma_ok = std::is_same<T, double>::value && reinterpret_cast<uintptr_t>(entry) % 8 == 0 &&
@@ -663,7 +678,7 @@ static int csr_spmv(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const
         if (rc != 0) return rc;
         return after_launch(ctx);
     }
-    RedScratch rs = {nullptr, nullptr, nullptr, nullptr};
+    RedScratch rs = {nullptr, nullptr, nullptr, nullptr, 0};
     if (ndot > 0) rs = next_scratch(ctx);
     if (variant == LSK_SPMV_LANES) {
         if (tma_ok) {  // round-1 kernel (LSK_SPMV_IMPL=tma)

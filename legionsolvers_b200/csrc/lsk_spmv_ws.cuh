@@ -387,7 +387,7 @@ csr_ws_kernel(TmaSpmvArgs a, WsGate gate, RedScratch rs, double *out_yw, double 
         double *out[NDOT];
         out[0] = out_yw;
         if constexpr (NDOT >= 2) out[NDOT - 1] = out_yy;
-        grid_reduce_finish<NDOT, double, kWsThreads>(dacc, rs.partials, rs.ticket, out, rs.peers, nullptr);
+        grid_reduce_finish<NDOT, double, kWsThreads>(dacc, rs.partials, rs.ticket, out, rs.peers, nullptr, rs.defer != 0);
     }
 }
 

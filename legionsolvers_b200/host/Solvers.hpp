@@ -67,7 +67,12 @@ public:
             return;
         }
         if (fused) {
+            // several ranks: the two dot products are only SENT by their producers; the next kernel -- their only
+            // consumer -- forms the cross-rank sums at its start, so the NVLink flight overlaps the kernel boundary
+            const bool defer = planner.can_defer_allreduce(P, R);
+            if (defer) planner.defer_next_allreduce();
             planner.matvec_dot(Q, P, P, p_norm);                     // Q = A P and P.Q in one pass
+            if (defer) planner.defer_next_allreduce();
             planner.cg_update(SOL, R, rr_cur, p_norm, P, Q, rr_new);  // both axpys and R.R in one pass
             // append rr_new, P = R + (rr_new/rr_cur) P (boundary into the neighbours' ghosts), rr_cur <- rr_new: one launch
             if (planner.cg_direction(P, rr_new, rr_cur, R, residual_norm_squared)) return;

@@ -234,6 +234,23 @@ public:
         halo_fresh.insert(vec_idx);
     }
 
+    // Deferred all-reduces of the fused CG step (lsk_ctx_defer_next_allreduce): possible when the reductions are fused into
+    // the producing kernels, this rank holds one piece, and cg_direction will be the consumer of r.r
+    bool can_defer_allreduce(std::size_t p, std::size_t r) {
+        static const bool off = [] { const char *e = getenv("LSK_DEFER_AR"); return e && e[0] == '0'; }();  // developer A/B switch
+        if (off || !rt->fused_collectives() || get_num_spaces() != 1 || total_local_pieces() != 1) return false;
+        if constexpr (!std::is_same<T, double>::value) {
+            return false;
+        } else {
+            const IndexPartition &part = *canonical_index_partitions[0];
+            const int64_t lo = part.own_lo(), cnt = part.own_hi() - part.own_lo() + 1;
+            return cnt > 0 && lsk_cg_direction_supported(cnt, get_vector(r, 0).ptr(lo), get_vector(p, 0).ptr(lo)) != 0 && can_fuse_matvec_dot();
+        }
+    }
+    void defer_next_allreduce() {
+        rt->enqueue("defer all-reduce", [&] { return lsk_ctx_defer_next_allreduce(rt->ctx()); });
+    }
+
     // true when xpay_halo pushes the boundary itself (then a step that ends with it leaves the ghosts current)
     bool halo_push_is_fused() const {
         return std::is_same<T, double>::value && rt->fused_collectives() && row_partitioned_matrices.size() == 1 &&
