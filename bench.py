@@ -429,7 +429,7 @@ def run_ours(args):
     for s in range(spaces):
         pl.add_row_partitioned_matrix(mat, s, s)
     if solver == "cg":
-        sv = S.CGSolver(pl, fused=not args.unfused, persistent=True if args.persistent else None)
+        sv = S.CGSolver(pl, fused=not args.unfused)
     elif solver == "bicgstab":
         sv = S.BiCGStabSolver(pl, fused=not args.unfused)
     else:
@@ -470,7 +470,6 @@ def run_ours(args):
     rt.fence()
     launches0 = rt.kernel_launches
     cs0 = rt.comm_stats() if world > 1 else None
-    ph0 = rt.cg_phase_stats() if getattr(sv, "persistent", False) else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     wall0 = time.time()
@@ -492,15 +491,9 @@ def run_ours(args):
         allv = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allv, mine)
         comm_us = {"allreduce_us_per_iteration_by_rank": [round(float(v[0]), 2) for v in allv],
-                   "halo_close_us_per_iteration_by_rank": [round(float(v[1]), 2) for v in allv]}
+                   "halo_poll_us_per_iteration_by_rank": [round(float(v[1]), 2) for v in allv]}
     ms_per_step = elapsed_ms / args.steps
     value = args.steps * ipt / (elapsed_ms * 1e-3)
-    phase_us = None
-    if ph0 is not None:
-        ph1 = rt.cg_phase_stats()
-        its = max(1, ph1["iterations"] - ph0["iterations"])
-        phase_us = {k[:-3] + "_us_per_iteration": round((ph1[k] - ph0[k]) / 1e3 / its, 2) for k in ph1 if k.endswith("_ns")}
-
     # ---- roofline of the dominant kernel: the (fused) mat-vec, timed alone on the same stream -----------------
     L = _abi.lib()
     e_ptr, c_ptr, third_ptr = mat.device_fields()
@@ -597,6 +590,7 @@ def run_ours(args):
         cs = copy_stream.cuda_stream
 
         e2e_trace = os.environ.get("LSK_E2E_TRACE") == "1"  # developer switch: device-side timeline of the e2e loop
+        e2e_skip = os.environ.get("LSK_E2E_SKIP", "")       # developer switch: "h2d" / "d2h" leaves that copy out (diagnosis only)
         marks = []
 
         def mark(stream_, what, k):
@@ -622,7 +616,7 @@ def run_ours(args):
                 rt.end_trace(TRACE_RESET)
                 ev_reset.record(tstream)
                 mark(tstream, "iters_begin", k)
-                if k + 1 < nsteps:                        # H2D of the NEXT step's right-hand side, under this step's iterations
+                if k + 1 < nsteps and "h2d" not in e2e_skip:  # H2D of the NEXT step's right-hand side, under this step's iterations
                     copy_stream.wait_event(ev_reset)
                     mark(copy_stream, "h2d_begin", k + 1)
                     for s in range(spaces):
@@ -643,7 +637,7 @@ def run_ours(args):
                 d2h_stream.wait_event(ev_solved)
                 mark(d2h_stream, "d2h_begin", k)
                 with torch.cuda.stream(d2h_stream):       # D2H under the next step's iterations
-                    for s in range(spaces):
+                    for s in range(spaces if "d2h" not in e2e_skip else 0):
                         x_host[s][own_lo:own_lo + n_local].copy_(x_stage[s], non_blocking=True)
                     hist_host[k].copy_(hist_stage, non_blocking=True)
                 mark(d2h_stream, "d2h_end", k)
@@ -655,9 +649,14 @@ def run_ours(args):
         e2e_run(2)
         barrier()
         marks.clear()
+        cs_e0 = rt.comm_stats() if world > 1 else None
         t0 = time.perf_counter()
         e2e_run(e2e_steps)
         e2e_s = max_over_ranks(time.perf_counter() - t0)
+        if cs_e0 is not None and e2e_trace:
+            cs_e1 = rt.comm_stats()
+            print(f"e2e-trace rank {rank}: inside all-reduces {(cs_e1['ar_ns'] - cs_e0['ar_ns']) / 1e3 / (e2e_steps * ipt):.2f} us / iteration, "
+                  f"halo {(cs_e1['halo_ns'] - cs_e0['halo_ns']) / 1e3 / (e2e_steps * ipt):.2f} us / iteration (reset included)", file=sys.stderr)
         if e2e_trace and rank == 0 and marks:
             base_ev, base_t = marks[0][2], marks[0][3]
             for what, k, ev, th in marks:
@@ -726,8 +725,7 @@ def run_ours(args):
     if rank == 0:
         cfg = shared_config(args, n, nnz)
         cfg.update({
-            "solver_form": ("persistent kernel (grid barriers instead of kernel boundaries, one launch per step)" if getattr(sv, "persistent", False)
-                            else "fused (fewest HBM passes: CG 3, BiCGStab 5)" if not args.unfused else "unfused (reference call sequence)"),
+            "solver_form": "fused (fewest HBM passes: CG 3, BiCGStab 5)" if not args.unfused else "unfused (reference call sequence)",
             "gmres_restart": restart if solver == "gmres" else None,
             "trace": "CUDA graph replay of iters_per_step iterations", "rhs": "b = 1, x0 = 0 (BenchmarkStencil)",
             "l2": "working set per GPU exceeds the 126 MB L2 (matrix streamed once per iteration)" if (16 if is_csr else 24) * nnz_local > 2 * 126e6
@@ -736,7 +734,6 @@ def run_ours(args):
             "collectives": "none (1 GPU)" if world == 1 else rt.collectives,
             "comm_error": rt.comm_error() if world > 1 else 0,
             "time_inside_collectives": comm_us,
-            "persistent_kernel_phases": phase_us,
             "spmv_ms_per_launch_by_rank": spmv_ms_by_rank,
             "iteration_roofline": {"bytes_per_iteration_per_gpu": iter_bytes, "frac_of_peak": iter_frac,
                                    "frac_of_nominal_8TBs": iter_bytes * value / 1e9 / 8000.0},
@@ -790,7 +787,6 @@ def main():
     ap.add_argument("--spaces", type=int, default=1, choices=[1, 2], help="2 = BenchmarkStencil's doubled block-diagonal system")
     ap.add_argument("--shape", type=str, default=None, help="developer override nx,ny,nz of the workload's grid (c5: log2 N)")
     ap.add_argument("--unfused", action="store_true", help="run the reference's unfused call sequence on the GPU")
-    ap.add_argument("--persistent", action="store_true", help="CG as one persistent kernel per step (also LSK_CG_PERSISTENT=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the full-size comparison with the CPU oracle")
     ap.add_argument("--no-e2e", action="store_true")

@@ -329,8 +329,11 @@ int lsk_shard(int64_t point, int64_t volume, int64_t total_shards);
  * Collectives over NVLink / NVSwitch PEER MEMORY (one process per GPU, windows mapped with CUDA IPC).
  * The Krylov path has exactly two exchange steps: the ghost-x halo before a
  * mat-vec and the sum of per-rank dot partials.  Both are latency-bound (<= 512 KB, 8 bytes), so they
- * are single small kernels that store straight into the peers' memory and spin on epoch flags --
- * a few microseconds instead of one NCCL launch each.  Every rank must call them the same number of
+ * ride inside the kernels that produce the data and use NO FENCE AND NO FLAG: every 8-byte word that
+ * crosses NVLink carries 32 data bits and the 32-bit number of the exchange it belongs to ("LL packet";
+ * an aligned 8-byte store is atomic), so a packet both delivers its data and announces it.  A system-scope
+ * fence costs 1.9 us on an idle B200 and 13-20 us while a PCIe copy is in flight (tools/probe_fence.cu);
+ * an LL round trip costs 2.5 us either way.  Every rank must call the collectives the same number of
  * times in the same order (SPMD), on the stream that orders them with the producers / consumers.
  *
  * `lsk_peers.window[r]` is rank r's comm window (lsk_comm_window_bytes() bytes of zeroed device
@@ -344,20 +347,30 @@ typedef struct {
 size_t lsk_comm_window_bytes(void);
 /* slots[0..count) (count <= 2) := sum over ranks, identical bits on every rank (rank-order sum) */
 int lsk_allreduce_sum_f64(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, double *slots, int count);
-/* one halo move: copy n doubles from local `src` to `dst`, an address inside peer `peer`'s memory
- * as mapped into this process (n == 0: nothing to send, but a receive from that peer is expected
- * when `expect` is non-zero) */
+/* One halo move = what this rank trades with ONE peer in an exchange: `n` doubles at local `src` go to the peer, and
+ * `recv_n` doubles from the peer end up at local `recv_dst` (this rank's ghost region).  The values travel as LL
+ * packets into a LANDING BUFFER owned by the receiver -- lsk_halo_landing_bytes(count) bytes of zeroed device memory per
+ * (receiver, sender) pair, holding two exchanges (alternating) of count + 1 packets of 16 bytes -- and the RECEIVER copies
+ * them into its ghost region: ghost values are only ever written by the rank that reads them, in stream order.
+ *   ll_send  the peer's landing buffer for this rank's packets, as mapped into this process (sized for n)
+ *   ll_recv  this rank's landing buffer for the peer's packets (sized for recv_n)
+ * Both ranks of a pair must list each other in the same exchanges, even when one direction is empty (n == 0 or
+ * recv_n == 0): the count + 1st packet is a token that travels in both directions, which bounds how far one rank can
+ * run ahead of the other (at most one exchange: the two halves of a landing buffer are never overwritten while in use). */
 typedef struct {
     int peer;
-    int expect;        /* non-zero: this peer also sends to me in this exchange */
+    int reserved;
     const double *src;
-    double *dst;
     int64_t n;
+    void *ll_send;
+    double *recv_dst;
+    int64_t recv_n;
+    void *ll_recv;
 } lsk_halo_move;
 #define LSK_MAX_HALO_MOVES 32
-/* neighbour exchange with barrier semantics: when the kernel completes on this stream, every
- * peer's data destined for this rank has landed and this rank's data has been delivered.  A
- * ready-handshake precedes the stores, so a fast peer never overwrites ghost values still in use. */
+size_t lsk_halo_landing_bytes(int64_t count);
+/* neighbour exchange with barrier semantics: when the kernel completes on this stream, every peer's data destined for
+ * this rank is in place at recv_dst (and this rank's packets are on their way or have landed). */
 int lsk_halo_exchange_f64(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, const lsk_halo_move *moves,
                           int nmoves);
 /* FUSED forms: no launch of their own.
@@ -368,7 +381,7 @@ int lsk_halo_exchange_f64(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, co
 int lsk_ctx_set_peers(lsk_ctx *ctx, const lsk_peers *peers);
 /* DEFERRED form of the fused all-reduce, for a reduction whose only consumer is the next kernel on the stream (the p.q and
  * r.r of a fused CG step).  lsk_ctx_defer_next_allreduce(ctx) applies to the NEXT reducing launch through ctx, if it is
- * lsk_csr_spmv_f64 / lsk_csr_spmv_gated_f64 with dot_out only, or lsk_cg_update_f64: its last CTA only SENDS the rank's sum to
+ * lsk_csr_spmv_f64 with dot_out only, or lsk_cg_update_f64: its last CTA only SENDS the rank's sum to
  * the peers (the value it stores to the output slot is the rank-local one) and the kernel ends; the cross-rank sum is formed
  * by the next lsk_cg_update_f64 whose `pq`, or lsk_cg_direction_f64 whose `rr_new`, is that same slot -- every CTA of it polls
  * the packets in its own window at its start, and the global value is stored back to the slot.  The NVLink flight and the
@@ -377,92 +390,23 @@ int lsk_ctx_set_peers(lsk_ctx *ctx, const lsk_peers *peers);
  * never a wrong number.  No-op without lsk_ctx_set_peers. */
 int lsk_ctx_defer_next_allreduce(lsk_ctx *ctx);
 int lsk_ctx_settle(lsk_ctx *ctx, lsk_stream s);
-/* XpayTask fused with the halo push of its result: y = fma(alpha, y, x), and the elements of y that lie
- * in moves[i].src[0..n) (sub-ranges of y) are also stored to moves[i].dst in the neighbour's memory;
- * when the kernel completes every rank's ghosts of y are current.  There is NO ready-handshake: the
- * caller guarantees that the neighbours' readers of the previous ghost values finished before this
- * launch (in CG an all-reduce of p.Ap separates them).  Needs lsk_ctx_set_peers.  nmoves <= 4. */
+/* XpayTask fused with the halo exchange of its result: y = fma(alpha, y, x); the elements of y inside moves[i].src[0..n)
+ * (sub-ranges of y) also leave as packets for the neighbours while the pass runs, and the CTAs unpack the neighbours'
+ * packets into moves[i].recv_dst when they have finished their share of the pass; when the kernel completes this rank's
+ * ghosts of y are current.  Needs lsk_ctx_set_peers.  nmoves <= 4. */
 int lsk_xpay_halo_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, int n_terms, const double *f0, const double *f1,
                       const double *f2, const double *f3, const double *x, double *y, const lsk_halo_move *moves,
                       int nmoves);
 /* CGSolver::step lines src/CGSolver.hpp:53-54 in one launch:
  *   residual_norm_squared.push_back(rr_new);  p = fma(rr_new/rr_cur, p, r)   [xpay(P, rr_new, rr_cur, R)]
  * then *rr_cur = *rr_new for the next step.  `history` may be NULL (no append); otherwise circular like
- * lsk_scalar_append_f64.  With `moves` (nmoves <= 4; needs lsk_ctx_set_peers) the boundary of p is also stored into
- * the neighbours' ghost regions and the exchange epoch is closed, exactly as lsk_xpay_halo_f64 does.
- * TMA-streamed: r and p must be 32-byte congruent (lsk_cg_direction_supported).
- * halo_open != 0: the kernel publishes its halo but does NOT wait for the neighbours' -- the exchange stays open and its
- * consumer waits instead: lsk_csr_spmv_gated_f64 per row block (the halo wait leaves the critical path), or
- * lsk_halo_wait_f64 for any other reader of the ghosts. */
+ * lsk_scalar_append_f64.  With `moves` (nmoves <= 4; needs lsk_ctx_set_peers) the halo of p is exchanged inside the
+ * kernel exactly as lsk_xpay_halo_f64 does (boundary chunks are processed first, the unpacking comes last: the packets
+ * have landed by then).  TMA-streamed: r and p must be 32-byte congruent (lsk_cg_direction_supported). */
 int lsk_cg_direction_supported(int64_t n, const double *r, const double *p);
 int lsk_cg_direction_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, double *rr_cur, const double *rr_new, const double *r,
-                         double *p, const lsk_halo_move *moves, int nmoves, int halo_open, double *history,
+                         double *p, const lsk_halo_move *moves, int nmoves, double *history,
                          int64_t history_capacity, int64_t *history_count);
-/* Closes an open exchange: when the kernel completes, the data of every peer with moves[i].expect != 0 has landed. */
-int lsk_halo_wait_f64(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, const lsk_halo_move *moves, int nmoves);
-
-/* CSRMatvecTask on several GPUs with the halo wait INSIDE the mat-vec (needs lsk_ctx_set_peers): identical to
- * lsk_csr_spmv_f64, except that ghost columns of x (outside the rows this rank owns) may still be in flight from the
- * neighbours when the kernel starts.  `ghost_blocks` (lsk_csr_spmv_row_blocks() bytes, from lsk_csr_ghost_blocks; NULL =
- * every row block) marks the row blocks that reference a ghost column; before the kernel feeds the first such block to a
- * CTA it waits until every peer with moves[i].expect != 0 has published the pair's current exchange (the one an
- * open lsk_cg_direction_f64 / lsk_xpay_halo_f64 of this rank counted last), then fences.  Marked blocks are walked
- * last-ish (each CTA starts in the middle of its list), so on a banded matrix nobody waits.  Only moves[i].peer and
- * moves[i].expect are read.  STREAM / LANES variants only (lsk_csr_spmv_gated_supported). */
-int lsk_csr_spmv_gated_supported(int64_t rows, int64_t nnz, const double *entry, const int64_t *col, const lsk_rect *rowptr,
-                                 int variant);
-int64_t lsk_csr_spmv_row_blocks(int64_t rows, int64_t nnz, int variant);
-int lsk_csr_ghost_blocks(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const int64_t *col, const lsk_rect *rowptr,
-                         int64_t k_base, int64_t own_lo, int64_t own_n, int variant, uint8_t *flags);
-int lsk_csr_spmv_gated_f64(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const double *entry, const int64_t *col,
-                           const lsk_rect *rowptr, int64_t k_base, const double *x_shifted, double *y, const double *dot_w,
-                           double *dot_out, double *dot_yy_out, int variant, const uint8_t *ghost_blocks,
-                           const lsk_halo_move *moves, int nmoves);
-
-/* ------------------------------------------------------------------------------------------------
- * The whole CG step as one persistent kernel -- CGSolver::step (src/CGSolver.hpp:46-55) `niter` times:
- *     q = A p;  pq = p.q;  x = fma(rr/pq, p, x);  r = fma((-1*rr)/pq, q, r);  rr' = r.r;
- *     p = fma(rr'/rr, p, r);  history.push_back(rr');  rr = rr'
- * on one CSR piece per GPU, with grid barriers between the phases instead of kernel boundaries.  With
- * lsk_ctx_set_peers in effect the two dot products are summed across ranks inside the grid barrier
- * and the boundary of p is stored into the neighbours' ghost regions (`moves`, as for
- * lsk_xpay_halo_f64); a CTA waits for the neighbours' epoch only before it consumes a row block that references
- * ghost columns, so no rank ever waits at a halo barrier.
- * Element-wise arithmetic is identical to the leaf-task sequence.  Preconditions: the ghosts of p are
- * current at entry (they are again at exit); entry/col 16-byte aligned at the same elements.
- * ---------------------------------------------------------------------------------------------- */
-typedef struct {
-    int64_t rows, nnz;            /* this rank's rows and their non-zeros (the kernel piece) */
-    const double *entry;          /* as for lsk_csr_spmv_f64 */
-    const int64_t *col;
-    const lsk_rect *rowptr;
-    int64_t k_base;
-    double *p_shifted;            /* P, indexable by GLOBAL column id: owned rows and ghost interval */
-    int64_t own_lo;               /* global index of the first owned row (P's owned piece = p_shifted + own_lo) */
-    double *q, *x, *r;            /* Q, SOL, R: owned pieces */
-    double *rr_cur, *rr_new, *p_norm;   /* device scalars of the solver (read: rr_cur; written: all three) */
-    double *history;              /* residual_norm_squared: circular, like lsk_scalar_append_f64 */
-    int64_t history_capacity;
-    int64_t *history_count;
-    const lsk_halo_move *moves;   /* boundary sub-ranges of P's owned piece to push; NULL / 0 on one rank */
-    int nmoves;                   /* <= 4 */
-    const uint8_t *ghost_blocks;  /* optional (several ranks): lsk_cg_row_blocks() flags from lsk_cg_ghost_blocks; only
-                                     flagged row blocks wait for the neighbours' halo epoch before they are consumed.  NULL = every block does */
-} lsk_cg_problem;
-/* number of row blocks the kernel cuts `rows` into, and the flags "row block references a column outside the
- * owned rows [own_lo, own_lo + rows)" (one byte per row block, computed once per matrix piece) */
-int64_t lsk_cg_row_blocks(int64_t rows, int64_t nnz);
-int lsk_cg_ghost_blocks(lsk_ctx *ctx, lsk_stream s, const lsk_cg_problem *pb, uint8_t *flags);
-/* 1 if lsk_cg_steps_f64 can run this problem (alignment, move count), 0 = use the leaf-task sequence */
-int lsk_cg_steps_supported(const lsk_cg_problem *pb);
-int lsk_cg_steps_f64(lsk_ctx *ctx, lsk_stream s, const lsk_cg_problem *pb, int niter);
-/* accounting kept by the persistent kernel: ns that CTA 0 spent in {mat-vec, its p.q barrier, x/r update, its r.r
- * barrier, p update, its halo barrier} and the number of iterations, accumulated since context creation.  Synchronises. */
-int lsk_cg_phase_stats(lsk_ctx *ctx, lsk_stream s, uint64_t *host_out7);
-/* non-zero if a grid barrier or ghost wait of a persistent kernel gave up.  Synchronises. */
-int lsk_ctx_error(lsk_ctx *ctx, lsk_stream s, int *host_out);
-/* bytes of the grid-barrier block a context holds (internal; exported for the context) */
-size_t lsk_gridsync_bytes(void);
 
 /* accounting kept in the comm window: {all-reduce calls, ns inside them, halo closes, ns inside them}
  * (time between entering the collective and leaving it, on the thread that closes it).  Synchronises. */

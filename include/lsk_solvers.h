@@ -124,16 +124,11 @@ int lsk_planner_vector_from_async(lsk_planner *pl, int vec, int space, const dou
 
 /* ---- solvers (src/CGSolver.hpp, src/BiCGStabSolver.hpp, src/GMRESSolver.hpp) -------------------------------------- */
 enum lsk_solver_kind { LSK_SOLVER_CG = 1, LSK_SOLVER_BICGSTAB = 2, LSK_SOLVER_GMRES = 3 }; /* BenchmarkStencil -solver */
-/* fused = 0: the reference's call sequence, one launch per planner call; 1: fewest-pass form (leaf kernels);
- * 2 (CG): fewest-pass form as ONE persistent kernel per batch of steps (lsk_cg_steps_f64) when the problem is
- * eligible -- one CSR block, one piece per GPU -- else as 1 */
+/* fused = 0: the reference's call sequence, one launch per planner call; non-zero: the same arithmetic in the fewest
+ * passes over memory (CG 3 launches per step, BiCGStab 5) */
 int lsk_solver_create(lsk_planner *pl, int kind, int restart, int fused, lsk_solver **out);
 int lsk_solver_destroy(lsk_solver *s);
-/* CGSolver on one CSR piece per GPU defers: consecutive steps are issued as ONE persistent-kernel launch
- * (lsk_cg_steps_f64) when anything else touches the stream -- a fence, a history read, the end of a trace. */
 int lsk_solver_step(lsk_solver *s);
-/* 1 if the solver's step runs as a persistent kernel (lsk_cg_steps_f64), 0 = one launch per pass */
-int lsk_solver_persistent(lsk_solver *s);
 /* start a new solve from the current RHS with SOL taken as 0: re-runs the constructor's initialisation (CG: P <- RHS,
  * R <- RHS, rr0; BiCGStab: R, R~ <- RHS, P, V <- 0, rho = alpha' = omega = 1/0/1; GMRES keeps no state: no-op) */
 int lsk_solver_reset(lsk_solver *s);

@@ -56,15 +56,11 @@ def lib() -> C.CDLL:
 
 
 class HaloMove(C.Structure):  # lsk_halo_move
-    _fields_ = [("peer", ci), ("expect", ci), ("src", vp), ("dst", vp), ("n", i64)]
+    _fields_ = [("peer", ci), ("reserved", ci), ("src", vp), ("n", i64), ("ll_send", vp), ("recv_dst", vp), ("recv_n", i64), ("ll_recv", vp)]
 
 
-class CgProblem(C.Structure):  # lsk_cg_problem
-    _fields_ = [("rows", i64), ("nnz", i64), ("entry", vp), ("col", vp), ("rowptr", vp), ("k_base", i64),
-                ("p_shifted", vp), ("own_lo", i64), ("q", vp), ("x", vp), ("r", vp),
-                ("rr_cur", vp), ("rr_new", vp), ("p_norm", vp),
-                ("history", vp), ("history_capacity", i64), ("history_count", vp),
-                ("moves", C.POINTER(HaloMove)), ("nmoves", ci), ("ghost_blocks", vp)]
+class Peers(C.Structure):  # lsk_peers
+    _fields_ = [("rank", ci), ("nranks", ci), ("window", vp * 16)]
 
 
 def check(status: int, where: str) -> None:
@@ -104,21 +100,9 @@ def _declare(L: C.CDLL) -> None:
     L.lsk_bicg_p_update_f64.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp]
     L.lsk_bicg_tail_f64.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.lsk_cg_direction_supported.argtypes = [i64, vp, vp]
-    L.lsk_cg_direction_f64.argtypes = [vp, vp, i64, vp, vp, vp, vp, C.POINTER(HaloMove), ci, ci, vp, i64, vp]
-    L.lsk_halo_wait_f64.argtypes = [vp, vp, vp, C.POINTER(HaloMove), ci]
-    L.lsk_csr_spmv_gated_supported.argtypes = [i64, i64, vp, vp, vp, ci]
-    L.lsk_csr_spmv_row_blocks.argtypes = [i64, i64, ci]
-    L.lsk_csr_spmv_row_blocks.restype = i64
-    L.lsk_csr_ghost_blocks.argtypes = [vp, vp, i64, i64, vp, vp, i64, i64, i64, ci, vp]
-    L.lsk_csr_spmv_gated_f64.argtypes = [vp, vp, i64, i64, vp, vp, vp, i64, vp, vp, vp, vp, vp, ci, vp, C.POINTER(HaloMove), ci]
-    L.lsk_cg_steps_supported.argtypes = [C.POINTER(CgProblem)]
-    L.lsk_cg_steps_f64.argtypes = [vp, vp, C.POINTER(CgProblem), ci]
-    L.lsk_cg_row_blocks.argtypes = [i64, i64]
-    L.lsk_cg_row_blocks.restype = i64
-    L.lsk_cg_ghost_blocks.argtypes = [vp, vp, C.POINTER(CgProblem), vp]
-    L.lsk_ctx_error.argtypes = [vp, vp, C.POINTER(ci)]
-    L.lsk_cg_phase_stats.argtypes = [vp, vp, C.POINTER(u64)]
-    L.lsk_gridsync_bytes.restype = C.c_size_t
+    L.lsk_cg_direction_f64.argtypes = [vp, vp, i64, vp, vp, vp, vp, C.POINTER(HaloMove), ci, vp, i64, vp]
+    L.lsk_halo_landing_bytes.argtypes = [i64]
+    L.lsk_halo_landing_bytes.restype = C.c_size_t
     # optional groups are declared by the modules that own them (setup / solvers / comm)
     from . import _abi_ext
 

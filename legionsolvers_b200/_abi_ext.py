@@ -113,7 +113,6 @@ def declare(L) -> None:
     L.lsk_solver_create.argtypes = [vp, ci, ci, ci, C.POINTER(vp)]
     L.lsk_solver_destroy.argtypes = [vp]
     L.lsk_solver_step.argtypes = [vp]
-    L.lsk_solver_persistent.argtypes = [vp]
     L.lsk_solver_reset.argtypes = [vp]
     L.lsk_solver_history.argtypes = [vp, ci, vp, i64, C.POINTER(i64)]
     L.lsk_solver_history_copy_async.argtypes = [vp, ci, vp, i64, vp]

@@ -124,26 +124,22 @@ static int launch_stream(lsk_ctx *ctx, lsk_stream s, F f, int64_t n, Span sp, bo
 }
 
 // ---------------------------------------------------------------------------------------------------
-// xpay fused with the halo push of its result (the p = r + beta p of CG feeds the next mat-vec):
-// elements that fall in a send range are also stored straight into the neighbour's ghost region over
-// NVLink; the last CTA publishes the epoch to the neighbours and waits for theirs, so when the kernel
-// completes the ghosts of y are current on every rank -- no separate exchange launch.
+// xpay fused with the halo exchange of its result (the p = r + beta p of CG feeds the next mat-vec):
+// elements that fall in a send range also leave as LL packets for the neighbour's landing buffer over
+// NVLink; every CTA then unpacks its share of the neighbours' packets into this rank's ghost region, so
+// when the kernel completes the ghosts of y are current -- no separate exchange launch, no fence, no flag.
+// The grid is sized so that all its CTAs are resident at once (a CTA polling for a neighbour's packet must
+// never keep a CTA that still has packets to send off the SMs).
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock)
+constexpr int kXpayHaloCtasPerSm = 4;
+__global__ void __launch_bounds__(kBlock, kXpayHaloCtasPerSm)
 xpay_halo_kernel(Alpha<double> al, const double *__restrict__ x, double *__restrict__ y, int64_t n, int64_t head,
                  int64_t npacks, HaloSpec h, const lsk_peers *peers) {
+    __shared__ HaloLive hl;
+    halo_begin(hl, h.m, h.nmoves, peers);
     const double a = fold_alpha(al);
     const int64_t tid = (int64_t) blockIdx.x * kBlock + threadIdx.x;
     const int64_t stride = (int64_t) gridDim.x * kBlock;
-    bool remote = false;
-    auto mirror = [&](int64_t i, double v) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if (q < h.nmoves && i >= h.lo[q] && i < h.lo[q] + h.m[q].n) {
-                h.m[q].dst[i - h.lo[q]] = v;
-                remote = true;
-            }
-    };
     for (int64_t p = tid; p < npacks; p += stride) {
         const int64_t i = head + p * 4;
         const Pack32 px = ld256(x + i);
@@ -155,22 +151,8 @@ xpay_halo_kernel(Alpha<double> al, const double *__restrict__ x, double *__restr
             PackOf<double>::set(py, e, v[e]);
         }
         st256(y + i, py);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            if (q < h.nmoves && i + 4 > h.lo[q] && i < h.lo[q] + h.m[q].n) {
-                double *d = h.m[q].dst + (i - h.lo[q]);
-                remote = true;
-                const bool inside = (i >= h.lo[q]) && (i + 4 <= h.lo[q] + h.m[q].n);
-                if (inside && (reinterpret_cast<uintptr_t>(d) & 15) == 0) {
-                    reinterpret_cast<double2 *>(d)[0] = make_double2(v[0], v[1]);
-                    reinterpret_cast<double2 *>(d)[1] = make_double2(v[2], v[3]);
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (i + e >= h.lo[q] && i + e < h.lo[q] + h.m[q].n) d[e] = v[e];
-                }
-            }
-        }
+        halo_send_pair(h, hl, i, v[0], v[1]);
+        halo_send_pair(h, hl, i + 2, v[2], v[3]);
     }
     const int64_t tail0 = head + npacks * 4;
     const int64_t nedge = head + (n - tail0);
@@ -178,12 +160,12 @@ xpay_halo_kernel(Alpha<double> al, const double *__restrict__ x, double *__restr
         const int64_t i = e < head ? e : tail0 + (e - head);
         const double v = fma_rn(a, y[i], x[i]);
         y[i] = v;
-        mirror(i, v);
+        halo_send_one(h, hl, i, v);
     }
-    // ---- epilogue: last CTA closes the exchange
+    halo_unpack(hl, h.m, h.nmoves, peers);
+    // ---- epilogue: the last CTA advances the pair counters
     CommWindow *me = static_cast<CommWindow *>(peers->window[peers->rank]);
     __shared__ bool s_last;
-    if (remote) __threadfence_system();  // my stores into the neighbours' memory are visible there
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -192,7 +174,7 @@ xpay_halo_kernel(Alpha<double> al, const double *__restrict__ x, double *__restr
     }
     __syncthreads();
     if (!s_last) return;
-    halo_publish(peers, h.m, h.nmoves, h.open == 0);
+    halo_finish(h.m, h.nmoves, peers);
     if (threadIdx.x == 0) me->halo_ticket = 0u;
 }
 
@@ -269,8 +251,9 @@ cg_update_tma_kernel(const double *rr_old, double *pq, const double *neg_one, co
 }
 
 // src/CGSolver.hpp:53-54: residual_norm_squared.push_back(rr_new); p = fma(rr_new/rr_cur, p, r) -- plus, on several
-// ranks, p's boundary stored into the neighbours' ghost regions and the exchange epoch closed (as xpay_halo_kernel),
-// and rr_cur <- rr_new for the next step.  Everything after the element loop is done by the last CTA to finish.
+// ranks, the halo exchange of p (as xpay_halo_kernel: boundary chunks are taken first and leave as LL packets, every
+// CTA unpacks its share of the neighbours' packets after its last chunk), and rr_cur <- rr_new for the next step.
+// The scalar bookkeeping is done by the last CTA to finish.
 __global__ void __launch_bounds__(kBlock, 3)
 cg_direction_tma_kernel(double *rr_cur, double *rr_new, const double *r, double *p, int64_t n, int64_t head, int64_t npacks,
                         HaloSpec h, RedScratch rs, double *hist, long long hist_cap, long long *hist_count, bool resolve,
@@ -278,17 +261,19 @@ cg_direction_tma_kernel(double *rr_cur, double *rr_new, const double *r, double 
     extern __shared__ __align__(128) unsigned char s_dyn[];
     __shared__ __align__(8) VecKernelShared sh;
     __shared__ bool s_last;
+    __shared__ HaloLive hl;
     pdl_launch_dependents();
     VecRing ring;
     vec_ring_init(ring, s_dyn, sh);
     pdl_wait();  // rr_new and r come from the update kernel before this one
     const lsk_peers *peers = rs.peers;
     const bool multi = (peers != nullptr && h.nmoves > 0);
+    if (multi) halo_begin(hl, h.m, h.nmoves, peers);
     __shared__ double s_rr[kMaxRed];
     if (resolve) allreduce_resolve(*resolve_peers, s_rr, 1, rr_new);  // the update kernel only SENT its rank's r.r
     const double rr_new_v = resolve ? s_rr[0] : *rr_new;
     const double beta = div_rn(rr_new_v, *rr_cur);  // xpay(P, rr_new, rr_cur, R): alpha = f0 / f1
-    bool remote = false, chunk_halo = false;
+    bool chunk_halo = false;
     const double *const in[2] = {p, r};
     const int64_t rot = multi ? halo_first_chunk(h, head, kVecStageBytes / 16) : 0;
     vec_stream<2>(ring, in, head, npacks * 4, rs.work, rot,
@@ -296,14 +281,14 @@ cg_direction_tma_kernel(double *rr_cur, double *rr_new, const double *r, double 
                   [&](int64_t i, const double (&v)[2][2]) {
                       const double p0 = fma_rn(beta, v[0][0], v[1][0]), p1 = fma_rn(beta, v[0][1], v[1][1]);
                       *reinterpret_cast<double2 *>(p + i) = make_double2(p0, p1);
-                      if (chunk_halo) remote |= halo_mirror_pair(h, i, p0, p1);
+                      if (chunk_halo) halo_send_pair(h, hl, i, p0, p1);
                   });
     for_each_edge(n, head, npacks, [&](int64_t i) {
         const double v = fma_rn(beta, p[i], r[i]);
         p[i] = v;
-        if (multi) remote |= halo_mirror_one(h, i, v);
+        if (multi) halo_send_one(h, hl, i, v);
     });
-    if (remote) __threadfence_system();  // my stores into the neighbours' memory are visible there
+    if (multi) halo_unpack(hl, h.m, h.nmoves, peers);
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -312,7 +297,7 @@ cg_direction_tma_kernel(double *rr_cur, double *rr_new, const double *r, double 
     }
     __syncthreads();
     if (!s_last) return;
-    if (multi) halo_publish(peers, h.m, h.nmoves, h.open == 0);  // publish; wait for the neighbours' unless the exchange stays open
+    if (multi) halo_finish(h.m, h.nmoves, peers);
     if (threadIdx.x == 0) {
         const double v = rr_new_v;
         if (hist != nullptr) {
@@ -775,19 +760,10 @@ int lsk_xpay_halo_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, int nt, const doubl
         if (rc != 0) return rc;
     }
     HaloSpec h;
-    h.nmoves = nmoves;
-    h.open = 0;
-    for (int i = 0; i < nmoves; ++i) {
-        h.m[i] = moves[i];
-        for (int j = 0; j < i; ++j)
-            if (moves[j].peer == moves[i].peer) return LSK_E_INVALID;  // exchanges are numbered per pair: one move per peer
-        if (moves[i].n < 0 || (moves[i].n > 0 && (!moves[i].dst || moves[i].src < y || moves[i].src + moves[i].n > y + n)))
-            return LSK_E_INVALID;
-        h.lo[i] = moves[i].n > 0 ? (int64_t) (moves[i].src - y) : 0;
-    }
+    if (!halo_spec_fill(h, moves, nmoves, y, n, ctx->h_peers.nranks)) return LSK_E_INVALID;
     const Span sp = plan_span<double>(n, {x, y});
     const int64_t items = sp.npacks > 0 ? sp.npacks : n;
-    const int grid = stream_grid(ctx, items > 0 ? items : 1, 8);
+    const int grid = stream_grid(ctx, items > 0 ? items : 1, kXpayHaloCtasPerSm);  // all CTAs resident (see the kernel)
     xpay_halo_kernel<<<grid, kBlock, 0, (cudaStream_t) s>>>(al, x, y, n, sp.head, sp.npacks, h, ctx->d_peers);
     return after_launch(ctx);
 }
@@ -883,7 +859,7 @@ int lsk_cg_update_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, const double *rr_ol
 }
 
 int lsk_cg_direction_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, double *rr_cur, const double *rr_new, const double *r, double *p,
-                         const lsk_halo_move *moves, int nmoves, int halo_open, double *history, int64_t history_capacity,
+                         const lsk_halo_move *moves, int nmoves, double *history, int64_t history_capacity,
                          int64_t *history_count) {
     if (!ctx || n < 0 || !rr_cur || !rr_new || (n > 0 && (!r || !p)) || nmoves < 0 || nmoves > 4 || (nmoves > 0 && !moves))
         return LSK_E_INVALID;
@@ -900,20 +876,7 @@ int lsk_cg_direction_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, double *rr_cur, 
         if (rc != 0) return rc;
     }
     HaloSpec h;
-    h.nmoves = nmoves;
-    h.open = halo_open ? 1 : 0;
-    for (int i = 0; i < 4; ++i) {
-        h.lo[i] = 0;
-        h.m[i].peer = 0; h.m[i].expect = 0; h.m[i].src = nullptr; h.m[i].dst = nullptr; h.m[i].n = 0;
-    }
-    for (int i = 0; i < nmoves; ++i) {
-        if (moves[i].n < 0 || (moves[i].n > 0 && (!moves[i].dst || moves[i].src < p || moves[i].src + moves[i].n > p + n)))
-            return LSK_E_INVALID;
-        for (int j = 0; j < i; ++j)
-            if (moves[j].peer == moves[i].peer) return LSK_E_INVALID;
-        h.m[i] = moves[i];
-        h.lo[i] = moves[i].n > 0 ? (int64_t) (moves[i].src - p) : 0;
-    }
+    if (!halo_spec_fill(h, moves, nmoves, p, n, ctx->d_peers ? ctx->h_peers.nranks : 1)) return LSK_E_INVALID;
     const int64_t nchunks = (sp.npacks * 4 + 1023) / 1024;
     const int64_t cap = (int64_t) ctx->sm_count * 3;
     const int grid = (int) (nchunks < cap ? nchunks : cap);

@@ -1,11 +1,12 @@
 // lsk_comm.cu -- the two collectives of the Krylov path over NVLink / NVSwitch peer memory.
 //
-// One process per GPU; each rank's comm window and its vectors' buffers are mapped into every peer
+// One process per GPU; each rank's comm window and its halo landing buffers are mapped into every peer
 // with CUDA IPC (host side: host/Runtime.cpp).  Stores to a mapped peer address travel over NVLink
-// through the NVSwitch and land in the peer's L2 / HBM; visibility is ordered with
-// __threadfence_system() before the epoch-flag store, and the reader polls the flag in its OWN
-// memory with volatile (L1-bypassing) loads.  Epochs are monotonic device-side counters, so the
-// kernels can be recorded in a CUDA graph and replayed without patching arguments.
+// through the NVSwitch and land in the peer's L2 / HBM.  Everything that crosses the link is an LL
+// packet: 32 data bits + the 32-bit number of the exchange in one atomic 8-byte word, so there is no
+// fence and no flag anywhere (lsk_common.cuh); the reader polls the packets in its OWN memory with
+// volatile (L1-bypassing) loads.  Exchange numbers are monotonic device-side counters, so the kernels
+// can be recorded in a CUDA graph and replayed without patching arguments.
 #include "lsk_common.cuh"
 
 namespace lsk {
@@ -40,62 +41,43 @@ struct HaloArgs {
     lsk_halo_move m[LSK_MAX_HALO_MOVES];
 };
 
+// Stand-alone exchange (the fused forms live in lsk_blas1.cu): send my boundary values as packets, unpack the
+// neighbours'.  At most 32 CTAs: all resident, so a CTA polling for a packet never keeps a sender off the SMs.
 __global__ void __launch_bounds__(kBlock) halo_exchange_kernel(lsk_peers peers, HaloArgs a) {
     CommWindow *me = static_cast<CommWindow *>(peers.window[peers.rank]);
     __shared__ bool s_last;
-    // exchange number of each pair (me, peer): the pair counters are written only by the last CTA, after everyone read them
-    // 1. tell every peer I receive from that my ghost region may be overwritten (all my earlier kernels
-    //    on this stream -- the readers of the previous ghost values -- have completed)
-    if (blockIdx.x == 0 && threadIdx.x < a.nmoves && a.m[threadIdx.x].expect) {
-        const int p = a.m[threadIdx.x].peer;
-        CommWindow *dst = static_cast<CommWindow *>(peers.window[p]);
-        *reinterpret_cast<volatile unsigned long long *>(&dst->halo_ready[peers.rank]) = me->halo_sent[p] + 1;
-    }
-    // 2. wait until every peer I send to is ready
-    if (threadIdx.x < a.nmoves && a.m[threadIdx.x].n > 0) {
-        const int p = a.m[threadIdx.x].peer;
-        spin_until(&me->halo_ready[p], me->halo_sent[p] + 1, &me->error);
-    }
-    __syncthreads();
-    // 3. store my boundary values straight into the peers' ghost regions
+    const int64_t tid = (int64_t) blockIdx.x * kBlock + threadIdx.x, stride = (int64_t) gridDim.x * kBlock;
     for (int i = 0; i < a.nmoves; ++i) {
+        HaloLive one;
+        halo_live_move(one, 0, a.m[i], me);
         const double *src = a.m[i].src;
-        double *dst = a.m[i].dst;
         const int64_t n = a.m[i].n;
-        const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
-        const int64_t tid = (int64_t) blockIdx.x * kBlock + threadIdx.x, stride = (int64_t) gridDim.x * kBlock;
-        if (vec) {
-            const int64_t n2 = n >> 1;
-            for (int64_t k = tid; k < n2; k += stride)
-                reinterpret_cast<double2 *>(dst)[k] = reinterpret_cast<const double2 *>(src)[k];
-            if (tid == 0 && (n & 1)) dst[n - 1] = src[n - 1];
-        } else {
-            for (int64_t k = tid; k < n; k += stride) dst[k] = src[k];
-        }
+        for (int64_t k = tid; k < n; k += stride) ll_store(one.send_slot[0], k, src[k], one.tag[0]);
+        if (tid == 0) ll_store(one.send_slot[0], n, 0.0, one.tag[0]);  // the token
     }
-    // 4. the last CTA to finish publishes "done" to the peers, waits for theirs, and advances the pair counters
-    __threadfence_system();
+    for (int i = 0; i < a.nmoves; ++i) {
+        HaloLive one;
+        halo_live_move(one, 0, a.m[i], me);
+        halo_unpack(one, &a.m[i], 1, &peers);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence();
         const unsigned int t = atomicAdd(&me->halo_ticket, 1u);
         s_last = (t == gridDim.x - 1);
     }
     __syncthreads();
     if (!s_last) return;
-    halo_publish(&peers, a.m, a.nmoves, true);
-    if (threadIdx.x == 0) me->halo_ticket = 0u;
-}
-
-// Closes an OPEN exchange (halo_publish without wait) for consumers that cannot wait per row block: one thread per
-// peer this rank receives from blocks until that peer's data of the pair's latest exchange has landed.
-__global__ void __launch_bounds__(32) halo_wait_kernel(lsk_peers peers, HaloArgs a) {
-    CommWindow *me = static_cast<CommWindow *>(peers.window[peers.rank]);
-    if (threadIdx.x < a.nmoves && a.m[threadIdx.x].expect) {
-        const int p = a.m[threadIdx.x].peer;
-        spin_until(&me->halo_done[p], me->halo_sent[p], &me->error);
+    for (int i0 = 0; i0 < a.nmoves; i0 += kBlock) {
+        const int i = i0 + (int) threadIdx.x;
+        if (i < a.nmoves) me->halo_sent[a.m[i].peer] += 1;
     }
-    __syncwarp();
-    __threadfence_system();
+    if (threadIdx.x == 0) {
+        me->halo_calls += 1;
+        me->halo_wait_ns += me->halo_poll_ns;
+        me->halo_poll_ns = 0;
+        me->halo_ticket = 0u;
+    }
 }
 
 }  // namespace lsk
@@ -120,6 +102,8 @@ int lsk_allreduce_sum_f64(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, do
     return after_launch(ctx);
 }
 
+size_t lsk_halo_landing_bytes(int64_t count) { return count < 0 ? 0 : (size_t) 2 * (size_t) (count + 1) * 16; }
+
 int lsk_halo_exchange_f64(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, const lsk_halo_move *moves, int nmoves) {
     if (!ctx || !peers_ok(peers) || nmoves < 0 || nmoves > LSK_MAX_HALO_MOVES || (nmoves > 0 && !moves)) return LSK_E_INVALID;
     if (nmoves == 0) return 0;
@@ -128,30 +112,16 @@ int lsk_halo_exchange_f64(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, co
     int64_t total = 0;
     for (int i = 0; i < nmoves; ++i) {
         a.m[i] = moves[i];
-        if (moves[i].peer < 0 || moves[i].peer >= peers->nranks || moves[i].n < 0) return LSK_E_INVALID;
-        if (moves[i].n > 0 && (!moves[i].src || !moves[i].dst)) return LSK_E_INVALID;
+        if (!halo_move_ok(moves[i], nullptr, 0, peers->nranks) || moves[i].peer == peers->rank) return LSK_E_INVALID;
         for (int j = 0; j < i; ++j)
             if (moves[j].peer == moves[i].peer) return LSK_E_INVALID;  // exchanges are numbered per pair: one move per peer
-        total += moves[i].n;
+        total += moves[i].n + moves[i].recv_n;
     }
-    // enough CTAs to keep NVLink busy for a few hundred KB, few enough that the epilogue stays cheap
+    // enough CTAs to keep NVLink busy for a few hundred KB, few enough that all of them are resident
     int grid = (int) ((total + 4 * kBlock - 1) / (4 * kBlock));
     if (grid < 1) grid = 1;
     if (grid > 32) grid = 32;
     halo_exchange_kernel<<<grid, kBlock, 0, (cudaStream_t) s>>>(*peers, a);
-    return after_launch(ctx);
-}
-
-int lsk_halo_wait_f64(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, const lsk_halo_move *moves, int nmoves) {
-    if (!ctx || !peers_ok(peers) || nmoves < 0 || nmoves > 32 || (nmoves > 0 && !moves)) return LSK_E_INVALID;
-    if (nmoves == 0) return 0;
-    HaloArgs a;
-    a.nmoves = nmoves;
-    for (int i = 0; i < nmoves; ++i) {
-        if (moves[i].peer < 0 || moves[i].peer >= peers->nranks) return LSK_E_INVALID;
-        a.m[i] = moves[i];
-    }
-    halo_wait_kernel<<<1, 32, 0, (cudaStream_t) s>>>(*peers, a);
     return after_launch(ctx);
 }
 

@@ -32,14 +32,12 @@ struct lsk_ctx {
     int cursor;                // next scratch set
     unsigned long long launches;
     lsk_peers *d_peers;        // device copy of the peer windows; non-null = reducing kernels all-reduce in their tail
-    lsk_peers h_peers;         // host copy (valid while d_peers is non-null): window addresses for the gated mat-vec
+    lsk_peers h_peers;         // host copy (valid while d_peers is non-null)
     int defer_next;            // lsk_ctx_defer_next_allreduce: the next fused reduction sends without waiting
     const void *pending_slot;  // device scalar whose cross-rank sum is still in flight (resolved by its consumer)
     unsigned long long *work;  // [kScratchSets] dynamic work counters of the TMA-streamed vector kernels, zero between launches
     unsigned long long configured;  // one bit per kernel family whose dynamic shared-memory opt-in was done on THIS device
                                     // (function attributes are per device: a process may hold contexts on several GPUs)
-    void *gridsync;            // lsk::GridSync: grid barrier + partials of the persistent solver kernels
-    int cg_blocks_per_sm;      // occupancy of the persistent CG kernel (0 = not queried yet)
 };
 
 namespace lsk {
@@ -195,18 +193,18 @@ struct CommWindow {
     // written by PEERS (remote stores over NVLink)
     unsigned long long ar_pkt[2][LSK_MAX_RANKS][kMaxRed][2];  // all-reduce packets {32 data bits | epoch << 32},
                                                                // by epoch parity, source rank, value, half
-    unsigned long long halo_ready[LSK_MAX_RANKS];      // peer r is ready to RECEIVE exchange #e of the pair (me, r)
-    unsigned long long halo_done[LSK_MAX_RANKS];       // peer r's data of exchange #e of the pair (me, r) has landed here
     // local state
     unsigned long long ar_epoch;
-    // Exchanges are counted PER PAIR of ranks: halo_sent[r] = exchanges this rank has started with peer r.  Two ranks
-    // trade data in an exchange iff either sends to the other, so both advance their pair counter together even when
-    // other pairs of the job skip that exchange (different halos per block, ranks without neighbours).
+    // Halo exchanges are counted PER PAIR of ranks: halo_sent[r] = exchanges this rank has completed with peer r.  Both
+    // ranks of a pair list each other in the same exchanges (lsk_halo_move), so their pair counters advance together even
+    // when other pairs of the job skip that exchange (different halos per block, ranks without neighbours).
     unsigned long long halo_sent[LSK_MAX_RANKS];
     unsigned int halo_ticket;
     int error;
-    // accounting (cheap, always on): time spent inside the collectives by the thread that closes them
+    // accounting (cheap, always on): all-reduce = time inside it on the thread that closes it; halo = per exchange, the
+    // longest time any thread spent polling for a packet that had not landed yet
     unsigned long long ar_calls, ar_wait_ns, halo_calls, halo_wait_ns;
+    unsigned long long halo_poll_ns;  // of the exchange in progress (atomicMax; folded into halo_wait_ns by the last CTA)
 };
 
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -367,38 +365,92 @@ __device__ __forceinline__ void allreduce_resolve(const lsk_peers &peers, double
     __syncthreads();
 }
 
-// boundary sub-ranges of a vector y that are mirrored into the neighbours' ghost regions (xpay_halo, CG kernel)
+// ---- halo exchange as LL packets (lsk.h: lsk_halo_move) ----------------------------------------------------------------
+// A double travels as one 16-byte packet {lo32 | tag, hi32 | tag}, tag = exchange number of the pair << 32: the packet
+// delivers the data AND announces it, so the exchange needs no fence and no flag (a system-scope fence is 1.9 us on an
+// idle B200 and 13-20 us while a PCIe copy is in flight; see tools/probe_fence.cu).  Packets land in a buffer owned by the
+// receiver (two exchanges, alternating); the receiver's own CTAs copy them into its ghost region.
+constexpr int kMaxFusedMoves = 4;  // moves a fused (xpay / direction) kernel carries by value
+
+__device__ __forceinline__ void ll_store(char *slot, int64_t idx, double v, unsigned long long tag) {
+    const unsigned long long bits = (unsigned long long) __double_as_longlong(v);
+    const unsigned long long a = tag | (bits & 0xffffffffull), b = tag | (bits >> 32);
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(slot + idx * 16), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ bool ll_try_load(const char *slot, int64_t idx, unsigned long long tag, double &v) {
+    unsigned long long a, b;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(slot + idx * 16) : "memory");
+    if ((a >> 32) != (tag >> 32) || (b >> 32) != (tag >> 32)) return false;
+    v = __longlong_as_double((long long) ((a & 0xffffffffull) | (b << 32)));
+    return true;
+}
+
 struct HaloSpec {
     int nmoves;
-    int open;       // non-zero: publish only, the consumer of the ghosts waits (see halo_publish)
-    lsk_halo_move m[4];
-    int64_t lo[4];  // send range start as an element index into y
+    lsk_halo_move m[kMaxFusedMoves];
+    int64_t lo[kMaxFusedMoves];  // send range start as an element index into the vector the kernel updates
 };
-
-// Executed by ALL threads of the last CTA of a kernel that stored halo data into its neighbours (after its own
-// system-scope fence and the ticket that made it the last): publish "exchange #e of our pair has landed" to every
-// peer this rank sent to, advance the pair counters, and -- when `wait` -- block until the peers' data of the same
-// exchange has landed here.  Without `wait` the exchange stays OPEN: its consumer must wait for
-// halo_done[peer] >= halo_sent[peer] itself (the gated mat-vec does, per row block; lsk_halo_wait_f64 otherwise).
-__device__ __forceinline__ void halo_publish(const lsk_peers *peers, const lsk_halo_move *m, int nmoves, bool wait) {
-    CommWindow *me = static_cast<CommWindow *>(peers->window[peers->rank]);
-    const unsigned long long t0 = global_ns();
-    __threadfence_system();
+// the exchange a kernel is performing, per move (shared memory; halo_begin fills it)
+struct HaloLive {
+    unsigned long long tag[kMaxFusedMoves];
+    char *send_slot[kMaxFusedMoves];        // the half of the peer's landing buffer this exchange writes
+    const char *recv_slot[kMaxFusedMoves];  // the half of this rank's landing buffer the peer writes
+};
+__device__ __forceinline__ void halo_live_move(HaloLive &hl, int q, const lsk_halo_move &mv, const CommWindow *me) {
+    // the pair counter is advanced by the LAST CTA of an exchanging kernel, after every CTA has read it here
+    const unsigned long long e = *reinterpret_cast<const volatile unsigned long long *>(&me->halo_sent[mv.peer]) + 1;
+    hl.tag[q] = (e & 0xffffffffull) << 32;
+    hl.send_slot[q] = static_cast<char *>(mv.ll_send) + (size_t) (e & 1) * (size_t) (mv.n + 1) * 16;
+    hl.recv_slot[q] = static_cast<const char *>(mv.ll_recv) + (size_t) (e & 1) * (size_t) (mv.recv_n + 1) * 16;
+}
+// All threads of the CTA call it (after pdl_wait: the pair counters belong to the preceding kernel).  CTA 0 also sends
+// the token packets: the (n + 1)st packet of every move, in both directions, data or not.
+__device__ __forceinline__ void halo_begin(HaloLive &hl, const lsk_halo_move *m, int nmoves, const lsk_peers *peers) {
+    const CommWindow *me = static_cast<const CommWindow *>(peers->window[peers->rank]);
     if ((int) threadIdx.x < nmoves) {
-        const lsk_halo_move &mv = m[threadIdx.x];
-        const unsigned long long e = me->halo_sent[mv.peer] + 1;
-        if (mv.n > 0) {
-            CommWindow *dst = static_cast<CommWindow *>(peers->window[mv.peer]);
-            *reinterpret_cast<volatile unsigned long long *>(&dst->halo_done[peers->rank]) = e;
-        }
-        if (wait && mv.expect) spin_until(&me->halo_done[mv.peer], e, &me->error);
-        me->halo_sent[mv.peer] = e;
+        halo_live_move(hl, threadIdx.x, m[threadIdx.x], me);
+        if (blockIdx.x == 0) ll_store(hl.send_slot[threadIdx.x], m[threadIdx.x].n, 0.0, hl.tag[threadIdx.x]);
     }
     __syncthreads();
-    if (wait) __threadfence_system();  // acquire side: the neighbours' data is visible to whatever runs next on this stream
+}
+// All threads of all CTAs call it once their own packets are out: copy the neighbours' values into the ghost regions.
+// Packet idx of move q is handled by global thread (idx mod grid threads); a packet that has not landed yet is polled.
+__device__ __forceinline__ void halo_unpack(const HaloLive &hl, const lsk_halo_move *m, int nmoves, const lsk_peers *peers) {
+    CommWindow *me = static_cast<CommWindow *>(peers->window[peers->rank]);
+    const int64_t g = (int64_t) blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t) gridDim.x * blockDim.x;
+    unsigned long long waited = 0;
+    for (int q = 0; q < nmoves; ++q) {
+        const int64_t cnt = m[q].recv_n;
+        double *dst = m[q].recv_dst;
+        for (int64_t idx = g; idx <= cnt; idx += stride) {  // idx == cnt: the token
+            double v;
+            if (!ll_try_load(hl.recv_slot[q], idx, hl.tag[q], v)) {
+                const unsigned long long t0 = global_ns();
+                unsigned int polls = 0;
+                unsigned long long t_start = 0;
+                while (!ll_try_load(hl.recv_slot[q], idx, hl.tag[q], v)) {
+                    if (spin_expired(polls, t_start)) {
+                        me->error = 1;
+                        v = __longlong_as_double(0x7ff8000000000000ll);  // a value that never arrived must not look like a number
+                        break;
+                    }
+                }
+                waited += global_ns() - t0;
+            }
+            if (idx < cnt) dst[idx] = v;
+        }
+    }
+    if (waited) atomicMax(&me->halo_poll_ns, waited);
+}
+// Executed by all threads of the LAST CTA of the kernel (after the ticket that made it the last): the exchange is complete
+// on this rank -- advance the pair counters.
+__device__ __forceinline__ void halo_finish(const lsk_halo_move *m, int nmoves, const lsk_peers *peers) {
+    CommWindow *me = static_cast<CommWindow *>(peers->window[peers->rank]);
+    if ((int) threadIdx.x < nmoves) me->halo_sent[m[threadIdx.x].peer] += 1;
     if (threadIdx.x == 0) {
         me->halo_calls += 1;
-        me->halo_wait_ns += global_ns() - t0;
+        me->halo_wait_ns += me->halo_poll_ns;
+        me->halo_poll_ns = 0;
     }
 }
 
@@ -563,6 +615,33 @@ inline int configure_once(lsk_ctx *ctx, int family, Setup setup) {
     ctx->configured |= bit;
     return 0;
 }
+
+// one halo move as the entry points accept it; y / n: the vector a fused kernel updates (send ranges are sub-ranges of it), or null
+inline bool halo_move_ok(const lsk_halo_move &m, const double *y, int64_t n, int nranks) {
+    if (m.peer < 0 || m.peer >= nranks || m.n < 0 || m.recv_n < 0) return false;
+    if (!m.ll_send || !m.ll_recv || ((reinterpret_cast<uintptr_t>(m.ll_send) | reinterpret_cast<uintptr_t>(m.ll_recv)) & 15) != 0) return false;
+    if (m.n > 0 && (!m.src || (y != nullptr && (m.src < y || m.src + m.n > y + n)))) return false;
+    if (m.recv_n > 0 && !m.recv_dst) return false;
+    return true;
+}
+#ifdef __CUDACC__
+inline bool halo_spec_fill(HaloSpec &h, const lsk_halo_move *moves, int nmoves, const double *y, int64_t n, int nranks) {
+    if (nmoves < 0 || nmoves > kMaxFusedMoves || (nmoves > 0 && !moves)) return false;
+    h.nmoves = nmoves;
+    for (int i = 0; i < kMaxFusedMoves; ++i) {
+        h.lo[i] = 0;
+        h.m[i] = lsk_halo_move{};
+    }
+    for (int i = 0; i < nmoves; ++i) {
+        if (!halo_move_ok(moves[i], y, n, nranks)) return false;
+        for (int j = 0; j < i; ++j)
+            if (moves[j].peer == moves[i].peer) return false;  // exchanges are numbered per pair: one move per peer
+        h.m[i] = moves[i];
+        h.lo[i] = (moves[i].n > 0 && y != nullptr) ? (int64_t) (moves[i].src - y) : 0;
+    }
+    return true;
+}
+#endif
 
 // claim a pending lsk_ctx_defer_next_allreduce request for this launch (only meaningful with peers)
 inline bool take_defer(lsk_ctx *ctx) {

@@ -8,8 +8,6 @@
 
 using namespace lsk;
 
-extern "C" size_t lsk_gridsync_bytes(void);  // lsk_cg.cu
-
 extern "C" {
 
 int lsk_version(void) { return LSK_VERSION; }
@@ -47,10 +45,8 @@ int lsk_ctx_create(int device, lsk_ctx **out) {
     ctx->cursor = 0;
     ctx->launches = 0;
     ctx->d_peers = nullptr;
-    ctx->gridsync = nullptr;
     ctx->work = nullptr;
     ctx->configured = 0;
-    ctx->cg_blocks_per_sm = 0;
     ctx->defer_next = 0;
     ctx->pending_slot = nullptr;
     const size_t pbytes = sizeof(double) * (size_t) kScratchSets * kMaxRed * kMaxPartials;
@@ -59,8 +55,6 @@ int lsk_ctx_create(int device, lsk_ctx **out) {
     if (e == cudaSuccess) e = cudaMalloc(&ctx->consts, sizeof(double) * 4);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->work, sizeof(unsigned long long) * kScratchSets);
     if (e == cudaSuccess) e = cudaMemset(ctx->work, 0, sizeof(unsigned long long) * kScratchSets);
-    if (e == cudaSuccess) e = cudaMalloc(&ctx->gridsync, lsk_gridsync_bytes());
-    if (e == cudaSuccess) e = cudaMemset(ctx->gridsync, 0, lsk_gridsync_bytes());
     if (e == cudaSuccess) e = cudaMemset(ctx->partials, 0, pbytes);
     if (e == cudaSuccess) e = cudaMemset(ctx->tickets, 0, sizeof(unsigned int) * kScratchSets);
     const double consts[4] = {1.0, -1.0, 0.0, 0.0};
@@ -80,7 +74,6 @@ int lsk_ctx_destroy(lsk_ctx *ctx) {
     if (ctx->tickets) cudaFree(ctx->tickets);
     if (ctx->consts) cudaFree(ctx->consts);
     if (ctx->d_peers) cudaFree(ctx->d_peers);
-    if (ctx->gridsync) cudaFree(ctx->gridsync);
     if (ctx->work) cudaFree(ctx->work);
     delete ctx;
     return 0;

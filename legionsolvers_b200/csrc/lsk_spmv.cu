@@ -542,31 +542,22 @@ static int launch_tma_kernel(lsk_ctx *ctx, int lpr, int ndot, cudaStream_t st, i
     }
 }
 
-// ---- the warp-specialised kernel (lsk_spmv_ws.cuh): lanes per row 1 .. 8, optional ghost gate ------------------------
-template <int LPR, bool GATED>
-static int launch_ws_kernel_cfg(lsk_ctx *ctx, int ndot, int grid, cudaStream_t st, const TmaSpmvArgs &a, const WsGate &g, RedScratch rs,
-                                double *o0, double *o1) {
+// ---- the warp-specialised kernel (lsk_spmv_ws.cuh): lanes per row 1 .. 8 ---------------------------------------------
+template <int LPR>
+static int launch_ws_kernel_lpr(lsk_ctx *ctx, int ndot, int grid, cudaStream_t st, const TmaSpmvArgs &a, RedScratch rs, double *o0, double *o1) {
     static const int family = configure_family_index();
     const int rc = configure_once(ctx, family, [] {
-        cudaError_t e = cudaFuncSetAttribute(csr_ws_kernel<0, LPR, GATED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kWsSmem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(csr_ws_kernel<1, LPR, GATED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kWsSmem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(csr_ws_kernel<2, LPR, GATED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kWsSmem);
+        cudaError_t e = cudaFuncSetAttribute(csr_ws_kernel<0, LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kWsSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(csr_ws_kernel<1, LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kWsSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(csr_ws_kernel<2, LPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kWsSmem);
         return e;
     });
     if (rc != 0) return rc;
     cudaError_t e;
-    if (ndot == 0) e = launch_pdl(kPdlSpmv, csr_ws_kernel<0, LPR, GATED>, grid, kWsThreads, kWsSmem, st, a, g, rs, o0, o1);
-    else if (ndot == 1) e = launch_pdl(kPdlSpmv, csr_ws_kernel<1, LPR, GATED>, grid, kWsThreads, kWsSmem, st, a, g, rs, o0, o1);
-    else e = launch_pdl(kPdlSpmv, csr_ws_kernel<2, LPR, GATED>, grid, kWsThreads, kWsSmem, st, a, g, rs, o0, o1);
+    if (ndot == 0) e = launch_pdl(kPdlSpmv, csr_ws_kernel<0, LPR>, grid, kWsThreads, kWsSmem, st, a, rs, o0, o1);
+    else if (ndot == 1) e = launch_pdl(kPdlSpmv, csr_ws_kernel<1, LPR>, grid, kWsThreads, kWsSmem, st, a, rs, o0, o1);
+    else e = launch_pdl(kPdlSpmv, csr_ws_kernel<2, LPR>, grid, kWsThreads, kWsSmem, st, a, rs, o0, o1);
     return (int) e;
-}
-
-template <int LPR>
-static int launch_ws_kernel_lpr(lsk_ctx *ctx, int ndot, int grid, cudaStream_t st, const TmaSpmvArgs &a, const WsGate *g, RedScratch rs,
-                                double *o0, double *o1) {
-    WsGate none = {};
-    if (g != nullptr) return launch_ws_kernel_cfg<LPR, true>(ctx, ndot, grid, st, a, *g, rs, o0, o1);
-    return launch_ws_kernel_cfg<LPR, false>(ctx, ndot, grid, st, a, none, rs, o0, o1);
 }
 
 static int ws_lanes_per_row(int64_t rows, int64_t nnz, int variant) {
@@ -582,7 +573,7 @@ static int ws_lanes_per_row(int64_t rows, int64_t nnz, int variant) {
 
 static int launch_ws_kernel(lsk_ctx *ctx, int lpr, int ndot, cudaStream_t st, int64_t rows, int64_t nnz, const double *entry,
                             const long long *col, const lsk_rect *rowptr, int64_t k_base, const double *x, double *y,
-                            const double *dot_w, const WsGate *gate, double *o0, double *o1, bool accumulate) {
+                            const double *dot_w, double *o0, double *o1, bool accumulate) {
     const int rpb = ws_rows_per_block(rows, nnz, lpr);
     const int64_t nrb = rows > 0 ? (rows + rpb - 1) / rpb : 0;  // no rows: one CTA that only finishes the fused dots (0)
     static const char *cta_env = getenv("LSK_WS_CTAS");  // developer knob: CTAs per SM
@@ -600,23 +591,10 @@ static int launch_ws_kernel(lsk_ctx *ctx, int lpr, int ndot, cudaStream_t st, in
         ctx->pending_slot = o0;
     }
     switch (lpr) {
-    case 1: return launch_ws_kernel_lpr<1>(ctx, ndot, grid, st, a, gate, rs, o0, o1);
-    case 2: return launch_ws_kernel_lpr<2>(ctx, ndot, grid, st, a, gate, rs, o0, o1);
-    case 4: return launch_ws_kernel_lpr<4>(ctx, ndot, grid, st, a, gate, rs, o0, o1);
-    default: return launch_ws_kernel_lpr<8>(ctx, ndot, grid, st, a, gate, rs, o0, o1);
-    }
-}
-
-// one thread per row: flags[row / rpb] = 1 if the row references a column outside [own_lo, own_lo + own_n)
-__global__ void __launch_bounds__(kBlock) csr_ghost_blocks_kernel(int64_t rows, int rpb, const lsk_rect *__restrict__ rowptr,
-                                                                  int64_t k_base, const long long *__restrict__ col, long long own_lo,
-                                                                  unsigned long long own_n, unsigned char *flags) {
-    for (int64_t r = (int64_t) blockIdx.x * kBlock + threadIdx.x; r < rows; r += (int64_t) gridDim.x * kBlock) {
-        const longlong2 rc = __ldg(reinterpret_cast<const longlong2 *>(rowptr + r));
-        bool ghost = false;
-        for (long long k = rc.x - k_base; k <= rc.y - k_base; ++k)
-            ghost |= ((unsigned long long) (__ldg(col + k) - own_lo) >= own_n);
-        if (ghost) flags[r / rpb] = 1;
+    case 1: return launch_ws_kernel_lpr<1>(ctx, ndot, grid, st, a, rs, o0, o1);
+    case 2: return launch_ws_kernel_lpr<2>(ctx, ndot, grid, st, a, rs, o0, o1);
+    case 4: return launch_ws_kernel_lpr<4>(ctx, ndot, grid, st, a, rs, o0, o1);
+    default: return launch_ws_kernel_lpr<8>(ctx, ndot, grid, st, a, rs, o0, o1);
     }
 }
 
@@ -635,7 +613,7 @@ static void launch_vector_kernel(int ndot, int grid, cudaStream_t st, int64_t ro
 template <typename T>
 static int csr_spmv(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const T *entry,
                     const int64_t *col, const lsk_rect *rowptr, int64_t k_base, const T *x_shifted, T *y,
-                    const T *dot_w, T *dot_out, T *dot_yy_out, int variant, const WsGate *gate = nullptr) {
+                    const T *dot_w, T *dot_out, T *dot_yy_out, int variant) {
     if (!ctx || rows < 0 || nnz < 0) return LSK_E_INVALID;
     if (rows > 0 && (!rowptr || !y || !x_shifted)) return LSK_E_INVALID;
     if (nnz > 0 && (!entry || !col)) return LSK_E_INVALID;
@@ -669,12 +647,11 @@ static int csr_spmv(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const
     const int impl = !impl_env ? 0 : (impl_env[0] == 't' ? 3 : impl_env[0] == 'p' ? 1 : impl_env[0] == 'r' ? 2 : 0);
     // ... and the warp-specialised one copies the rects with TMA as well: rowptr 16-byte aligned
     const bool ws_ok = tma_ok && reinterpret_cast<uintptr_t>(rowptr) % 16 == 0 && (variant == LSK_SPMV_STREAM || variant == LSK_SPMV_LANES);
-    if (gate != nullptr && !ws_ok) return LSK_E_INVALID;  // callers check lsk_csr_spmv_gated_supported
-    if (ws_ok && (impl == 0 || gate != nullptr)) {
+    if (ws_ok && impl == 0) {
         // the warp-specialised TMA pipeline: thread per row (bit-exact) or 2-8 lanes per row
         const int rc = launch_ws_kernel(ctx, ws_lanes_per_row(rows, nnz, variant), ndot, st, rows, nnz, reinterpret_cast<const double *>(entry),
                                         colp, rowptr, k_base, reinterpret_cast<const double *>(x_shifted), reinterpret_cast<double *>(y),
-                                        reinterpret_cast<const double *>(w), gate, reinterpret_cast<double *>(o0), reinterpret_cast<double *>(o1), accumulate);
+                                        reinterpret_cast<const double *>(w), reinterpret_cast<double *>(o0), reinterpret_cast<double *>(o1), accumulate);
         if (rc != 0) return rc;
         return after_launch(ctx);
     }
@@ -768,59 +745,6 @@ int lsk_csr_spmv_f64(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, cons
     return csr_spmv<double>(ctx, s, rows, nnz, entry, col, rowptr, k_base, x_shifted, y, dot_w, dot_out,
                             dot_yy_out, variant);
 }
-// ---- gated form (several GPUs): ghost columns guarded per row block --------------------------------------------------
-static int gated_variant(int64_t rows, int64_t nnz, int variant) {
-    variant &= ~LSK_SPMV_ACCUMULATE;
-    if (variant == LSK_SPMV_AUTO) variant = pick_variant(rows, nnz);
-    return variant;
-}
-int lsk_csr_spmv_gated_supported(int64_t rows, int64_t nnz, const double *entry, const int64_t *col, const lsk_rect *rowptr, int variant) {
-    if (rows <= 0 || nnz <= 0 || !entry || !col || !rowptr) return 0;
-    if (reinterpret_cast<uintptr_t>(rowptr) % 16 != 0) return 0;
-    const uintptr_t e = reinterpret_cast<uintptr_t>(entry), c = reinterpret_cast<uintptr_t>(col);
-    if (e % 8 != 0 || c % 8 != 0 || ((e >> 3) & 1) != ((c >> 3) & 1)) return 0;
-    variant = gated_variant(rows, nnz, variant);
-    return (variant == LSK_SPMV_STREAM || variant == LSK_SPMV_LANES) ? 1 : 0;
-}
-int64_t lsk_csr_spmv_row_blocks(int64_t rows, int64_t nnz, int variant) {
-    if (rows <= 0) return 0;
-    variant = gated_variant(rows, nnz, variant);
-    const int rpb = ws_rows_per_block(rows, nnz, ws_lanes_per_row(rows, nnz, variant));
-    return (rows + rpb - 1) / rpb;
-}
-int lsk_csr_ghost_blocks(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const int64_t *col, const lsk_rect *rowptr,
-                         int64_t k_base, int64_t own_lo, int64_t own_n, int variant, uint8_t *flags) {
-    if (!ctx || !flags || rows <= 0 || !rowptr || !col || own_n < 0) return LSK_E_INVALID;
-    variant = gated_variant(rows, nnz, variant);
-    const int rpb = ws_rows_per_block(rows, nnz, ws_lanes_per_row(rows, nnz, variant));
-    const int64_t nrb = (rows + rpb - 1) / rpb;
-    LSK_RETURN_IF_CUDA(cudaMemsetAsync(flags, 0, (size_t) nrb, (cudaStream_t) s));
-    const int grid = stream_grid(ctx, rows, 8);
-    csr_ghost_blocks_kernel<<<grid, kBlock, 0, (cudaStream_t) s>>>(rows, rpb, rowptr, k_base, reinterpret_cast<const long long *>(col),
-                                                                  own_lo, (unsigned long long) own_n, flags);
-    return after_launch(ctx);
-}
-int lsk_csr_spmv_gated_f64(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const double *entry, const int64_t *col,
-                           const lsk_rect *rowptr, int64_t k_base, const double *x_shifted, double *y, const double *dot_w,
-                           double *dot_out, double *dot_yy_out, int variant, const uint8_t *ghost_blocks, const lsk_halo_move *moves,
-                           int nmoves) {
-    if (!ctx || nmoves < 0 || nmoves > 4 || (nmoves > 0 && !moves)) return LSK_E_INVALID;
-    if (!ctx->d_peers) return LSK_E_INVALID;  // needs lsk_ctx_set_peers
-    if (!lsk_csr_spmv_gated_supported(rows, nnz, entry, col, rowptr, variant)) return LSK_E_INVALID;
-    CommWindow *me = static_cast<CommWindow *>(ctx->h_peers.window[ctx->h_peers.rank]);
-    WsGate g = {};
-    g.blocks = ghost_blocks;
-    g.error = &me->error;
-    for (int i = 0; i < nmoves; ++i) {
-        if (moves[i].peer < 0 || moves[i].peer >= ctx->h_peers.nranks) return LSK_E_INVALID;
-        if (!moves[i].expect) continue;
-        g.flag[g.nflags] = &me->halo_done[moves[i].peer];
-        g.want[g.nflags] = &me->halo_sent[moves[i].peer];
-        ++g.nflags;
-    }
-    return csr_spmv<double>(ctx, s, rows, nnz, entry, col, rowptr, k_base, x_shifted, y, dot_w, dot_out, dot_yy_out, variant, &g);
-}
-
 int lsk_csr_spmv_f32(lsk_ctx *ctx, lsk_stream s, int64_t rows, int64_t nnz, const float *entry,
                      const int64_t *col, const lsk_rect *rowptr, int64_t k_base, const float *x_shifted,
                      float *y, const float *dot_w, float *dot_out, float *dot_yy_out, int variant) {

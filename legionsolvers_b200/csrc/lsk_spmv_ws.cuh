@@ -27,10 +27,10 @@
 //
 // Tiles over-fetch to 16-byte boundaries inside [0, nnz) instead of patching single elements with scalar loads (the
 // neighbours' elements land in shared memory and are never read); scalar patching remains only at the two ends of the
-// piece.  Optional ghost gate (several GPUs): before the producer feeds a row block that references ghost columns it
-// waits for the neighbours' halo of the current exchange and fences at system scope; the mbarrier hand-over orders
-// the consumers' gathers after it.  Programmatic dependent launch: the producer needs nothing from the preceding
-// kernel (the matrix is constant), so the pipeline fills while the predecessor drains; consumers wait.
+// piece.  On several GPUs the ghost values of x are in place when the kernel starts (the kernel that produced x
+// exchanged its halo itself, lsk_blas1.cu), so the mat-vec knows nothing about ranks.  Programmatic dependent launch:
+// the producer needs nothing from the preceding kernel (the matrix is constant), so the pipeline fills while the
+// predecessor drains; consumers wait.
 #pragma once
 
 #include <limits.h>
@@ -72,17 +72,6 @@ struct WsMeta {
     int last;          // last tile of the row block: rows are finished
 };
 
-// ghost gate of the leaf mat-vec (see GhostGate in lsk_spmv_tma.cuh for the in-kernel form): which row blocks
-// reference ghost columns, and for every peer this rank receives from, the flag the peer writes and the pair's
-// exchange counter to compare it with (read when the gate is taken, i.e. after the preceding kernel completed)
-struct WsGate {
-    const unsigned char *blocks;   // one byte per row block; null = every block is guarded
-    int nflags;
-    const volatile unsigned long long *flag[4];
-    const volatile unsigned long long *want[4];
-    int *error;
-};
-
 // 64-bit warp min / max with redux.sync (one instruction per 32-bit half instead of five shuffle steps): first the
 // signed high words, then the unsigned low words of the lanes that hold the winning high word
 __device__ __forceinline__ long long warp_min_ll_redux(long long v) {
@@ -111,10 +100,9 @@ __device__ __forceinline__ longlong2 ld_rect_policy(const lsk_rect *p, uint64_t 
 
 //   NDOT   0: y only; 1: + y.w; 2: + y.w and y.y
 //   LPR    lanes per row (1 = thread per row, bit-exact; 2, 4, 8 = tree-combined partial sums)
-//   GATED  ghost columns are written by peers while the kernel runs (x is then read on the coherent path)
-template <int NDOT, int LPR, bool GATED>
+template <int NDOT, int LPR>
 __global__ void __launch_bounds__(kWsThreads, LSK_WS_MINB)
-csr_ws_kernel(TmaSpmvArgs a, WsGate gate, RedScratch rs, double *out_yw, double *out_yy) {
+csr_ws_kernel(TmaSpmvArgs a, RedScratch rs, double *out_yw, double *out_yy) {
     constexpr int S = kWsStages;
     constexpr int RPW = 32 / LPR;  // rows per consumer warp
     extern __shared__ __align__(128) unsigned char s_dyn[];
@@ -157,17 +145,9 @@ csr_ws_kernel(TmaSpmvArgs a, WsGate gate, RedScratch rs, double *out_yw, double 
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
         auto par = [&](long long j) { return (long long) ((reinterpret_cast<uintptr_t>(col + j) >> 3) & 1); };
 
-        // ---- the walk: position w = 0, 1, ... of this CTA -> row block blockIdx.x + v * G (nrb = none left); gated
-        // kernels start in the middle of the CTA's list (the first and last row blocks of a banded slab are the ones
-        // that read ghost columns: by then the halo has long arrived)
+        // ---- the walk: position w = 0, 1, ... of this CTA -> row block blockIdx.x + w * G (nrb = none left)
         const int64_t mine = nrb > (int64_t) blockIdx.x ? (nrb - 1 - blockIdx.x) / G + 1 : 0;
-        const int64_t kk0 = GATED ? mine / 2 : 0;
-        auto block_at = [&](int64_t k) -> int64_t {
-            if (k >= mine) return nrb;
-            int64_t v = k + kk0;
-            if (v >= mine) v -= mine;
-            return (int64_t) blockIdx.x + v * G;
-        };
+        auto block_at = [&](int64_t k) -> int64_t { return k >= mine ? nrb : (int64_t) blockIdx.x + k * G; };
         // sample rect of this lane for row block rb: lanes 0-15 the block's first rows, lanes 16-31 its last ones
         auto sample = [&](int64_t rb) -> longlong2 {
             longlong2 rc = make_longlong2(0, -1);
@@ -188,7 +168,6 @@ csr_ws_kernel(TmaSpmvArgs a, WsGate gate, RedScratch rs, double *out_yw, double 
         int64_t rb = block_at(0);
         int stage = 0;
         uint32_t empty_phase = (1u << S) - 1u;  // a fresh barrier passes a wait on the preceding phase
-        bool gate_open = false;
 
         while (rb < nrb) {
             const longlong2 rc = q[0];
@@ -209,17 +188,6 @@ csr_ws_kernel(TmaSpmvArgs a, WsGate gate, RedScratch rs, double *out_yw, double 
             // rows stored in scattered order can make the sampled interval arbitrarily long: beyond kWsMaxSpanTiles the
             // block gets an empty run and its rows take the direct path (bounded work for any input)
             if (je - jb > (long long) kWsMaxSpanTiles * kWsTile) jb = je = 0;
-            if constexpr (GATED) {
-                if (!gate_open && (gate.blocks == nullptr || __ldg(gate.blocks + rb) != 0)) {
-                    if (lane == 0) {
-                        pdl_wait();  // the pair counters are advanced by the kernel before this one
-                        for (int i = 0; i < gate.nflags; ++i) spin_until(gate.flag[i], *gate.want[i], gate.error);
-                        __threadfence_system();
-                    }
-                    __syncwarp();
-                    gate_open = true;
-                }
-            }
             const int64_t r0 = rb * rpb;
             const int64_t left = rows - r0;
             const uint32_t rect_bytes = (uint32_t) (left < rpb ? left : rpb) * 16u;
@@ -315,7 +283,7 @@ csr_ws_kernel(TmaSpmvArgs a, WsGate gate, RedScratch rs, double *out_yw, double 
                 acc = (a.accumulate && tsub == 0 && have) ? a.y[r] : 0.0;
                 if constexpr (NDOT >= 1) {  // requested now: its latency hides behind the gathers
                     // (w == y: the y.y-only form of the C ABI; the row's own result is used instead, below)
-                    if (tsub == 0 && have && a.dot_w != a.y) wv = GATED ? ld_f64(a.dot_w + r) : __ldg(a.dot_w + r);
+                    if (tsub == 0 && have && a.dot_w != a.y) wv = __ldg(a.dot_w + r);
                 }
             }
             if (!direct) {
@@ -334,7 +302,7 @@ csr_ws_kernel(TmaSpmvArgs a, WsGate gate, RedScratch rs, double *out_yw, double 
                         double xv[kChunk];
 #pragma unroll
                         for (int e = 0; e < kChunk; ++e)
-                            xv[e] = (j + e * LPR < kb) ? (GATED ? ld_f64(x + sc[j + e * LPR]) : __ldg(x + sc[j + e * LPR])) : 0.0;
+                            xv[e] = (j + e * LPR < kb) ? __ldg(x + sc[j + e * LPR]) : 0.0;
 #pragma unroll
                         for (int e = 0; e < kChunk; ++e)
                             if (j + e * LPR < kb) acc = add_rn(acc, mul_rn(se[j + e * LPR], xv[e]));
@@ -343,7 +311,7 @@ csr_ws_kernel(TmaSpmvArgs a, WsGate gate, RedScratch rs, double *out_yw, double 
                     for (; j + kChunk <= kb; j += kChunk) {
                         double xv[kChunk];
 #pragma unroll
-                        for (int e = 0; e < kChunk; ++e) xv[e] = GATED ? ld_f64(x + sc[j + e]) : __ldg(x + sc[j + e]);
+                        for (int e = 0; e < kChunk; ++e) xv[e] = __ldg(x + sc[j + e]);
 #pragma unroll
                         for (int e = 0; e < kChunk; ++e) acc = add_rn(acc, mul_rn(se[j + e], xv[e]));
                     }
@@ -352,7 +320,7 @@ csr_ws_kernel(TmaSpmvArgs a, WsGate gate, RedScratch rs, double *out_yw, double 
                         double xv[kChunk - 1];
 #pragma unroll
                         for (int e = 0; e < kChunk - 1; ++e)
-                            xv[e] = (e < rem) ? (GATED ? ld_f64(x + sc[j + e]) : __ldg(x + sc[j + e])) : 0.0;
+                            xv[e] = (e < rem) ? (__ldg(x + sc[j + e])) : 0.0;
 #pragma unroll
                         for (int e = 0; e < kChunk - 1; ++e)
                             if (e < rem) acc = add_rn(acc, mul_rn(se[j + e], xv[e]));
@@ -367,7 +335,7 @@ csr_ws_kernel(TmaSpmvArgs a, WsGate gate, RedScratch rs, double *out_yw, double 
                     // rows stored out of order: the tiles did not cover this one.  Same sum, same order, from global memory.
                     for (long long k = lo; k < hi1; ++k) {
                         const long long c = load1_stream(a.col + k);
-                        acc = add_rn(acc, mul_rn(load1_stream(a.entry + k), GATED ? ld_f64(x + c) : __ldg(x + c)));
+                        acc = add_rn(acc, mul_rn(load1_stream(a.entry + k), __ldg(x + c)));
                     }
                 }
                 if constexpr (LPR > 1) {

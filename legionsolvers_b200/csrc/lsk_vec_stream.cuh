@@ -131,34 +131,20 @@ __device__ __forceinline__ bool halo_chunk_overlaps(const HaloSpec &h, int64_t i
     for (int q = 0; q < 4; ++q) any |= (q < h.nmoves && i0 + cnt > h.lo[q] && i0 < h.lo[q] + h.m[q].n);
     return any;
 }
-// store the new values of elements i, i + 1 into every neighbour whose range holds them; true if anything went out
-__device__ __forceinline__ bool halo_mirror_pair(const HaloSpec &h, int64_t i, double p0, double p1) {
-    bool remote = false;
+// the new values of elements i, i + 1 leave as packets for every neighbour whose send range holds them
+__device__ __forceinline__ void halo_send_pair(const HaloSpec &h, const HaloLive &hl, int64_t i, double p0, double p1) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < kMaxFusedMoves; ++q) {
         if (q < h.nmoves && i + 2 > h.lo[q] && i < h.lo[q] + h.m[q].n) {
-            double *d = h.m[q].dst + (i - h.lo[q]);
-            remote = true;
-            const bool inside = (i >= h.lo[q]) && (i + 2 <= h.lo[q] + h.m[q].n);
-            if (inside && (reinterpret_cast<uintptr_t>(d) & 15) == 0) {
-                *reinterpret_cast<double2 *>(d) = make_double2(p0, p1);
-            } else {
-                if (i >= h.lo[q] && i < h.lo[q] + h.m[q].n) d[0] = p0;
-                if (i + 1 >= h.lo[q] && i + 1 < h.lo[q] + h.m[q].n) d[1] = p1;
-            }
+            if (i >= h.lo[q]) ll_store(hl.send_slot[q], i - h.lo[q], p0, hl.tag[q]);
+            if (i + 1 < h.lo[q] + h.m[q].n) ll_store(hl.send_slot[q], i + 1 - h.lo[q], p1, hl.tag[q]);
         }
     }
-    return remote;
 }
-__device__ __forceinline__ bool halo_mirror_one(const HaloSpec &h, int64_t i, double v) {
-    bool remote = false;
+__device__ __forceinline__ void halo_send_one(const HaloSpec &h, const HaloLive &hl, int64_t i, double v) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-        if (q < h.nmoves && i >= h.lo[q] && i < h.lo[q] + h.m[q].n) {
-            h.m[q].dst[i - h.lo[q]] = v;
-            remote = true;
-        }
-    return remote;
+    for (int q = 0; q < kMaxFusedMoves; ++q)
+        if (q < h.nmoves && i >= h.lo[q] && i < h.lo[q] + h.m[q].n) ll_store(hl.send_slot[q], i - h.lo[q], v, hl.tag[q]);
 }
 // chunks from the first one that overlaps a send range not at the start of the vector are taken first: their
 // results also travel over NVLink, which then overlaps the rest of the pass

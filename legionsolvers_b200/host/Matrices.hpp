@@ -27,14 +27,6 @@ struct MatvecFusion {
     std::vector<T *> yw, yy;                  // indexed by colour; null = not wanted
 };
 
-// optional ghost gate of a mat-vec on several GPUs: the halo exchange of `src` is still OPEN (published by the
-// producing kernel, not yet awaited); the mat-vec kernel waits per row block (lsk_csr_spmv_gated_f64)
-struct MatvecGate {
-    const uint8_t *blocks = nullptr;        // flags of the (single) local piece, from gate_flags()
-    const lsk_halo_move *moves = nullptr;   // peers to expect data from
-    int nmoves = 0;
-};
-
 template <typename T>
 class AbstractLinearOperator {
 public:
@@ -57,19 +49,12 @@ public:
     // accumulate: dst += A src instead of dst = A src (matrices that overwrite, i.e. CSR: a further block on the same rows)
     virtual void matvec(PartitionedVector<T> &dst, const PartitionedVector<T> &src, const IntervalPartition &kernel_partition,
                         const IntervalPartition &ghost_partition, const MatvecFusion<T> *fusion = nullptr,
-                        const MatvecGate *gate = nullptr, bool accumulate = false) const = 0;
+                        bool accumulate = false) const = 0;
     // dst += A^T src (CSRRmatvecTask / COORmatvecTask, reserved but unimplemented in the reference): dst lives on the DOMAIN
     // space, src on the range space; accumulates.  dst must hold every column the local pieces reference.
     virtual void rmatvec(PartitionedVector<T> &dst, const PartitionedVector<T> &src, const IntervalPartition &kernel_partition,
                          const IntervalPartition &ghost_partition) const = 0;
     virtual bool overwrites_output() const = 0;  // CSR: beta = 0; COO: beta = 1 (reference GPU variants)
-    // gated mat-vec of the piece of colour c (rows [r_lo, r_lo + nrow)): 0 = not available for this matrix / piece,
-    // else the number of row-block flags; gate_flags computes them (which row blocks reference a column outside the rows)
-    virtual int64_t gate_row_blocks(int /*c*/, int64_t /*r_lo*/, int64_t /*nrow*/, const IntervalPartition & /*kp*/) const { return 0; }
-    virtual void gate_flags(int /*c*/, int64_t /*r_lo*/, int64_t /*nrow*/, const IntervalPartition & /*kp*/, uint8_t * /*flags*/) const {}
-    // CSR fields of the piece of colour c (rows r_lo.., kernel piece kp), for kernels that take the whole
-    // problem (lsk_cg_steps_f64); false = not a CSR matrix of this entry type
-    virtual bool csr_piece(int /*c*/, int64_t /*r_lo*/, const IntervalPartition & /*kp*/, lsk_cg_problem * /*out*/) const { return false; }
 
     IntervalPartition domain_partition_from_range_partition(int64_t domain_volume,
                                                             const IndexPartition &range_partition) const override {
@@ -190,21 +175,6 @@ public:
         return gp;
     }
 
-    bool csr_piece(int c, int64_t r_lo, const IntervalPartition &kp, lsk_cg_problem *out) const override {
-        if constexpr (!std::is_same<T, double>::value) {
-            return false;
-        } else {
-            const int64_t k_lo = kp.lo[(size_t) c], nk = kp.hi[(size_t) c] - k_lo + 1;
-            if (nk <= 0 || r_lo < slab_r_lo) return false;
-            out->nnz = nk;
-            out->entry = entry.ptr + (k_lo - slab_k_lo);
-            out->col = col.ptr + (k_lo - slab_k_lo);
-            out->rowptr = rowptr.ptr + (r_lo - slab_r_lo);
-            out->k_base = k_lo;
-            return true;
-        }
-    }
-
     void rmatvec(PartitionedVector<T> &dst, const PartitionedVector<T> &src, const IntervalPartition &kp,
                  const IntervalPartition &gp) const override {
         if constexpr (!std::is_same<T, double>::value) {
@@ -228,32 +198,10 @@ public:
         }
     }
 
-    int64_t gate_row_blocks(int c, int64_t r_lo, int64_t nrow, const IntervalPartition &kp) const override {
-        if constexpr (!std::is_same<T, double>::value) {
-            return 0;
-        } else {
-            const int64_t k_lo = kp.lo[(size_t) c], nk = kp.hi[(size_t) c] - k_lo + 1;
-            if (nk <= 0 || nrow <= 0 || r_lo < slab_r_lo) return 0;
-            if (!lsk_csr_spmv_gated_supported(nrow, nk, entry.ptr + (k_lo - slab_k_lo), col.ptr + (k_lo - slab_k_lo),
-                                              rowptr.ptr + (r_lo - slab_r_lo), LSK_SPMV_AUTO))
-                return 0;
-            return lsk_csr_spmv_row_blocks(nrow, nk, LSK_SPMV_AUTO);
-        }
-    }
-    void gate_flags(int c, int64_t r_lo, int64_t nrow, const IntervalPartition &kp, uint8_t *flags) const override {
-        const int64_t k_lo = kp.lo[(size_t) c], nk = kp.hi[(size_t) c] - k_lo + 1;
-        const int64_t *cc = col.ptr + (k_lo - slab_k_lo);
-        const lsk_rect *rp = rowptr.ptr + (r_lo - slab_r_lo);
-        rt->enqueue("csr ghost blocks", [&] {
-            return lsk_csr_ghost_blocks(rt->ctx(), rt->stream(), nrow, nk, cc, rp, k_lo, r_lo, nrow, LSK_SPMV_AUTO, flags);
-        });
-    }
-
     // CSRMatrix::matvec (src/CSRMatrix.cpp:158-214): one CSRMatvecTask per piece of dst with regions
     // {dst piece, kernel piece, rowptr piece, ghost piece of src}
     void matvec(PartitionedVector<T> &dst, const PartitionedVector<T> &src, const IntervalPartition &kp,
-                const IntervalPartition &gp, const MatvecFusion<T> *fusion = nullptr, const MatvecGate *gate = nullptr,
-                bool accumulate = false) const override {
+                const IntervalPartition &gp, const MatvecFusion<T> *fusion = nullptr, bool accumulate = false) const override {
         const IndexPartition &p = dst.partition();
         for (int c = p.first_color; c < p.end_color; ++c) {
             const int64_t r_lo = p.lo[(size_t) c], nrow = p.piece_size(c);
@@ -268,15 +216,6 @@ public:
             const T *w = (fusion && fusion->w && fusion->yw[(size_t) c]) ? fusion->w->ptr(r_lo) : nullptr;
             T *ow = w ? fusion->yw[(size_t) c] : nullptr;
             T *oyy = (fusion && !fusion->yy.empty()) ? fusion->yy[(size_t) c] : nullptr;
-            if constexpr (std::is_same<T, double>::value) {
-                if (gate != nullptr && !accumulate) {  // the halo of src is still in flight: the kernel waits per row block
-                    rt->enqueue("csr matvec (gated)", [&] {
-                        return lsk_csr_spmv_gated_f64(rt->ctx(), rt->stream(), nrow, nk, e, cc, rp, k_lo, x, y, w, ow, oyy, LSK_SPMV_AUTO,
-                                                      gate->blocks, gate->moves, gate->nmoves);
-                    });
-                    continue;
-                }
-            }
             rt->enqueue("csr matvec", [&] {
                 return SpmvKernels<T>::csr(rt->ctx(), rt->stream(), nrow, nk > 0 ? nk : 0, e, cc, rp, nk > 0 ? k_lo : 0, x, y, w, ow, oyy, accumulate);
             });
@@ -374,7 +313,7 @@ public:
 
     // COOMatrix::matvec (src/COOMatrix.cpp:144-191): accumulates into dst (beta = 1)
     void matvec(PartitionedVector<T> &dst, const PartitionedVector<T> &src, const IntervalPartition &kp,
-                const IntervalPartition &gp, const MatvecFusion<T> * = nullptr, const MatvecGate * = nullptr, bool = false) const override {
+                const IntervalPartition &gp, const MatvecFusion<T> * = nullptr, bool = false) const override {
         const IndexPartition &p = dst.partition();
         for (int c = p.first_color; c < p.end_color; ++c) {
             const int64_t k_lo = kp.lo[(size_t) c], nk = kp.hi[(size_t) c] - k_lo + 1;

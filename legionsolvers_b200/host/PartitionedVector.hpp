@@ -98,8 +98,6 @@ class PartitionedVector {
         int64_t buf_lo = 0, buf_hi = -1;  // global range held on this rank (owned rows + halo)
         void *raw = nullptr;              // allocation
         T *base = nullptr;                // element buf_lo
-        Runtime::Exported peers;          // the same vector's buffers on the other ranks (CUDA IPC), if exported
-        bool exported = false;
         ~Storage() {
             if (raw) rt->free(raw);
         }
@@ -143,28 +141,10 @@ public:
     int64_t buf_lo() const { return st->buf_lo; }
     int64_t buf_hi() const { return st->buf_hi; }
 
-    // COLLECTIVE in multi-rank peer-memory mode: map this vector's buffer into every peer so that
-    // halo values can be stored straight into the neighbours' ghost regions
-    void export_to_peers() {
-        Runtime *rt = st->rt;
-        if (!rt->p2p() || !std::is_same<T, double>::value) return;
-        const int64_t elem0_off = (int64_t) (reinterpret_cast<char *>(st->base) - reinterpret_cast<char *>(st->raw));
-        st->peers = rt->export_allocation(st->raw, elem0_off, st->buf_lo);
-        st->exported = true;
-    }
-    bool exported() const { return st->exported; }
-    // address of global element `g` of this vector on rank r, as mapped into this process
-    T *peer_ptr(int r, int64_t g) const {
-        return reinterpret_cast<T *>(st->peers.base[(size_t) r] + st->peers.tag0[(size_t) r]) + (g - st->peers.tag1[(size_t) r]);
-    }
-
-    // make room for a ghost interval [lo, hi]; owned data is preserved (set-up time only).
-    // COLLECTIVE in multi-rank mode (every rank calls it for the same vectors in the same order).
+    // make room for a ghost interval [lo, hi]; owned data is preserved (set-up time only).  Ghost values are only ever
+    // written by this rank's own kernels (the halo exchange unpacks the neighbours' packets locally), so a vector's
+    // buffer is never mapped into another process and can be re-allocated freely.
     void ensure_range(int64_t lo, int64_t hi) {
-        ensure_range_local(lo, hi);
-        export_to_peers();
-    }
-    void ensure_range_local(int64_t lo, int64_t hi) {
         if (hi < lo) return;
         const int64_t nlo = std::min(lo, st->buf_lo), nhi = std::max(hi, st->buf_hi);
         if (st->buf_hi >= st->buf_lo && nlo == st->buf_lo && nhi == st->buf_hi) return;

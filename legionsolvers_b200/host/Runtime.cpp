@@ -27,7 +27,6 @@ Runtime::Runtime(int device, int rank, int nranks, void *external_stream)
 }
 
 Runtime::~Runtime() {
-    has_deferred_ = false;
     cudaSetDevice(device_);
     cudaStreamSynchronize(stream_);
     for (auto &kv : traces_)
@@ -162,10 +161,6 @@ void Runtime::halo_exchange_p2p(const lsk_halo_move *moves, int nmoves) {
     enqueue("halo exchange", [&] { return lsk_halo_exchange_f64(ctx_, stream_, &peers_, moves, nmoves); });
 }
 
-void Runtime::halo_wait_p2p(const lsk_halo_move *moves, int nmoves) {
-    enqueue("halo wait", [&] { return lsk_halo_wait_f64(ctx_, stream_, &peers_, moves, nmoves); });
-}
-
 void Runtime::set_fused_collectives(bool on) {
     if (on && !p2p_) return;
     if (on == fused_) return;
@@ -178,14 +173,11 @@ void Runtime::set_fused_collectives(bool on) {
 }
 
 int Runtime::comm_error() {
-    flush_deferred();
-    int e = 0, g = 0;
-    int rc = lsk_ctx_error(ctx_, stream_, &g);
-    if (rc != 0) fail(rc, "lsk_ctx_error");
-    if (!p2p_) return g;
-    rc = lsk_comm_error(ctx_, stream_, &peers_, &e);
+    int e = 0;
+    if (!p2p_) return 0;
+    const int rc = lsk_comm_error(ctx_, stream_, &peers_, &e);
     if (rc != 0) fail(rc, "lsk_comm_error");
-    return e | g;
+    return e;
 }
 
 #define LSK_NCCL(expr, what)                              \
@@ -194,7 +186,6 @@ int Runtime::comm_error() {
     } while (0)
 
 void Runtime::allreduce_sum(double *slots, int count) {
-    flush_deferred();
     if (nranks_ == 1 || mode_ == Mode::Replay) return;
     if (fused_) fail(LSK_E_INVALID, "stand-alone all-reduce while reductions are fused (would double count)");
     if (p2p_) {
@@ -207,7 +198,6 @@ void Runtime::allreduce_sum(double *slots, int count) {
 }
 
 void Runtime::allgather_i64(const int64_t *send_dev, int64_t *recv_dev, int count_per_rank) {
-    flush_deferred();
     if (nranks_ == 1) {
         check_cuda(cudaMemcpyAsync(recv_dev, send_dev, sizeof(int64_t) * (size_t) count_per_rank,
                                    cudaMemcpyDeviceToDevice, stream_), "allgather copy");
@@ -219,7 +209,6 @@ void Runtime::allgather_i64(const int64_t *send_dev, int64_t *recv_dev, int coun
 }
 
 void Runtime::group_start() {
-    flush_deferred();
     if (nranks_ > 1 && mode_ != Mode::Replay) LSK_NCCL(ncclGroupStart(), "ncclGroupStart");
 }
 void Runtime::group_end() {
@@ -245,7 +234,6 @@ void *Runtime::alloc(size_t bytes) {
 
 void Runtime::free(void *p) {
     if (!p) return;
-    flush_deferred();
     auto it = std::find(allocations_.begin(), allocations_.end(), p);
     if (it != allocations_.end()) {
         allocations_.erase(it);
@@ -273,7 +261,6 @@ double *Runtime::new_slot() {
 
 // ---- tracing ---------------------------------------------------------------------------------------------
 void Runtime::begin_trace(int id) {
-    flush_deferred();  // work deferred before the trace does not belong to it
     if (mode_ != Mode::Eager || eager_trace_) fail(LSK_E_INVALID, "begin_trace: traces do not nest");
     active_trace_ = id;
     static const bool eager = [] { const char *e = std::getenv("LSK_TRACE"); return e && std::string(e) == "eager"; }();
@@ -292,7 +279,6 @@ void Runtime::begin_trace(int id) {
 }
 
 void Runtime::end_trace(int id) {
-    flush_deferred();  // work deferred inside the trace is recorded (or, on replay, skipped) now
     if (eager_trace_ && id == active_trace_) {
         eager_trace_ = false;
         active_trace_ = -1;
@@ -319,14 +305,13 @@ void Runtime::end_trace(int id) {
 }
 
 void Runtime::fence() {
-    flush_deferred();
     check_cuda(cudaStreamSynchronize(stream_), "cudaStreamSynchronize");
-    // A spin-wait of a peer-memory collective (or of a persistent kernel's barrier) that gave up only raises a device
+    // A spin-wait of a peer-memory collective that gave up only raises a device
     // flag (and poisons the reduced value with NaN): surface it here, at the first host synchronisation after it, instead
     // of returning numbers computed from stale ghosts with status 0.
     if (nranks_ > 1 && p2p_ && mode_ == Mode::Eager) {
-        int e = 0, g = 0;
-        if (lsk_comm_error(ctx_, stream_, &peers_, &e) == 0 && lsk_ctx_error(ctx_, stream_, &g) == 0 && (e | g) != 0)
+        int e = 0;
+        if (lsk_comm_error(ctx_, stream_, &peers_, &e) == 0 && e != 0)
             fail(LSK_E_NCCL, "a peer-memory collective timed out (dead or diverged peer): results are invalid");
     }
 }

@@ -43,38 +43,7 @@ public:
     Runtime &operator=(const Runtime &) = delete;
 
     lsk_ctx *ctx() const { return ctx_; }
-    // Every device operation obtains the stream here, so work a solver has DEFERRED (see defer()) is
-    // issued first and stream order equals program order.
-    cudaStream_t stream() const {
-        if (has_deferred_) const_cast<Runtime *>(this)->flush_deferred();
-        return stream_;
-    }
-
-    // ---- deferred execution -------------------------------------------------------------------------
-    // Like Legion, the runtime may delay issuing work: CGSolver::step() only counts, and the steps that
-    // have accumulated are issued as ONE persistent-kernel launch when anything else touches the stream
-    // (another operation, a fence, the end of a trace).  One owner at a time; a different owner flushes.
-    void defer(const void *owner, std::function<void()> flush) {
-        if (has_deferred_ && deferred_owner_ != owner) flush_deferred();
-        deferred_owner_ = owner;
-        deferred_ = std::move(flush);
-        has_deferred_ = true;
-    }
-    void flush_deferred() {
-        if (!has_deferred_) return;
-        has_deferred_ = false;
-        std::function<void()> f = std::move(deferred_);
-        deferred_ = nullptr;
-        deferred_owner_ = nullptr;
-        f();
-    }
-    void drop_deferred(const void *owner) {  // the owner is going away
-        if (has_deferred_ && deferred_owner_ == owner) {
-            has_deferred_ = false;
-            deferred_ = nullptr;
-            deferred_owner_ = nullptr;
-        }
-    }
+    cudaStream_t stream() const { return stream_; }
     int device() const { return device_; }
     int rank() const { return rank_; }
     int nranks() const { return nranks_; }
@@ -94,13 +63,12 @@ public:
     // COLLECTIVE (every rank, same order): export `raw` and map everybody else's
     Exported export_allocation(void *raw, int64_t tag0, int64_t tag1);
     void halo_exchange_p2p(const lsk_halo_move *moves, int nmoves);
-    void halo_wait_p2p(const lsk_halo_move *moves, int nmoves);  // closes an open exchange (lsk_halo_wait_f64)
     // Fused collectives: every reducing kernel finishes with the cross-rank sum in its own tail, and
     // lsk_xpay_halo_f64 may be used.  Valid only while every rank launches exactly the same reducing
     // kernels (one local piece per rank); the planner switches it on when that holds.
     void set_fused_collectives(bool on);
     bool fused_collectives() const { return fused_; }
-    int comm_error();   // non-zero if a spin-wait of a collective or of a persistent kernel gave up
+    int comm_error();   // non-zero if a spin-wait of a collective gave up
     void allgather_i64(const int64_t *send_dev, int64_t *recv_dev, int count_per_rank);
     void group_start();
     void group_end();
@@ -122,7 +90,6 @@ public:
     // is being replayed (the graph launch at end_trace does the work), checked otherwise.
     template <class F>
     void enqueue(const char *what, F &&f) {
-        if (has_deferred_) flush_deferred();
         if (mode_ == Mode::Replay) return;
         const int rc = f();
         if (rc != 0) fail(rc, what);
@@ -154,9 +121,6 @@ private:
     std::vector<void *> ipc_opened_;
     std::map<std::string, void *> ipc_cache_;
     Mode mode_ = Mode::Eager;
-    bool has_deferred_ = false;
-    const void *deferred_owner_ = nullptr;
-    std::function<void()> deferred_;
     int active_trace_ = -1;
     bool eager_trace_ = false;
     uint64_t capture_mark_ = 0;

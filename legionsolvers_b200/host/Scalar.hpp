@@ -133,7 +133,7 @@ public:
             return lsk_scalar_append_f64(rt->ctx(), rt->stream(), v, hist.ptr, capacity, count.ptr, a);
         });
     }
-    // raw views for kernels that append by themselves (the persistent CG kernel)
+    // raw views for kernels that append by themselves (lsk_cg_direction_f64)
     double *data() const { return hist.ptr; }
     int64_t *count_ptr() const { return count.ptr; }
     int64_t get_capacity() const { return capacity; }
@@ -143,7 +143,6 @@ public:
     }
     int64_t size() const {
         int64_t n = 0;
-        rt->flush_deferred();
         rt->check_cuda(cudaMemcpyAsync(&n, count.ptr, sizeof(n), cudaMemcpyDeviceToHost, rt->stream()), "history size");
         rt->fence();
         return n;

@@ -29,43 +29,28 @@ private:
 
 public:
     // constructor (src/CGSolver.hpp:32-44): workspace(3); P <- RHS; R <- RHS (x0 = 0 assumed); rr0 = R.R
-    // `use_persistent`: run the whole step as the persistent kernel (lsk_cg_steps_f64) when the problem is eligible.
-    // Off by default: on the 256^3 benchmark the three leaf kernels are ~2 % faster at 1, 2 and 8 GPUs.
-    explicit CGSolver(SquarePlanner<T> &planner_, bool fused_ = true, int64_t history_capacity = 1 << 16, bool use_persistent = false)
+    explicit CGSolver(SquarePlanner<T> &planner_, bool fused_ = true, int64_t history_capacity = 1 << 16)
         : planner(planner_), residual_norm_squared(planner_.get_runtime(), history_capacity),
           negative_one(planner_.get_runtime(), static_cast<T>(-1)), fused(fused_), rr_cur(planner_.get_runtime()),
           rr_new(planner_.get_runtime()), p_norm(planner_.get_runtime()) {
         planner.allocate_workspace(3);
-        if (fused && use_persistent) {
-            lsk_cg_problem pb{};
-            lsk_halo_move moves[4];
-            persistent = planner.cg_problem(SOL, R, P, Q, &pb, moves);
-        }
         reset();
     }
 
     // start a new solve with the current RHS (and SOL taken as 0, like the constructor)
     void reset() {
-        planner.get_runtime()->flush_deferred();
         residual_norm_squared.clear();
         planner.copy(P, RHS);
         planner.copy(R, RHS);
         planner.dot_into(R, R, rr_cur);
         residual_norm_squared.push_back(rr_cur);
-        // when the xpay pushes P's boundary itself, every step ends with current ghosts; make it START so too,
+        // when the xpay exchanges P's halo itself, every step ends with current ghosts; make it START so too,
         // so that the launch sequence of a step is the same from the first one on (traces are replayed)
-        if (fused && (persistent || planner.halo_push_is_fused())) planner.refresh_halo(P);
+        if (fused && planner.halo_push_is_fused()) planner.refresh_halo(P);
     }
 
     // step (src/CGSolver.hpp:46-55)
     void step() {
-        if (persistent) {
-            // deferred: consecutive steps are issued as ONE persistent-kernel launch when anything else
-            // touches the stream (Runtime::defer)
-            ++pending;
-            planner.get_runtime()->defer(this, [this] { flush(); });
-            return;
-        }
         if (fused) {
             // several ranks: the two dot products are only SENT by their producers; the next kernel -- their only
             // consumer -- forms the cross-rank sums at its start, so the NVLink flight overlaps the kernel boundary
@@ -74,9 +59,9 @@ public:
             planner.matvec_dot(Q, P, P, p_norm);                     // Q = A P and P.Q in one pass
             if (defer) planner.defer_next_allreduce();
             planner.cg_update(SOL, R, rr_cur, p_norm, P, Q, rr_new);  // both axpys and R.R in one pass
-            // append rr_new, P = R + (rr_new/rr_cur) P (boundary into the neighbours' ghosts), rr_cur <- rr_new: one launch
+            // append rr_new, P = R + (rr_new/rr_cur) P (halo of P exchanged by the same kernel), rr_cur <- rr_new: one launch
             if (planner.cg_direction(P, rr_new, rr_cur, R, residual_norm_squared)) return;
-            planner.xpay_halo(P, rr_new, rr_cur, R);                  // P's boundary goes to the neighbours' ghosts
+            planner.xpay_halo(P, rr_new, rr_cur, R);                  // P's halo is exchanged by the same kernel
         } else {
             planner.matvec(Q, P);
             planner.dot_into(P, Q, p_norm);
@@ -88,20 +73,8 @@ public:
         residual_norm_squared.push_back(rr_new, &rr_cur);  // append, and rr_cur <- rr_new for the next step
     }
 
-    ~CGSolver() { planner.get_runtime()->drop_deferred(this); }
     CGSolver(const CGSolver &) = delete;
     CGSolver &operator=(const CGSolver &) = delete;
-
-    bool is_persistent() const { return persistent; }
-
-private:
-    bool persistent = false;  // the whole step runs as lsk_cg_steps_f64
-    int pending = 0;
-    void flush() {
-        const int n = pending;
-        pending = 0;
-        if (n > 0) planner.cg_steps(SOL, R, P, Q, rr_cur, rr_new, p_norm, residual_norm_squared, n);
-    }
 };
 
 template <typename T>

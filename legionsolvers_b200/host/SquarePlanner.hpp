@@ -30,9 +30,13 @@ class SquarePlanner {
         IntervalPartition kernel_partition, ghost_partition;
         std::vector<HaloMove> halo;  // what to trade with each peer before a mat-vec
         std::vector<Scalar<T>> part_yw, part_yy;  // per-colour partial slots of the fused dots
-        // gated mat-vec (one local piece, CSR): which row blocks reference ghost columns; -1 = not looked at yet, 0 = unavailable
-        int64_t gate_nrb = -1;
-        DeviceBuffer<uint8_t> gate_blocks;
+        // peer-memory exchange (lsk_halo_move): ONE landing allocation per block and rank, holding the landing buffer of
+        // every peer this rank trades with, in the order of `halo`; recv_off / send_off = byte offset of move i's landing
+        // buffer inside this rank's / inside the peer's allocation
+        DeviceBuffer<char> landing;
+        Runtime::Exported landing_peers;
+        std::vector<size_t> recv_off, send_off;
+        bool landing_ready = false;
     };
 
     Runtime *rt;
@@ -43,59 +47,25 @@ class SquarePlanner {
     std::vector<std::pair<int64_t, int64_t>> space_need;  // ghost range every vector of a space must hold
     std::vector<std::vector<Scalar<T>>> piece_partials;   // [slot set][space-major local piece]
     uint64_t halo_bytes_per_matvec = 0;
-    DeviceBuffer<uint8_t> cg_ghost_blocks;  // lsk_cg_ghost_blocks flags of the (single) CSR block, see cg_problem
     std::set<std::size_t> halo_fresh;  // vector ids whose ghost values are current on every rank
-    // vector ids whose boundary has been pushed into the neighbours but whose own ghosts have not been awaited yet (an OPEN
-    // exchange, lsk_cg_direction_f64 halo_open): the next mat-vec of that vector waits per row block, any other reader of the
-    // ghosts closes the exchange first (close_halo)
-    std::set<std::size_t> halo_open;
-    void mark_dirty(std::size_t vec_idx) {
-        halo_fresh.erase(vec_idx);
-        halo_open.erase(vec_idx);
-    }
+    void mark_dirty(std::size_t vec_idx) { halo_fresh.erase(vec_idx); }
 
+    // the block's halo plan as lsk_halo_move's of vector v (send ranges and ghost regions are v's, landing buffers the block's)
     int fill_moves(const Block &b, const PartitionedVector<T> &v, lsk_halo_move *moves) const {
         int n = 0;
-        for (const HaloMove &m : b.halo) {
-            moves[n].peer = m.peer;
-            moves[n].expect = m.recv_n > 0 ? 1 : 0;
-            moves[n].n = m.send_n;
-            moves[n].src = m.send_n > 0 ? reinterpret_cast<const double *>(v.ptr(m.send_lo)) : nullptr;
-            moves[n].dst = m.send_n > 0 ? reinterpret_cast<double *>(v.peer_ptr(m.peer, m.send_lo)) : nullptr;
-            ++n;
+        for (size_t i = 0; i < b.halo.size(); ++i) {
+            const HaloMove &m = b.halo[i];
+            lsk_halo_move &o = moves[n++];
+            o.peer = m.peer;
+            o.reserved = 0;
+            o.n = m.send_n;
+            o.src = m.send_n > 0 ? reinterpret_cast<const double *>(v.ptr(m.send_lo)) : nullptr;
+            o.ll_send = b.landing_peers.base[(size_t) m.peer] + b.send_off[i];
+            o.recv_n = m.recv_n;
+            o.recv_dst = m.recv_n > 0 ? reinterpret_cast<double *>(v.ptr(m.recv_lo)) : nullptr;
+            o.ll_recv = b.landing.ptr + b.recv_off[i];
         }
         return n;
-    }
-
-    // the gated mat-vec is available for block b: one CSR piece per rank, flags computed (once, outside any trace)
-    bool gate_ready(Block &b) {
-        if (!halo_push_is_fused() || total_local_pieces() != 1) return false;
-        static const bool off = [] { const char *e = getenv("LSK_HALO_OPEN"); return e && e[0] == '0'; }();  // developer A/B switch
-        if (off) return false;
-        if (b.gate_nrb < 0) {
-            if (rt->capturing() || rt->replaying()) return false;
-            const IndexPartition &range = *canonical_index_partitions[b.range_index];
-            const int c = range.first_color;
-            b.gate_nrb = b.matrix->gate_row_blocks(c, range.lo[(size_t) c], range.piece_size(c), b.kernel_partition);
-            if (b.gate_nrb > 0) {
-                b.gate_blocks = DeviceBuffer<uint8_t>(rt, (size_t) b.gate_nrb);
-                b.matrix->gate_flags(c, range.lo[(size_t) c], range.piece_size(c), b.kernel_partition, b.gate_blocks.ptr);
-            }
-        }
-        return b.gate_nrb > 0;
-    }
-
-    // close an open exchange of vector `vec_idx` for readers that cannot wait per row block
-    void close_halo(std::size_t vec_idx) {
-        if (!halo_open.count(vec_idx)) return;
-        if constexpr (std::is_same<T, double>::value) {
-            const Block &b = row_partitioned_matrices[0];
-            lsk_halo_move moves[LSK_MAX_HALO_MOVES];
-            const int n = fill_moves(b, get_vector(vec_idx, b.domain_index), moves);
-            rt->halo_wait_p2p(moves, n);
-        }
-        halo_open.erase(vec_idx);
-        halo_fresh.insert(vec_idx);
     }
 
     void register_space(size_t idx, const PartitionedVector<T> &v) {
@@ -160,8 +130,8 @@ class SquarePlanner {
     void exchange_halo(const Block &b, const PartitionedVector<T> &v) {
         if (b.halo.empty()) return;
         if constexpr (std::is_same<T, double>::value) {
-            if (rt->p2p() && v.exported() && b.halo.size() <= LSK_MAX_HALO_MOVES) {
-                // one kernel: ready-handshake, P2P stores into the peers' ghost regions, epoch flags
+            if (b.landing_ready && b.halo.size() <= LSK_MAX_HALO_MOVES) {
+                // one kernel: my boundary leaves as packets for the peers' landing buffers, theirs are unpacked into my ghosts
                 lsk_halo_move moves[LSK_MAX_HALO_MOVES];
                 const int n = fill_moves(b, v, moves);
                 rt->halo_exchange_p2p(moves, n);
@@ -221,8 +191,6 @@ public:
         // one space, one piece per rank: every reducing kernel is launched identically on every rank, so
         // the all-reduces can ride in the kernels' tails and the halo push in the producing xpay
         rt->set_fused_collectives(rt->p2p() && get_num_spaces() == 1 && canonical_index_partitions[0]->pieces == rt->nranks());
-        // the ghost-block flags of the gated mat-vec are computed now, outside any trace
-        for (Block &b : row_partitioned_matrices) (void) gate_ready(b);
     }
 
     // bring the ghost values of vector `vec_idx` up to date on every rank (stand-alone exchange)
@@ -230,7 +198,6 @@ public:
         std::set<size_t> done;
         for (const Block &b : row_partitioned_matrices)
             if (done.insert(b.domain_index).second) exchange_halo(b, get_vector(vec_idx, b.domain_index));
-        halo_open.erase(vec_idx);  // a full exchange supersedes an open one (pair counters only move forward)
         halo_fresh.insert(vec_idx);
     }
 
@@ -251,18 +218,18 @@ public:
         rt->enqueue("defer all-reduce", [&] { return lsk_ctx_defer_next_allreduce(rt->ctx()); });
     }
 
-    // true when xpay_halo pushes the boundary itself (then a step that ends with it leaves the ghosts current)
+    // true when xpay_halo exchanges the halo itself (then a step that ends with it leaves the ghosts current)
     bool halo_push_is_fused() const {
         return std::is_same<T, double>::value && rt->fused_collectives() && row_partitioned_matrices.size() == 1 &&
-               row_partitioned_matrices[0].halo.size() <= 4;
+               row_partitioned_matrices[0].landing_ready && row_partitioned_matrices[0].halo.size() <= 4;
     }
 
     // xpay (2 scalars) whose result is the source of the next mat-vec: when the collectives are fused, the
-    // boundary values are pushed into the neighbours' ghost regions by the same kernel
+    // same kernel exchanges the halo of the result with the neighbours
     void xpay_halo(std::size_t dst, Scalar<T> numer, Scalar<T> denom, std::size_t src) {
         if constexpr (std::is_same<T, double>::value) {
             const Block *blk = row_partitioned_matrices.size() == 1 ? &row_partitioned_matrices[0] : nullptr;
-            if (rt->fused_collectives() && blk && blk->halo.size() <= 4 && get_vector(dst, 0).exported()) {
+            if (blk && halo_push_is_fused()) {
                 PartitionedVector<T> &y = get_vector(dst, 0);
                 const PartitionedVector<T> &x = get_vector(src, 0);
                 const IndexPartition &p = *canonical_index_partitions[0];
@@ -283,8 +250,8 @@ public:
     }
 
     // CGSolver::step lines src/CGSolver.hpp:53-54 in ONE launch when this rank holds one piece of one space:
-    // history.push_back(rr_new); P = fma(rr_new/rr_cur, P, R) [+ P's boundary into the neighbours' ghosts, as
-    // xpay_halo]; rr_cur <- rr_new.  false = not possible here (the caller issues xpay_halo + push_back instead).
+    // history.push_back(rr_new); P = fma(rr_new/rr_cur, P, R) [+ the halo exchange of P, as xpay_halo];
+    // rr_cur <- rr_new.  false = not possible here (the caller issues xpay_halo + push_back instead).
     bool cg_direction(std::size_t p, const Scalar<T> &rr_new, const Scalar<T> &rr_cur, std::size_t r, const ScalarHistory &history) {
         if constexpr (!std::is_same<T, double>::value) {
             return false;
@@ -297,87 +264,17 @@ public:
             if (cnt <= 0 || !lsk_cg_direction_supported(cnt, x.ptr(lo), y.ptr(lo))) return false;
             lsk_halo_move moves[4];
             int n = 0;
-            const bool push = halo_push_is_fused() && y.exported();
+            const bool push = halo_push_is_fused();
             if (push) n = fill_moves(row_partitioned_matrices[0], y, moves);
-            // leave the exchange open when the next mat-vec can wait for the neighbours per row block: the halo
-            // wait then sits behind ~all of that mat-vec instead of at the end of this kernel
-            const bool open = push && n > 0 && gate_ready(row_partitioned_matrices[0]);
             const T *xs = x.ptr(lo);
             T *ys = y.ptr(lo);
             mark_dirty(p);
             rt->enqueue("cg_direction", [&] {
                 return lsk_cg_direction_f64(rt->ctx(), rt->stream(), cnt, rr_cur.ptr(), rr_new.ptr(), xs, ys, n > 0 ? moves : nullptr, n,
-                                            open ? 1 : 0, history.data(), history.get_capacity(), history.count_ptr());
+                                            history.data(), history.get_capacity(), history.count_ptr());
             });
-            if (open) halo_open.insert(p);
-            else if (push) halo_fresh.insert(p);
+            if (push) halo_fresh.insert(p);
             return true;
-        }
-    }
-
-    // ---- the whole CG step as one persistent kernel (lsk_cg_steps_f64) ------------------------------------
-    // Possible when this rank holds ONE piece of ONE space whose only operator is a CSR block, and (on
-    // several ranks) the collectives run over peer memory with P's buffer mapped into the neighbours.
-    bool cg_problem(std::size_t sol, std::size_t r, std::size_t p, std::size_t q, lsk_cg_problem *pb, lsk_halo_move (&moves)[4]) {
-        if constexpr (!std::is_same<T, double>::value) {
-            return false;
-        } else {
-            if (get_num_spaces() != 1 || row_partitioned_matrices.size() != 1 || total_local_pieces() != 1) return false;
-            const Block &blk = row_partitioned_matrices[0];
-            if (blk.domain_index != 0 || blk.range_index != 0) return false;
-            const IndexPartition &part = *canonical_index_partitions[0];
-            const int c = part.first_color;
-            const int64_t lo = part.lo[(size_t) c], n = part.piece_size(c);
-            if (n <= 0) return false;
-            if (!blk.matrix->csr_piece(c, lo, blk.kernel_partition, pb)) return false;
-            PartitionedVector<T> &vp = get_vector(p, 0);
-            if (rt->nranks() > 1) {
-                if (!rt->fused_collectives() || blk.halo.size() > 4) return false;
-                if (!blk.halo.empty() && !vp.exported()) return false;
-            }
-            pb->rows = n;
-            pb->p_shifted = vp.shifted();
-            pb->own_lo = lo;
-            pb->q = get_vector(q, 0).ptr(lo);
-            pb->x = get_vector(sol, 0).ptr(lo);
-            pb->r = get_vector(r, 0).ptr(lo);
-            const int nm = fill_moves(blk, vp, moves);
-            pb->moves = nm > 0 ? moves : nullptr;
-            pb->nmoves = nm;
-            pb->ghost_blocks = nullptr;
-            if (!lsk_cg_steps_supported(pb)) return false;
-            if (nm > 0) {
-                // which row blocks reference ghost columns: computed once (outside any trace), so that only
-                // those wait for the neighbours' halo epoch inside the kernel
-                if (cg_ghost_blocks.count == 0 && !rt->capturing() && !rt->replaying()) {
-                    cg_ghost_blocks = DeviceBuffer<uint8_t>(rt, (size_t) lsk_cg_row_blocks(pb->rows, pb->nnz));
-                    uint8_t *flags = cg_ghost_blocks.ptr;
-                    rt->enqueue("cg ghost blocks", [&] { return lsk_cg_ghost_blocks(rt->ctx(), rt->stream(), pb, flags); });
-                }
-                if (cg_ghost_blocks.count == (size_t) lsk_cg_row_blocks(pb->rows, pb->nnz)) pb->ghost_blocks = cg_ghost_blocks.ptr;
-            }
-            return true;
-        }
-    }
-    // `niter` CG steps; P's ghosts must be current at entry (they are at exit)
-    void cg_steps(std::size_t sol, std::size_t r, std::size_t p, std::size_t q, const Scalar<T> &rr_cur, const Scalar<T> &rr_new,
-                  const Scalar<T> &p_norm, const ScalarHistory &history, int niter) {
-        if constexpr (std::is_same<T, double>::value) {
-            lsk_cg_problem pb{};
-            lsk_halo_move moves[4];
-            if (!cg_problem(sol, r, p, q, &pb, moves)) rt->fail(LSK_E_INVALID, "cg_steps: problem not eligible");
-            pb.rr_cur = rr_cur.ptr();
-            pb.rr_new = rr_new.ptr();
-            pb.p_norm = p_norm.ptr();
-            pb.history = history.data();
-            pb.history_capacity = history.get_capacity();
-            pb.history_count = history.count_ptr();
-            close_halo(p);
-            mark_dirty(sol);
-            mark_dirty(r);
-            mark_dirty(q);
-            rt->enqueue("cg_steps", [&] { return lsk_cg_steps_f64(rt->ctx(), rt->stream(), &pb, niter); });
-            halo_fresh.insert(p);
         }
     }
 
@@ -431,6 +328,44 @@ public:
             m.recv_n = moves[(size_t) i * 5 + 4];
             b.halo.push_back(m);
             halo_bytes_per_matvec += (uint64_t) m.recv_n * sizeof(T);
+        }
+        // Peer-memory exchange: this rank's landing buffers (one per peer it trades with, in plan order) live in one
+        // zeroed allocation, mapped into every peer.  Where MY packets land inside a peer's allocation follows from that
+        // peer's own plan, which is the same host arithmetic on the same all-gathered ranges.  COLLECTIVE: every rank
+        // exports, halo or not.
+        if (std::is_same<T, double>::value && rt->p2p()) {
+            auto landing_layout = [&](int r, std::vector<int64_t> &mv, int &nmv, std::vector<size_t> &off) -> size_t {
+                mv.assign((size_t) R * 5, 0);
+                if (lsk_halo_plan(r, R, all.data(), mv.data(), &nmv) != 0) rt->fail(LSK_E_INVALID, "lsk_halo_plan");
+                size_t total = 0;
+                off.clear();
+                for (int i = 0; i < nmv; ++i) {
+                    off.push_back(total);
+                    total += (lsk_halo_landing_bytes(mv[(size_t) i * 5 + 4]) + 255) & ~size_t(255);
+                }
+                return total;
+            };
+            std::vector<int64_t> mv;
+            std::vector<size_t> off;
+            int nmv = 0;
+            const size_t bytes = landing_layout(rt->rank(), mv, nmv, b.recv_off);
+            b.landing = DeviceBuffer<char>(rt, bytes + 256);
+            rt->check_cuda(cudaMemsetAsync(b.landing.ptr, 0, bytes + 256, rt->stream()), "landing buffers");
+            b.send_off.assign(b.halo.size(), 0);
+            for (size_t i = 0; i < b.halo.size(); ++i) {
+                landing_layout(b.halo[i].peer, mv, nmv, off);
+                bool found = false;
+                for (int j = 0; j < nmv; ++j)
+                    if ((int) mv[(size_t) j * 5] == rt->rank()) {
+                        if (mv[(size_t) j * 5 + 4] != b.halo[i].send_n) rt->fail(LSK_E_INVALID, "halo plans of two ranks disagree");
+                        b.send_off[i] = off[(size_t) j];
+                        found = true;
+                    }
+                if (!found) rt->fail(LSK_E_INVALID, "halo plan: the peer does not list this rank");
+            }
+            rt->fence();  // the buffers are zero before any peer can learn their address
+            b.landing_peers = rt->export_allocation(b.landing.ptr, 0, 0);
+            b.landing_ready = true;
         }
         // every vector of the domain space must be able to hold the ghost interval
         if (g_hi >= g_lo) {
@@ -512,7 +447,6 @@ public:
     // references a ghost column.
     void rmatvec(std::size_t dst_idx, std::size_t src_idx) {
         mark_dirty(dst_idx);
-        close_halo(src_idx);
         for (std::size_t i = 0; i < get_num_spaces(); ++i) get_vector(dst_idx, i).zero_fill();
         for (const Block &b : row_partitioned_matrices) {
             if (rt->nranks() > 1 && !b.halo.empty()) rt->fail(LSK_E_INVALID, "rmatvec on several ranks needs a reverse halo exchange (not implemented)");
@@ -625,26 +559,6 @@ private:
     void matvec_impl(std::size_t dst_idx, std::size_t src_idx, const Scalar<T> *yw, const Scalar<T> *yy, std::size_t w_idx) {
         const size_t S = get_num_spaces();
         mark_dirty(dst_idx);
-        // Ghosts of src pushed by the kernel that produced it (fresh, or an exchange still OPEN): the (single) CSR block
-        // runs the gated kernel, which waits for the neighbours per row block.  It is used for fresh ghosts as well --
-        // the gate is then already satisfied -- so that a step launches the same kernels whether its source's exchange
-        // has been closed or not (a recorded trace is replayed from either state).
-        lsk_halo_move gate_moves[4];
-        MatvecGate gate;
-        bool gated = false;
-        if (halo_open.count(src_idx) || halo_fresh.count(src_idx)) {
-            Block &b0 = row_partitioned_matrices[0];
-            if (row_partitioned_matrices.size() == 1 && !b0.halo.empty() && b0.halo.size() <= 4 && gate_ready(b0)) {
-                gate.blocks = b0.gate_blocks.ptr;
-                gate.nmoves = fill_moves(b0, get_vector(src_idx, b0.domain_index), gate_moves);
-                gate.moves = gate_moves;
-                gated = true;
-                halo_open.erase(src_idx);
-                halo_fresh.insert(src_idx);  // once that kernel has completed
-            } else {
-                close_halo(src_idx);
-            }
-        }
         const bool src_fresh = halo_fresh.count(src_idx) != 0;
         std::vector<bool> overwritten(S, false);
         for (const Block &b : row_partitioned_matrices)
@@ -675,10 +589,9 @@ private:
                         parts_yy.push_back(fz.yy[(size_t) c]);
                     }
                 }
-                b.matrix->matvec(get_vector(dst_idx, b.range_index), src, b.kernel_partition, b.ghost_partition, &fz, gated ? &gate : nullptr);
+                b.matrix->matvec(get_vector(dst_idx, b.range_index), src, b.kernel_partition, b.ghost_partition, &fz);
             } else {
-                b.matrix->matvec(get_vector(dst_idx, b.range_index), src, b.kernel_partition, b.ghost_partition, nullptr, gated ? &gate : nullptr,
-                                 accumulate);
+                b.matrix->matvec(get_vector(dst_idx, b.range_index), src, b.kernel_partition, b.ghost_partition, nullptr, accumulate);
             }
         };
         // overwriting (CSR) blocks first, accumulating (COO) blocks after

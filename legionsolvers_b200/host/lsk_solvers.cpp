@@ -309,9 +309,8 @@ int lsk_planner_create(lsk_runtime *rt, lsk_planner **out) {
 }
 int lsk_planner_destroy(lsk_planner *pl) {
     if (!pl) return 0;
-    const int rc = guard([&] { pl->rt->flush_deferred(); });
     delete pl;
-    return rc;
+    return 0;
 }
 int lsk_planner_add_sol_vector(lsk_planner *pl, lsk_vector *v) {
     REQUIRE(pl && v);
@@ -412,14 +411,12 @@ int lsk_planner_vector_from_host(lsk_planner *pl, int vec, int space, const doub
 int lsk_planner_vector_to_async(lsk_planner *pl, int vec, int space, double *global, void *stream) {
     REQUIRE(pl && global && vec >= 0 && space >= 0);
     return guard([&] {
-        pl->rt->flush_deferred();
         pl->pl->get_vector((size_t) vec, (size_t) space).copy_to_async(global, static_cast<cudaStream_t>(stream));
     });
 }
 int lsk_planner_vector_from_async(lsk_planner *pl, int vec, int space, const double *global, void *stream) {
     REQUIRE(pl && global && vec >= 0 && space >= 0);
     return guard([&] {
-        pl->rt->flush_deferred();  // steps a solver has deferred are issued before the copy can be ordered against them
         pl->pl->vector_written((size_t) vec);
         pl->pl->get_vector((size_t) vec, (size_t) space).copy_from_async(global, static_cast<cudaStream_t>(stream));
     });
@@ -433,7 +430,7 @@ int lsk_solver_create(lsk_planner *pl, int kind, int restart, int fused, lsk_sol
         auto h = std::make_unique<lsk_solver>();
         h->rt = pl->rt;
         h->kind = kind;
-        if (kind == LSK_SOLVER_CG) h->cg = std::make_unique<CGSolver<double>>(*pl->pl, fused != 0, int64_t(1) << 16, fused == 2);
+        if (kind == LSK_SOLVER_CG) h->cg = std::make_unique<CGSolver<double>>(*pl->pl, fused != 0, int64_t(1) << 16);
         else if (kind == LSK_SOLVER_BICGSTAB) h->bicg = std::make_unique<BiCGStabSolver<double>>(*pl->pl, fused != 0);
         else if (kind == LSK_SOLVER_GMRES) {
             if (restart <= 0) pl->rt->fail(LSK_E_INVALID, "GMRES restart");
@@ -444,11 +441,9 @@ int lsk_solver_create(lsk_planner *pl, int kind, int restart, int fused, lsk_sol
 }
 int lsk_solver_destroy(lsk_solver *s) {
     if (!s) return 0;
-    const int rc = guard([&] { s->rt->flush_deferred(); });  // deferred steps of this solver still happen
     delete s;
-    return rc;
+    return 0;
 }
-int lsk_solver_persistent(lsk_solver *s) { return (s && s->cg && s->cg->is_persistent()) ? 1 : 0; }
 int lsk_solver_step(lsk_solver *s) {
     REQUIRE(s);
     return guard([&] {
@@ -481,7 +476,6 @@ int lsk_solver_history_copy_async(lsk_solver *s, int which, double *dst, int64_t
         else s->rt->fail(LSK_E_INVALID, "GMRESSolver keeps no history");
         if (n > h->get_capacity()) s->rt->fail(LSK_E_INVALID, "history_copy_async: more entries than the history holds");
         cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : s->rt->stream();
-        if (!stream) s->rt->flush_deferred();
         if (n > 0) s->rt->check_cuda(cudaMemcpyAsync(dst, h->data(), sizeof(double) * (size_t) n, cudaMemcpyDefault, st), "history copy (async)");
     });
 }

@@ -140,30 +140,9 @@ class Context:
         """history.push_back(rr_new); p = fma(rr_new/rr_cur, p, r); rr_cur <- rr_new  (src/CGSolver.hpp:53-54)."""
         if not _abi.lib().lsk_cg_direction_supported(p.numel(), _ptr(r), _ptr(p)):
             raise RuntimeError("lsk_cg_direction_f64: r and p are not 32-byte congruent")
-        _abi.check(_abi.lib().lsk_cg_direction_f64(self.h, _stream(), p.numel(), _ptr(rr_cur), _ptr(rr_new), _ptr(r), _ptr(p), None, 0, 0,
+        _abi.check(_abi.lib().lsk_cg_direction_f64(self.h, _stream(), p.numel(), _ptr(rr_cur), _ptr(rr_new), _ptr(r), _ptr(p), None, 0,
                                                    _ptr(history), history.numel() if history is not None else 0,
                                                    _ptr(history_count)), "lsk_cg_direction")
-
-    def cg_steps(self, entry, col, rowptr, k_base, p_full, own_lo, q, x, r, rr_cur, rr_new, p_norm, history, history_count,
-                 niter, col_lo=0):
-        """`niter` whole CG steps in one persistent launch (single rank).  p_full holds P for global columns
-        [col_lo, col_lo + len); the owned piece starts at global row own_lo."""
-        pb = _abi.CgProblem()
-        pb.rows, pb.nnz = q.numel(), entry.numel()
-        pb.entry, pb.col, pb.rowptr, pb.k_base = _ptr(entry), _ptr(col), _ptr(rowptr), k_base
-        pb.p_shifted, pb.own_lo = p_full.data_ptr() - 8 * col_lo, own_lo
-        pb.q, pb.x, pb.r = _ptr(q), _ptr(x), _ptr(r)
-        pb.rr_cur, pb.rr_new, pb.p_norm = _ptr(rr_cur), _ptr(rr_new), _ptr(p_norm)
-        pb.history, pb.history_capacity, pb.history_count = _ptr(history), history.numel(), _ptr(history_count)
-        pb.moves, pb.nmoves, pb.ghost_blocks = None, 0, None
-        if not _abi.lib().lsk_cg_steps_supported(C.byref(pb)):
-            raise RuntimeError("lsk_cg_steps_f64: problem not eligible (alignment)")
-        _abi.check(_abi.lib().lsk_cg_steps_f64(self.h, _stream(), C.byref(pb), niter), "lsk_cg_steps")
-
-    def error(self) -> int:
-        e = C.c_int(0)
-        _abi.check(_abi.lib().lsk_ctx_error(self.h, _stream(), C.byref(e)), "lsk_ctx_error")
-        return e.value
 
     def axpy_dot(self, terms, x, y, w, out):
         n, p = _terms(terms)

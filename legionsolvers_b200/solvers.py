@@ -85,15 +85,6 @@ class Runtime:
         _check(_abi.lib().lsk_rt_comm_stats(self.h, out), "lsk_rt_comm_stats")
         return {"ar_calls": out[0], "ar_ns": out[1], "halo_calls": out[2], "halo_ns": out[3]}
 
-    def cg_phase_stats(self) -> dict:
-        """Accounting of the persistent CG kernel (CTA 0's view): ns in the three phases and in the grid barrier
-        that ends each, and iterations, accumulated since the runtime was created.  Synchronises."""
-        self.fence()
-        out = (C.c_uint64 * 7)()
-        _check(_abi.lib().lsk_cg_phase_stats(self.ctx, self.stream, out), "lsk_cg_phase_stats")
-        return {"matvec_ns": out[0], "matvec_sync_ns": out[1], "update_ns": out[2], "update_sync_ns": out[3],
-                "direction_ns": out[4], "direction_sync_ns": out[5], "iterations": out[6]}
-
     def comm_error(self) -> int:
         out = C.c_int()
         _check(_abi.lib().lsk_rt_comm_error(self.h, C.byref(out)), "lsk_rt_comm_error")
@@ -380,17 +371,8 @@ class _Solver:
 class CGSolver(_Solver):
     KIND = SOLVER_CG
 
-    def __init__(self, planner, fused=True, persistent=None):
-        """persistent: run the step as the persistent CG kernel when eligible (None: LSK_CG_PERSISTENT=1 in the
-        environment switches it on; the default is the leaf-kernel form, which is ~2 % faster on the benchmark)."""
-        if persistent is None:
-            persistent = os.environ.get("LSK_CG_PERSISTENT", "0") == "1"
-        super().__init__(planner, 0, 2 if (fused and persistent) else int(bool(fused)))
-
-    @property
-    def persistent(self) -> bool:
-        """True when step() runs as the persistent CG kernel (steps are deferred and batched per launch)."""
-        return bool(_abi.lib().lsk_solver_persistent(self.h))
+    def __init__(self, planner, fused=True):
+        super().__init__(planner, 0, int(bool(fused)))
 
     @property
     def residual_norm_squared(self) -> np.ndarray:

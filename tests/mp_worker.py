@@ -33,8 +33,7 @@ def main():
     trace = iter(range(100, 10000))
     for name, dim_flag, shape, ppr, solver, its in [
         ("cg_7pt", 3, (24, 20, 16), 1, "cg", 40),
-        ("cg_7pt_persistent", 3, (24, 20, 16), 1, "cg_persistent", 40),
-        ("cg_2d_persistent", 2, (64, 48, 1), 1, "cg_persistent", 50),
+        ("cg_7pt_unfused", 3, (24, 20, 16), 1, "cg_unfused", 40),
         ("cg_7pt_2pieces_per_rank", 3, (24, 20, 16), 2, "cg", 40),
         ("cg_27pt", 4, (16, 16, 16), 1, "cg", 30),
         ("cg_2d", 2, (64, 48, 1), 1, "cg", 50),
@@ -69,11 +68,9 @@ def main():
                       and pl.ghost_bounds(0, col) == opl.ghost_bounds(0, col) for col in range(first, end))
         tid = next(trace)
         if solver == "cg":
-            s, o = S.CGSolver(pl, persistent=False), orc.CGSolver(opl)
-        elif solver == "cg_persistent":
-            s, o = S.CGSolver(pl, persistent=True), orc.CGSolver(opl)
-            # the whole step as one persistent kernel -- on peer memory; on plain NCCL it falls back to leaf kernels
-            assert s.persistent == (world == 1 or rt.collectives.startswith("peer-memory, fused"))
+            s, o = S.CGSolver(pl), orc.CGSolver(opl)
+        elif solver == "cg_unfused":  # the reference's call sequence: stand-alone halo exchange before every mat-vec
+            s, o = S.CGSolver(pl, fused=False), orc.CGSolver(opl)
             solver = "cg"
         elif solver == "bicgstab":
             s, o = S.BiCGStabSolver(pl), orc.BiCGStabSolver(opl)

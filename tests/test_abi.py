@@ -66,21 +66,8 @@ def test_spmv_variant_choice_by_row_length_statistics():
 
 
 def test_host_only_entry_points_of_the_cg_step():
-    """Eligibility checks and row-block arithmetic of the persistent / fused CG kernels run on the host: no GPU needed."""
+    """Eligibility checks of the fused CG kernels and the landing-buffer arithmetic run on the host: no GPU needed."""
     L = _abi.lib()
-    # row blocks: one block's non-zeros fill about one 2048-element tile, at most 256 rows (one thread each)
-    assert L.lsk_cg_row_blocks(0, 0) == 0
-    assert L.lsk_cg_row_blocks(1 << 20, 7 << 20) == (1 << 20) // 256    # 7 nnz / row -> 256 rows per block
-    assert L.lsk_cg_row_blocks(1 << 20, 27 << 20) == (1 << 20) // 64    # 27 nnz / row -> 64 rows per block
-    pb = _abi.CgProblem()
-    assert L.lsk_cg_steps_supported(C.byref(pb)) == 0                   # empty problem
-    pb.rows, pb.nnz = 100, 298
-    pb.entry, pb.col, pb.rowptr = 0x1000, 0x2000, 0x3000
-    assert L.lsk_cg_steps_supported(C.byref(pb)) == 1
-    pb.col = 0x2008                                                    # col / entry not 16-byte aligned at the same elements
-    assert L.lsk_cg_steps_supported(C.byref(pb)) == 0
-    pb.col, pb.nmoves = 0x2000, 5                                      # more neighbours than the kernel mirrors to
-    assert L.lsk_cg_steps_supported(C.byref(pb)) == 0
     # the fused direction kernel streams r and p with TMA: they must be 32-byte congruent and hold one aligned pack
     assert L.lsk_cg_direction_supported(1000, 0x10000, 0x20000) == 1
     assert L.lsk_cg_direction_supported(1000, 0x10008, 0x20008) == 1
@@ -88,19 +75,13 @@ def test_host_only_entry_points_of_the_cg_step():
     assert L.lsk_cg_direction_supported(3, 0x10008, 0x20008) == 0
     assert L.lsk_cg_direction_supported(0, 0x10000, 0x20000) == 0
     # calls that would touch the device are refused without a context
-    assert L.lsk_cg_steps_f64(None, None, C.byref(pb), 1) == -1
-    assert L.lsk_cg_direction_f64(None, None, 8, None, None, None, None, None, 0, 0, None, 0, None) == -1
-    assert L.lsk_gridsync_bytes() > 4096 * 16
-    # the gated mat-vec: same row-block arithmetic as the kernel, eligibility by alignment and variant
-    assert L.lsk_csr_spmv_row_blocks(1 << 20, 7 << 20, 0) == (1 << 20) // 256
-    assert L.lsk_csr_spmv_row_blocks(1 << 20, 27 << 20, 0) == (1 << 20) // 64   # 4 lanes per row: 64 rows per block
-    assert L.lsk_csr_spmv_row_blocks(0, 0, 0) == 0
-    assert L.lsk_csr_spmv_gated_supported(100, 700, 0x1000, 0x2000, 0x3000, 0) == 1
-    assert L.lsk_csr_spmv_gated_supported(100, 700, 0x1008, 0x2000, 0x3000, 0) == 0    # col / entry not aligned together
-    assert L.lsk_csr_spmv_gated_supported(100, 700, 0x1000, 0x2000, 0x3008, 0) == 0    # rects are copied with TMA: 16-byte aligned
-    assert L.lsk_csr_spmv_gated_supported(100, 100000, 0x1000, 0x2000, 0x3000, 0) == 0  # warp-per-row variant has no gate
-    assert L.lsk_csr_spmv_gated_f64(None, None, 1, 1, None, None, None, 0, None, None, None, None, None, 0, None, None, 0) == -1
-    assert L.lsk_halo_wait_f64(None, None, None, None, 0) == -1
+    assert L.lsk_cg_direction_f64(None, None, 8, None, None, None, None, None, 0, None, 0, None) == -1
+    assert L.lsk_halo_exchange_f64(None, None, None, None, 0) == -1
+    # a landing buffer holds two exchanges of count + 1 (the token) packets of 16 bytes
+    assert L.lsk_halo_landing_bytes(0) == 32
+    assert L.lsk_halo_landing_bytes(65536) == 2 * 65537 * 16
+    assert L.lsk_halo_landing_bytes(-1) == 0
+    assert C.sizeof(_abi.HaloMove) == 56
 
 
 # ---- integration/: the reference-side binding is real code, not prose ----------------------------------------------------

@@ -259,17 +259,15 @@ CG_CASES = [
 
 
 @pytest.mark.parametrize("name,dim_flag,shape,pieces,spaces,its", CG_CASES, ids=[c[0] for c in CG_CASES])
-@pytest.mark.parametrize("fused", [True, False, "persistent"])
+@pytest.mark.parametrize("fused", [True, False])
 def test_cg_history_vs_oracle(rt, oracle, name, dim_flag, shape, pieces, spaces, its, fused):
-    """CG residual histories within 1e-10 relative (north_star tolerance), solution within 1e-10.
-    "persistent" = the whole step as one persistent kernel where eligible (one piece of one CSR block)."""
+    """CG residual histories within 1e-10 relative (north_star tolerance), solution within 1e-10."""
     from legionsolvers_b200.solvers import CGSolver
 
     off, val = oracle.benchmark_stencil(dim_flag)
     m = oracle.stencil_csr(shape, off, val)
     pl, opl, _, _ = build_system(rt, oracle, m, pieces, spaces=spaces)
-    cg, ocg = CGSolver(pl, fused=bool(fused), persistent=(fused == "persistent")), oracle.CGSolver(opl)
-    assert cg.persistent == (fused == "persistent" and pieces == 1 and spaces == 1)
+    cg, ocg = CGSolver(pl, fused=bool(fused)), oracle.CGSolver(opl)
     tid = new_trace_id()
     for i in range(its):
         rt.begin_trace(tid)
@@ -404,22 +402,8 @@ def test_kernel_launch_accounting(rt, oracle):
     off, val = oracle.benchmark_stencil(3)
     m = oracle.stencil_csr((16, 16, 16), off, val)
     pl, _, _, _ = build_system(rt, oracle, m, 1)
-    cg = CGSolver(pl, fused=True, persistent=True)
-    rt.fence()
-    before = rt.kernel_launches
-    tid = new_trace_id()
-    for _ in range(5):
-        rt.begin_trace(tid)
-        cg.step()
-        rt.end_trace(tid)
-    rt.fence()
-    # one piece of one CSR block: the whole step is one persistent-kernel launch
-    assert cg.persistent
-    assert rt.kernel_launches - before == 5 * 1
-    # the leaf-kernel form of the fused step: spmv+dot, cg_update, cg_direction (xpay + history append)
-    pl1, _, _, _ = build_system(rt, oracle, m, 1)
-    cg1 = CGSolver(pl1, fused=True, persistent=False)
-    assert not cg1.persistent
+    # the fused step on one piece: spmv+dot, cg_update, cg_direction (xpay + history append)
+    cg1 = CGSolver(pl, fused=True)
     rt.fence()
     before = rt.kernel_launches
     tid = new_trace_id()
@@ -431,8 +415,7 @@ def test_kernel_launch_accounting(rt, oracle):
     assert rt.kernel_launches - before == 5 * 3
     # ... and on 4 local pieces
     pl4, _, _, _ = build_system(rt, oracle, m, 4)
-    cg4 = CGSolver(pl4, fused=True, persistent=True)
-    assert not cg4.persistent
+    cg4 = CGSolver(pl4, fused=True)
     rt.fence()
     before = rt.kernel_launches
     tid = new_trace_id()
