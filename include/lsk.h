@@ -408,6 +408,18 @@ int lsk_cg_direction_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, double *rr_cur, 
                          double *p, const lsk_halo_move *moves, int nmoves, double *history,
                          int64_t history_capacity, int64_t *history_count);
 
+/* CGSolver::step lines src/CGSolver.hpp:50-54 in ONE launch -- lsk_cg_update_f64 followed by lsk_cg_direction_f64 -- for
+ * vectors small enough to live in the L2 (the slab of a multi-GPU run): one CTA per SM owns the same elements in both
+ * passes (its new r waits in shared memory), and the kernel boundary between them becomes a grid-wide wait on one word
+ * that carries the global r.r (cross-rank sum included, with lsk_ctx_set_peers).  Same element-wise arithmetic; r.r is
+ * folded in a fixed order of its own.  `pq` may be a deferred reduction of the preceding mat-vec
+ * (lsk_ctx_defer_next_allreduce); `moves` as for lsk_cg_direction_f64.  lsk_cg_tail_supported: p, q, x, r 32-byte
+ * congruent and below the size where the TMA-streamed kernels take over. */
+int lsk_cg_tail_supported(lsk_ctx *ctx, int64_t n, const double *p, const double *q, const double *x, const double *r);
+int lsk_cg_tail_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, double *rr_cur, const double *pq, double *rr_new, double *p,
+                    const double *q, double *x, double *r, const lsk_halo_move *moves, int nmoves, double *history,
+                    int64_t history_capacity, int64_t *history_count);
+
 /* accounting kept in the comm window: {all-reduce calls, ns inside them, halo closes, ns inside them}
  * (time between entering the collective and leaving it, on the thread that closes it).  Synchronises. */
 int lsk_comm_stats(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, uint64_t *host_out4);

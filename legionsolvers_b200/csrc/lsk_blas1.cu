@@ -311,6 +311,209 @@ cg_direction_tma_kernel(double *rr_cur, double *rr_new, const double *r, double 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// The two vector passes above as ONE launch, for slabs whose vectors are L2-resident (a multi-GPU run's 2-4 M rows per
+// rank, where a 10-15 us kernel is mostly ramp, tail and launch): src/CGSolver.hpp:50-54 --
+//     x = fma(rr/pq, p, x);  r = fma((-1*rr)/pq, q, r);  rr' = r.r;                                   [phase 1]
+//     history.push_back(rr');  p = fma(rr'/rr, p, r) (+ halo exchange of p);  rr = rr'               [phase 2]
+// One CTA per SM, each owning a contiguous run of 32-byte packs in both phases, so the r it produced in phase 1 waits in
+// shared memory for phase 2 (16 MB less L2 traffic per iteration on a 2 M-row slab) and the kernel boundary between the
+// passes becomes a grid-wide wait on ONE word: the CTA that draws the last ticket folds the CTAs' r.r partials in block
+// order, sums across ranks (LL all-reduce), and publishes {value, launch number} as a packet in device memory that every
+// CTA polls.  Element-wise arithmetic is that of cg_update / cg_direction; r.r is folded in a different (fixed) order.
+// All CTAs must be resident at once: the grid never exceeds the SM count and the kernel needs one CTA per SM.
+// ---------------------------------------------------------------------------------------------------
+#ifndef LSK_TAIL_UNROLL
+#define LSK_TAIL_UNROLL 1
+#endif
+#ifndef LSK_TAIL_THREADS
+#define LSK_TAIL_THREADS 512  // half an SM's registers: the next mat-vec's CTAs (launched programmatically) fit beside it
+#endif
+constexpr int kTailThreads = LSK_TAIL_THREADS;
+constexpr int kTailUnroll = LSK_TAIL_UNROLL;
+struct TailSync {  // per context, zeroed at creation
+    unsigned long long pkt[2];   // {lo32 | tag, hi32 | tag} of the global r.r of launch `tag`
+    unsigned long long launches; // completed launches (the next one's tag is launches + 1)
+    unsigned int ticket1, ticket2;
+};
+struct CgTailArgs {
+    double *rr_cur, *pq, *rr_new;
+    const double *neg_one, *q;
+    double *p, *x, *r;
+    int64_t n, head, npacks, per;  // per: packs per CTA
+    HaloSpec h;
+    double *partials;
+    TailSync *sync;
+    const lsk_peers *peers;  // null: one rank
+    int resolve_pq;
+    double *hist;
+    long long hist_cap;
+    long long *hist_count;
+};
+
+#ifndef LSK_TAIL_MINB
+#define LSK_TAIL_MINB 1  // measured (2 M-row slab, one B200): 116 registers 67.6 us per iteration, capped at 64 registers 70.5
+#endif
+__global__ void __launch_bounds__(kTailThreads, LSK_TAIL_MINB) cg_tail_kernel(CgTailArgs a) {
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    Pack32 *s_r = reinterpret_cast<Pack32 *>(s_dyn);
+    __shared__ double s_red[kTailThreads / 32];
+    __shared__ double s_val[kMaxRed];
+    __shared__ unsigned long long s_tag;
+    __shared__ bool s_last;
+    __shared__ HaloLive hl;
+    const int tid = threadIdx.x;
+    const bool multi = (a.peers != nullptr && a.h.nmoves > 0);
+    // the mat-vec that follows may start now: its producer warps fill their rings from the (constant) matrix while this
+    // kernel runs, its consumers wait for this kernel's completion.  Every CTA of THIS grid is resident by the time the
+    // last of them has executed this, so the early CTAs of the successor never stand in the way of the grid-wide wait.
+    pdl_launch_dependents();
+    if (tid == 0) s_tag = ((*reinterpret_cast<volatile unsigned long long *>(&a.sync->launches) + 1) & 0xffffffffull) << 32;
+    if (multi) halo_begin(hl, a.h.m, a.h.nmoves, a.peers);  // (ends with a CTA barrier)
+    double pqv;
+    if (a.resolve_pq) {  // the mat-vec only SENT its rank's p.q
+        allreduce_resolve(*a.peers, s_val, 1, a.pq);
+        pqv = s_val[0];
+    } else {
+        pqv = *a.pq;
+    }
+    __syncthreads();
+    const unsigned long long tag = s_tag;
+    const double rr_old = *a.rr_cur;
+    const double a1 = div_rn(rr_old, pqv);
+    const double a2 = div_rn(mul_rn(*a.neg_one, rr_old), pqv);
+    const int64_t pk_lo = (int64_t) blockIdx.x * a.per;
+    const int64_t pk_hi = pk_lo + a.per < a.npacks ? pk_lo + a.per : a.npacks;
+    const int64_t mine = pk_hi > pk_lo ? pk_hi - pk_lo : 0;
+    // the upper half of the grid walks its packs backwards: the slab's last rows (a send range) then leave first
+    const bool backwards = (blockIdx.x >= (gridDim.x + 1) / 2);
+    const int64_t tail0 = a.head + a.npacks * 4;
+    const int64_t nedge = a.head + (a.n - tail0);
+    // ---- phase 1
+    double acc = 0.0;
+#pragma unroll kTailUnroll
+    for (int64_t k = tid; k < mine; k += kTailThreads) {
+        const int64_t j = backwards ? mine - 1 - k : k;
+        const int64_t i = a.head + (pk_lo + j) * 4;
+        const Pack32 pp = ld256(a.p + i);
+        const Pack32 pq4 = ld256(a.q + i);
+        Pack32 px = ld256(a.x + i);
+        Pack32 pr = ld256(a.r + i);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            PackOf<double>::set(px, e, fma_rn(a1, PackOf<double>::get(pp, e), PackOf<double>::get(px, e)));
+            const double rn = fma_rn(a2, PackOf<double>::get(pq4, e), PackOf<double>::get(pr, e));
+            PackOf<double>::set(pr, e, rn);
+            acc = fma(rn, rn, acc);
+        }
+        st256(a.x + i, px);
+        st256(a.r + i, pr);
+        s_r[j] = pr;
+    }
+    if (blockIdx.x == 0)
+        for (int64_t e = tid; e < nedge; e += kTailThreads) {
+            const int64_t i = e < a.head ? e : tail0 + (e - a.head);
+            a.x[i] = fma_rn(a1, a.p[i], a.x[i]);
+            const double rn = fma_rn(a2, a.q[i], a.r[i]);
+            a.r[i] = rn;
+            acc = fma(rn, rn, acc);
+        }
+    // ---- r.r: block partial -> ticket -> the last CTA folds, sums across ranks and publishes
+    {
+        const double b = block_sum<kTailThreads>(acc, s_red);
+        if (tid == 0) {
+            a.partials[blockIdx.x] = b;
+            __threadfence();
+            s_last = (atomicAdd(&a.sync->ticket1, 1u) == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            double v = 0.0;
+            const volatile double *pj = a.partials;
+            if (tid < kBlock)
+                for (unsigned int i = tid; i < gridDim.x; i += kBlock) v += pj[i];
+            v = block_sum<kTailThreads>(v, s_red);
+            if (tid < 32) {
+                double vv[1] = {__shfl_sync(0xffffffffu, v, 0)};
+                if (a.peers != nullptr && a.peers->nranks > 1) allreduce_warp(*a.peers, vv, 1);
+                if (tid == 0) {
+                    const unsigned long long bits = (unsigned long long) __double_as_longlong(vv[0]);
+                    *a.rr_new = vv[0];
+                    a.sync->ticket1 = 0u;
+                    volatile unsigned long long *pk = a.sync->pkt;
+                    pk[0] = tag | (bits & 0xffffffffull);
+                    pk[1] = tag | (bits >> 32);
+                }
+            }
+        }
+        if (tid == 0) {
+            const volatile unsigned long long *pk = a.sync->pkt;
+            unsigned long long lo, hi;
+            unsigned int polls = 0;
+            unsigned long long t_start = 0;
+            bool bad = false;
+            do {
+                lo = pk[0];
+                hi = pk[1];
+                if (spin_expired(polls, t_start)) {
+                    bad = true;
+                    break;
+                }
+            } while ((lo >> 32) != (tag >> 32) || (hi >> 32) != (tag >> 32));
+            s_val[0] = bad ? __longlong_as_double(0x7ff8000000000000ll) : __longlong_as_double((long long) ((lo & 0xffffffffull) | (hi << 32)));
+        }
+        __syncthreads();
+    }
+    const double rr_new_v = s_val[0];
+    const double beta = div_rn(rr_new_v, rr_old);  // xpay(P, rr_new, rr_cur, R): alpha = f0 / f1
+    // ---- phase 2
+#pragma unroll kTailUnroll
+    for (int64_t k = tid; k < mine; k += kTailThreads) {
+        const int64_t j = backwards ? mine - 1 - k : k;
+        const int64_t i = a.head + (pk_lo + j) * 4;
+        Pack32 pp = ld256(a.p + i);
+        const Pack32 pr = s_r[j];
+        double v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            v[e] = fma_rn(beta, PackOf<double>::get(pp, e), PackOf<double>::get(pr, e));
+            PackOf<double>::set(pp, e, v[e]);
+        }
+        st256(a.p + i, pp);
+        if (multi) {
+            halo_send_pair(a.h, hl, i, v[0], v[1]);
+            halo_send_pair(a.h, hl, i + 2, v[2], v[3]);
+        }
+    }
+    if (blockIdx.x == 0)
+        for (int64_t e = tid; e < nedge; e += kTailThreads) {
+            const int64_t i = e < a.head ? e : tail0 + (e - a.head);
+            const double v = fma_rn(beta, a.p[i], a.r[i]);
+            a.p[i] = v;
+            if (multi) halo_send_one(a.h, hl, i, v);
+        }
+    if (multi) halo_unpack(hl, a.h.m, a.h.nmoves, a.peers);
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        s_last = (atomicAdd(&a.sync->ticket2, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    if (multi) halo_finish(a.h.m, a.h.nmoves, a.peers);
+    if (tid == 0) {
+        if (a.hist != nullptr) {
+            const long long c = *a.hist_count;
+            a.hist[c % a.hist_cap] = rr_new_v;
+            *a.hist_count = c + 1;
+        }
+        *a.rr_cur = rr_new_v;  // every CTA read the old value at its start
+        a.sync->launches += 1;
+        a.sync->ticket2 = 0u;
+    }
+}
+
 // The same traversal for any fp64 functor that names its input arrays (NIN <= 4) and provides pair(i, v, acc):
 // scal / axpy / xpay / dot / dot2 / axpy_dot / bicg_p_update above 6 M elements (below, the vectors of the benchmark
 // slabs are L2-resident and the grid-stride kernel with 2048 threads per SM is faster).
@@ -431,6 +634,15 @@ struct FillF {  // IndexFill
         for (int e = 0; e < PackOf<T>::N; ++e) PackOf<T>::set(px, e, v);
         st256(x + i, px);
     }
+};
+
+struct CopyF {  // PartitionedVector::operator= (a region copy in the reference): dst = src
+    using T = double;
+    static constexpr int NRED = 0;
+    const double *src; double *dst;
+    __device__ void init() {}
+    __device__ void scalar(int64_t i, double *) { dst[i] = src[i]; }
+    __device__ void pack(int64_t i, double *) { st256(dst + i, ld256(src + i)); }
 };
 
 template <typename TT>
@@ -799,6 +1011,14 @@ int lsk_fill_dev_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, const double *value,
 int lsk_copy_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, const double *src, double *dst) {
     if (!ctx || n < 0 || (n > 0 && (!src || !dst))) return LSK_E_INVALID;
     if (n == 0) return 0;
+    // A kernel, not cudaMemcpyAsync: a device-to-device copy issued as a memcpy may be scheduled on a copy engine that is
+    // busy with the caller's host <-> device traffic (bench.py's end-to-end loop: reset() took 0.19 instead of 0.07 ms)
+    const Span sp = plan_span<double>(n, {src, dst});
+    if (sp.npacks > 0) {
+        CopyF f;
+        f.src = src; f.dst = dst;
+        return launch_stream(ctx, s, f, n, sp);
+    }
     LSK_RETURN_IF_CUDA(cudaMemcpyAsync(dst, src, (size_t) n * sizeof(double), cudaMemcpyDeviceToDevice,
                                        (cudaStream_t) s));
     return 0;
@@ -885,6 +1105,60 @@ int lsk_cg_direction_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, double *rr_cur, 
     LSK_RETURN_IF_CUDA(launch_pdl(kPdlDirection, cg_direction_tma_kernel, grid, kBlock, (size_t) kVecStages * kVecStageBytes, (cudaStream_t) s, rr_cur,
                                   const_cast<double *>(rr_new), r, p, n, sp.head, sp.npacks, h, rs, history, (long long) history_capacity,
                                   reinterpret_cast<long long *>(history_count), resolve, (const lsk_peers *) ctx->d_peers));
+    return after_launch(ctx);
+}
+
+// largest slab the one-launch form is used for (measured on one B200: 2.1 M rows 70.7 -> 67.5 us per iteration, 4.2 M rows
+// -- r no longer fits beside the mat-vec's CTA -- 138.5 -> 140.2 us)
+constexpr size_t kTailSmemMax = 152 * 1024;
+constexpr int64_t kTailPacksPerCta = (int64_t) (kTailSmemMax / sizeof(Pack32));
+int lsk_cg_tail_supported(lsk_ctx *ctx, int64_t n, const double *p, const double *q, const double *x, const double *r) {
+    if (!ctx || n <= 0 || !p || !q || !x || !r) return 0;
+    static const bool off = [] { const char *e = getenv("LSK_CG_TAIL"); return e && e[0] == '0'; }();  // developer A/B switch
+    if (off) return 0;
+    const Span sp = plan_span<double>(n, {p, q, x, r});
+    // every CTA keeps its share of r in shared memory, next to one CTA of the following mat-vec (72 KB)
+    return (sp.npacks >= 1 && sp.npacks <= (int64_t) ctx->sm_count * kTailPacksPerCta && ctx->tail_sync != nullptr) ? 1 : 0;
+}
+
+int lsk_cg_tail_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, double *rr_cur, const double *pq, double *rr_new, double *p, const double *q,
+                    double *x, double *r, const lsk_halo_move *moves, int nmoves, double *history, int64_t history_capacity,
+                    int64_t *history_count) {
+    if (!ctx || n <= 0 || !rr_cur || !pq || !rr_new || !p || !q || !x || !r || nmoves < 0) return LSK_E_INVALID;
+    if (history && (!history_count || history_capacity <= 0)) return LSK_E_INVALID;
+    if (nmoves > 0 && !ctx->d_peers) return LSK_E_INVALID;  // needs lsk_ctx_set_peers
+    if (!lsk_cg_tail_supported(ctx, n, p, q, x, r)) return LSK_E_INVALID;
+    const bool resolve = ctx->pending_slot != nullptr && ctx->pending_slot == pq && ctx->d_peers != nullptr;
+    if (resolve) {
+        ctx->pending_slot = nullptr;
+    } else {
+        const int rc = settle_pending(ctx, (cudaStream_t) s);
+        if (rc != 0) return rc;
+    }
+    CgTailArgs a;
+    if (!halo_spec_fill(a.h, moves, nmoves, p, n, ctx->d_peers ? ctx->h_peers.nranks : 1)) return LSK_E_INVALID;
+    const Span sp = plan_span<double>(n, {p, q, x, r});
+    a.rr_cur = rr_cur; a.pq = const_cast<double *>(pq); a.rr_new = rr_new; a.neg_one = ctx->consts + 1;
+    a.p = p; a.q = q; a.x = x; a.r = r; a.n = n; a.head = sp.head; a.npacks = sp.npacks;
+    // one CTA per SM, at least ~2 packs per thread so that tiny vectors do not pay for a wide barrier
+    int64_t grid = (sp.npacks + 2 * kTailThreads - 1) / (2 * kTailThreads);
+    if (grid > ctx->sm_count) grid = ctx->sm_count;
+    if (grid < 1) grid = 1;
+    a.per = (sp.npacks + grid - 1) / grid;
+    grid = (sp.npacks + a.per - 1) / a.per;
+    const size_t smem = (size_t) a.per * sizeof(Pack32);  // <= kTailSmemMax (lsk_cg_tail_supported)
+    static const int family = configure_family_index();
+    {
+        const int rc = configure_once(ctx, family, [] { return cudaFuncSetAttribute(cg_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kTailSmemMax); });
+        if (rc != 0) return rc;
+    }
+    const RedScratch rs = next_scratch(ctx);
+    a.partials = rs.partials;
+    a.sync = static_cast<TailSync *>(ctx->tail_sync);
+    a.peers = ctx->d_peers;
+    a.resolve_pq = resolve ? 1 : 0;
+    a.hist = history; a.hist_cap = (long long) history_capacity; a.hist_count = reinterpret_cast<long long *>(history_count);
+    cg_tail_kernel<<<(unsigned) grid, kTailThreads, smem, (cudaStream_t) s>>>(a);
     return after_launch(ctx);
 }
 

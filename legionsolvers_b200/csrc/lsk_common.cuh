@@ -36,6 +36,7 @@ struct lsk_ctx {
     int defer_next;            // lsk_ctx_defer_next_allreduce: the next fused reduction sends without waiting
     const void *pending_slot;  // device scalar whose cross-rank sum is still in flight (resolved by its consumer)
     unsigned long long *work;  // [kScratchSets] dynamic work counters of the TMA-streamed vector kernels, zero between launches
+    void *tail_sync;           // lsk::TailSync of the one-launch CG tail (lsk_cg_tail_f64), zeroed
     unsigned long long configured;  // one bit per kernel family whose dynamic shared-memory opt-in was done on THIS device
                                     // (function attributes are per device: a process may hold contexts on several GPUs)
 };

@@ -46,6 +46,7 @@ int lsk_ctx_create(int device, lsk_ctx **out) {
     ctx->launches = 0;
     ctx->d_peers = nullptr;
     ctx->work = nullptr;
+    ctx->tail_sync = nullptr;
     ctx->configured = 0;
     ctx->defer_next = 0;
     ctx->pending_slot = nullptr;
@@ -55,6 +56,8 @@ int lsk_ctx_create(int device, lsk_ctx **out) {
     if (e == cudaSuccess) e = cudaMalloc(&ctx->consts, sizeof(double) * 4);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->work, sizeof(unsigned long long) * kScratchSets);
     if (e == cudaSuccess) e = cudaMemset(ctx->work, 0, sizeof(unsigned long long) * kScratchSets);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->tail_sync, 256);
+    if (e == cudaSuccess) e = cudaMemset(ctx->tail_sync, 0, 256);
     if (e == cudaSuccess) e = cudaMemset(ctx->partials, 0, pbytes);
     if (e == cudaSuccess) e = cudaMemset(ctx->tickets, 0, sizeof(unsigned int) * kScratchSets);
     const double consts[4] = {1.0, -1.0, 0.0, 0.0};
@@ -75,6 +78,7 @@ int lsk_ctx_destroy(lsk_ctx *ctx) {
     if (ctx->consts) cudaFree(ctx->consts);
     if (ctx->d_peers) cudaFree(ctx->d_peers);
     if (ctx->work) cudaFree(ctx->work);
+    if (ctx->tail_sync) cudaFree(ctx->tail_sync);
     delete ctx;
     return 0;
 }

@@ -199,8 +199,9 @@ public:
             T *d = ptr(lo);
             const T *s = x.ptr(lo);
             rt->enqueue("copy", [&] {
-                return n == 0 ? 0
-                              : (int) cudaMemcpyAsync(d, s, sizeof(T) * (size_t) n, cudaMemcpyDeviceToDevice, rt->stream());
+                if (n == 0) return 0;
+                if constexpr (std::is_same<T, double>::value) return lsk_copy_f64(rt->ctx(), rt->stream(), n, s, d);  // a kernel: never queues behind host copies
+                else return (int) cudaMemcpyAsync(d, s, sizeof(T) * (size_t) n, cudaMemcpyDeviceToDevice, rt->stream());
             });
         });
         return x;

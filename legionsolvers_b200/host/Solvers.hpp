@@ -57,6 +57,11 @@ public:
             const bool defer = planner.can_defer_allreduce(P, R);
             if (defer) planner.defer_next_allreduce();
             planner.matvec_dot(Q, P, P, p_norm);                     // Q = A P and P.Q in one pass
+            // an L2-resident slab (several GPUs): both vector passes, the r.r sum and the halo exchange of P in ONE launch
+            if (planner.cg_tail_ready(SOL, R, P, Q)) {
+                planner.cg_tail(SOL, R, P, Q, rr_cur, p_norm, rr_new, residual_norm_squared);
+                return;
+            }
             if (defer) planner.defer_next_allreduce();
             planner.cg_update(SOL, R, rr_cur, p_norm, P, Q, rr_new);  // both axpys and R.R in one pass
             // append rr_new, P = R + (rr_new/rr_cur) P (halo of P exchanged by the same kernel), rr_cur <- rr_new: one launch

@@ -278,6 +278,44 @@ public:
         }
     }
 
+    // CGSolver::step lines src/CGSolver.hpp:50-54 in ONE launch (lsk_cg_tail_f64) when this rank holds one piece of one
+    // space and its vectors are small enough to live in the L2 -- the slab of a multi-GPU run.  false = not possible here
+    // (the caller issues cg_update + cg_direction).  Must be preceded by a mat-vec whose p.q may be a deferred reduction.
+    bool cg_tail_ready(std::size_t sol, std::size_t r, std::size_t p, std::size_t q) {
+        if constexpr (!std::is_same<T, double>::value) {
+            return false;
+        } else {
+            if (get_num_spaces() != 1 || total_local_pieces() != 1) return false;
+            if (rt->nranks() > 1 && !halo_push_is_fused()) return false;
+            const IndexPartition &part = *canonical_index_partitions[0];
+            const int64_t lo = part.own_lo(), cnt = part.own_hi() - part.own_lo() + 1;
+            return cnt > 0 && lsk_cg_tail_supported(rt->ctx(), cnt, get_vector(p, 0).ptr(lo), get_vector(q, 0).ptr(lo), get_vector(sol, 0).ptr(lo),
+                                                    get_vector(r, 0).ptr(lo)) != 0;
+        }
+    }
+    void cg_tail(std::size_t sol, std::size_t r, std::size_t p, std::size_t q, const Scalar<T> &rr_cur, const Scalar<T> &pq, const Scalar<T> &rr_new,
+                 const ScalarHistory &history) {
+        if constexpr (std::is_same<T, double>::value) {
+            const IndexPartition &part = *canonical_index_partitions[0];
+            const int64_t lo = part.own_lo(), cnt = part.own_hi() - part.own_lo() + 1;
+            PartitionedVector<T> &vp = get_vector(p, 0);
+            lsk_halo_move moves[4];
+            int n = 0;
+            const bool push = halo_push_is_fused();
+            if (push) n = fill_moves(row_partitioned_matrices[0], vp, moves);
+            T *pp = vp.ptr(lo), *xx = get_vector(sol, 0).ptr(lo), *rr = get_vector(r, 0).ptr(lo);
+            const T *qq = get_vector(q, 0).ptr(lo);
+            mark_dirty(sol);
+            mark_dirty(r);
+            mark_dirty(p);
+            rt->enqueue("cg_tail", [&] {
+                return lsk_cg_tail_f64(rt->ctx(), rt->stream(), cnt, rr_cur.ptr(), pq.ptr(), rr_new.ptr(), pp, qq, xx, rr, n > 0 ? moves : nullptr, n,
+                                       history.data(), history.get_capacity(), history.count_ptr());
+            });
+            if (push) halo_fresh.insert(p);
+        }
+    }
+
     // add_row_partitioned_matrix (:209-235): kernel partition from the range partition, ghost
     // partition from the kernel partition -- computed once, on the GPU -- plus the halo plan
     void add_row_partitioned_matrix(const AbstractMatrix<T> &matrix, std::size_t domain_index, std::size_t range_index) {

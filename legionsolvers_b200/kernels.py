@@ -144,6 +144,14 @@ class Context:
                                                    _ptr(history), history.numel() if history is not None else 0,
                                                    _ptr(history_count)), "lsk_cg_direction")
 
+    def cg_tail(self, rr_cur, pq, rr_new, p, q, x, r, history=None, history_count=None, moves=None, nmoves=0):
+        """cg_update followed by cg_direction in ONE launch (src/CGSolver.hpp:50-54), for L2-resident vectors."""
+        if not _abi.lib().lsk_cg_tail_supported(self.h, p.numel(), _ptr(p), _ptr(q), _ptr(x), _ptr(r)):
+            raise RuntimeError("lsk_cg_tail_f64: vectors not 32-byte congruent, or too large for the one-launch form")
+        _abi.check(_abi.lib().lsk_cg_tail_f64(self.h, _stream(), p.numel(), _ptr(rr_cur), _ptr(pq), _ptr(rr_new), _ptr(p), _ptr(q), _ptr(x),
+                                              _ptr(r), moves, nmoves, _ptr(history), history.numel() if history is not None else 0,
+                                              _ptr(history_count)), "lsk_cg_tail")
+
     def axpy_dot(self, terms, x, y, w, out):
         n, p = _terms(terms)
         _abi.check(_abi.lib().lsk_axpy_dot_f64(self.h, _stream(), y.numel(), n, *p, _ptr(x), _ptr(y), _ptr(w),

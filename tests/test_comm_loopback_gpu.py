@@ -183,11 +183,13 @@ def test_xpay_halo_two_ranks_one_gpu(ranks, oracle, n, lo_send, hi_send, off):
     assert all(r.comm_error() == 0 for r in ranks)
 
 
-def test_fused_cg_step_two_ranks_one_gpu(ranks, oracle):
+@pytest.mark.parametrize("tail", [False, True], ids=["update + direction", "one-launch tail"])
+def test_fused_cg_step_two_ranks_one_gpu(ranks, oracle, tail):
     """The whole fused CG step of a row-partitioned system on two ranks that share one GPU: mat-vec with fused p.q (deferred
     all-reduce: sent by the mat-vec, resolved by the update kernel), x / r update with fused r.r (sent by the update kernel,
     resolved by the direction kernel), direction update with the halo exchange of p inside.  Residual history within 1e-10
-    of the oracle's single-process CG, solution within 1e-10."""
+    of the oracle's single-process CG, solution within 1e-10.  tail: lsk_cg_tail_f64 instead of the last two launches (its
+    r.r all-reduce happens inside the kernel, between its two phases)."""
     from legionsolvers_b200 import _abi
     from legionsolvers_b200 import kernels as K
 
@@ -240,6 +242,7 @@ def test_fused_cg_step_two_ranks_one_gpu(ranks, oracle):
                             dot_w=tp, dot_out=tmp["pq"])
             rk.ctx.cg_update(tmp["rr_cur"], tmp["pq"], tp, tmp["q"], tmp["x"], tmp["r"], tmp["rr_new"])
             rk.ctx.cg_direction(tmp["rr_cur"], tmp["rr_new"], tmp["r"], tp, tmp["hist"], tmp["count"])
+            rk.ctx.cg_tail(tmp["rr_cur"], tmp["pq"], tmp["rr_new"], tp, tmp["q"], tmp["x"], tmp["r"], tmp["hist"], tmp["count"])
     torch.cuda.synchronize()
     for r in ranks:
         r.set_peers()
@@ -250,6 +253,11 @@ def test_fused_cg_step_two_ranks_one_gpu(ranks, oracle):
                 _abi.check(L.lsk_ctx_defer_next_allreduce(h), "defer")
                 rk.ctx.csr_spmv(own_n[rk.rank], d["nnz"], d["entry"], d["col"], d["rowptr"], d["k_lo"], d["p_full"], g_lo[rk.rank], d["q"],
                                 dot_w=d["p"], dot_out=d["pq"])
+                if tail:
+                    _abi.check(L.lsk_cg_tail_f64(h, s, own_n[rk.rank], d["rr_cur"].data_ptr(), d["pq"].data_ptr(), d["rr_new"].data_ptr(),
+                                                 d["p"].data_ptr(), d["q"].data_ptr(), d["x"].data_ptr(), d["r"].data_ptr(), moves[rk.rank], 1,
+                                                 d["hist"].data_ptr(), its + 1, d["count"].data_ptr()), "cg_tail")
+                    continue
                 _abi.check(L.lsk_ctx_defer_next_allreduce(h), "defer")
                 rk.ctx.cg_update(d["rr_cur"], d["pq"], d["p"], d["q"], d["x"], d["r"], d["rr_new"])
                 assert L.lsk_cg_direction_supported(own_n[rk.rank], d["r"].data_ptr(), d["p"].data_ptr())

@@ -667,6 +667,44 @@ def test_cg_steps_misaligned_vectors_and_odd_k(ctx, oracle):
     assert np.max(np.abs(st["x"].cpu().numpy() - xo)) <= 1e-10 * np.max(np.abs(xo))
 
 
+@pytest.mark.parametrize("n,off", [(4, 0), (7, 1), (1000, 0), (4099, 3), (300_001, 2), (2_097_152, 0), (2_800_003, 1)])
+def test_cg_tail_equals_update_then_direction(ctx, n, off):
+    """lsk_cg_tail_f64 (both vector passes of the CG step in one launch) against lsk_cg_update_f64 + lsk_cg_direction_f64:
+    x and r bit-identical; r.r within 1e-12 (its fold order differs); p within what that difference does to beta; history,
+    rr_cur and the second launch (re-armed tickets, next launch number) included."""
+    from legionsolvers_b200 import _abi
+
+    g = torch.Generator(device="cuda").manual_seed(n)
+    mk = lambda: (torch.rand(n + 8, dtype=torch.float64, device="cuda", generator=g) - 0.5)[off:off + n]  # noqa: E731
+    p0, q0, x0, r0 = mk(), mk(), mk(), mk()
+    if not _abi.lib().lsk_cg_direction_supported(n, r0.data_ptr(), p0.data_ptr()):
+        pytest.skip("reference pair needs the streamed direction kernel")
+    st = {}
+    for name in ("pair", "tail"):
+        st[name] = dict(rr_cur=torch.tensor([3.25], dtype=torch.float64, device="cuda"), pq=torch.tensor([1.75], dtype=torch.float64, device="cuda"),
+                        rr_new=torch.zeros(1, dtype=torch.float64, device="cuda"), hist=torch.zeros(4, dtype=torch.float64, device="cuda"),
+                        count=torch.zeros(1, dtype=torch.int64, device="cuda"))
+        for k, src in (("p", p0), ("q", q0), ("x", x0), ("r", r0)):  # both states see the same alignment
+            buf = torch.zeros(n + 8, dtype=torch.float64, device="cuda")
+            buf[off:off + n].copy_(src)
+            st[name][k] = buf[off:off + n]
+    for launch in range(2):
+        a, b = st["pair"], st["tail"]
+        ctx.cg_update(a["rr_cur"], a["pq"], a["p"], a["q"], a["x"], a["r"], a["rr_new"])
+        ctx.cg_direction(a["rr_cur"], a["rr_new"], a["r"], a["p"], a["hist"], a["count"])
+        ctx.cg_tail(b["rr_cur"], b["pq"], b["rr_new"], b["p"], b["q"], b["x"], b["r"], b["hist"], b["count"])
+        torch.cuda.synchronize()
+        if launch == 0:
+            assert torch.equal(a["x"], b["x"]) and torch.equal(a["r"], b["r"])
+        rr_a, rr_b = a["rr_new"].item(), b["rr_new"].item()
+        assert abs(rr_a - rr_b) <= 1e-12 * abs(rr_a)
+        assert b["rr_cur"].item() == rr_b and int(b["count"].item()) == launch + 1 and b["hist"][launch].item() == rr_b
+        scale = float(a["p"].abs().max())
+        assert float((a["p"] - b["p"]).abs().max()) <= 1e-11 * scale
+        for d in (a, b):
+            d["pq"].fill_(2.5)
+
+
 @pytest.mark.parametrize("off", [0, 1, 2, 3])
 def test_blas1_tma_streamed_large(ctx, oracle, off):
     """Above 6 M elements scal / axpy / xpay / dot / dot2 / axpy_dot / bicg_p_update take the TMA-streamed, dynamically
