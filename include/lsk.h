@@ -350,7 +350,7 @@ int lsk_allreduce_sum_f64(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, do
 /* One halo move = what this rank trades with ONE peer in an exchange: `n` doubles at local `src` go to the peer, and
  * `recv_n` doubles from the peer end up at local `recv_dst` (this rank's ghost region).  The values travel as LL
  * packets into a LANDING BUFFER owned by the receiver -- lsk_halo_landing_bytes(count) bytes of zeroed device memory per
- * (receiver, sender) pair, holding two exchanges (alternating) of count + 1 packets of 16 bytes -- and the RECEIVER copies
+ * (receiver, sender) pair, 32-byte aligned, holding two exchanges (alternating) of count + 1 packets of 16 bytes -- and the RECEIVER copies
  * them into its ghost region: ghost values are only ever written by the rank that reads them, in stream order.
  *   ll_send  the peer's landing buffer for this rank's packets, as mapped into this process (sized for n)
  *   ll_recv  this rank's landing buffer for the peer's packets (sized for recv_n)

@@ -324,7 +324,7 @@ cg_direction_tma_kernel(double *rr_cur, double *rr_new, const double *r, double 
 // All CTAs must be resident at once: the grid never exceeds the SM count and the kernel needs one CTA per SM.
 // ---------------------------------------------------------------------------------------------------
 #ifndef LSK_TAIL_UNROLL
-#define LSK_TAIL_UNROLL 1
+#define LSK_TAIL_UNROLL 2
 #endif
 #ifndef LSK_TAIL_THREADS
 #define LSK_TAIL_THREADS 512  // half an SM's registers: the next mat-vec's CTAs (launched programmatically) fit beside it
@@ -385,8 +385,7 @@ __global__ void __launch_bounds__(kTailThreads, LSK_TAIL_MINB) cg_tail_kernel(Cg
     const int64_t pk_lo = (int64_t) blockIdx.x * a.per;
     const int64_t pk_hi = pk_lo + a.per < a.npacks ? pk_lo + a.per : a.npacks;
     const int64_t mine = pk_hi > pk_lo ? pk_hi - pk_lo : 0;
-    // the upper half of the grid walks its packs backwards: the slab's last rows (a send range) then leave first
-    const bool backwards = (blockIdx.x >= (gridDim.x + 1) / 2);
+    const bool backwards = false;  // (kept for experiments: the upper half of the grid walking its packs backwards)
     const int64_t tail0 = a.head + a.npacks * 4;
     const int64_t nedge = a.head + (a.n - tail0);
     // ---- phase 1
@@ -468,9 +467,50 @@ __global__ void __launch_bounds__(kTailThreads, LSK_TAIL_MINB) cg_tail_kernel(Cg
     const double rr_new_v = s_val[0];
     const double beta = div_rn(rr_new_v, rr_old);  // xpay(P, rr_new, rr_cur, R): alpha = f0 / f1
     // ---- phase 2
+    // Packs that overlap a send range first, and by ALL CTAs (global thread k takes boundary pack k): the 2 x 1 MB of
+    // packets of a 256^3 halo leave from every SM at once instead of from the few CTAs that own the slab's ends
+    // (measured on 8 GPUs: 30 us of waiting per iteration otherwise).  Their r comes from global memory -- written in
+    // phase 1 by the owning CTA, ordered by its fence before the ticket -- and their owners skip them below.
+    auto boundary_pack = [&](int64_t pk) -> bool {  // does pack pk hold an element some neighbour receives?
+        if (!multi) return false;
+        const int64_t i = a.head + pk * 4;
+        bool any = false;
+#pragma unroll
+        for (int q = 0; q < kMaxFusedMoves; ++q) any |= (q < a.h.nmoves && i + 4 > a.h.lo[q] && i < a.h.lo[q] + a.h.m[q].n);
+        return any;
+    };
+    if (multi) {
+        const int64_t g = (int64_t) blockIdx.x * kTailThreads + tid, gstride = (int64_t) gridDim.x * kTailThreads;
+        for (int q = 0; q < a.h.nmoves; ++q) {
+            if (a.h.m[q].n <= 0) continue;
+            // packs [b0, b1) touch this move's range; a pack shared with an earlier move's range was done there
+            int64_t b0 = (a.h.lo[q] - a.head) / 4, b1 = (a.h.lo[q] + a.h.m[q].n - a.head + 3) / 4;
+            if (a.h.lo[q] < a.head) b0 = 0;
+            if (b1 > a.npacks) b1 = a.npacks;
+            for (int64_t pk = b0 + g; pk < b1; pk += gstride) {
+                const int64_t i = a.head + pk * 4;
+                bool earlier = false;
+                for (int q2 = 0; q2 < q; ++q2) earlier |= (i + 4 > a.h.lo[q2] && i < a.h.lo[q2] + a.h.m[q2].n);
+                if (earlier) continue;
+                Pack32 pp = ld256(a.p + i);
+                Pack32 pr;
+                asm volatile("ld.global.cg.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(pr.q[0]), "=l"(pr.q[1]), "=l"(pr.q[2]), "=l"(pr.q[3]) : "l"(a.r + i) : "memory");
+                double v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    v[e] = fma_rn(beta, PackOf<double>::get(pp, e), PackOf<double>::get(pr, e));
+                    PackOf<double>::set(pp, e, v[e]);
+                }
+                st256(a.p + i, pp);
+                halo_send_pair(a.h, hl, i, v[0], v[1]);
+                halo_send_pair(a.h, hl, i + 2, v[2], v[3]);
+            }
+        }
+    }
 #pragma unroll kTailUnroll
     for (int64_t k = tid; k < mine; k += kTailThreads) {
         const int64_t j = backwards ? mine - 1 - k : k;
+        if (boundary_pack(pk_lo + j)) continue;
         const int64_t i = a.head + (pk_lo + j) * 4;
         Pack32 pp = ld256(a.p + i);
         const Pack32 pr = s_r[j];
@@ -481,10 +521,6 @@ __global__ void __launch_bounds__(kTailThreads, LSK_TAIL_MINB) cg_tail_kernel(Cg
             PackOf<double>::set(pp, e, v[e]);
         }
         st256(a.p + i, pp);
-        if (multi) {
-            halo_send_pair(a.h, hl, i, v[0], v[1]);
-            halo_send_pair(a.h, hl, i + 2, v[2], v[3]);
-        }
     }
     if (blockIdx.x == 0)
         for (int64_t e = tid; e < nedge; e += kTailThreads) {

@@ -52,7 +52,12 @@ __global__ void __launch_bounds__(kBlock) halo_exchange_kernel(lsk_peers peers, 
         halo_live_move(one, 0, a.m[i], me);
         const double *src = a.m[i].src;
         const int64_t n = a.m[i].n;
-        for (int64_t k = tid; k < n; k += stride) ll_store(one.send_slot[0], k, src[k], one.tag[0]);
+        if ((reinterpret_cast<uintptr_t>(one.send_slot[0]) & 31) == 0) {  // two packets per 32-byte store, a warp writes whole sectors
+            for (int64_t k = 2 * tid; k + 1 < n; k += 2 * stride) ll_store2(one.send_slot[0], k, src[k], src[k + 1], one.tag[0]);
+            if (tid == 0 && (n & 1)) ll_store(one.send_slot[0], n - 1, src[n - 1], one.tag[0]);
+        } else {
+            for (int64_t k = tid; k < n; k += stride) ll_store(one.send_slot[0], k, src[k], one.tag[0]);
+        }
         if (tid == 0) ll_store(one.send_slot[0], n, 0.0, one.tag[0]);  // the token
     }
     for (int i = 0; i < a.nmoves; ++i) {
@@ -102,7 +107,7 @@ int lsk_allreduce_sum_f64(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, do
     return after_launch(ctx);
 }
 
-size_t lsk_halo_landing_bytes(int64_t count) { return count < 0 ? 0 : (size_t) 2 * (size_t) (count + 1) * 16; }
+size_t lsk_halo_landing_bytes(int64_t count) { return count < 0 ? 0 : 2 * ll_half_bytes(count); }
 
 int lsk_halo_exchange_f64(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, const lsk_halo_move *moves, int nmoves) {
     if (!ctx || !peers_ok(peers) || nmoves < 0 || nmoves > LSK_MAX_HALO_MOVES || (nmoves > 0 && !moves)) return LSK_E_INVALID;

@@ -136,8 +136,13 @@ __device__ __forceinline__ void halo_send_pair(const HaloSpec &h, const HaloLive
 #pragma unroll
     for (int q = 0; q < kMaxFusedMoves; ++q) {
         if (q < h.nmoves && i + 2 > h.lo[q] && i < h.lo[q] + h.m[q].n) {
-            if (i >= h.lo[q]) ll_store(hl.send_slot[q], i - h.lo[q], p0, hl.tag[q]);
-            if (i + 1 < h.lo[q] + h.m[q].n) ll_store(hl.send_slot[q], i + 1 - h.lo[q], p1, hl.tag[q]);
+            const int64_t k = i - h.lo[q];
+            if (k >= 0 && k + 1 < h.m[q].n && ((reinterpret_cast<uintptr_t>(hl.send_slot[q]) + (uintptr_t) k * 16) & 31) == 0) {
+                ll_store2(hl.send_slot[q], k, p0, p1, hl.tag[q]);
+            } else {
+                if (k >= 0) ll_store(hl.send_slot[q], k, p0, hl.tag[q]);
+                if (k + 1 < h.m[q].n) ll_store(hl.send_slot[q], k + 1, p1, hl.tag[q]);
+            }
         }
     }
 }

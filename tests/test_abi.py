@@ -78,8 +78,9 @@ def test_host_only_entry_points_of_the_cg_step():
     assert L.lsk_cg_direction_f64(None, None, 8, None, None, None, None, None, 0, None, 0, None) == -1
     assert L.lsk_halo_exchange_f64(None, None, None, None, 0) == -1
     # a landing buffer holds two exchanges of count + 1 (the token) packets of 16 bytes
-    assert L.lsk_halo_landing_bytes(0) == 32
-    assert L.lsk_halo_landing_bytes(65536) == 2 * 65537 * 16
+    assert L.lsk_halo_landing_bytes(0) == 64                      # each half rounded up to 32 bytes
+    assert L.lsk_halo_landing_bytes(65536) == 2 * (65537 * 16 + 16)
+    assert L.lsk_halo_landing_bytes(65535) == 2 * 65536 * 16
     assert L.lsk_halo_landing_bytes(-1) == 0
     assert C.sizeof(_abi.HaloMove) == 56
 

@@ -183,8 +183,9 @@ def test_xpay_halo_two_ranks_one_gpu(ranks, oracle, n, lo_send, hi_send, off):
     assert all(r.comm_error() == 0 for r in ranks)
 
 
+@pytest.mark.parametrize("shape", [(24, 20, 16), (64, 32, 32)], ids=["24x20x16", "64x32x32 (several CTAs per kernel)"])
 @pytest.mark.parametrize("tail", [False, True], ids=["update + direction", "one-launch tail"])
-def test_fused_cg_step_two_ranks_one_gpu(ranks, oracle, tail):
+def test_fused_cg_step_two_ranks_one_gpu(ranks, oracle, tail, shape):
     """The whole fused CG step of a row-partitioned system on two ranks that share one GPU: mat-vec with fused p.q (deferred
     all-reduce: sent by the mat-vec, resolved by the update kernel), x / r update with fused r.r (sent by the update kernel,
     resolved by the direction kernel), direction update with the halo exchange of p inside.  Residual history within 1e-10
@@ -195,7 +196,6 @@ def test_fused_cg_step_two_ranks_one_gpu(ranks, oracle, tail):
 
     L = _abi.lib()
     off, val = oracle.benchmark_stencil(3)
-    shape = (24, 20, 16)
     m = oracle.stencil_csr(shape, off, val)
     n, its = m.n_rows, 30
     plane = shape[1] * shape[2]
