@@ -492,6 +492,14 @@ def run_ours(args):
         dist.all_gather(allv, mine)
         comm_us = {"allreduce_us_per_iteration_by_rank": [round(float(v[0]), 2) for v in allv],
                    "halo_poll_us_per_iteration_by_rank": [round(float(v[1]), 2) for v in allv]}
+    if os.environ.get("LSK_TAIL_STATS") == "1":  # developer switch: phase accounting of the one-launch CG tail (cumulative, warm-up included)
+        import ctypes as C
+
+        ts = (C.c_uint64 * 6)()
+        _abi.check(_abi.lib().lsk_cg_tail_stats(rt.ctx, stream, ts), "lsk_cg_tail_stats")
+        if ts[5]:
+            print(f"tail-stats rank {rank}: " + ", ".join(f"{nm} {ts[i] / 1e3 / ts[5]:.2f} us" for i, nm in enumerate(("resolve", "phase1", "rr wait", "phase2", "unpack")))
+                  + f" per launch ({ts[5]} launches)", file=sys.stderr)
     ms_per_step = elapsed_ms / args.steps
     value = args.steps * ipt / (elapsed_ms * 1e-3)
     # ---- roofline of the dominant kernel: the (fused) mat-vec, timed alone on the same stream -----------------

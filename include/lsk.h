@@ -373,6 +373,10 @@ size_t lsk_halo_landing_bytes(int64_t count);
  * this rank is in place at recv_dst (and this rank's packets are on their way or have landed). */
 int lsk_halo_exchange_f64(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, const lsk_halo_move *moves,
                           int nmoves);
+/* the same exchange, except that the values received are ADDED to recv_dst: the REVERSE halo exchange of a transposed
+ * mat-vec (a rank's contributions to columns it does not own travel to their owners; src = its ghost region, recv_dst =
+ * its boundary rows).  Needs landing buffers of its own, sized for the reversed counts. */
+int lsk_halo_reduce_f64(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, const lsk_halo_move *moves, int nmoves);
 /* FUSED forms: no launch of their own.
  * lsk_ctx_set_peers(ctx, peers): from now on EVERY reducing kernel launched through ctx (dot, dot2,
  * cg_update, axpy_dot, bicg_tail, the fused SpMV dots) finishes with the cross-rank sum in the tail of
@@ -416,6 +420,9 @@ int lsk_cg_direction_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, double *rr_cur, 
  * (lsk_ctx_defer_next_allreduce); `moves` as for lsk_cg_direction_f64.  lsk_cg_tail_supported: p, q, x, r 32-byte
  * congruent and below the size where the TMA-streamed kernels take over. */
 int lsk_cg_tail_supported(lsk_ctx *ctx, int64_t n, const double *p, const double *q, const double *x, const double *r);
+/* accounting kept by lsk_cg_tail_f64 (CTA 0's view, accumulated since context creation): ns in {p.q resolve, phase 1,
+ * wait for the global r.r, phase 2, unpacking the neighbours' halo} and the number of launches.  Synchronises. */
+int lsk_cg_tail_stats(lsk_ctx *ctx, lsk_stream s, uint64_t *host_out6);
 int lsk_cg_tail_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, double *rr_cur, const double *pq, double *rr_new, double *p,
                     const double *q, double *x, double *r, const lsk_halo_move *moves, int nmoves, double *history,
                     int64_t history_capacity, int64_t *history_count);

@@ -146,6 +146,29 @@ int lsk_solver_history_copy_async(lsk_solver *s, int which, double *dst, int64_t
  * *n = number available.  Synchronises. */
 int lsk_solver_history(lsk_solver *s, int which, double *out, int64_t cap, int64_t *n);
 
+/* ---- utilities: Matrix Market files ----------------------------------------------------------------------------------
+ * The reference names "reading in matrices from file formats like MATLAB or Matrix Market and storing them in standard
+ * formats (e.g. COO, CSR, ELL, ...)" as the first of its planned utilities (README.md:90-99) and ships no reader.
+ * Host-only (no CUDA).  Supported: `matrix coordinate {real|integer|pattern} {general|symmetric|skew-symmetric}`;
+ * indices become 0-based, symmetric storage is expanded (the mirrored entry follows its original), pattern entries get
+ * the value 1.  Dense (`array`) and complex files are refused.  Errors: status LSK_E_INVALID + lsk_mm_last_error(). */
+enum lsk_mm_field { LSK_MM_REAL = 0, LSK_MM_INTEGER = 1, LSK_MM_PATTERN = 2 };
+enum lsk_mm_symmetry { LSK_MM_GENERAL = 0, LSK_MM_SYMMETRIC = 1, LSK_MM_SKEW_SYMMETRIC = 2 };
+typedef struct {
+    int64_t rows, cols, entries;   /* entries = lines stored in the file; the expanded matrix holds at most 2 * entries */
+    int field, symmetry;
+} lsk_mm_info;
+const char *lsk_mm_last_error(void);
+int lsk_mm_read_info(const char *path, lsk_mm_info *out);
+/* fills entry / row / col (COOMatrix fields, what lsk_coo_create uploads) with the EXPANDED matrix, in file order */
+int lsk_mm_read_coo_f64(const char *path, int64_t capacity, double *entry, int64_t *row, int64_t *col, int64_t *nnz_out);
+int lsk_mm_write_coo_f64(const char *path, int64_t rows, int64_t cols, int64_t nnz, const double *entry, const int64_t *row,
+                         const int64_t *col);
+/* COO in any order -> the CSRMatrix fields (what lsk_csr_create uploads): entries grouped by row, a row's entries in input
+ * order; rowptr[r] = INCLUSIVE {first k, last k}, empty rows lo > hi (src/CSRMatrix.hpp field layout) */
+int lsk_coo_to_csr_f64(int64_t rows, int64_t nnz, const double *entry, const int64_t *row, const int64_t *col, double *entry_out,
+                       int64_t *col_out, lsk_rect *rowptr_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -102,6 +102,7 @@ def _declare(L: C.CDLL) -> None:
     L.lsk_cg_direction_supported.argtypes = [i64, vp, vp]
     L.lsk_cg_direction_f64.argtypes = [vp, vp, i64, vp, vp, vp, vp, C.POINTER(HaloMove), ci, vp, i64, vp]
     L.lsk_cg_tail_supported.argtypes = [vp, i64, vp, vp, vp, vp]
+    L.lsk_cg_tail_stats.argtypes = [vp, vp, C.POINTER(u64)]
     L.lsk_cg_tail_f64.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, C.POINTER(HaloMove), ci, vp, i64, vp]
     L.lsk_halo_landing_bytes.argtypes = [i64]
     L.lsk_halo_landing_bytes.restype = C.c_size_t

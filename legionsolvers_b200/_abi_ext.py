@@ -41,12 +41,18 @@ def declare(L) -> None:
     L.lsk_comm_window_bytes.restype = C.c_size_t
     L.lsk_allreduce_sum_f64.argtypes = [vp, vp, vp, vp, ci]
     L.lsk_halo_exchange_f64.argtypes = [vp, vp, vp, vp, ci]
+    L.lsk_halo_reduce_f64.argtypes = [vp, vp, vp, vp, ci]
     L.lsk_comm_error.argtypes = [vp, vp, vp, vp]
     L.lsk_ctx_set_peers.argtypes = [vp, vp]
     L.lsk_ctx_defer_next_allreduce.argtypes = [vp]
     L.lsk_ctx_settle.argtypes = [vp, vp]
     L.lsk_xpay_halo_f64.argtypes = [vp, vp, i64, ci, vp, vp, vp, vp, vp, vp, vp, ci]
     L.lsk_halo_plan.argtypes = [ci, ci, vp, vp, C.POINTER(ci)]
+    L.lsk_mm_last_error.restype = C.c_char_p
+    L.lsk_mm_read_info.argtypes = [C.c_char_p, vp]
+    L.lsk_mm_read_coo_f64.argtypes = [C.c_char_p, i64, vp, vp, vp, C.POINTER(i64)]
+    L.lsk_mm_write_coo_f64.argtypes = [C.c_char_p, i64, i64, i64, vp, vp, vp]
+    L.lsk_coo_to_csr_f64.argtypes = [i64, i64, vp, vp, vp, vp, vp, vp]
     L.lsk_last_error.restype = C.c_char_p
     L.lsk_rt_create.argtypes = [ci, ci, ci, vp, C.POINTER(vp)]
     L.lsk_rt_destroy.argtypes = [vp]

@@ -335,6 +335,8 @@ struct TailSync {  // per context, zeroed at creation
     unsigned long long pkt[2];   // {lo32 | tag, hi32 | tag} of the global r.r of launch `tag`
     unsigned long long launches; // completed launches (the next one's tag is launches + 1)
     unsigned int ticket1, ticket2;
+    // accounting (CTA 0's view, accumulated): ns in {p.q resolve, phase 1, r.r wait, phase 2, unpack}, launches
+    unsigned long long ns[5], counted;
 };
 struct CgTailArgs {
     double *rr_cur, *pq, *rr_new;
@@ -345,7 +347,7 @@ struct CgTailArgs {
     double *partials;
     TailSync *sync;
     const lsk_peers *peers;  // null: one rank
-    int resolve_pq;
+    int resolve_pq, pdl;
     double *hist;
     long long hist_cap;
     long long *hist_count;
@@ -367,7 +369,8 @@ __global__ void __launch_bounds__(kTailThreads, LSK_TAIL_MINB) cg_tail_kernel(Cg
     // the mat-vec that follows may start now: its producer warps fill their rings from the (constant) matrix while this
     // kernel runs, its consumers wait for this kernel's completion.  Every CTA of THIS grid is resident by the time the
     // last of them has executed this, so the early CTAs of the successor never stand in the way of the grid-wide wait.
-    pdl_launch_dependents();
+    if (a.pdl) pdl_launch_dependents();
+    const unsigned long long t_0 = (blockIdx.x == 0 && tid == 0) ? global_ns() : 0ull;
     if (tid == 0) s_tag = ((*reinterpret_cast<volatile unsigned long long *>(&a.sync->launches) + 1) & 0xffffffffull) << 32;
     if (multi) halo_begin(hl, a.h.m, a.h.nmoves, a.peers);  // (ends with a CTA barrier)
     double pqv;
@@ -378,6 +381,7 @@ __global__ void __launch_bounds__(kTailThreads, LSK_TAIL_MINB) cg_tail_kernel(Cg
         pqv = *a.pq;
     }
     __syncthreads();
+    const unsigned long long t_1 = (blockIdx.x == 0 && tid == 0) ? global_ns() : 0ull;
     const unsigned long long tag = s_tag;
     const double rr_old = *a.rr_cur;
     const double a1 = div_rn(rr_old, pqv);
@@ -418,8 +422,10 @@ __global__ void __launch_bounds__(kTailThreads, LSK_TAIL_MINB) cg_tail_kernel(Cg
             acc = fma(rn, rn, acc);
         }
     // ---- r.r: block partial -> ticket -> the last CTA folds, sums across ranks and publishes
+    unsigned long long t_2 = 0;
     {
         const double b = block_sum<kTailThreads>(acc, s_red);
+        if (blockIdx.x == 0 && tid == 0) t_2 = global_ns();
         if (tid == 0) {
             a.partials[blockIdx.x] = b;
             __threadfence();
@@ -464,6 +470,7 @@ __global__ void __launch_bounds__(kTailThreads, LSK_TAIL_MINB) cg_tail_kernel(Cg
         }
         __syncthreads();
     }
+    const unsigned long long t_3 = (blockIdx.x == 0 && tid == 0) ? global_ns() : 0ull;
     const double rr_new_v = s_val[0];
     const double beta = div_rn(rr_new_v, rr_old);  // xpay(P, rr_new, rr_cur, R): alpha = f0 / f1
     // ---- phase 2
@@ -529,9 +536,15 @@ __global__ void __launch_bounds__(kTailThreads, LSK_TAIL_MINB) cg_tail_kernel(Cg
             a.p[i] = v;
             if (multi) halo_send_one(a.h, hl, i, v);
         }
+    const unsigned long long t_4 = (blockIdx.x == 0 && tid == 0) ? global_ns() : 0ull;
     if (multi) halo_unpack(hl, a.h.m, a.h.nmoves, a.peers);
     __syncthreads();
     if (tid == 0) {
+        if (blockIdx.x == 0) {
+            const unsigned long long t_5 = global_ns();
+            a.sync->ns[0] += t_1 - t_0; a.sync->ns[1] += t_2 - t_1; a.sync->ns[2] += t_3 - t_2; a.sync->ns[3] += t_4 - t_3; a.sync->ns[4] += t_5 - t_4;
+            a.sync->counted += 1;
+        }
         __threadfence();
         s_last = (atomicAdd(&a.sync->ticket2, 1u) == gridDim.x - 1);
     }
@@ -1157,6 +1170,14 @@ int lsk_cg_tail_supported(lsk_ctx *ctx, int64_t n, const double *p, const double
     return (sp.npacks >= 1 && sp.npacks <= (int64_t) ctx->sm_count * kTailPacksPerCta && ctx->tail_sync != nullptr) ? 1 : 0;
 }
 
+int lsk_cg_tail_stats(lsk_ctx *ctx, lsk_stream s, uint64_t *host_out6) {
+    if (!ctx || !host_out6 || !ctx->tail_sync) return LSK_E_INVALID;
+    const TailSync *ts = static_cast<const TailSync *>(ctx->tail_sync);
+    LSK_RETURN_IF_CUDA(cudaMemcpyAsync(host_out6, ts->ns, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost, (cudaStream_t) s));
+    LSK_RETURN_IF_CUDA(cudaStreamSynchronize((cudaStream_t) s));
+    return 0;
+}
+
 int lsk_cg_tail_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, double *rr_cur, const double *pq, double *rr_new, double *p, const double *q,
                     double *x, double *r, const lsk_halo_move *moves, int nmoves, double *history, int64_t history_capacity,
                     int64_t *history_count) {
@@ -1193,6 +1214,8 @@ int lsk_cg_tail_f64(lsk_ctx *ctx, lsk_stream s, int64_t n, double *rr_cur, const
     a.sync = static_cast<TailSync *>(ctx->tail_sync);
     a.peers = ctx->d_peers;
     a.resolve_pq = resolve ? 1 : 0;
+    static const bool tail_pdl = [] { const char *e = getenv("LSK_TAIL_PDL"); return !(e && e[0] == '0'); }();  // developer A/B switch
+    a.pdl = tail_pdl ? 1 : 0;
     a.hist = history; a.hist_cap = (long long) history_capacity; a.hist_count = reinterpret_cast<long long *>(history_count);
     cg_tail_kernel<<<(unsigned) grid, kTailThreads, smem, (cudaStream_t) s>>>(a);
     return after_launch(ctx);

@@ -43,6 +43,7 @@ struct HaloArgs {
 
 // Stand-alone exchange (the fused forms live in lsk_blas1.cu): send my boundary values as packets, unpack the
 // neighbours'.  At most 32 CTAs: all resident, so a CTA polling for a packet never keeps a sender off the SMs.
+template <bool ADD>
 __global__ void __launch_bounds__(kBlock) halo_exchange_kernel(lsk_peers peers, HaloArgs a) {
     CommWindow *me = static_cast<CommWindow *>(peers.window[peers.rank]);
     __shared__ bool s_last;
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(kBlock) halo_exchange_kernel(lsk_peers peers, 
     for (int i = 0; i < a.nmoves; ++i) {
         HaloLive one;
         halo_live_move(one, 0, a.m[i], me);
-        halo_unpack(one, &a.m[i], 1, &peers);
+        halo_unpack<ADD>(one, &a.m[i], 1, &peers);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -109,7 +110,7 @@ int lsk_allreduce_sum_f64(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, do
 
 size_t lsk_halo_landing_bytes(int64_t count) { return count < 0 ? 0 : 2 * ll_half_bytes(count); }
 
-int lsk_halo_exchange_f64(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, const lsk_halo_move *moves, int nmoves) {
+static int halo_exchange(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, const lsk_halo_move *moves, int nmoves, bool add) {
     if (!ctx || !peers_ok(peers) || nmoves < 0 || nmoves > LSK_MAX_HALO_MOVES || (nmoves > 0 && !moves)) return LSK_E_INVALID;
     if (nmoves == 0) return 0;
     HaloArgs a;
@@ -126,8 +127,16 @@ int lsk_halo_exchange_f64(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, co
     int grid = (int) ((total + 4 * kBlock - 1) / (4 * kBlock));
     if (grid < 1) grid = 1;
     if (grid > 32) grid = 32;
-    halo_exchange_kernel<<<grid, kBlock, 0, (cudaStream_t) s>>>(*peers, a);
+    if (add) halo_exchange_kernel<true><<<grid, kBlock, 0, (cudaStream_t) s>>>(*peers, a);
+    else halo_exchange_kernel<false><<<grid, kBlock, 0, (cudaStream_t) s>>>(*peers, a);
     return after_launch(ctx);
+}
+
+int lsk_halo_exchange_f64(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, const lsk_halo_move *moves, int nmoves) {
+    return halo_exchange(ctx, s, peers, moves, nmoves, false);
+}
+int lsk_halo_reduce_f64(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, const lsk_halo_move *moves, int nmoves) {
+    return halo_exchange(ctx, s, peers, moves, nmoves, true);
 }
 
 int lsk_comm_stats(lsk_ctx *ctx, lsk_stream s, const lsk_peers *peers, uint64_t *host_out4) {

@@ -428,6 +428,8 @@ __device__ __forceinline__ void halo_begin(HaloLive &hl, const lsk_halo_move *m,
 }
 // All threads of all CTAs call it once their own packets are out: copy the neighbours' values into the ghost regions.
 // Packet idx of move q is handled by global thread (idx mod grid threads); a packet that has not landed yet is polled.
+// ADD: the values are added to what recv_dst holds (the reverse exchange of a transposed mat-vec) instead of replacing it
+template <bool ADD = false>
 __device__ __forceinline__ void halo_unpack(const HaloLive &hl, const lsk_halo_move *m, int nmoves, const lsk_peers *peers) {
     CommWindow *me = static_cast<CommWindow *>(peers->window[peers->rank]);
     const int64_t g = (int64_t) blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t) gridDim.x * blockDim.x;
@@ -438,10 +440,15 @@ __device__ __forceinline__ void halo_unpack(const HaloLive &hl, const lsk_halo_m
         for (int64_t idx = g; idx <= cnt; idx += stride) {  // idx == cnt: the token
             double v;
             if (!ll_try_load(hl.recv_slot[q], idx, hl.tag[q], v)) {
+                // Not there yet: back off between polls.  Tens of thousands of threads re-reading their packets as fast as the
+                // L2 answers crowd out the very NVLink writes they are waiting for (measured: the one-launch CG tail, whose
+                // unpacking follows its sends by ~5 us, waited 10-30 us per iteration without the back-off).
                 const unsigned long long t0 = global_ns();
-                unsigned int polls = 0;
+                unsigned int polls = 0, nap = 64;
                 unsigned long long t_start = 0;
                 while (!ll_try_load(hl.recv_slot[q], idx, hl.tag[q], v)) {
+                    __nanosleep(nap);
+                    if (nap < 1024) nap <<= 1;
                     if (spin_expired(polls, t_start)) {
                         me->error = 1;
                         v = __longlong_as_double(0x7ff8000000000000ll);  // a value that never arrived must not look like a number
@@ -450,7 +457,7 @@ __device__ __forceinline__ void halo_unpack(const HaloLive &hl, const lsk_halo_m
                 }
                 waited += global_ns() - t0;
             }
-            if (idx < cnt) dst[idx] = v;
+            if (idx < cnt) dst[idx] = ADD ? add_rn(dst[idx], v) : v;
         }
     }
     if (waited) atomicMax(&me->halo_poll_ns, waited);

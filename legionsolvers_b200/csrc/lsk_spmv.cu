@@ -353,9 +353,9 @@ csr_tma_kernel(TmaSpmvArgs a, double *partials, unsigned int *ticket, double *ou
     // prologue (rowptr rects of the first row blocks, TMA copy of the first matrix tile) does not depend on the kernel
     // before this one; x, the fused dot's w and y do
     TmaCursor cur;
-    csr_tma_run<NDOT, false, false, 1, false, LPR>(a, st, s_dyn, s_full, s_lo, s_hi, dacc, nullptr, &cur);
+    csr_tma_run<NDOT, 1, LPR>(a, st, s_dyn, s_full, s_lo, s_hi, dacc, &cur);
     pdl_wait();
-    csr_tma_run<NDOT, false, false, 2, false, LPR>(a, st, s_dyn, s_full, s_lo, s_hi, dacc, nullptr, &cur);
+    csr_tma_run<NDOT, 2, LPR>(a, st, s_dyn, s_full, s_lo, s_hi, dacc, &cur);
     if constexpr (NDOT > 0) {
         double *out[NDOT];
         out[0] = out_yw;

@@ -1,7 +1,7 @@
 // lsk_spmv_tma.cuh -- the TMA-staged, thread-per-row CSR mat-vec as a device-side building block.
 //
-// Used by csr_tma_kernel (lsk_spmv.cu: one mat-vec per launch) and by the persistent CG kernel
-// (lsk_cg.cu: the mat-vec phase of every iteration).  See lsk_spmv.cu for the design notes: the
+// Used by csr_tma_kernel (lsk_spmv.cu: one mat-vec per launch) -- round 1's single-role kernel, kept for pieces whose rowptr
+// is not 16-byte aligned (the warp-specialised kernel copies the rects with TMA) and as LSK_SPMV_IMPL=tma for A/B runs.  See lsk_spmv.cu for the design notes: the
 // CTA's contiguous run of (col, entry) is copied global->shared by the TMA engine
 // (cp.async.bulk, mbarrier completion, L2 evict-first, two stages), threads own ROWS and add their
 // rounded products in ascending k in a register -- bit-identical to the reference CPU body
@@ -107,13 +107,6 @@ __device__ __forceinline__ longlong2 ld_rect_stream(const lsk_rect *p) {
     return r;
 }
 
-// weak, L1-cacheable load on the COHERENT path (never LDG.CONSTANT): for vectors that the same kernel
-// also writes in another phase, made visible by a grid barrier (fence + L1 invalidation)
-__device__ __forceinline__ double ld_f64(const double *p) {
-    double v;
-    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
-}
 struct TmaSpmvArgs {
     int64_t rows, nnz;
     int rpb;                 // rows per row block (<= kBlock, one thread per row)
@@ -127,24 +120,6 @@ struct TmaSpmvArgs {
     const double *dot_w;     // NDOT >= 1
     int accumulate;          // non-zero: y = y + A x (a further block of a multi-operator system on the same rows)
 };
-
-// Ghost columns (outside the owned rows) are written by peer GPUs while the kernel runs.  Before a CTA
-// consumes a row block that references one (blocks[rb] != 0, computed once at plan time; null = every block),
-// its thread 0 waits until every peer this rank receives from has published epoch `want`, then fences at
-// system scope -- MEMBAR.SC.SYS + CCTL.IVALL, which also drops every L1 line of the SM -- and the CTA barrier
-// of the tile loop releases the other threads, which then gather ghosts like any other column.
-struct GhostGate {
-    const unsigned char *blocks;
-    int nflags;
-    const volatile unsigned long long *flag[4];   // halo_done[peer] in this rank's window
-    unsigned long long want[4];                   // the pair's exchange number (per peer, see CommWindow::halo_sent)
-    int *error;
-};
-
-static __device__ __noinline__ void ghost_gate_wait(const GhostGate &g) {
-    for (int q = 0; q < g.nflags; ++q) spin_until(g.flag[q], g.want[q], g.error);
-    __threadfence_system();
-}
 
 struct TmaSpmvState {
     uint64_t policy;   // thread 0 only
@@ -165,36 +140,20 @@ __device__ __forceinline__ void csr_tma_init(TmaSpmvState &st, uint64_t *s_full)
 
 // One mat-vec over the row blocks blockIdx.x, blockIdx.x + gridDim.x, ...
 //   NDOT      0: y only; 1: dacc[0] += y.w; 2: also dacc[1] += y.y
-//   COHERENT  false: x is read-only for the kernel's lifetime (LDG.CONSTANT path)
-//             true : x was written earlier in this kernel (plain ld.global)
-//   GATED     (needs COHERENT) ghost columns are guarded by `gate`; row blocks that reference none (per
-//             gate->blocks) take the same straight-line gather loop as the ungated kernel
 //   PART      0: the whole mat-vec.  1: only the prologue -- the rects of this CTA's first two row blocks are
-//             loaded into `cur` and the TMA copy of its first tile is started (the matrix is constant, so a
-//             persistent kernel does this BEFORE the grid barrier that precedes the mat-vec).  2: the rest.
-//   DYN       row blocks are handed out first come, first served from a global counter instead of the static
-//             blockIdx.x + k * gridDim.x walk: SMs do not all get the same share of the memory system, and with a
-//             static split HBM idles while the slow ones finish.  Thread 0 grabs two blocks ahead (the atomic's
-//             latency hides behind a whole block) and broadcasts the id through shared memory one CTA barrier
-//             before it is needed.  Grabbed index g maps to row block (g + rot) % n_row_blocks.
+//             loaded into `cur` and the TMA copy of its first tile is started (the matrix is constant, so a kernel
+//             launched programmatically does this BEFORE it waits for its predecessor).  2: the rest.
 struct TmaCursor {
     long long lo, hi1, nlo, nhi1;
-    long long rb, rb_next, pend;
-};
-struct TmaDynamic {
-    unsigned long long *counter;  // global, zero at the start of the mat-vec
-    long long *s_rbq;             // shared, 2 entries
-    long long rot;
 };
 //   LPR       lanes per row (1, 2, 4, 8).  1: a thread owns a row and adds its products in ascending k (bit-identical to
 //             the reference CPU body).  > 1, for rows of a few dozen non-zeros where one thread per row would leave
 //             most lanes of a tile idle: LPR adjacent lanes stride one row and their partial sums are combined with
 //             shuffles (fixed tree order: deterministic, <= 1e-12 from the sequential sum).
-template <int NDOT, bool COHERENT, bool GATED, int PART = 0, bool DYN = false, int LPR = 1>
+template <int NDOT, int PART = 0, int LPR = 1>
 __device__ __forceinline__ void csr_tma_run(const TmaSpmvArgs &a, TmaSpmvState &st, unsigned char *s_dyn, uint64_t *s_full,
                                             long long (*s_lo)[kWarps], long long (*s_hi)[kWarps],
-                                            double (&dacc)[NDOT > 0 ? NDOT : 1], const GhostGate *gate,
-                                            TmaCursor *cur = nullptr, const TmaDynamic *dyn = nullptr) {
+                                            double (&dacc)[NDOT > 0 ? NDOT : 1], TmaCursor *cur = nullptr) {
     constexpr int S = kTmaStages;
     long long (*s_col)[kTmaTile] = reinterpret_cast<long long (*)[kTmaTile]>(s_dyn);
     double (*s_ent)[kTmaTile] = reinterpret_cast<double (*)[kTmaTile]>(s_dyn + (size_t) S * kTmaTile * sizeof(long long));
@@ -214,13 +173,6 @@ __device__ __forceinline__ void csr_tma_run(const TmaSpmvArgs &a, TmaSpmvState &
     const int64_t k_base = a.k_base;
     const double *x = a.x;
     const uint64_t policy = st.policy;
-    bool ghost_ok = false;  // thread 0: the gate has been passed in this run
-    auto block_checked = [&](int64_t rb) -> bool {
-        if constexpr (!GATED) return false;
-        const unsigned char *blk_flags = gate->blocks;
-        if (blk_flags == nullptr) return true;
-        return rb < n_row_blocks ? (__ldg(blk_flags + rb) != 0) : false;
-    };
 
     auto load_rect = [&](int64_t rb, long long &lo, long long &hi1) {
         lo = LLONG_MAX;
@@ -282,47 +234,11 @@ __device__ __forceinline__ void csr_tma_run(const TmaSpmvArgs &a, TmaSpmvState &
     };
 
     uint32_t phases = st.phases;
-    // This CTA's row blocks are blockIdx.x + kk * G, kk = 0 .. mine-1.  GATED kernels walk them starting from the
-    // middle (kk = mine/2, wrapping): the first and last row blocks of a banded matrix are the ones that read
-    // ghost columns, and by mid-phase the neighbours' halo has long arrived -- nobody stalls at the phase start.
-    int64_t rb_start = blockIdx.x;
-    if constexpr (GATED && !DYN) {
-        const int64_t mine = n_row_blocks > (int64_t) blockIdx.x ? (n_row_blocks - 1 - blockIdx.x) / G + 1 : 0;
-        rb_start += (mine / 2) * G;
-    }
-    auto next_rb = [&](int64_t r) -> int64_t {  // static walk: successor; n_row_blocks = none
-        int64_t n = r + G;
-        if constexpr (GATED) {
-            if (n >= n_row_blocks) n = blockIdx.x;
-            if (n == rb_start) n = n_row_blocks;
-        }
-        return n;
-    };
-    auto dyn_map = [&](long long g) -> int64_t {  // grabbed index -> row block
-        if (g >= n_row_blocks) return n_row_blocks;
-        long long c = g + dyn->rot;
-        if (c >= n_row_blocks) c -= n_row_blocks;
-        return c;
-    };
-    auto dyn_grab = [&](long long prev) -> long long {  // thread 0; stops asking once the work has run out
-        return prev < n_row_blocks ? (long long) atomicAdd(dyn->counter, 1ull) : prev;
-    };
-    int64_t rb, rb_next;
-    long long pend = 0;  // DYN, thread 0: grabbed index of the block after rb_next
-    int par = 0;
-    if constexpr (DYN) {
-        if constexpr (PART != 2) {
-            if (tid == 0) dyn->s_rbq[0] = (long long) atomicAdd(dyn->counter, 2ull);
-            __syncthreads();
-            const long long g0 = dyn->s_rbq[0];
-            rb = dyn_map(g0);
-            rb_next = dyn_map(g0 + 1);
-            if (tid == 0) pend = dyn_grab(g0 + 1);
-        }
-    } else {
-        rb = rb_start < n_row_blocks ? rb_start : n_row_blocks;
-        rb_next = rb < n_row_blocks ? next_rb(rb) : n_row_blocks;
-    }
+    // This CTA's row blocks are blockIdx.x + kk * G, kk = 0, 1, ...
+    auto next_rb = [&](int64_t r) -> int64_t { return r + G; };  // successor; >= n_row_blocks = none
+    int64_t rb = (int64_t) blockIdx.x < n_row_blocks ? (int64_t) blockIdx.x : n_row_blocks;
+    int64_t rb_next = rb < n_row_blocks ? next_rb(rb) : n_row_blocks;
+    if (rb_next > n_row_blocks) rb_next = n_row_blocks;
     long long lo, hi1, jb, je, nlo, nhi1;
     long long t0;
     if constexpr (PART != 2) {
@@ -335,33 +251,19 @@ __device__ __forceinline__ void csr_tma_run(const TmaSpmvArgs &a, TmaSpmvState &
         load_rect(rb_next, nlo, nhi1);
         if constexpr (PART == 1) {
             cur->lo = lo; cur->hi1 = hi1; cur->nlo = nlo; cur->nhi1 = nhi1;
-            if constexpr (DYN) { cur->rb = rb; cur->rb_next = rb_next; cur->pend = pend; }
             return;
         }
     } else {
         lo = cur->lo; hi1 = cur->hi1; nlo = cur->nlo; nhi1 = cur->nhi1;
-        if constexpr (DYN) { rb = cur->rb; rb_next = cur->rb_next; pend = cur->pend; }
         read_span(0, jb, je);  // still published: nothing has touched s_lo / s_hi since the prologue
         t0 = tile_start(jb);
     }
     int stage = 0, pb = 1;
-    bool checked = block_checked(rb), nchecked = block_checked(rb_next);
-    bool new_block = true;
     double acc = 0.0;
 
     while (rb < n_row_blocks) {
         const bool last_tile = (t0 + kTmaTile >= je);
         if (last_tile) publish_span(pb, nlo, nhi1);
-        if constexpr (DYN) {
-            if (new_block && tid == 0) dyn->s_rbq[par] = pend;  // read by everybody at the end of this block
-            new_block = false;
-        }
-        if constexpr (GATED) {
-            if (checked && tid == 0 && !ghost_ok) {  // released to the other threads by the barrier below
-                ghost_gate_wait(*gate);
-                ghost_ok = true;
-            }
-        }
         // one barrier per tile: (i) stage^1, consumed last iteration, may now be overwritten;
         // (ii) the next block's span is published; (iii) ragged elements stored by thread 0 are visible
         __syncthreads();
@@ -379,7 +281,7 @@ __device__ __forceinline__ void csr_tma_run(const TmaSpmvArgs &a, TmaSpmvState &
         double wv = 0.0;
         if constexpr (NDOT >= 1) {
             const int64_t r = rb * rpb + trow;
-            if (last_tile && tsub == 0 && trow < rpb && r < rows && a.dot_w != a.y) wv = COHERENT ? ld_f64(a.dot_w + r) : __ldg(a.dot_w + r);
+            if (last_tile && tsub == 0 && trow < rpb && r < rows && a.dot_w != a.y) wv = __ldg(a.dot_w + r);
         }
         mbar_wait(&s_full[stage], (phases >> stage) & 1u);
         phases ^= (1u << stage);
@@ -398,7 +300,7 @@ __device__ __forceinline__ void csr_tma_run(const TmaSpmvArgs &a, TmaSpmvState &
                     double xv[kChunk];
 #pragma unroll
                     for (int e = 0; e < kChunk; ++e)
-                        xv[e] = (j + e * LPR < kb) ? (COHERENT ? ld_f64(x + sc[o + e * LPR]) : __ldg(x + sc[o + e * LPR])) : 0.0;
+                        xv[e] = (j + e * LPR < kb) ? __ldg(x + sc[o + e * LPR]) : 0.0;
 #pragma unroll
                     for (int e = 0; e < kChunk; ++e)
                         if (j + e * LPR < kb) acc = add_rn(acc, mul_rn(se[o + e * LPR], xv[e]));
@@ -409,7 +311,7 @@ __device__ __forceinline__ void csr_tma_run(const TmaSpmvArgs &a, TmaSpmvState &
                 const int o = (int) (j - t0);
                 double xv[kChunk];
 #pragma unroll
-                for (int e = 0; e < kChunk; ++e) xv[e] = COHERENT ? ld_f64(x + sc[o + e]) : __ldg(x + sc[o + e]);
+                for (int e = 0; e < kChunk; ++e) xv[e] = __ldg(x + sc[o + e]);
 #pragma unroll
                 for (int e = 0; e < kChunk; ++e) acc = add_rn(acc, mul_rn(se[o + e], xv[e]));
             }
@@ -419,7 +321,7 @@ __device__ __forceinline__ void csr_tma_run(const TmaSpmvArgs &a, TmaSpmvState &
                 double xv[kChunk - 1];
 #pragma unroll
                 for (int e = 0; e < kChunk - 1; ++e)
-                    xv[e] = (e < rem) ? (COHERENT ? ld_f64(x + sc[o + e]) : __ldg(x + sc[o + e])) : 0.0;
+                    xv[e] = (e < rem) ? __ldg(x + sc[o + e]) : 0.0;
 #pragma unroll
                 for (int e = 0; e < kChunk - 1; ++e)
                     if (e < rem) acc = add_rn(acc, mul_rn(se[o + e], xv[e]));
@@ -439,23 +341,14 @@ __device__ __forceinline__ void csr_tma_run(const TmaSpmvArgs &a, TmaSpmvState &
             }
             acc = 0.0;
             rb = rb_next;
-            if constexpr (DYN) {
-                const long long g2 = dyn->s_rbq[par];
-                par ^= 1;
-                rb_next = dyn_map(g2);
-                if (tid == 0) pend = dyn_grab(g2);
-                new_block = true;
-            } else {
-                rb_next = rb < n_row_blocks ? next_rb(rb) : n_row_blocks;
-            }
+            rb_next = rb < n_row_blocks ? next_rb(rb) : n_row_blocks;
+            if (rb_next > n_row_blocks) rb_next = n_row_blocks;
             lo = nlo;
             hi1 = nhi1;
             jb = njb;
             je = nje;
             t0 = tile_start(jb);
             load_rect(rb_next, nlo, nhi1);
-            checked = nchecked;
-            nchecked = block_checked(rb_next);
         } else {
             t0 += kTmaTile;
         }

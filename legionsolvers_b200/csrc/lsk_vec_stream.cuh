@@ -1,7 +1,6 @@
 // lsk_vec_stream.cuh -- TMA-streamed, dynamically scheduled traversal of congruent vectors.
 //
-// Building block of the vector phases of the persistent CG kernel (lsk_cg.cu) and of the stand-alone fused
-// vector kernels of the CG step (lsk_blas1.cu).  Measured on B200 (256^3, 805 MB pass): a grid-stride kernel with
+// Building block of the fused vector kernels of the CG step (lsk_blas1.cu).  Measured on B200 (256^3, 805 MB pass): a grid-stride kernel with
 // register-staged 256-bit loads reaches 6.3 TB/s, the torch copy 6.5 TB/s; this traversal reaches 7.0 TB/s.
 #pragma once
 
@@ -13,9 +12,8 @@ namespace lsk {
 #ifdef __CUDACC__
 
 // ---- TMA-streamed vector phases ---------------------------------------------------------------------------
-// The BLAS-1 phases run on the mat-vec's CTA shape (3 x 256 threads per SM, ~80 registers), which cannot keep
-// enough register-staged loads in flight to saturate HBM.  So they stream too: the 64 KB shared-memory ring
-// of the mat-vec becomes 4 stages of 16 KB, each holding one chunk of every input vector, filled by
+// A CTA shape of 3 x 256 threads per SM cannot keep enough register-staged loads in flight to saturate HBM, so the
+// vector passes stream too: a 64 KB shared-memory ring of 4 stages of 16 KB, each holding one chunk of every input vector, filled by
 // cp.async.bulk three chunks ahead; threads read the chunk from shared memory, compute, and store results
 // straight from registers.
 constexpr int kVecStages = 4;

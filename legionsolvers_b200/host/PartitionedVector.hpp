@@ -185,6 +185,21 @@ public:
         });
     }
     void zero_fill() { constant_fill(static_cast<T>(0)); }
+    // the ghost elements this rank holds beside its owned rows := 0 (before a transposed mat-vec accumulates into them)
+    void zero_ghosts() {
+        Runtime *rt = st->rt;
+        const int64_t own_lo = st->part->own_lo(), own_hi = st->part->own_hi();
+        const int64_t lo_n = own_lo > st->buf_lo ? own_lo - st->buf_lo : 0;
+        const int64_t hi_n = st->buf_hi > own_hi ? st->buf_hi - std::max(own_hi, st->buf_lo - 1) : 0;
+        if (lo_n > 0) {
+            T *x = ptr(st->buf_lo);
+            rt->enqueue("fill", [&] { return VectorKernels<T>::fill(rt->ctx(), rt->stream(), lo_n, (T) 0, x); });
+        }
+        if (hi_n > 0) {
+            T *x = ptr(st->buf_hi - hi_n + 1);
+            rt->enqueue("fill", [&] { return VectorKernels<T>::fill(rt->ctx(), rt->stream(), hi_n, (T) 0, x); });
+        }
+    }
     T operator=(T value) {
         constant_fill(value);
         return value;

@@ -161,6 +161,10 @@ void Runtime::halo_exchange_p2p(const lsk_halo_move *moves, int nmoves) {
     enqueue("halo exchange", [&] { return lsk_halo_exchange_f64(ctx_, stream_, &peers_, moves, nmoves); });
 }
 
+void Runtime::halo_reduce_p2p(const lsk_halo_move *moves, int nmoves) {
+    enqueue("halo reduce", [&] { return lsk_halo_reduce_f64(ctx_, stream_, &peers_, moves, nmoves); });
+}
+
 void Runtime::set_fused_collectives(bool on) {
     if (on && !p2p_) return;
     if (on == fused_) return;

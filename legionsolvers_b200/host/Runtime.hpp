@@ -63,6 +63,7 @@ public:
     // COLLECTIVE (every rank, same order): export `raw` and map everybody else's
     Exported export_allocation(void *raw, int64_t tag0, int64_t tag1);
     void halo_exchange_p2p(const lsk_halo_move *moves, int nmoves);
+    void halo_reduce_p2p(const lsk_halo_move *moves, int nmoves);  // values received are added (lsk_halo_reduce_f64)
     // Fused collectives: every reducing kernel finishes with the cross-rank sum in its own tail, and
     // lsk_xpay_halo_f64 may be used.  Valid only while every rank launches exactly the same reducing
     // kernels (one local piece per rank); the planner switches it on when that holds.

@@ -37,6 +37,10 @@ class SquarePlanner {
         Runtime::Exported landing_peers;
         std::vector<size_t> recv_off, send_off;
         bool landing_ready = false;
+        // the same for the REVERSE exchange of a transposed mat-vec (counts swapped: what I send forward I receive there)
+        DeviceBuffer<char> rev_landing;
+        Runtime::Exported rev_landing_peers;
+        std::vector<size_t> rev_recv_off, rev_send_off;
     };
 
     Runtime *rt;
@@ -66,6 +70,59 @@ class SquarePlanner {
             o.ll_recv = b.landing.ptr + b.recv_off[i];
         }
         return n;
+    }
+
+    // REVERSE exchange (transposed mat-vec): the contributions this rank accumulated in its ghost elements of v travel to the
+    // rows' owners, which add them to their boundary rows -- the forward plan with the two directions swapped
+    void reduce_halo(const Block &b, const PartitionedVector<T> &v) {
+        if (b.halo.empty()) return;
+        if constexpr (std::is_same<T, double>::value) {
+            if (!b.landing_ready || b.halo.size() > LSK_MAX_HALO_MOVES) {
+                // NCCL: the peers' contributions land in a scratch buffer, then one axpy (alpha = 1) per peer adds them
+                if (rt->capturing() || rt->replaying()) rt->fail(LSK_E_INVALID, "rmatvec over NCCL allocates scratch: not inside a trace");
+                int64_t total = 0;
+                for (const HaloMove &m : b.halo) total += m.send_n;
+                DeviceBuffer<T> tmp(rt, (size_t) (total > 0 ? total : 1));
+                rt->group_start();
+                int64_t off = 0;
+                for (const HaloMove &m : b.halo) {
+                    if (m.recv_n > 0) rt->send(v.ptr(m.recv_lo), (size_t) m.recv_n * sizeof(T), m.peer);
+                    if (m.send_n > 0) rt->recv(tmp.ptr + off, (size_t) m.send_n * sizeof(T), m.peer);
+                    off += m.send_n;
+                }
+                rt->group_end();
+                off = 0;
+                for (const HaloMove &m : b.halo) {
+                    if (m.send_n > 0) {
+                        T *const none[4] = {nullptr, nullptr, nullptr, nullptr};
+                        const T *x = tmp.ptr + off;
+                        T *y = v.ptr(m.send_lo);
+                        const int64_t cnt = m.send_n;
+                        rt->enqueue("halo reduce (add)", [&] { return VectorKernels<T>::axpy(rt->ctx(), rt->stream(), cnt, 0, none, x, y); });
+                    }
+                    off += m.send_n;
+                }
+                rt->fence();  // tmp is released on return
+                return;
+            }
+            lsk_halo_move moves[LSK_MAX_HALO_MOVES];
+            int n = 0;
+            for (size_t i = 0; i < b.halo.size(); ++i) {
+                const HaloMove &m = b.halo[i];
+                lsk_halo_move &o = moves[n++];
+                o.peer = m.peer;
+                o.reserved = 0;
+                o.n = m.recv_n;  // my ghost elements owned by the peer
+                o.src = m.recv_n > 0 ? reinterpret_cast<const double *>(v.ptr(m.recv_lo)) : nullptr;
+                o.ll_send = b.rev_landing_peers.base[(size_t) m.peer] + b.rev_send_off[i];
+                o.recv_n = m.send_n;  // my boundary rows the peer holds ghosts of
+                o.recv_dst = m.send_n > 0 ? reinterpret_cast<double *>(v.ptr(m.send_lo)) : nullptr;
+                o.ll_recv = b.rev_landing.ptr + b.rev_recv_off[i];
+            }
+            rt->halo_reduce_p2p(moves, n);
+        } else {
+            rt->fail(LSK_E_INVALID, "the reverse halo exchange is instantiated for fp64");
+        }
     }
 
     void register_space(size_t idx, const PartitionedVector<T> &v) {
@@ -286,7 +343,15 @@ public:
             return false;
         } else {
             if (get_num_spaces() != 1 || total_local_pieces() != 1) return false;
-            if (rt->nranks() > 1 && !halo_push_is_fused()) return false;
+            // Several ranks: measured SLOWER than update + direction (2 GPUs, 2.1 M rows each: 94.7 vs 77.1 us per iteration;
+            // 8 GPUs: 118 vs 82), although the same kernel wins on one GPU (67.5 vs 70.7 us): the packets of the deferred
+            // p.q and of the halo reach a rank ~10 us after its tail kernel started (lsk_cg_tail_stats).
+            // Opt-in there (LSK_CG_TAIL=multi) until that is understood; the kernel itself is exercised on two ranks by
+            // tests/test_comm_loopback_gpu.py.
+            if (rt->nranks() > 1) {
+                static const bool multi = [] { const char *e = getenv("LSK_CG_TAIL"); return e && std::string(e) == "multi"; }();
+                if (!multi || !halo_push_is_fused()) return false;
+            }
             const IndexPartition &part = *canonical_index_partitions[0];
             const int64_t lo = part.own_lo(), cnt = part.own_hi() - part.own_lo() + 1;
             return cnt > 0 && lsk_cg_tail_supported(rt->ctx(), cnt, get_vector(p, 0).ptr(lo), get_vector(q, 0).ptr(lo), get_vector(sol, 0).ptr(lo),
@@ -372,37 +437,43 @@ public:
         // peer's own plan, which is the same host arithmetic on the same all-gathered ranges.  COLLECTIVE: every rank
         // exports, halo or not.
         if (std::is_same<T, double>::value && rt->p2p()) {
-            auto landing_layout = [&](int r, std::vector<int64_t> &mv, int &nmv, std::vector<size_t> &off) -> size_t {
+            // `what` = index of the count a landing buffer is sized for in a plan entry: 4 (recv_n) forward, 2 (send_n) reverse
+            auto landing_layout = [&](int r, int what, std::vector<int64_t> &mv, int &nmv, std::vector<size_t> &off) -> size_t {
                 mv.assign((size_t) R * 5, 0);
                 if (lsk_halo_plan(r, R, all.data(), mv.data(), &nmv) != 0) rt->fail(LSK_E_INVALID, "lsk_halo_plan");
                 size_t total = 0;
                 off.clear();
                 for (int i = 0; i < nmv; ++i) {
                     off.push_back(total);
-                    total += (lsk_halo_landing_bytes(mv[(size_t) i * 5 + 4]) + 255) & ~size_t(255);
+                    total += (lsk_halo_landing_bytes(mv[(size_t) i * 5 + (size_t) what]) + 255) & ~size_t(255);
                 }
                 return total;
             };
-            std::vector<int64_t> mv;
-            std::vector<size_t> off;
-            int nmv = 0;
-            const size_t bytes = landing_layout(rt->rank(), mv, nmv, b.recv_off);
-            b.landing = DeviceBuffer<char>(rt, bytes + 256);
-            rt->check_cuda(cudaMemsetAsync(b.landing.ptr, 0, bytes + 256, rt->stream()), "landing buffers");
-            b.send_off.assign(b.halo.size(), 0);
-            for (size_t i = 0; i < b.halo.size(); ++i) {
-                landing_layout(b.halo[i].peer, mv, nmv, off);
-                bool found = false;
-                for (int j = 0; j < nmv; ++j)
-                    if ((int) mv[(size_t) j * 5] == rt->rank()) {
-                        if (mv[(size_t) j * 5 + 4] != b.halo[i].send_n) rt->fail(LSK_E_INVALID, "halo plans of two ranks disagree");
-                        b.send_off[i] = off[(size_t) j];
-                        found = true;
-                    }
-                if (!found) rt->fail(LSK_E_INVALID, "halo plan: the peer does not list this rank");
-            }
-            rt->fence();  // the buffers are zero before any peer can learn their address
-            b.landing_peers = rt->export_allocation(b.landing.ptr, 0, 0);
+            auto make_landing = [&](int what, DeviceBuffer<char> &buf, Runtime::Exported &peers, std::vector<size_t> &recv_off, std::vector<size_t> &send_off) {
+                std::vector<int64_t> mv;
+                std::vector<size_t> off;
+                int nmv = 0;
+                const size_t bytes = landing_layout(rt->rank(), what, mv, nmv, recv_off);
+                buf = DeviceBuffer<char>(rt, bytes + 256);
+                rt->check_cuda(cudaMemsetAsync(buf.ptr, 0, bytes + 256, rt->stream()), "landing buffers");
+                send_off.assign(b.halo.size(), 0);
+                for (size_t i = 0; i < b.halo.size(); ++i) {
+                    landing_layout(b.halo[i].peer, what, mv, nmv, off);
+                    const int64_t mine = what == 4 ? b.halo[i].send_n : b.halo[i].recv_n;  // what the peer sized its buffer for
+                    bool found = false;
+                    for (int j = 0; j < nmv; ++j)
+                        if ((int) mv[(size_t) j * 5] == rt->rank()) {
+                            if (mv[(size_t) j * 5 + (size_t) what] != mine) rt->fail(LSK_E_INVALID, "halo plans of two ranks disagree");
+                            send_off[i] = off[(size_t) j];
+                            found = true;
+                        }
+                    if (!found) rt->fail(LSK_E_INVALID, "halo plan: the peer does not list this rank");
+                }
+                rt->fence();  // the buffers are zero before any peer can learn their address
+                peers = rt->export_allocation(buf.ptr, 0, 0);
+            };
+            make_landing(4, b.landing, b.landing_peers, b.recv_off, b.send_off);
+            make_landing(2, b.rev_landing, b.rev_landing_peers, b.rev_recv_off, b.rev_send_off);
             b.landing_ready = true;
         }
         // every vector of the domain space must be able to hold the ghost interval
@@ -481,14 +552,17 @@ public:
     // rmatvec: dst = A^T src over all registered blocks -- the transposed operator the reference reserves TaskIDs for
     // (CSRRmatvecTask / COORmatvecTask) and never implemented.  zero_fill(dst), then every block accumulates its piece's
     // contribution into the columns it references.  On several ranks the contributions to columns owned by OTHER ranks
-    // would have to travel back (a reverse halo exchange); that is not built: the call fails loudly when a local piece
-    // references a ghost column.
+    // accumulate in this rank's ghost elements of dst and travel back to their owners in a REVERSE halo exchange
+    // (lsk_halo_reduce_f64: the forward plan with the directions swapped, received values are added).
     void rmatvec(std::size_t dst_idx, std::size_t src_idx) {
         mark_dirty(dst_idx);
         for (std::size_t i = 0; i < get_num_spaces(); ++i) get_vector(dst_idx, i).zero_fill();
         for (const Block &b : row_partitioned_matrices) {
-            if (rt->nranks() > 1 && !b.halo.empty()) rt->fail(LSK_E_INVALID, "rmatvec on several ranks needs a reverse halo exchange (not implemented)");
-            b.matrix->rmatvec(get_vector(dst_idx, b.domain_index), get_vector(src_idx, b.range_index), b.kernel_partition, b.ghost_partition);
+            PartitionedVector<T> &dst = get_vector(dst_idx, b.domain_index);
+            const bool remote = rt->nranks() > 1 && !b.halo.empty();
+            if (remote) dst.zero_ghosts();
+            b.matrix->rmatvec(dst, get_vector(src_idx, b.range_index), b.kernel_partition, b.ghost_partition);
+            if (remote) reduce_halo(b, dst);
         }
     }
 

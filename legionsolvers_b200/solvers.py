@@ -195,6 +195,44 @@ class _Matrix:
             self.h = None
 
 
+# ---- utilities: Matrix Market files (the reference's planned I/O helper, README.md:90-99; host-only) -----------------------
+class MMInfo(C.Structure):  # lsk_mm_info
+    _fields_ = [("rows", C.c_int64), ("cols", C.c_int64), ("entries", C.c_int64), ("field", C.c_int), ("symmetry", C.c_int)]
+
+
+def _mm_check(status: int, where: str) -> None:
+    if status != 0:
+        raise RuntimeError(f"{where} failed ({status}): {_abi.lib().lsk_mm_last_error().decode(errors='replace')}")
+
+
+def read_matrix_market(path):
+    """-> (rows, cols, entry, row, col): the EXPANDED matrix of a `coordinate` file as 0-based COO arrays, in file order."""
+    info = MMInfo()
+    _mm_check(_abi.lib().lsk_mm_read_info(str(path).encode(), C.byref(info)), "lsk_mm_read_info")
+    cap = int(info.entries) * (1 if info.symmetry == 0 else 2)
+    entry, row, col = np.zeros(cap, dtype=np.float64), np.zeros(cap, dtype=np.int64), np.zeros(cap, dtype=np.int64)
+    nnz = C.c_int64(0)
+    _mm_check(_abi.lib().lsk_mm_read_coo_f64(str(path).encode(), cap, _np_ptr(entry, np.float64), _np_ptr(row, np.int64), _np_ptr(col, np.int64),
+                                             C.byref(nnz)), "lsk_mm_read_coo_f64")
+    n = int(nnz.value)
+    return int(info.rows), int(info.cols), entry[:n].copy(), row[:n].copy(), col[:n].copy()
+
+
+def write_matrix_market(path, rows, cols, entry, row, col):
+    e, r, c = (np.ascontiguousarray(entry, dtype=np.float64), np.ascontiguousarray(row, dtype=np.int64), np.ascontiguousarray(col, dtype=np.int64))
+    _mm_check(_abi.lib().lsk_mm_write_coo_f64(str(path).encode(), rows, cols, e.size, _np_ptr(e, np.float64), _np_ptr(r, np.int64), _np_ptr(c, np.int64)),
+              "lsk_mm_write_coo_f64")
+
+
+def coo_to_csr(rows, entry, row, col):
+    """COO arrays in any order -> (entry, col, rowptr) in the CSRMatrix field layout (inclusive rects, a row's entries in input order)."""
+    e, r, c = (np.ascontiguousarray(entry, dtype=np.float64), np.ascontiguousarray(row, dtype=np.int64), np.ascontiguousarray(col, dtype=np.int64))
+    eo, co, rp = np.zeros_like(e), np.zeros_like(c), np.zeros(rows, dtype=RECT_DTYPE)
+    _mm_check(_abi.lib().lsk_coo_to_csr_f64(rows, e.size, _np_ptr(e, np.float64), _np_ptr(r, np.int64), _np_ptr(c, np.int64), _np_ptr(eo, np.float64),
+                                            _np_ptr(co, np.int64), rp.ctypes.data_as(C.c_void_p)), "lsk_coo_to_csr_f64")
+    return eo, co, rp
+
+
 class CSRMatrix(_Matrix):
     @classmethod
     def from_host(cls, rt, rows, cols, entry, col, rowptr, r_range=None, k_range=None, nnz_global=None):
@@ -211,6 +249,13 @@ class CSRMatrix(_Matrix):
         return cls(rt, h)
 
     @classmethod
+    def from_matrix_market(cls, rt, path):
+        """The whole matrix of a Matrix Market file on this rank (single-rank use; slabs: read_matrix_market + from_host)."""
+        rows, cols, entry, row, col = read_matrix_market(path)
+        e, c, rp = coo_to_csr(rows, entry, row, col)
+        return cls.from_host(rt, rows, cols, e, c, rp)
+
+    @classmethod
     def stencil(cls, rt, st: Stencil, pieces: int):
         """create_linearized_csr_stencil_matrix, filled on the GPU."""
         h = C.c_void_p()
@@ -219,6 +264,11 @@ class CSRMatrix(_Matrix):
 
 
 class COOMatrix(_Matrix):
+    @classmethod
+    def from_matrix_market(cls, rt, path):
+        rows, cols, entry, row, col = read_matrix_market(path)
+        return cls.from_host(rt, rows, cols, entry, row, col)
+
     @classmethod
     def from_host(cls, rt, rows, cols, entry, row, col, k_range=None, nnz_global=None):
         k_lo, k_hi = k_range if k_range else (0, entry.size - 1)

@@ -96,6 +96,14 @@ def main():
         lo, hi = sol.owned_range()
         x, xo = sol.to_numpy()[lo:hi + 1], opl.vector(0)[lo:hi + 1]
         xerr = float(np.max(np.abs(x - xo)) / np.max(np.abs(opl.vector(0))))
+        if name in ("cg_7pt", "cg_7pt_2pieces_per_rank", "cg_27pt"):
+            # transposed mat-vec across ranks: y = A^T x; a rank's contributions to columns it does not own accumulate in its
+            # ghost elements and travel back to their owners in the reverse halo exchange (lsk_halo_reduce_f64)
+            pl.rmatvec(3, 0)
+            yt = pl.vector_to_numpy(3, 0, n)[lo:hi + 1]
+            want_t = np.zeros(n)
+            orc.rmatvec(m, opl.vector(0), want_t)
+            xerr = max(xerr, float(np.max(np.abs(yt - want_t[lo:hi + 1])) / np.max(np.abs(want_t))))
         results[name] = {"hist_err": err, "tol": tol, "x_err": xerr, "gen": bool(ok_gen), "part": bool(ok_part),
                          "halo_bytes": pl.halo_bytes_per_matvec, "n_hist": int(np.size(got))}
     comm_err = rt.comm_error()

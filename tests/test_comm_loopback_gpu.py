@@ -123,6 +123,30 @@ def test_halo_exchange_two_ranks_one_gpu(ranks, n01, n10):
     assert all(r.comm_error() == 0 for r in ranks)
 
 
+def test_halo_reduce_two_ranks_one_gpu(ranks):
+    """lsk_halo_reduce_f64, the reverse exchange of a transposed mat-vec: what arrives is ADDED to the destination."""
+    from legionsolvers_b200 import _abi
+
+    L = _abi.lib()
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    n01, n10 = 777, 4096
+    rnd = lambda k: torch.rand(k, dtype=torch.float64, device="cuda", generator=gen) - 0.5  # noqa: E731
+    send = [rnd(n01), rnd(n10)]
+    recv = [rnd(n10), rnd(n01)]
+    land = [landing(n10), landing(n01)]
+    moves = make_moves(send, recv, land)
+    want = [recv[0].clone(), recv[1].clone()]
+    for it in range(4):
+        torch.cuda.synchronize()
+        for r in ranks:
+            _abi.check(L.lsk_halo_reduce_f64(r.ctx.h, r.stream.cuda_stream, C.byref(r.peers), moves[r.rank], 1), "halo reduce")
+        torch.cuda.synchronize()
+        want[0] += send[1]
+        want[1] += send[0]
+        assert torch.equal(recv[0], want[0]) and torch.equal(recv[1], want[1])  # one rounded addition per element and exchange
+    assert all(r.comm_error() == 0 for r in ranks)
+
+
 def test_halo_exchange_rejects_bad_moves(ranks):
     from legionsolvers_b200 import _abi
 

@@ -396,6 +396,44 @@ def test_gmres_hessenberg_vs_oracle(rt, oracle, dim_flag, shape, pieces, restart
             assert np.max(np.abs(x - xo)) <= 50.0 * np.max(np.abs(xo_alt - xo)) + 1e-10 * np.max(np.abs(xo))
 
 
+def test_matrix_market_to_gpu_solve(rt, oracle, tmp_path):
+    """A matrix written to / read from a Matrix Market file (lsk_mm_*), uploaded as CSR and as COO: the mat-vec equals the one
+    of the matrix it came from bit for bit (CSR, thread-per-row) / to 1e-12 (COO)."""
+    import scipy.io
+    import scipy.sparse as sp
+
+    from legionsolvers_b200 import solvers as S
+
+    off, val = oracle.benchmark_stencil(2)
+    m = oracle.stencil_csr((40, 36), off, val)
+    n = m.n_rows
+    rp = np.ascontiguousarray(m.rowptr).view(np.int64).reshape(-1, 2)
+    rows_of = np.repeat(np.arange(n), rp[:, 1] - rp[:, 0] + 1)
+    path = tmp_path / "laplace2d.mtx"
+    S.write_matrix_market(path, n, n, m.entry, rows_of, m.col)
+    a = sp.csr_matrix(scipy.io.mmread(str(path)))        # an independent reader agrees on the file's content
+    x = np.random.default_rng(3).standard_normal(n)
+    for cls, exact in ((S.CSRMatrix, True), (S.COOMatrix, False)):
+        gm = cls.from_matrix_market(rt, path)
+        pl = S.SquarePlanner(rt)
+        sol, rhs = S.PartitionedVector(rt, "sol", n, 4), S.PartitionedVector(rt, "rhs", n, 4)
+        sol.zero_fill()
+        rhs.from_numpy(x)
+        pl.add_sol_vector(sol)
+        pl.add_rhs_vector(rhs)
+        pl.add_row_partitioned_matrix(gm, 0, 0)
+        pl.allocate_workspace(1)
+        pl.matvec(2, 1)
+        y = pl.vector_to_numpy(2, 0, n)
+        want = np.zeros(n)
+        oracle.csr_matvec(m, x, want)
+        if exact:
+            np.testing.assert_array_equal(y, want)
+        else:
+            assert np.max(np.abs(y - want)) <= 1e-12 * np.max(np.abs(want))
+        assert np.max(np.abs(y - a @ x)) <= 1e-12 * np.max(np.abs(want))
+
+
 def test_kernel_launch_accounting(rt, oracle):
     from legionsolvers_b200.solvers import CGSolver
 
