@@ -77,6 +77,10 @@ def test_host_only_entry_points_of_the_cg_step():
     # calls that would touch the device are refused without a context
     assert L.lsk_cg_direction_f64(None, None, 8, None, None, None, None, None, 0, None, 0, None) == -1
     assert L.lsk_halo_exchange_f64(None, None, None, None, 0) == -1
+    assert L.lsk_halo_reduce_f64(None, None, None, None, 0) == -1
+    assert L.lsk_cg_tail_supported(None, 1000, 0x10000, 0x20000, 0x30000, 0x40000) == 0
+    assert L.lsk_cg_tail_f64(None, None, 8, None, None, None, None, None, None, None, None, 0, None, 0, None) == -1
+    assert L.lsk_cg_tail_stats(None, None, None) == -1
     # a landing buffer holds two exchanges of count + 1 (the token) packets of 16 bytes
     assert L.lsk_halo_landing_bytes(0) == 64                      # each half rounded up to 32 bytes
     assert L.lsk_halo_landing_bytes(65536) == 2 * (65537 * 16 + 16)
