@@ -339,6 +339,10 @@ int lsk_shard(int64_t point, int64_t volume, int64_t total_shards);
  * `lsk_peers.window[r]` is rank r's comm window (lsk_comm_window_bytes() bytes of zeroed device
  * memory, cudaMalloc'ed) as mapped INTO THE CALLING PROCESS; window[rank] is the local one.
  * ---------------------------------------------------------------------------------------------- */
+/* Limits, stated rather than silent: at most LSK_MAX_RANKS ranks share peer-memory windows (one NVSwitch domain; the host
+ * layer falls back to NCCL beyond that).  Packet tags are the low 32 bits of 64-bit exchange counters: a tag is only ever
+ * compared for EQUALITY with the one expected next, and the slot it is looked for in holds the tag of two exchanges
+ * earlier at worst, so the wrap after 2^32 exchanges (days of solver iterations) is harmless. */
 #define LSK_MAX_RANKS 16
 typedef struct {
     int rank, nranks;
