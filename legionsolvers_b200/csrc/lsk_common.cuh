@@ -437,12 +437,51 @@ __device__ __forceinline__ void halo_unpack(const HaloLive &hl, const lsk_halo_m
     for (int q = 0; q < nmoves; ++q) {
         const int64_t cnt = m[q].recv_n;
         double *dst = m[q].recv_dst;
+        {   // CTA-level gate: ONE thread looks (at the last packet of the CTA's first pass) until it is there; then everybody
+            // reads.  Reading a packet's sector BEFORE the NVLink write lands is what makes the landing slow.  Measured with
+            // the one-launch CG tail on 2 GPUs (2.1 M rows each, gpurun_out/r2ak-r2am): every thread polling its own packet
+            // right away 94.5 us per iteration (15 us of it waiting for packets that are in place after 10 us when nobody
+            // looks); one lane per warp first 88.6; this gate 77.7 -- the two-kernel form, whose unpacking starts 10+ us
+            // after the sends anyway, 78-79.
+            const int64_t first = (int64_t) blockIdx.x * blockDim.x;
+            if (threadIdx.x == 0 && first <= cnt) {
+                const int64_t sentinel = first + blockDim.x - 1 < cnt ? first + blockDim.x - 1 : cnt;
+                double vs;
+                unsigned int nap0 = 128, polls0 = 0;
+                unsigned long long t_start0 = 0;
+                const unsigned long long t00 = global_ns();
+                bool hit = true;
+                while (!ll_try_load(hl.recv_slot[q], sentinel, hl.tag[q], vs)) {
+                    hit = false;
+                    __nanosleep(nap0);
+                    if (nap0 < 1024) nap0 <<= 1;
+                    if (spin_expired(polls0, t_start0)) break;  // (the loop below reports the timeout)
+                }
+                if (!hit) waited += global_ns() - t00;
+            }
+            __syncthreads();
+        }
         for (int64_t idx = g; idx <= cnt; idx += stride) {  // idx == cnt: the token
             double v;
+            // (later passes, and packets the gate did not vouch for:) lane 0 looks first, the other 31 lanes only once its
+            // packet is there -- a warp's packets were sent by one or two store instructions of the peer and land together
+            if ((threadIdx.x & 31) == 0) {
+                unsigned int nap0 = 128;
+                unsigned int polls0 = 0;
+                unsigned long long t_start0 = 0;
+                const unsigned long long t00 = global_ns();
+                bool first = true;
+                while (!ll_try_load(hl.recv_slot[q], idx, hl.tag[q], v)) {
+                    first = false;
+                    __nanosleep(nap0);
+                    if (nap0 < 2048) nap0 <<= 1;
+                    if (spin_expired(polls0, t_start0)) break;  // (the loop below reports the timeout)
+                }
+                if (!first) waited += global_ns() - t00;
+            }
+            __syncwarp(__activemask());
             if (!ll_try_load(hl.recv_slot[q], idx, hl.tag[q], v)) {
-                // Not there yet: back off between polls.  Tens of thousands of threads re-reading their packets as fast as the
-                // L2 answers crowd out the very NVLink writes they are waiting for (measured: the one-launch CG tail, whose
-                // unpacking follows its sends by ~5 us, waited 10-30 us per iteration without the back-off).
+                // Not there yet: back off between polls.
                 const unsigned long long t0 = global_ns();
                 unsigned int polls = 0, nap = 64;
                 unsigned long long t_start = 0;
