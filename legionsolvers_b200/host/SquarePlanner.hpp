@@ -343,10 +343,10 @@ public:
             return false;
         } else {
             if (get_num_spaces() != 1 || total_local_pieces() != 1) return false;
-            // Several ranks: measured SLOWER than update + direction (2 GPUs, 2.1 M rows each: 94.7 vs 77.1 us per iteration;
-            // 8 GPUs: 118 vs 82), although the same kernel wins on one GPU (67.5 vs 70.7 us): the packets of the deferred
-            // p.q and of the halo reach a rank ~10 us after its tail kernel started (lsk_cg_tail_stats).
-            // Opt-in there (LSK_CG_TAIL=multi) until that is understood; the kernel itself is exercised on two ranks by
+            // Several ranks: opt-in (LSK_CG_TAIL=multi).  It first lost there (2 GPUs: 94.7 vs 77.1 us per iteration) because its
+            // unpacking polled for the neighbours' packets before they could have landed, which delays the landing itself;
+            // since halo_unpack lets one thread per CTA look first it wins on 2 GPUs too (77.7 vs 79.2 us).  The 8-GPU
+            // confirmation is outstanding (profiles/r02_multi_gpu.md); the kernel is exercised on two ranks by
             // tests/test_comm_loopback_gpu.py.
             if (rt->nranks() > 1) {
                 static const bool multi = [] { const char *e = getenv("LSK_CG_TAIL"); return e && std::string(e) == "multi"; }();
